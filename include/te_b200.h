@@ -1,0 +1,146 @@
+/* te_b200 — C ABI of the B200-native transformer-attribution engine.
+ *
+ * Drop-in boundary for the `transformer_attribution` path of hila-chefer/Transformer-Explainability.
+ * The reference has no FFI: its interface for this path is a Python "relprop protocol"
+ * (every layer has forward()/relprop(R, alpha); generators call model(x) -> backward -> model.relprop()).
+ * Each entry point below names the reference interface (file:line under /root/reference) it replaces.
+ *
+ * Conventions
+ *  - all tensors are contiguous row-major fp32 in DEVICE memory, borrowed from the caller
+ *    (the library never allocates or frees caller memory; scratch comes from a caller `workspace`
+ *    whose size is queried with the matching *_workspace_bytes function);
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *  - return value: 0 = ok, negative = error (TE_ERR_*); te_last_error() returns a message.
+ *    No exceptions cross the boundary; there is NO CPU fallback: a missing GPU is an error;
+ *  - a "batch" is a set of INDEPENDENT B=1 explanations: every reduction the reference does over
+ *    a whole B=1 tensor (Add.relprop's sums) is done per sample.
+ */
+#ifndef TE_B200_H
+#define TE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TE_API __attribute__((visibility("default")))
+#else
+#define TE_API
+#endif
+
+#define TE_OK 0
+#define TE_ERR_ARG (-1)
+#define TE_ERR_WORKSPACE (-2)
+#define TE_ERR_CUDA (-3)
+#define TE_ERR_UNSUPPORTED (-4)
+
+/* te_vit_attribute / te_vit_explain flags */
+#define TE_FLAG_ZPLUS_TENSOR_CORES 1u /* z+ Linear-rule GEMMs on tcgen05 (TF32 in, fp32 acc) instead of fp32 SIMT */
+#define TE_FLAG_ROLLOUT_FUSED 2u      /* single fused aggregation+rollout kernel instead of aggregate + bmm chain */
+#define TE_FLAG_KEEP_ALL_CAMS 4u      /* run the relprop below start_layer too (accessor parity with the reference) */
+
+TE_API const char* te_last_error(void);
+TE_API int te_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * ViT / DeiT model description  (baselines/ViT/ViT_LRP.py:247-303 VisionTransformer.__init__)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct te_vit_config {
+    int img_size;     /* 224 */
+    int patch_size;   /* 16  */
+    int in_chans;     /* 3   */
+    int num_classes;  /* 1000 */
+    int dim;          /* embed_dim */
+    int depth;        /* number of blocks */
+    int heads;
+    int mlp_dim;      /* int(dim*mlp_ratio) */
+    int distilled;    /* 1: extra dist_token + head_dist, logits averaged (DeiT-distilled extension) */
+    float eps_block;  /* 1e-6, ViT_LRP.py:184,187 */
+    float eps_final;  /* 1e-5, ViT_LRP.py:266 */
+} te_vit_config;
+
+/* Frozen weights live in ONE flat fp32 device buffer (also the unit of the NCCL broadcast).
+ * Tensor i has the reference state_dict key te_vit_weight_name(i), te_vit_weight_numel(i) floats,
+ * and starts at float offset te_vit_weight_offset(i) (every offset is a multiple of 32 floats). */
+TE_API int te_vit_num_weights(const te_vit_config* cfg);
+TE_API const char* te_vit_weight_name(const te_vit_config* cfg, int i);
+TE_API long long te_vit_weight_numel(const te_vit_config* cfg, int i);
+TE_API long long te_vit_weight_offset(const te_vit_config* cfg, int i);
+TE_API long long te_vit_weight_total(const te_vit_config* cfg); /* floats */
+
+/* Scratch for `batch` samples processed together (activations of every block are kept for the
+ * relprop, like the reference's forward hooks, modules/layers_ours.py:16-27). */
+TE_API long long te_vit_workspace_bytes(const te_vit_config* cfg, int batch);
+
+/* model(x): VisionTransformer.forward (ViT_LRP.py:305-322).  images [batch,in_chans,img,img];
+ * logits [batch,num_classes] (may be NULL).  Leaves every saved activation in `workspace`. */
+TE_API int te_vit_forward(const te_vit_config* cfg, const float* weights, const float* images, int batch,
+                   float* logits, void* workspace, long long workspace_bytes, void* stream);
+
+/* The rest of LRP.generate_LRP (ViT_explanation_generator.py:27-41) + VisionTransformer.relprop with
+ * method="transformer_attribution" (ViT_LRP.py:324-369) on the activations te_vit_forward left behind:
+ * arg-max (where index[b] < 0), one-hot, class gradient of every attention map, LRP relprop through
+ * every block >= start_layer, relu(grad*cam) head-mean, +I, rollout, row 0 without the prefix token(s).
+ * index [batch] int32 in/out (device); maps [batch, tokens-prefix] (device). */
+TE_API int te_vit_attribute(const te_vit_config* cfg, const float* weights, int batch, int* index, int start_layer,
+                     unsigned flags, float* maps, void* workspace, long long workspace_bytes, void* stream);
+
+/* te_vit_forward + te_vit_attribute: one call per batch = LRP.generate_LRP for `batch` independent inputs. */
+TE_API int te_vit_explain(const te_vit_config* cfg, const float* weights, const float* images, int batch, int* index,
+                   int start_layer, unsigned flags, float* maps, float* logits, void* workspace,
+                   long long workspace_bytes, void* stream);
+
+/* Accessors into the workspace — get_attn / get_attn_gradients / get_attn_cam / get_v ...
+ * (ViT_LRP.py:102-130).  name in {"attn","attn_grad","attn_cam","qkv","x_in","ctx","logits","rollout_mats"}.
+ * Returns a device pointer, 4 dims and 4 element strides (unused dims are 1). */
+TE_API int te_vit_tensor(const te_vit_config* cfg, int batch, void* workspace, const char* name, int layer,
+                  float** ptr, long long dims[4], long long strides[4]);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stand-alone LRP rules (modules/layers_ours.py) — the same kernels the engine chains, exported so
+ * that each rule can be parity-tested against the reference layer class it replaces.
+ * ---------------------------------------------------------------------------------------------- */
+/* Linear.relprop, alpha=1 (layers_ours.py:207-230): x [rows,in], w [out,in], r [rows,out] -> out [rows,in].
+ * scratch: rows*out floats. */
+TE_API int te_linear_relprop(const float* x, const float* w, const float* r, float* out, float* scratch, int rows,
+                      int in_features, int out_features, unsigned flags, void* stream);
+/* Add.relprop (layers_ours.py:97-120) per sample: x1,x2,r [batch,per_sample] -> r1,r2.
+ * scratch: batch*48 doubles. */
+TE_API int te_add_relprop(const float* x1, const float* x2, const float* r, float* r1, float* r2, void* scratch,
+                   int batch, long long per_sample, void* stream);
+/* Clone.relprop (layers_ours.py:151-169): out = x * (sd(r1,x)+sd(r2,x)[+sd(r3,x)]); r3 may be NULL. */
+TE_API int te_clone_relprop(const float* x, const float* r1, const float* r2, const float* r3, float* out, long long n,
+                     void* stream);
+/* einsum('bhij,bhjd->bhid').relprop (layers_ours.py:48-60,122-127): p [bh,n,n], v [bh,n,d], r [bh,n,d]
+ * -> rp [bh,n,n], rv [bh,n,d]  (UN-halved).  scratch: bh*n*d floats. */
+TE_API int te_matmul_av_relprop(const float* p, const float* v, const float* r, float* rp, float* rv, float* scratch,
+                         int bh, int n, int d, void* stream);
+/* einsum('bhid,bhjd->bhij').relprop: q,k [bh,n,d], r [bh,n,n] -> rq, rk [bh,n,d] (UN-halved).
+ * scratch: bh*n*n floats. */
+TE_API int te_matmul_qk_relprop(const float* q, const float* k, const float* r, float* rq, float* rk, float* scratch,
+                         int bh, int n, int d, void* stream);
+/* IndexSelect.relprop for token 0 (layers_ours.py:129-147): x [b,n,d], r [b,d] -> out [b,n,d]. */
+TE_API int te_index_select_relprop(const float* x, const float* r, float* out, int batch, int n, int d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Aggregation + rollout  (ViT_LRP.py:357-368, :38-49 ; ExplanationGenerator.py:47-59, :7-18)
+ * ---------------------------------------------------------------------------------------------- */
+/* grad, cam: [layers, batch, heads, n, ld] (ld >= n row stride).  Computes
+ * M_l = mean_h relu(grad_l*cam_l) + I (rows normalised if normalize), J = M_{L-1}...M_{start};
+ * joint [batch,n,n] (may be NULL) receives J, row0 [batch,n] (may be NULL) receives J[:,0,:]. */
+TE_API long long te_rollout_workspace_bytes(int layers, int batch, int n);
+TE_API int te_attribution_rollout(const float* grad, const float* cam, int layers, int batch, int heads, int n, int ld,
+                           int start_layer, int normalize, unsigned flags, float* joint, float* row0,
+                           void* workspace, long long workspace_bytes, void* stream);
+/* compute_rollout_attention(all_layer_matrices, start_layer): mats [layers,batch,n,n] -> joint [batch,n,n]. */
+TE_API int te_compute_rollout_attention(const float* mats, int layers, int batch, int n, int start_layer, int normalize,
+                                 float* joint, void* workspace, long long workspace_bytes, void* stream);
+
+/* Plain fp32 GEMM C[m,n] = A[m,k] * W[n,k]^T (+bias) — exported for kernel unit tests only. */
+TE_API int te_linear_forward(const float* x, const float* w, const float* bias, float* y, int rows, int in_features,
+                      int out_features, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TE_B200_H */

@@ -45,16 +45,42 @@ def _cpu_cuda_shim():
         torch.Tensor.cuda = orig
 
 
+_TOP = ("modules", "baselines", "BERT_explainability", "BERT_rationale_benchmark")
+_REF_MODS = {}
+
+
+def _is_ref_name(k):
+    return any(k == t or k.startswith(t + ".") for t in _TOP)
+
+
+@contextlib.contextmanager
+def _ref_imports():
+    """Import the reference's top-level packages (``modules``, ``baselines`` ...) even when the product's
+    ``install_aliases()`` has registered its own modules under the same names: swap sys.modules entries in,
+    run, swap back."""
+    if not available():
+        raise RuntimeError("reference not present at %s" % REF)
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if _is_ref_name(k)}
+    sys.modules.update(_REF_MODS)
+    sys.path.insert(0, REF)
+    try:
+        yield
+    finally:
+        sys.path.remove(REF)
+        for k in list(sys.modules):
+            if _is_ref_name(k):
+                _REF_MODS[k] = sys.modules.pop(k)
+        sys.modules.update(saved)
+
+
 def _ensure_path():
     if not available():
         raise RuntimeError("reference not present at %s" % REF)
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
 
 
 def vit_module():
-    _ensure_path()
-    import baselines.ViT.ViT_LRP as m          # noqa: E402  (the reference's own module)
+    with _ref_imports():
+        import baselines.ViT.ViT_LRP as m          # noqa: E402  (the reference's own module)
     return m
 
 
@@ -74,8 +100,8 @@ def build_vit(name="vit_base_patch16_224", seed=0, dtype=torch.float32, state_di
 
 def vit_generate_lrp(model, x, index=None, start_layer=0, method="transformer_attribution", taps=False):
     """``LRP(model).generate_LRP`` of the reference, B=1, on CPU.  Returns a dict."""
-    _ensure_path()
-    from baselines.ViT.ViT_explanation_generator import LRP
+    with _ref_imports():
+        from baselines.ViT.ViT_explanation_generator import LRP
     assert x.shape[0] == 1, "the reference path is only correct at B=1 (SURVEY.md §0-6)"
     with _cpu_cuda_shim():
         if x.dtype == torch.float64:
@@ -158,7 +184,8 @@ def _prepare_bert_imports():
 def build_bert(seed=0, dtype=torch.float32, state_dict=None, **cfg_over):
     _prepare_bert_imports()
     from transformers import BertConfig
-    from BERT_explainability.modules.BERT.BertForSequenceClassification import BertForSequenceClassification
+    with _ref_imports():
+        from BERT_explainability.modules.BERT.BertForSequenceClassification import BertForSequenceClassification
     cfg = BertConfig(num_labels=2, return_dict=False, **cfg_over)     # shim 7
     torch.manual_seed(seed)
     old = torch.get_default_dtype()
@@ -172,7 +199,8 @@ def build_bert(seed=0, dtype=torch.float32, state_dict=None, **cfg_over):
 
 def bert_generate_lrp(model, input_ids, attention_mask, index=None, start_layer=11, taps=False):
     _prepare_bert_imports()
-    from BERT_explainability.modules.BERT.ExplanationGenerator import Generator
+    with _ref_imports():
+        from BERT_explainability.modules.BERT.ExplanationGenerator import Generator
     assert input_ids.shape[0] == 1
     with _cpu_cuda_shim():
         out = Generator(model).generate_LRP(input_ids, attention_mask, index=index, start_layer=start_layer)

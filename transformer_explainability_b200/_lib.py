@@ -1,0 +1,93 @@
+"""ctypes binding of the C-ABI CUDA library (``include/te_b200.h``).
+
+There is no CPU fallback: if ``lib/libte_b200.so`` is missing (and cannot be built with nvcc)
+importing this module raises, and every call checks the returned status code.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libte_b200.so")
+
+c_int, c_ll, c_uint, c_void_p, c_char_p, c_float = (ctypes.c_int, ctypes.c_longlong, ctypes.c_uint, ctypes.c_void_p,
+                                                    ctypes.c_char_p, ctypes.c_float)
+
+
+class TeVitConfig(ctypes.Structure):
+    """``te_vit_config`` of include/te_b200.h."""
+    _fields_ = [("img_size", c_int), ("patch_size", c_int), ("in_chans", c_int), ("num_classes", c_int),
+                ("dim", c_int), ("depth", c_int), ("heads", c_int), ("mlp_dim", c_int), ("distilled", c_int),
+                ("eps_block", c_float), ("eps_final", c_float)]
+
+
+FLAG_ZPLUS_TENSOR_CORES = 1
+FLAG_ROLLOUT_FUSED = 2
+FLAG_KEEP_ALL_CAMS = 4
+
+_P = c_void_p
+_CFG = ctypes.POINTER(TeVitConfig)
+
+# name -> (restype, argtypes)   — exactly the prototypes of include/te_b200.h
+PROTOTYPES = {
+    "te_last_error": (c_char_p, []),
+    "te_version": (c_int, []),
+    "te_vit_num_weights": (c_int, [_CFG]),
+    "te_vit_weight_name": (c_char_p, [_CFG, c_int]),
+    "te_vit_weight_numel": (c_ll, [_CFG, c_int]),
+    "te_vit_weight_offset": (c_ll, [_CFG, c_int]),
+    "te_vit_weight_total": (c_ll, [_CFG]),
+    "te_vit_workspace_bytes": (c_ll, [_CFG, c_int]),
+    "te_vit_forward": (c_int, [_CFG, _P, _P, c_int, _P, _P, c_ll, _P]),
+    "te_vit_attribute": (c_int, [_CFG, _P, c_int, _P, c_int, c_uint, _P, _P, c_ll, _P]),
+    "te_vit_explain": (c_int, [_CFG, _P, _P, c_int, _P, c_int, c_uint, _P, _P, _P, c_ll, _P]),
+    "te_vit_tensor": (c_int, [_CFG, c_int, _P, c_char_p, c_int, ctypes.POINTER(_P), ctypes.POINTER(c_ll),
+                              ctypes.POINTER(c_ll)]),
+    "te_linear_relprop": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_uint, _P]),
+    "te_add_relprop": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_ll, _P]),
+    "te_clone_relprop": (c_int, [_P, _P, _P, _P, _P, c_ll, _P]),
+    "te_matmul_av_relprop": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "te_matmul_qk_relprop": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "te_index_select_relprop": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
+    "te_rollout_workspace_bytes": (c_ll, [c_int, c_int, c_int]),
+    "te_attribution_rollout": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_uint, _P, _P, _P,
+                                       c_ll, _P]),
+    "te_compute_rollout_attention": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_ll, _P]),
+    "te_linear_forward": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load (building first if the .so is absent and nvcc is available).  Raises on failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build()
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)          # AttributeError here == header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class TeError(RuntimeError):
+    pass
+
+
+def check(status, what=""):
+    if status < 0:
+        msg = load().te_last_error()
+        raise TeError("%s failed (%d): %s" % (what or "te_b200 call", status, msg.decode() if msg else ""))
+    return status
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())

@@ -1,0 +1,160 @@
+// C-ABI wrappers for the stand-alone rules and rollout entry points declared in include/te_b200.h.
+#include <string.h>
+#include <string>
+
+#include "../../include/te_b200.h"
+#include "te_kernels.h"
+#include "te_rollout.h"
+#include "te_zplus.h"
+
+static thread_local std::string g_last_error;
+void te_set_last_error(const char* msg) { g_last_error = msg ? msg : ""; }
+
+extern "C" const char* te_last_error(void) { return g_last_error.c_str(); }
+extern "C" int te_version(void) { return 100; }
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define REQ(c, msg) do { if (!(c)) { te_set_last_error(msg); return TE_ERR_ARG; } } while (0)
+
+static TeGemm g0(int nb) {
+    TeGemm p;
+    memset(&p, 0, sizeof(p));
+    p.nb1 = nb; p.nb2 = 1; p.alpha = 1.f;
+    return p;
+}
+
+extern "C" int te_linear_forward(const float* x, const float* w, const float* bias, float* y, int rows,
+                                 int in_features, int out_features, void* stream) {
+    REQ(x && w && y && rows > 0 && in_features > 0 && out_features > 0, "te_linear_forward: bad argument");
+    TeGemm p = g0(1);
+    p.A = x; p.lda = in_features; p.B = w; p.ldb = in_features; p.C = y; p.ldc = out_features; p.bias = bias;
+    p.M = rows; p.N = out_features; p.K = in_features;
+    return te_gemm_launch(p, TE_L_K, TE_L_K, TE_XF_NONE, TE_EPI_BIAS, ST(stream));
+}
+
+extern "C" int te_linear_relprop(const float* x, const float* w, const float* r, float* out, float* scratch, int rows,
+                                 int in_features, int out_features, unsigned flags, void* stream) {
+    REQ(x && w && r && out && scratch && rows > 0 && in_features > 0 && out_features > 0, "te_linear_relprop: bad argument");
+    return te_zplus_linear_relprop(x, in_features, w, r, out, scratch, rows, in_features, out_features,
+                                   (flags & TE_FLAG_ZPLUS_TENSOR_CORES) != 0, ST(stream));
+}
+
+extern "C" int te_add_relprop(const float* x1, const float* x2, const float* r, float* r1, float* r2, void* scratch,
+                              int batch, long long per_sample, void* stream) {
+    REQ(x1 && x2 && r && r1 && r2 && scratch && batch > 0 && per_sample > 0, "te_add_relprop: bad argument");
+    return te_launch_add_relprop(x1, x2, r, r1, r2, reinterpret_cast<double*>(scratch), batch, per_sample, ST(stream));
+}
+
+extern "C" int te_clone_relprop(const float* x, const float* r1, const float* r2, const float* r3, float* out,
+                                long long n, void* stream) {
+    REQ(x && r1 && r2 && out && n > 0, "te_clone_relprop: bad argument");
+    return te_launch_clone_relprop(x, r1, r2, r3, out, n, ST(stream));
+}
+
+extern "C" int te_index_select_relprop(const float* x, const float* r, float* out, int batch, int n, int d,
+                                       void* stream) {
+    REQ(x && r && out && batch > 0 && n > 0 && d > 0, "te_index_select_relprop: bad argument");
+    return te_launch_index_select_relprop(x, r, nullptr, out, batch, n, d, ST(stream));
+}
+
+extern "C" int te_matmul_av_relprop(const float* p_, const float* v, const float* r, float* rp, float* rv,
+                                    float* scratch, int bh, int n, int d, void* stream) {
+    REQ(p_ && v && r && rp && rv && scratch && bh > 0 && n > 0 && d > 0 && d % 4 == 0, "te_matmul_av_relprop: bad argument");
+    cudaStream_t st = ST(stream);
+    const long long nn = (long long)n * n, nd = (long long)n * d;
+    // Z = P V
+    TeGemm g = g0(bh);
+    g.A = p_; g.lda = n; g.sA1 = nn; g.B = v; g.ldb = d; g.sB1 = nd; g.C = scratch; g.ldc = d; g.sC1 = nd;
+    g.M = n; g.N = d; g.K = n;
+    TE_TRY(te_gemm_launch(g, TE_L_K, TE_L_MN, TE_XF_NONE, TE_EPI_STORE, st));
+    // S = sd(R, Z)
+    TE_TRY(te_launch_sd(r, scratch, scratch, (long long)bh * nd, st));
+    // R_P = P * (S V^T)
+    g = g0(bh);
+    g.A = scratch; g.lda = d; g.sA1 = nd; g.B = v; g.ldb = d; g.sB1 = nd; g.C = rp; g.ldc = n; g.sC1 = nn;
+    g.E0 = p_; g.lde0 = n; g.sE1 = nn; g.M = n; g.N = n; g.K = d;
+    TE_TRY(te_gemm_launch(g, TE_L_K, TE_L_K, TE_XF_NONE, TE_EPI_MUL, st));
+    // R_V = V * (P^T S)
+    g = g0(bh);
+    g.A = p_; g.lda = n; g.sA1 = nn; g.B = scratch; g.ldb = d; g.sB1 = nd; g.C = rv; g.ldc = d; g.sC1 = nd;
+    g.E0 = v; g.lde0 = d; g.sE1 = nd; g.M = n; g.N = d; g.K = n;
+    TE_TRY(te_gemm_launch(g, TE_L_MN, TE_L_MN, TE_XF_NONE, TE_EPI_MUL, st));
+    return TE_OK;
+}
+
+extern "C" int te_matmul_qk_relprop(const float* q, const float* k, const float* r, float* rq, float* rk,
+                                    float* scratch, int bh, int n, int d, void* stream) {
+    REQ(q && k && r && rq && rk && scratch && bh > 0 && n > 0 && d > 0, "te_matmul_qk_relprop: bad argument");
+    cudaStream_t st = ST(stream);
+    const long long nn = (long long)n * n, nd = (long long)n * d;
+    // S = sd(R, Q K^T)
+    TeGemm g = g0(bh);
+    g.A = q; g.lda = d; g.sA1 = nd; g.B = k; g.ldb = d; g.sB1 = nd; g.C = scratch; g.ldc = n; g.sC1 = nn;
+    g.E0 = r; g.lde0 = n; g.sE1 = nn; g.M = n; g.N = n; g.K = d;
+    TE_TRY(te_gemm_launch(g, TE_L_K, TE_L_K, TE_XF_NONE, TE_EPI_SD, st));
+    // R_Q = Q * (S K)
+    g = g0(bh);
+    g.A = scratch; g.lda = n; g.sA1 = nn; g.B = k; g.ldb = d; g.sB1 = nd; g.C = rq; g.ldc = d; g.sC1 = nd;
+    g.E0 = q; g.lde0 = d; g.sE1 = nd; g.M = n; g.N = d; g.K = n;
+    TE_TRY(te_gemm_launch(g, TE_L_K, TE_L_MN, TE_XF_NONE, TE_EPI_MUL, st));
+    // R_K = K * (S^T Q)
+    g = g0(bh);
+    g.A = scratch; g.lda = n; g.sA1 = nn; g.B = q; g.ldb = d; g.sB1 = nd; g.C = rk; g.ldc = d; g.sC1 = nd;
+    g.E0 = k; g.lde0 = d; g.sE1 = nd; g.M = n; g.N = d; g.K = n;
+    TE_TRY(te_gemm_launch(g, TE_L_MN, TE_L_MN, TE_XF_NONE, TE_EPI_MUL, st));
+    return TE_OK;
+}
+
+// ---- rollout -------------------------------------------------------------------------------------
+static long long ro_align(long long bytes) { return ((bytes + 255) / 256) * 256; }
+
+extern "C" long long te_rollout_workspace_bytes(int layers, int batch, int n) {
+    if (layers <= 0 || batch <= 0 || n <= 0) return TE_ERR_ARG;
+    const long long ld = (n + 3) & ~3;
+    return ro_align((long long)layers * batch * n * ld * 4) + 2 * ro_align((long long)batch * n * ld * 4);
+}
+
+static int ro_carve(void* workspace, long long bytes, int layers, int batch, int n, float** mats, float** ja,
+                    float** jb, int* ld) {
+    REQ(workspace && (((uintptr_t)workspace) & 255u) == 0, "rollout: workspace null or not 256-byte aligned");
+    if (te_rollout_workspace_bytes(layers, batch, n) > bytes) { te_set_last_error("rollout: workspace too small"); return TE_ERR_WORKSPACE; }
+    *ld = (n + 3) & ~3;
+    char* b = reinterpret_cast<char*>(workspace);
+    *mats = reinterpret_cast<float*>(b);
+    b += ro_align((long long)layers * batch * n * (*ld) * 4);
+    *ja = reinterpret_cast<float*>(b);
+    b += ro_align((long long)batch * n * (*ld) * 4);
+    *jb = reinterpret_cast<float*>(b);
+    return TE_OK;
+}
+
+extern "C" int te_attribution_rollout(const float* grad, const float* cam, int layers, int batch, int heads, int n,
+                                      int ld, int start_layer, int normalize, unsigned flags, float* joint,
+                                      float* row0, void* workspace, long long workspace_bytes, void* stream) {
+    REQ(grad && cam && layers > 0 && batch > 0 && heads > 0 && n > 0 && ld >= n, "te_attribution_rollout: bad argument");
+    float *mats, *ja, *jb;
+    int ldw;
+    TE_TRY(ro_carve(workspace, workspace_bytes, layers, batch, n, &mats, &ja, &jb, &ldw));
+    return te_rollout_layers(grad, cam, (long long)batch * heads * n * ld, layers, batch, heads, n, ld, ldw, start_layer,
+                             normalize, flags, mats, ja, jb, joint, row0, /*first=*/0, /*bert_fix=*/0, ST(stream));
+}
+
+extern "C" int te_compute_rollout_attention(const float* mats_in, int layers, int batch, int n, int start_layer,
+                                            int normalize, float* joint, void* workspace, long long workspace_bytes,
+                                            void* stream) {
+    REQ(mats_in && joint && layers > 0 && batch > 0 && n > 0 && start_layer >= 0 && start_layer < layers,
+        "te_compute_rollout_attention: bad argument");
+    float *mats, *ja, *jb;
+    int ldw;
+    TE_TRY(ro_carve(workspace, workspace_bytes, layers, batch, n, &mats, &ja, &jb, &ldw));
+    cudaStream_t st = ST(stream);
+    TE_TRY(te_launch_prep_mats(mats_in, mats, (long long)layers * batch * n, n, n, ldw, normalize, st));
+    const float* res = nullptr;
+    TE_TRY(te_rollout_chain(mats, layers, batch, n, ldw, start_layer, ja, jb, &res, st));
+    if (cudaMemcpy2DAsync(joint, sizeof(float) * n, res, sizeof(float) * ldw, sizeof(float) * n, (size_t)batch * n,
+                          cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+        te_set_last_error("te_compute_rollout_attention: copy failed");
+        return TE_ERR_CUDA;
+    }
+    return TE_OK;
+}

@@ -1,0 +1,567 @@
+// Row-wise and elementwise kernels of the attribution path: embedding assembly, LayerNorm
+// fwd/bwd, softmax fwd/bwd, arg-max / one-hot seed, the elementwise LRP rules (Add, Clone,
+// IndexSelect, safe_divide) and the head-mean aggregation.  All HBM-bound: one warp per row with
+// float4 accesses, or flat grid-stride float4 streams; per-sample reductions accumulate in fp64.
+//
+// Reference semantics: modules/layers_ours.py (rules), baselines/ViT/ViT_LRP.py (wiring).
+#include "te_kernels.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------------------------------------
+// embedding
+// ------------------------------------------------------------------------------------------------
+__global__ void im2col_kernel(const float* __restrict__ img, float* __restrict__ patches, int B, int C, int H,
+                              int W, int P) {
+    // one thread per float4 of a patch row: K index = c*P*P + iy*P + ix  (conv weight [D,C,P,P] flattened)
+    const int gw = W / P, gh = H / P, pq = P / 4;
+    const long long total = (long long)B * gh * gw * C * P * pq;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        long long r = t;
+        const int q = (int)(r % pq); r /= pq;
+        const int iy = (int)(r % P); r /= P;
+        const int c = (int)(r % C); r /= C;
+        const int px = (int)(r % gw); r /= gw;
+        const int py = (int)(r % gh); r /= gh;
+        const int b = (int)r;
+        const float4 v = *reinterpret_cast<const float4*>(
+            img + (((long long)b * C + c) * H + (py * P + iy)) * W + px * P + q * 4);
+        const long long row = ((long long)b * gh + py) * gw + px;
+        *reinterpret_cast<float4*>(patches + row * ((long long)C * P * P) + (c * P + iy) * P + q * 4) = v;
+    }
+}
+
+__global__ void assemble_tokens_kernel(const float* __restrict__ patch_out, const float* __restrict__ cls,
+                                       const float* __restrict__ dist, const float* __restrict__ pos,
+                                       float* __restrict__ x, int B, int N, int D, int n_prefix) {
+    // x = cat(cls[,dist], patches) + pos_embed      (ViT_LRP.py:309-311)
+    const int d4 = D / 4;
+    const long long total = (long long)B * N * d4;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(t % d4);
+        const long long rt = t / d4;
+        const int tok = (int)(rt % N);
+        const int b = (int)(rt / N);
+        float4 v;
+        if (tok < n_prefix) v = *reinterpret_cast<const float4*>((tok == 0 ? cls : dist) + q * 4);
+        else v = *reinterpret_cast<const float4*>(patch_out + ((long long)b * (N - n_prefix) + tok - n_prefix) * D + q * 4);
+        const float4 pe = *reinterpret_cast<const float4*>(pos + (long long)tok * D + q * 4);
+        v.x += pe.x; v.y += pe.y; v.z += pe.z; v.w += pe.w;
+        *reinterpret_cast<float4*>(x + rt * D + q * 4) = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, three cached passes (mean, variance, write)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void row_stats(const float* __restrict__ xr, int D, int lane, float eps, float& mean,
+                                          float& rstd) {
+    float s = 0.f;
+    for (int i = lane * 4; i < D; i += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + i);
+        s += (v.x + v.y) + (v.z + v.w);
+    }
+    mean = te_warp_sum(s) / (float)D;
+    float q = 0.f;
+    for (int i = lane * 4; i < D; i += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + i);
+        const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float var = te_warp_sum(q) / (float)D;
+    rstd = 1.0f / sqrtf(var + eps);
+}
+
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                 const float* __restrict__ b, float* __restrict__ y, float* __restrict__ mean_o,
+                                 float* __restrict__ rstd_o, long long rows, int D, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* xr = x + row * D;
+    float mean, rstd;
+    row_stats(xr, D, lane, eps, mean, rstd);
+    float* yr = y + row * D;
+    for (int i = lane * 4; i < D; i += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + i);
+        const float4 ww = *reinterpret_cast<const float4*>(w + i);
+        const float4 bb = *reinterpret_cast<const float4*>(b + i);
+        float4 o;
+        o.x = (v.x - mean) * rstd * ww.x + bb.x;
+        o.y = (v.y - mean) * rstd * ww.y + bb.y;
+        o.z = (v.z - mean) * rstd * ww.z + bb.z;
+        o.w = (v.w - mean) * rstd * ww.w + bb.w;
+        *reinterpret_cast<float4*>(yr + i) = o;
+    }
+    if (lane == 0) {
+        if (mean_o) mean_o[row] = mean;
+        if (rstd_o) rstd_o[row] = rstd;
+    }
+}
+
+// dx = dres + rstd * (g - mean(g) - xhat*mean(g*xhat)),  g = dy*w, xhat = (x-mean)*rstd
+__device__ __forceinline__ void ln_bwd_row(const float* __restrict__ dyr, const float* __restrict__ xr,
+                                           const float* __restrict__ w, const float* __restrict__ dresr,
+                                           float* __restrict__ dxr, int D, int lane, float mean, float rstd) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = lane * 4; i < D; i += 128) {
+        const float4 dy = *reinterpret_cast<const float4*>(dyr + i);
+        const float4 xv = *reinterpret_cast<const float4*>(xr + i);
+        const float4 ww = *reinterpret_cast<const float4*>(w + i);
+        const float g0 = dy.x * ww.x, g1 = dy.y * ww.y, g2 = dy.z * ww.z, g3 = dy.w * ww.w;
+        s1 += (g0 + g1) + (g2 + g3);
+        s2 += (g0 * ((xv.x - mean) * rstd) + g1 * ((xv.y - mean) * rstd)) +
+              (g2 * ((xv.z - mean) * rstd) + g3 * ((xv.w - mean) * rstd));
+    }
+    const float c1 = te_warp_sum(s1) / (float)D;
+    const float c2 = te_warp_sum(s2) / (float)D;
+    for (int i = lane * 4; i < D; i += 128) {
+        const float4 dy = *reinterpret_cast<const float4*>(dyr + i);
+        const float4 xv = *reinterpret_cast<const float4*>(xr + i);
+        const float4 ww = *reinterpret_cast<const float4*>(w + i);
+        float4 o;
+        o.x = rstd * (dy.x * ww.x - c1 - (xv.x - mean) * rstd * c2);
+        o.y = rstd * (dy.y * ww.y - c1 - (xv.y - mean) * rstd * c2);
+        o.z = rstd * (dy.z * ww.z - c1 - (xv.z - mean) * rstd * c2);
+        o.w = rstd * (dy.w * ww.w - c1 - (xv.w - mean) * rstd * c2);
+        if (dresr) {
+            const float4 r = *reinterpret_cast<const float4*>(dresr + i);
+            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        *reinterpret_cast<float4*>(dxr + i) = o;
+    }
+}
+
+__global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                     const float* __restrict__ w, const float* __restrict__ mean,
+                                     const float* __restrict__ rstd, const float* __restrict__ dres,
+                                     float* __restrict__ dx, long long rows, int D) {
+    const int lane = threadIdx.x & 31;
+    const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    ln_bwd_row(dy + row * D, x + row * D, w, dres ? dres + row * D : nullptr, dx + row * D, D, lane, mean[row],
+               rstd[row]);
+}
+
+__global__ void layernorm_bwd_strided_kernel(const float* __restrict__ dy, long long dy_stride,
+                                             const float* __restrict__ x, long long x_stride,
+                                             const float* __restrict__ w, float eps, float* __restrict__ dx,
+                                             long long dx_stride, int rows, int D) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* xr = x + row * x_stride;
+    float mean, rstd;
+    row_stats(xr, D, lane, eps, mean, rstd);
+    ln_bwd_row(dy + row * dy_stride, xr, w, nullptr, dx + row * dx_stride, D, lane, mean, rstd);
+}
+
+// ------------------------------------------------------------------------------------------------
+// softmax over the last dim (row length N, row stride ld >= N, pad columns zeroed)
+// ------------------------------------------------------------------------------------------------
+__global__ void softmax_kernel(float* __restrict__ s, long long rows, int N, int ld) {
+    const int lane = threadIdx.x & 31;
+    const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float* r = s + row * ld;
+    float m = -INFINITY;
+    for (int j = lane; j < N; j += 32) m = fmaxf(m, r[j]);
+    m = te_warp_max(m);
+    float sum = 0.f;
+    for (int j = lane; j < N; j += 32) {
+        const float e = expf(r[j] - m);
+        r[j] = e;
+        sum += e;
+    }
+    sum = te_warp_sum(sum);
+    for (int j = lane; j < ld; j += 32) r[j] = (j < N) ? r[j] / sum : 0.f;
+}
+
+__global__ void softmax_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp,
+                                   float* __restrict__ ds, long long rows, int N, int ld, float scale) {
+    const int lane = threadIdx.x & 31;
+    const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* pr = p + row * ld;
+    const float* gr = dp + row * ld;
+    float dot = 0.f;
+    for (int j = lane; j < N; j += 32) dot = fmaf(pr[j], gr[j], dot);
+    dot = te_warp_sum(dot);
+    float* o = ds + row * ld;
+    for (int j = lane; j < ld; j += 32) o[j] = (j < N) ? pr[j] * (gr[j] - dot) * scale : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// arg-max (first maximum, like numpy.argmax — ViT_explanation_generator.py:29) and one-hot seed
+// ------------------------------------------------------------------------------------------------
+__global__ void argmax_kernel(const float* __restrict__ logits, int* __restrict__ index, int B, int C,
+                              int only_negative) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const float* r = logits + (long long)b * C;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int j = lane; j < C; j += 32) {
+        const float v = r[j];
+        if (v > best || (v == best && j < bi)) { best = v; bi = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0 && (!only_negative || index[b] < 0)) index[b] = (bi == 0x7fffffff) ? 0 : bi;
+}
+
+__global__ void onehot_kernel(const int* __restrict__ index, float* __restrict__ seed, int B, int C, float value) {
+    const long long total = (long long)B * C;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(t / C), c = (int)(t % C);
+        seed[t] = (index[b] == c) ? value : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LRP elementwise rules
+// ------------------------------------------------------------------------------------------------
+__global__ void sd_kernel(const float* a, const float* b, float* out,
+                          long long n4) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n4;
+         t += (long long)gridDim.x * blockDim.x) {
+        const float4 va = reinterpret_cast<const float4*>(a)[t];
+        const float4 vb = reinterpret_cast<const float4*>(b)[t];
+        reinterpret_cast<float4*>(out)[t] =
+            make_float4(te_sd(va.x, vb.x), te_sd(va.y, vb.y), te_sd(va.z, vb.z), te_sd(va.w, vb.w));
+    }
+}
+
+// Clone.relprop (layers_ours.py:151-169): R = X * ((sd(R1,X) + sd(R2,X)) [+ sd(R3,X)])
+__global__ void clone_relprop_kernel(const float* __restrict__ x, const float* __restrict__ r1,
+                                     const float* __restrict__ r2, const float* __restrict__ r3,
+                                     float* __restrict__ out, long long n4) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n4;
+         t += (long long)gridDim.x * blockDim.x) {
+        const float4 xv = reinterpret_cast<const float4*>(x)[t];
+        const float4 a = reinterpret_cast<const float4*>(r1)[t];
+        const float4 b = reinterpret_cast<const float4*>(r2)[t];
+        float4 c = make_float4(te_sd(a.x, xv.x) + te_sd(b.x, xv.x), te_sd(a.y, xv.y) + te_sd(b.y, xv.y),
+                               te_sd(a.z, xv.z) + te_sd(b.z, xv.z), te_sd(a.w, xv.w) + te_sd(b.w, xv.w));
+        if (r3) {
+            const float4 d = reinterpret_cast<const float4*>(r3)[t];
+            c.x += te_sd(d.x, xv.x); c.y += te_sd(d.y, xv.y); c.z += te_sd(d.z, xv.z); c.w += te_sd(d.w, xv.w);
+        }
+        reinterpret_cast<float4*>(out)[t] = make_float4(xv.x * c.x, xv.y * c.y, xv.z * c.z, xv.w * c.w);
+    }
+}
+
+// Add.relprop (layers_ours.py:97-120), reductions PER SAMPLE (the reference is B=1), fp64 sums.
+// pass 1: partial[b][split] = (sum a, sum b, sum R),  a = x1*sd(R,x1+x2), b = x2*sd(R,x1+x2)
+__global__ void add_reduce_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
+                                  const float* __restrict__ r, double* __restrict__ partial, long long per4) {
+    const int b = blockIdx.y, sp = blockIdx.x;
+    const long long chunk = (per4 + TE_ADD_SPLIT - 1) / TE_ADD_SPLIT;
+    const long long lo = sp * chunk, hi = min(per4, lo + chunk);
+    const float4* p1 = reinterpret_cast<const float4*>(x1) + b * per4;
+    const float4* p2 = reinterpret_cast<const float4*>(x2) + b * per4;
+    const float4* pr = reinterpret_cast<const float4*>(r) + b * per4;
+    double sa = 0.0, sb = 0.0, sr = 0.0;
+    for (long long t = lo + threadIdx.x; t < hi; t += blockDim.x) {
+        const float4 a = p1[t], c = p2[t], rr = pr[t];
+        const float s0 = te_sd(rr.x, a.x + c.x), s1 = te_sd(rr.y, a.y + c.y);
+        const float s2 = te_sd(rr.z, a.z + c.z), s3 = te_sd(rr.w, a.w + c.w);
+        sa += ((double)(a.x * s0) + (double)(a.y * s1)) + ((double)(a.z * s2) + (double)(a.w * s3));
+        sb += ((double)(c.x * s0) + (double)(c.y * s1)) + ((double)(c.z * s2) + (double)(c.w * s3));
+        sr += ((double)rr.x + (double)rr.y) + ((double)rr.z + (double)rr.w);
+    }
+    __shared__ double red[3][kThreads / 32];
+    sa = te_warp_sum(sa); sb = te_warp_sum(sb); sr = te_warp_sum(sr);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { red[0][wid] = sa; red[1][wid] = sb; red[2][wid] = sr; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ta = 0, tb = 0, tr = 0;
+        for (int i = 0; i < kThreads / 32; ++i) { ta += red[0][i]; tb += red[1][i]; tr += red[2][i]; }
+        double* o = partial + ((long long)b * TE_ADD_SPLIT + sp) * 3;
+        o[0] = ta; o[1] = tb; o[2] = tr;
+    }
+}
+
+// pass 2: a *= sd( sd(|A|,|A|+|B|)*rho , A ) ; b likewise
+__global__ void add_scale_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
+                                 const float* __restrict__ r, float* __restrict__ r1, float* __restrict__ r2,
+                                 const double* __restrict__ partial, long long per4) {
+    const int b = blockIdx.y;
+    __shared__ float fa_s, fb_s;
+    if (threadIdx.x == 0) {
+        double A = 0, Bs = 0, rho = 0;
+        const double* q = partial + (long long)b * TE_ADD_SPLIT * 3;
+        for (int i = 0; i < TE_ADD_SPLIT; ++i) { A += q[i * 3]; Bs += q[i * 3 + 1]; rho += q[i * 3 + 2]; }
+        const double den = fabs(A) + fabs(Bs);
+        const double a_fact = te_sd(fabs(A), den) * rho;
+        const double b_fact = te_sd(fabs(Bs), den) * rho;
+        fa_s = (float)te_sd(a_fact, A);
+        fb_s = (float)te_sd(b_fact, Bs);
+    }
+    __syncthreads();
+    const float fa = fa_s, fb = fb_s;
+    const float4* p1 = reinterpret_cast<const float4*>(x1) + b * per4;
+    const float4* p2 = reinterpret_cast<const float4*>(x2) + b * per4;
+    const float4* pr = reinterpret_cast<const float4*>(r) + b * per4;
+    float4* o1 = reinterpret_cast<float4*>(r1) + b * per4;
+    float4* o2 = reinterpret_cast<float4*>(r2) + b * per4;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < per4;
+         t += (long long)gridDim.x * blockDim.x) {
+        const float4 a = p1[t], c = p2[t], rr = pr[t];
+        const float s0 = te_sd(rr.x, a.x + c.x), s1 = te_sd(rr.y, a.y + c.y);
+        const float s2 = te_sd(rr.z, a.z + c.z), s3 = te_sd(rr.w, a.w + c.w);
+        o1[t] = make_float4(a.x * s0 * fa, a.y * s1 * fa, a.z * s2 * fa, a.w * s3 * fa);
+        o2[t] = make_float4(c.x * s0 * fb, c.y * s1 * fb, c.z * s2 * fb, c.w * s3 * fb);
+    }
+}
+
+// IndexSelect.relprop (layers_ours.py:129-147) for the CLS (and distillation) token
+__global__ void index_select_relprop_kernel(const float* __restrict__ x, const float* __restrict__ r0,
+                                            const float* __restrict__ r1, float* __restrict__ out, int B, int N,
+                                            int D) {
+    const long long total = (long long)B * N * D;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int d = (int)(t % D);
+        const long long rt = t / D;
+        const int tok = (int)(rt % N);
+        const int b = (int)(rt / N);
+        float v = 0.f;
+        if (tok == 0) v = x[t] * te_sd(r0[(long long)b * D + d], x[t]);
+        else if (tok == 1 && r1 != nullptr) v = x[t] * te_sd(r1[(long long)b * D + d], x[t]);
+        out[t] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// aggregation: M = mean_h relu(G*cam) (+I) (/rowsum)      ViT_LRP.py:359-365 ; ExplanationGenerator.py:49-55,12-14
+// ------------------------------------------------------------------------------------------------
+__global__ void aggregate_kernel(const float* __restrict__ G, const float* __restrict__ cam,
+                                 float* __restrict__ M, int B, int H, int N, int ld_in, int ld, int add_eye,
+                                 int normalize) {
+    const int lane = threadIdx.x & 31;
+    const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);   // b*N + i
+    if (row >= (long long)B * N) return;
+    const int b = (int)(row / N), i = (int)(row % N);
+    float* out = M + row * ld;
+    float rs = 0.f;
+    for (int j = lane; j < ld; j += 32) {
+        float v = 0.f;
+        if (j < N) {
+            float s = 0.f;
+            for (int h = 0; h < H; ++h) {
+                const long long o = (((long long)b * H + h) * N + i) * ld_in + j;
+                s += fmaxf(G[o] * cam[o], 0.f);
+            }
+            v = s / (float)H;
+            if (add_eye && j == i) v += 1.0f;
+        }
+        out[j] = v;
+        rs += v;
+    }
+    if (normalize) {
+        rs = te_warp_sum(rs);
+        __syncwarp();
+        for (int j = lane; j < N; j += 32) out[j] = out[j] / rs;
+    }
+}
+
+// all_layer_matrices[i] + eye (/ rowsum)     (ViT_LRP.py:41-44 ; ExplanationGenerator.py:11-14)
+__global__ void prep_mats_kernel(const float* __restrict__ in, float* __restrict__ out, long long rows, int N,
+                                 int ld_in, int ld_out, int normalize) {
+    const int lane = threadIdx.x & 31;
+    const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int i = (int)(row % N);
+    const float* r = in + row * ld_in;
+    float* o = out + row * ld_out;
+    float rs = 0.f;
+    for (int j = lane; j < ld_out; j += 32) {
+        float v = 0.f;
+        if (j < N) v = r[j] + ((j == i) ? 1.0f : 0.0f);
+        o[j] = v;
+        rs += v;
+    }
+    if (normalize) {
+        rs = te_warp_sum(rs);
+        __syncwarp();
+        for (int j = lane; j < N; j += 32) o[j] = o[j] / rs;
+    }
+}
+
+__global__ void extract_row_kernel(const float* __restrict__ joint, float* __restrict__ out, int B, int N, int ld,
+                                   int first, int bert_fix) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const float* r = joint + (long long)b * N * ld;
+    float mn = INFINITY;
+    if (bert_fix) {
+        for (int j = lane; j < N; j += 32) mn = fminf(mn, r[j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    float* o = out + (long long)b * (N - first);
+    for (int j = first + lane; j < N; j += 32) o[j - first] = (bert_fix && j == 0) ? mn : r[j];
+}
+
+__global__ void average2_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                                long long n) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
+         t += (long long)gridDim.x * blockDim.x) out[t] = (a[t] + b[t]) / 2.0f;
+}
+
+__global__ void fill_kernel(float* __restrict__ p, float v, long long n) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
+         t += (long long)gridDim.x * blockDim.x) p[t] = v;
+}
+
+inline int flat_grid(long long work) {
+    long long g = (work + kThreads - 1) / kThreads;
+    const long long cap = 148LL * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+inline int warp_rows_grid(long long rows) { return (int)((rows + (kThreads / 32) - 1) / (kThreads / 32)); }
+
+}  // namespace
+
+#define TE_REQ(c, msg) do { if (!(c)) { te_set_last_error(msg); return TE_ERR_ARG; } } while (0)
+
+int te_launch_im2col(const float* img, float* patches, int B, int C, int H, int W, int P, cudaStream_t st) {
+    TE_REQ(P % 4 == 0 && W % P == 0 && H % P == 0, "im2col: patch must divide the image and be a multiple of 4");
+    const long long total = (long long)B * (H / P) * (W / P) * C * P * (P / 4);
+    im2col_kernel<<<flat_grid(total), kThreads, 0, st>>>(img, patches, B, C, H, W, P);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_assemble_tokens(const float* patch_out, const float* cls, const float* dist, const float* pos,
+                              float* x, int B, int N, int D, int n_prefix, cudaStream_t st) {
+    TE_REQ(D % 4 == 0, "assemble: D % 4 != 0");
+    assemble_tokens_kernel<<<flat_grid((long long)B * N * (D / 4)), kThreads, 0, st>>>(patch_out, cls, dist, pos, x,
+                                                                                     B, N, D, n_prefix);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_layernorm(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd,
+                        long long rows, int D, float eps, cudaStream_t st) {
+    TE_REQ(D % 4 == 0, "layernorm: D % 4 != 0");
+    if (rows <= 0) return TE_OK;
+    layernorm_kernel<<<warp_rows_grid(rows), kThreads, 0, st>>>(x, w, b, y, mean, rstd, rows, D, eps);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean, const float* rstd,
+                            const float* dres, float* dx, long long rows, int D, cudaStream_t st) {
+    TE_REQ(D % 4 == 0, "layernorm_bwd: D % 4 != 0");
+    if (rows <= 0) return TE_OK;
+    layernorm_bwd_kernel<<<warp_rows_grid(rows), kThreads, 0, st>>>(dy, x, w, mean, rstd, dres, dx, rows, D);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_layernorm_bwd_strided(const float* dy, long long dy_stride, const float* x, long long x_stride,
+                                    const float* w, float eps, float* dx, long long dx_stride, int rows, int D,
+                                    cudaStream_t st) {
+    TE_REQ(D % 4 == 0 && dy_stride % 4 == 0 && x_stride % 4 == 0 && dx_stride % 4 == 0, "layernorm_bwd_strided: align");
+    if (rows <= 0) return TE_OK;
+    layernorm_bwd_strided_kernel<<<warp_rows_grid(rows), kThreads, 0, st>>>(dy, dy_stride, x, x_stride, w, eps, dx,
+                                                                          dx_stride, rows, D);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_softmax(float* s, long long rows, int N, int ld, cudaStream_t st) {
+    if (rows <= 0) return TE_OK;
+    softmax_kernel<<<warp_rows_grid(rows), kThreads, 0, st>>>(s, rows, N, ld);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_softmax_bwd(const float* p, const float* dp, float* ds, long long rows, int N, int ld, float scale,
+                          cudaStream_t st) {
+    if (rows <= 0) return TE_OK;
+    softmax_bwd_kernel<<<warp_rows_grid(rows), kThreads, 0, st>>>(p, dp, ds, rows, N, ld, scale);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_argmax(const float* logits, int* index, int B, int C, int only_negative, cudaStream_t st) {
+    argmax_kernel<<<warp_rows_grid(B), kThreads, 0, st>>>(logits, index, B, C, only_negative);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_onehot(const int* index, float* seed, int B, int C, float value, cudaStream_t st) {
+    onehot_kernel<<<flat_grid((long long)B * C), kThreads, 0, st>>>(index, seed, B, C, value);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_sd(const float* a, const float* b, float* out, long long n, cudaStream_t st) {
+    TE_REQ(n % 4 == 0, "sd: n % 4 != 0");
+    sd_kernel<<<flat_grid(n / 4), kThreads, 0, st>>>(a, b, out, n / 4);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_clone_relprop(const float* x, const float* r1, const float* r2, const float* r3, float* out,
+                            long long n, cudaStream_t st) {
+    TE_REQ(n % 4 == 0, "clone_relprop: n % 4 != 0");
+    clone_relprop_kernel<<<flat_grid(n / 4), kThreads, 0, st>>>(x, r1, r2, r3, out, n / 4);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_add_relprop(const float* x1, const float* x2, const float* r, float* r1, float* r2, double* partial,
+                          int B, long long per_sample, cudaStream_t st) {
+    TE_REQ(per_sample % 4 == 0, "add_relprop: per-sample size % 4 != 0");
+    TE_REQ(B <= 65535, "add_relprop: batch too large for one launch");
+    const long long per4 = per_sample / 4;
+    add_reduce_kernel<<<dim3(TE_ADD_SPLIT, B), kThreads, 0, st>>>(x1, x2, r, partial, per4);
+    TE_CUDA_CHECK_LAUNCH();
+    int gx = (int)((per4 + kThreads - 1) / kThreads);
+    gx = gx > 64 ? 64 : (gx < 1 ? 1 : gx);
+    add_scale_kernel<<<dim3(gx, B), kThreads, 0, st>>>(x1, x2, r, r1, r2, partial, per4);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_index_select_relprop(const float* x, const float* r_tok0, const float* r_tok1, float* out, int B,
+                                   int N, int D, cudaStream_t st) {
+    index_select_relprop_kernel<<<flat_grid((long long)B * N * D), kThreads, 0, st>>>(x, r_tok0, r_tok1, out, B, N, D);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_aggregate(const float* G, const float* cam, float* M, int B, int H, int N, int ld_in, int ld_out,
+                        int add_eye, int normalize, cudaStream_t st) {
+    aggregate_kernel<<<warp_rows_grid((long long)B * N), kThreads, 0, st>>>(G, cam, M, B, H, N, ld_in, ld_out, add_eye,
+                                                                          normalize);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_prep_mats(const float* in, float* out, long long rows, int N, int ld_in, int ld_out, int normalize,
+                        cudaStream_t st) {
+    if (rows <= 0) return TE_OK;
+    prep_mats_kernel<<<warp_rows_grid(rows), kThreads, 0, st>>>(in, out, rows, N, ld_in, ld_out, normalize);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_extract_row(const float* joint, float* out, int B, int N, int ld, int first, int bert_fix,
+                          cudaStream_t st) {
+    extract_row_kernel<<<warp_rows_grid(B), kThreads, 0, st>>>(joint, out, B, N, ld, first, bert_fix);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_average2(const float* a, const float* b, float* out, long long n, cudaStream_t st) {
+    average2_kernel<<<flat_grid(n), kThreads, 0, st>>>(a, b, out, n);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_fill(float* p, float v, long long n, cudaStream_t st) {
+    if (n <= 0) return TE_OK;
+    fill_kernel<<<flat_grid(n), kThreads, 0, st>>>(p, v, n);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}

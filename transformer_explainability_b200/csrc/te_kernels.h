@@ -1,0 +1,47 @@
+// Internal launcher prototypes (C++ side).  The public C ABI lives in include/te_b200.h.
+#pragma once
+#include "te_common.cuh"
+#include "te_gemm.cuh"
+
+// ---- embedding -------------------------------------------------------------------------------
+int te_launch_im2col(const float* img, float* patches, int B, int C, int H, int W, int P, cudaStream_t st);
+int te_launch_assemble_tokens(const float* patch_out, const float* cls, const float* dist, const float* pos,
+                              float* x, int B, int N, int D, int n_prefix, cudaStream_t st);
+// ---- normalisation ---------------------------------------------------------------------------
+int te_launch_layernorm(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd,
+                        long long rows, int D, float eps, cudaStream_t st);
+int te_launch_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean, const float* rstd,
+                            const float* dres, float* dx, long long rows, int D, cudaStream_t st);
+// rows of dy / x / dx addressed as base + row*row_stride (used for the CLS-only final norm)
+int te_launch_layernorm_bwd_strided(const float* dy, long long dy_stride, const float* x, long long x_stride,
+                                    const float* w, float eps, float* dx, long long dx_stride, int rows, int D,
+                                    cudaStream_t st);
+// ---- softmax ---------------------------------------------------------------------------------
+int te_launch_softmax(float* s, long long rows, int N, int ld, cudaStream_t st);
+int te_launch_softmax_bwd(const float* p, const float* dp, float* ds, long long rows, int N, int ld, float scale,
+                          cudaStream_t st);
+// ---- head / seed -----------------------------------------------------------------------------
+// only_negative: overwrite index[b] only where it is < 0 (caller-supplied class indices are kept)
+int te_launch_argmax(const float* logits, int* index, int B, int C, int only_negative, cudaStream_t st);
+int te_launch_average2(const float* a, const float* b, float* out, long long n, cudaStream_t st);
+int te_launch_onehot(const int* index, float* seed, int B, int C, float value, cudaStream_t st);
+// ---- LRP elementwise rules ---------------------------------------------------------------------
+int te_launch_sd(const float* a, const float* b, float* out, long long n, cudaStream_t st);
+int te_launch_clone_relprop(const float* x, const float* r1, const float* r2, const float* r3, float* out,
+                            long long n, cudaStream_t st);
+// Add rule with per-sample reductions; partial must hold B*TE_ADD_SPLIT*3 doubles.
+#define TE_ADD_SPLIT 16
+int te_launch_add_relprop(const float* x1, const float* x2, const float* r, float* r1, float* r2, double* partial,
+                          int B, long long per_sample, cudaStream_t st);
+// IndexSelect rule: out[b,tok,:] = x*sd(r,x), zero elsewhere.  r is [B,D] per token slot.
+int te_launch_index_select_relprop(const float* x, const float* r_tok0, const float* r_tok1, float* out, int B,
+                                   int N, int D, cudaStream_t st);
+// ---- aggregation / rollout ---------------------------------------------------------------------
+// M[b] = mean_h relu(G*cam) (+I) (row-normalised if normalize) ; G, cam [B,H,N,ld_in] ; M [B,N,ld_out]
+int te_launch_aggregate(const float* G, const float* cam, float* M, int B, int H, int N, int ld_in, int ld_out,
+                        int add_eye, int normalize, cudaStream_t st);
+int te_launch_prep_mats(const float* in, float* out, long long rows, int N, int ld_in, int ld_out, int normalize,
+                        cudaStream_t st);
+int te_launch_extract_row(const float* joint, float* out, int B, int N, int ld, int first, int bert_fix,
+                          cudaStream_t st);
+int te_launch_fill(float* p, float v, long long n, cudaStream_t st);

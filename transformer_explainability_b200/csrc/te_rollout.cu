@@ -1,0 +1,55 @@
+// Aggregation + rollout, composed path: one aggregation launch per layer + a chain of batched fp32
+// GEMMs.  (The fused single-kernel path is selected with TE_FLAG_ROLLOUT_FUSED, te_rollout_fused.cu.)
+#include "te_rollout.h"
+#include "te_kernels.h"
+#include "te_rollout_fused.h"
+#include <string.h>
+
+int te_rollout_chain(const float* mats, int L, int B, int N, int ld, int start_layer, float* joint_a, float* joint_b,
+                     const float** result, cudaStream_t st) {
+    // joint = M[start] ; for i > start: joint = M[i].bmm(joint)     (ViT_LRP.py:46-48)
+    const long long ms = (long long)B * N * ld;
+    const float* joint = mats + (long long)start_layer * ms;
+    float* bufs[2] = {joint_a, joint_b};
+    int which = 0;
+    for (int i = start_layer + 1; i < L; ++i) {
+        TeGemm p;
+        memset(&p, 0, sizeof(p));
+        p.alpha = 1.f; p.nb1 = B; p.nb2 = 1;
+        p.A = mats + (long long)i * ms; p.lda = ld; p.sA1 = (long long)N * ld;
+        p.B = joint; p.ldb = ld; p.sB1 = (long long)N * ld;
+        p.C = bufs[which]; p.ldc = ld; p.sC1 = (long long)N * ld;
+        p.M = N; p.N = N; p.K = N;
+        TE_TRY(te_gemm_launch(p, TE_L_K, TE_L_MN, TE_XF_NONE, TE_EPI_STORE, st));
+        joint = bufs[which];
+        which ^= 1;
+    }
+    *result = joint;
+    return TE_OK;
+}
+
+int te_rollout_layers(const float* G0, const float* cam0, long long layer_stride, int L, int B, int H, int N,
+                      int ld_in, int ld, int start_layer, int normalize, unsigned flags, float* mats, float* joint_a, float* joint_b,
+                      float* joint_out, float* row_out, int first, int bert_fix, cudaStream_t st) {
+    if (start_layer < 0 || start_layer >= L) { te_set_last_error("rollout: start_layer out of range"); return TE_ERR_ARG; }
+    const float* joint = nullptr;
+    if ((flags & 2u) && te_rollout_fused_supported(N, ld_in, ld)) {
+        TE_TRY(te_rollout_fused(G0, cam0, layer_stride, L, B, H, N, ld_in, ld, start_layer, normalize, joint_a, st));
+        joint = joint_a;
+    } else {
+        const long long ms = (long long)B * N * ld;
+        for (int l = start_layer; l < L; ++l)
+            TE_TRY(te_launch_aggregate(G0 + l * layer_stride, cam0 + l * layer_stride, mats + l * ms, B, H, N, ld_in, ld,
+                                       /*add_eye=*/1, normalize, st));
+        TE_TRY(te_rollout_chain(mats, L, B, N, ld, start_layer, joint_a, joint_b, &joint, st));
+    }
+    if (joint_out) {
+        if (cudaMemcpy2DAsync(joint_out, sizeof(float) * N, joint, sizeof(float) * ld, sizeof(float) * N,
+                              (size_t)B * N, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+            te_set_last_error("rollout: joint copy failed");
+            return TE_ERR_CUDA;
+        }
+    }
+    if (row_out) TE_TRY(te_launch_extract_row(joint, row_out, B, N, ld, first, bert_fix, st));
+    return TE_OK;
+}

@@ -1,0 +1,465 @@
+// ViT / DeiT transformer-attribution engine: forward with saved activations, activation-gradient
+// backward (attention gradients only — no dW), LRP relprop through every block, aggregation and
+// rollout.  Host-side orchestration of the kernels in te_gemm.cu / te_elementwise.cu /
+// te_rollout.cu; O(1) launches per block per BATCH, never per sample.
+//
+// Reference wiring: baselines/ViT/ViT_LRP.py (forward :305-322, relprop :324-369, Block :196-213,
+// Attention :132-177, Mlp :61-74), baselines/ViT/ViT_explanation_generator.py:25-41.
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/te_b200.h"
+#include "te_kernels.h"
+#include "te_rollout.h"
+#include "te_zplus.h"
+
+namespace {
+
+constexpr int kMaxDepth = 64;
+
+struct Dims {
+    int B, N, NP, D, H, dh, F, C, L, P, img, Cin, npatch, prefix, KP;
+    long long M;
+};
+
+static bool make_dims(const te_vit_config* c, int B, Dims& d) {
+    if (!c || c->depth <= 0 || c->depth > kMaxDepth || c->heads <= 0 || c->dim % c->heads != 0 || c->dim % 4 != 0 ||
+        c->mlp_dim % 4 != 0 || c->patch_size % 4 != 0 || c->img_size % c->patch_size != 0 || c->num_classes <= 0) {
+        te_set_last_error("te_vit: invalid config");
+        return false;
+    }
+    d.B = B; d.D = c->dim; d.H = c->heads; d.dh = c->dim / c->heads; d.F = c->mlp_dim; d.C = c->num_classes;
+    d.L = c->depth; d.P = c->patch_size; d.img = c->img_size; d.Cin = c->in_chans;
+    d.npatch = (c->img_size / c->patch_size) * (c->img_size / c->patch_size);
+    d.prefix = c->distilled ? 2 : 1;
+    d.N = d.npatch + d.prefix;
+    d.NP = (d.N + 3) & ~3;
+    d.KP = d.Cin * d.P * d.P;
+    d.M = (long long)B * d.N;
+    if (d.dh % 4 != 0) { te_set_last_error("te_vit: head_dim % 4 != 0"); return false; }
+    return true;
+}
+
+// ---- flat weight buffer ------------------------------------------------------------------------
+struct WEntry { std::string name; long long numel; long long offset; };
+
+static std::vector<WEntry> weight_table(const te_vit_config* c) {
+    Dims d;
+    std::vector<WEntry> t;
+    if (!make_dims(c, 1, d)) return t;
+    long long off = 0;
+    auto add = [&](const std::string& n, long long numel) {
+        t.push_back({n, numel, off});
+        off += (numel + 31) & ~31LL;
+    };
+    add("patch_embed.proj.weight", (long long)d.D * d.KP);
+    add("patch_embed.proj.bias", d.D);
+    add("cls_token", d.D);
+    if (c->distilled) add("dist_token", d.D);
+    add("pos_embed", (long long)d.N * d.D);
+    for (int i = 0; i < d.L; ++i) {
+        const std::string p = "blocks." + std::to_string(i) + ".";
+        add(p + "norm1.weight", d.D);
+        add(p + "norm1.bias", d.D);
+        add(p + "attn.qkv.weight", 3LL * d.D * d.D);
+        add(p + "attn.qkv.bias", 3LL * d.D);
+        add(p + "attn.proj.weight", (long long)d.D * d.D);
+        add(p + "attn.proj.bias", d.D);
+        add(p + "norm2.weight", d.D);
+        add(p + "norm2.bias", d.D);
+        add(p + "mlp.fc1.weight", (long long)d.F * d.D);
+        add(p + "mlp.fc1.bias", d.F);
+        add(p + "mlp.fc2.weight", (long long)d.D * d.F);
+        add(p + "mlp.fc2.bias", d.D);
+    }
+    add("norm.weight", d.D);
+    add("norm.bias", d.D);
+    add("head.weight", (long long)d.C * d.D);
+    add("head.bias", d.C);
+    if (c->distilled) {
+        add("head_dist.weight", (long long)d.C * d.D);
+        add("head_dist.bias", d.C);
+    }
+    t.push_back({"", 0, off});   // sentinel: total
+    return t;
+}
+
+struct BlockW {
+    const float *n1w, *n1b, *qkvw, *qkvb, *projw, *projb, *n2w, *n2b, *fc1w, *fc1b, *fc2w, *fc2b;
+};
+struct Weights {
+    const float *patchw, *patchb, *cls, *dist, *pos, *normw, *normb, *headw, *headb, *headdw, *headdb;
+    BlockW blk[kMaxDepth];
+};
+
+static void bind_weights(const te_vit_config* c, const float* base, Weights& w) {
+    const std::vector<WEntry> t = weight_table(c);
+    size_t i = 0;
+    auto next = [&]() { return base + t[i++].offset; };
+    w.patchw = next(); w.patchb = next(); w.cls = next();
+    w.dist = c->distilled ? next() : nullptr;
+    w.pos = next();
+    for (int l = 0; l < c->depth; ++l) {
+        BlockW& b = w.blk[l];
+        b.n1w = next(); b.n1b = next(); b.qkvw = next(); b.qkvb = next(); b.projw = next(); b.projb = next();
+        b.n2w = next(); b.n2b = next(); b.fc1w = next(); b.fc1b = next(); b.fc2w = next(); b.fc2b = next();
+    }
+    w.normw = next(); w.normb = next(); w.headw = next(); w.headb = next();
+    w.headdw = c->distilled ? next() : nullptr;
+    w.headdb = c->distilled ? next() : nullptr;
+}
+
+// ---- workspace ---------------------------------------------------------------------------------
+struct LayerAct {
+    float *x_in, *xn1, *mean1, *rstd1, *qkv, *P, *ctx, *attn_out, *x_mid, *xn2, *mean2, *rstd2, *h, *g, *mlp_out,
+        *G, *cam;
+};
+struct Workspace {
+    LayerAct layer[kMaxDepth];
+    float *x_last, *xf, *logits, *logits2, *seed, *dpool, *rhead0, *rhead1, *shead;
+    float *tD[4], *tF[2], *t3D[2], *tA;
+    float *mats, *joint[2];
+    double* addpart;
+    int* index_tmp;
+    long long bytes;
+};
+
+static void carve(const Dims& d, char* base, Workspace& ws) {
+    long long off = 0;
+    auto take = [&](long long nfloat) -> float* {
+        float* p = base ? reinterpret_cast<float*>(base + off) : nullptr;
+        off += ((nfloat * 4 + 255) / 256) * 256;
+        return p;
+    };
+    const long long MD = d.M * d.D, MF = d.M * d.F, M3D = d.M * 3LL * d.D;
+    const long long AT = (long long)d.B * d.H * d.N * d.NP;
+    for (int l = 0; l < d.L; ++l) {
+        LayerAct& a = ws.layer[l];
+        a.x_in = take(MD); a.xn1 = take(MD); a.mean1 = take(d.M); a.rstd1 = take(d.M);
+        a.qkv = take(M3D); a.P = take(AT); a.ctx = take(MD); a.attn_out = take(MD); a.x_mid = take(MD);
+        a.xn2 = take(MD); a.mean2 = take(d.M); a.rstd2 = take(d.M); a.h = take(MF); a.g = take(MF);
+        a.mlp_out = take(MD); a.G = take(AT); a.cam = take(AT);
+    }
+    ws.x_last = take(MD); ws.xf = take(MD);
+    ws.logits = take((long long)d.B * d.C); ws.logits2 = take((long long)d.B * d.C);
+    ws.seed = take((long long)d.B * d.C); ws.shead = take((long long)d.B * d.C);
+    ws.dpool = take((long long)d.B * d.D); ws.rhead0 = take((long long)d.B * d.D);
+    ws.rhead1 = take((long long)d.B * d.D);
+    for (int i = 0; i < 4; ++i) ws.tD[i] = take(MD);
+    const long long patches = (long long)d.B * d.npatch * d.KP;
+    ws.tF[0] = take(MF > patches ? MF : patches);
+    ws.tF[1] = take(MF);
+    ws.t3D[0] = take(M3D); ws.t3D[1] = take(M3D);
+    ws.tA = take(AT);
+    ws.mats = take((long long)d.L * d.B * d.N * d.NP);
+    ws.joint[0] = take((long long)d.B * d.N * d.NP);
+    ws.joint[1] = take((long long)d.B * d.N * d.NP);
+    ws.addpart = reinterpret_cast<double*>(take((long long)d.B * TE_ADD_SPLIT * 3 * 2));
+    ws.index_tmp = reinterpret_cast<int*>(take(d.B));
+    ws.bytes = off;
+}
+
+// ---- GEMM parameter helpers --------------------------------------------------------------------
+static TeGemm gemm0() {
+    TeGemm p;
+    memset(&p, 0, sizeof(p));
+    p.nb1 = 1; p.nb2 = 1; p.alpha = 1.f;
+    return p;
+}
+
+// y[M,out] = x[M,in] * W[out,in]^T  (+ epilogue)
+static int linear_fwd(const float* x, int lda, const float* w, const float* bias, float* y, float* y2,
+                      const float* e0, long long M, int in, int out, int epi, cudaStream_t st) {
+    TeGemm p = gemm0();
+    p.A = x; p.lda = lda; p.B = w; p.ldb = in; p.C = y; p.ldc = out; p.C2 = y2; p.ldc2 = out; p.E0 = e0; p.lde0 = out;
+    p.bias = bias; p.M = (int)M; p.N = out; p.K = in;
+    return te_gemm_launch(p, TE_L_K, TE_L_K, TE_XF_NONE, epi, st);
+}
+// dx[M,in] = dy[M,out] * W[out,in]
+static int linear_bwd(const float* dy, const float* w, float* dx, const float* e0, long long M, int in, int out,
+                      int epi, cudaStream_t st) {
+    TeGemm p = gemm0();
+    p.A = dy; p.lda = out; p.B = w; p.ldb = in; p.C = dx; p.ldc = in; p.E0 = e0; p.lde0 = in;
+    p.M = (int)M; p.N = in; p.K = out;
+    return te_gemm_launch(p, TE_L_K, TE_L_MN, TE_XF_NONE, epi, st);
+}
+
+// head-batched attention-shaped GEMM over the packed activations
+struct HeadOp {
+    const float* ptr; int ld; long long s1, s2;
+};
+static HeadOp head_rows(const float* base, int ld, int N, int dh) {      // [b, n, (h d)] slice, rows = tokens
+    return {base, ld, (long long)N * ld, (long long)dh};
+}
+static HeadOp attn_map(const float* base, const Dims& d) {               // [b, h, n, NP]
+    return {base, d.NP, (long long)d.H * d.N * d.NP, (long long)d.N * d.NP};
+}
+static int head_gemm(const Dims& d, HeadOp A, int alay, HeadOp B, int blay, HeadOp C, HeadOp E, int M, int N, int K,
+                     float alpha, int epi, cudaStream_t st) {
+    TeGemm p = gemm0();
+    p.A = A.ptr; p.lda = A.ld; p.sA1 = A.s1; p.sA2 = A.s2;
+    p.B = B.ptr; p.ldb = B.ld; p.sB1 = B.s1; p.sB2 = B.s2;
+    p.C = const_cast<float*>(C.ptr); p.ldc = C.ld; p.sC1 = C.s1; p.sC2 = C.s2;
+    p.E0 = E.ptr; p.lde0 = E.ld; p.sE1 = E.s1; p.sE2 = E.s2;
+    p.M = M; p.N = N; p.K = K; p.nb1 = d.B; p.nb2 = d.H; p.alpha = alpha;
+    return te_gemm_launch(p, alay, blay, TE_XF_NONE, epi, st);
+}
+
+static int check_ws(const te_vit_config* cfg, int batch, void* workspace, long long bytes, Dims& d, Workspace& ws) {
+    if (batch <= 0 || !workspace) { te_set_last_error("te_vit: batch <= 0 or null workspace"); return TE_ERR_ARG; }
+    if (!make_dims(cfg, batch, d)) return TE_ERR_ARG;
+    if (((uintptr_t)workspace & 255u) != 0) { te_set_last_error("te_vit: workspace must be 256-byte aligned"); return TE_ERR_ARG; }
+    carve(d, reinterpret_cast<char*>(workspace), ws);
+    if (ws.bytes > bytes) { te_set_last_error("te_vit: workspace too small"); return TE_ERR_WORKSPACE; }
+    return TE_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// public: weights / workspace description
+// ================================================================================================
+extern "C" int te_vit_num_weights(const te_vit_config* cfg) {
+    const auto t = weight_table(cfg);
+    return t.empty() ? TE_ERR_ARG : (int)t.size() - 1;
+}
+extern "C" const char* te_vit_weight_name(const te_vit_config* cfg, int i) {
+    static thread_local std::string s;
+    const auto t = weight_table(cfg);
+    if (i < 0 || i + 1 >= (int)t.size()) return nullptr;
+    s = t[i].name;
+    return s.c_str();
+}
+extern "C" long long te_vit_weight_numel(const te_vit_config* cfg, int i) {
+    const auto t = weight_table(cfg);
+    if (i < 0 || i + 1 >= (int)t.size()) return TE_ERR_ARG;
+    return t[i].numel;
+}
+extern "C" long long te_vit_weight_offset(const te_vit_config* cfg, int i) {
+    const auto t = weight_table(cfg);
+    if (i < 0 || i + 1 >= (int)t.size()) return TE_ERR_ARG;
+    return t[i].offset;
+}
+extern "C" long long te_vit_weight_total(const te_vit_config* cfg) {
+    const auto t = weight_table(cfg);
+    return t.empty() ? TE_ERR_ARG : t.back().offset;
+}
+extern "C" long long te_vit_workspace_bytes(const te_vit_config* cfg, int batch) {
+    Dims d;
+    if (batch <= 0 || !make_dims(cfg, batch, d)) return TE_ERR_ARG;
+    Workspace ws;
+    carve(d, nullptr, ws);
+    return ws.bytes;
+}
+
+// ================================================================================================
+// forward   (ViT_LRP.py:305-322)
+// ================================================================================================
+extern "C" int te_vit_forward(const te_vit_config* cfg, const float* weights, const float* images, int batch,
+                              float* logits, void* workspace, long long workspace_bytes, void* stream) {
+    Dims d; Workspace ws;
+    TE_TRY(check_ws(cfg, batch, workspace, workspace_bytes, d, ws));
+    if (!weights || !images) { te_set_last_error("te_vit_forward: null pointer"); return TE_ERR_ARG; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Weights w;
+    bind_weights(cfg, weights, w);
+    const float scale = 1.0f / sqrtf((float)d.dh);
+
+    // patch embedding: conv k=s=P  ==  im2col + GEMM   (PatchEmbed.forward :230-236)
+    float* patches = ws.tF[0];
+    float* patch_out = ws.tD[3];
+    TE_TRY(te_launch_im2col(images, patches, d.B, d.Cin, d.img, d.img, d.P, st));
+    TE_TRY(linear_fwd(patches, d.KP, w.patchw, w.patchb, patch_out, nullptr, nullptr, (long long)d.B * d.npatch, d.KP,
+                      d.D, TE_EPI_BIAS, st));
+    TE_TRY(te_launch_assemble_tokens(patch_out, w.cls, w.dist, w.pos, ws.layer[0].x_in, d.B, d.N, d.D, d.prefix, st));
+
+    for (int l = 0; l < d.L; ++l) {
+        LayerAct& a = ws.layer[l];
+        const BlockW& bw = w.blk[l];
+        float* x_next = (l + 1 < d.L) ? ws.layer[l + 1].x_in : ws.x_last;
+        TE_TRY(te_launch_layernorm(a.x_in, bw.n1w, bw.n1b, a.xn1, a.mean1, a.rstd1, d.M, d.D, cfg->eps_block, st));
+        TE_TRY(linear_fwd(a.xn1, d.D, bw.qkvw, bw.qkvb, a.qkv, nullptr, nullptr, d.M, d.D, 3 * d.D, TE_EPI_BIAS, st));
+        const HeadOp q = head_rows(a.qkv, 3 * d.D, d.N, d.dh);
+        const HeadOp k = head_rows(a.qkv + d.D, 3 * d.D, d.N, d.dh);
+        const HeadOp v = head_rows(a.qkv + 2 * d.D, 3 * d.D, d.N, d.dh);
+        const HeadOp none = {nullptr, 0, 0, 0};
+        // dots = q k^T * scale ; attn = softmax(dots)        (:139-141)
+        TE_TRY(head_gemm(d, q, TE_L_K, k, TE_L_K, attn_map(a.P, d), none, d.N, d.N, d.dh, scale, TE_EPI_STORE, st));
+        TE_TRY(te_launch_softmax(a.P, (long long)d.B * d.H * d.N, d.N, d.NP, st));
+        // out = attn v -> 'b h n d -> b n (h d)'              (:147-148)
+        TE_TRY(head_gemm(d, attn_map(a.P, d), TE_L_K, v, TE_L_MN, head_rows(a.ctx, d.D, d.N, d.dh), none, d.N, d.dh,
+                         d.N, 1.f, TE_EPI_STORE, st));
+        // proj + residual add1                                  (:150, :198)
+        TE_TRY(linear_fwd(a.ctx, d.D, bw.projw, bw.projb, a.attn_out, a.x_mid, a.x_in, d.M, d.D, d.D,
+                          TE_EPI_BIAS_ADD, st));
+        TE_TRY(te_launch_layernorm(a.x_mid, bw.n2w, bw.n2b, a.xn2, a.mean2, a.rstd2, d.M, d.D, cfg->eps_block, st));
+        TE_TRY(linear_fwd(a.xn2, d.D, bw.fc1w, bw.fc1b, a.h, a.g, nullptr, d.M, d.D, d.F, TE_EPI_BIAS_GELU, st));
+        TE_TRY(linear_fwd(a.g, d.F, bw.fc2w, bw.fc2b, a.mlp_out, x_next, a.x_mid, d.M, d.F, d.D, TE_EPI_BIAS_ADD, st));
+    }
+    // final norm, pool token 0 (and 1), head(s)                (:318-321)
+    TE_TRY(te_launch_layernorm(ws.x_last, w.normw, w.normb, ws.xf, nullptr, nullptr, d.M, d.D, cfg->eps_final, st));
+    TE_TRY(linear_fwd(ws.xf, d.N * d.D, w.headw, w.headb, ws.logits, nullptr, nullptr, d.B, d.D, d.C, TE_EPI_BIAS, st));
+    if (cfg->distilled) {
+        TE_TRY(linear_fwd(ws.xf + d.D, d.N * d.D, w.headdw, w.headdb, ws.logits2, nullptr, nullptr, d.B, d.D, d.C,
+                          TE_EPI_BIAS, st));
+        TE_TRY(te_launch_average2(ws.logits, ws.logits2, ws.logits, (long long)d.B * d.C, st));
+    }
+    if (logits) {
+        if (cudaMemcpyAsync(logits, ws.logits, sizeof(float) * d.B * d.C, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+            te_set_last_error("te_vit_forward: logits copy failed");
+            return TE_ERR_CUDA;
+        }
+    }
+    return TE_OK;
+}
+
+// ================================================================================================
+// attribute = class-gradient backward + relprop + aggregation + rollout
+// ================================================================================================
+extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, int batch, int* index,
+                                int start_layer, unsigned flags, float* maps, void* workspace,
+                                long long workspace_bytes, void* stream) {
+    Dims d; Workspace ws;
+    TE_TRY(check_ws(cfg, batch, workspace, workspace_bytes, d, ws));
+    if (!weights || !index || !maps) { te_set_last_error("te_vit_attribute: null pointer"); return TE_ERR_ARG; }
+    if (start_layer < 0 || start_layer >= d.L) { te_set_last_error("te_vit_attribute: start_layer out of range"); return TE_ERR_ARG; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Weights w;
+    bind_weights(cfg, weights, w);
+    const float scale = 1.0f / sqrtf((float)d.dh);
+    const HeadOp none = {nullptr, 0, 0, 0};
+    const long long MD = d.M * d.D;
+    const int low = (flags & TE_FLAG_KEEP_ALL_CAMS) ? 0 : start_layer;   // lowest block the relprop must reach
+    const bool tc = (flags & TE_FLAG_ZPLUS_TENSOR_CORES) != 0;
+
+    // ---- class index and seeds  (ViT_explanation_generator.py:28-35) ---------------------------
+    TE_TRY(te_launch_argmax(ws.logits, index, d.B, d.C, /*only_negative=*/1, st));
+    const float seedv = cfg->distilled ? 0.5f : 1.0f;   // averaged heads: each gets half of the seed
+    TE_TRY(te_launch_onehot(index, ws.seed, d.B, d.C, seedv, st));
+
+    // ---- backward: d logit_c / d attn_l for every block  (what :145's hook captures) -------------
+    float* dxa = ws.tD[0]; float* dxb = ws.tD[1]; float* dctx = ws.tD[2]; float* dxn = ws.tD[3];
+    float* dF = ws.tF[0]; float* dqkv = ws.t3D[0]; float* dS = ws.tA;
+    TE_TRY(te_launch_fill(dxa, 0.f, MD, st));
+    {
+        // d pooled = seed * W_head ; final LayerNorm backward touches only the pooled token rows
+        TE_TRY(linear_bwd(ws.seed, w.headw, ws.dpool, nullptr, d.B, d.D, d.C, TE_EPI_STORE, st));
+        TE_TRY(te_launch_layernorm_bwd_strided(ws.dpool, d.D, ws.x_last, (long long)d.N * d.D, w.normw, cfg->eps_final,
+                                               dxa, (long long)d.N * d.D, d.B, d.D, st));
+        if (cfg->distilled) {
+            TE_TRY(linear_bwd(ws.seed, w.headdw, ws.dpool, nullptr, d.B, d.D, d.C, TE_EPI_STORE, st));
+            TE_TRY(te_launch_layernorm_bwd_strided(ws.dpool, d.D, ws.x_last + d.D, (long long)d.N * d.D, w.normw,
+                                                   cfg->eps_final, dxa + d.D, (long long)d.N * d.D, d.B, d.D, st));
+        }
+    }
+    for (int l = d.L - 1; l >= start_layer; --l) {
+        LayerAct& a = ws.layer[l];
+        const BlockW& bw = w.blk[l];
+        const HeadOp q = head_rows(a.qkv, 3 * d.D, d.N, d.dh);
+        const HeadOp k = head_rows(a.qkv + d.D, 3 * d.D, d.N, d.dh);
+        const HeadOp v = head_rows(a.qkv + 2 * d.D, 3 * d.D, d.N, d.dh);
+        // mlp branch
+        TE_TRY(linear_bwd(dxa, bw.fc2w, dF, a.h, d.M, d.F, d.D, TE_EPI_GELU_BWD, st));
+        TE_TRY(linear_bwd(dF, bw.fc1w, dxn, nullptr, d.M, d.D, d.F, TE_EPI_STORE, st));
+        TE_TRY(te_launch_layernorm_bwd(dxn, a.x_mid, bw.n2w, a.mean2, a.rstd2, dxa, dxb, d.M, d.D, st));
+        // attention branch
+        TE_TRY(linear_bwd(dxb, bw.projw, dctx, nullptr, d.M, d.D, d.D, TE_EPI_STORE, st));
+        TE_TRY(head_gemm(d, head_rows(dctx, d.D, d.N, d.dh), TE_L_K, v, TE_L_K, attn_map(a.G, d), none, d.N, d.N, d.dh,
+                         1.f, TE_EPI_STORE, st));                                   // G = dctx v^T
+        if (l == start_layer) break;                                                // lower gradients are never read
+        TE_TRY(head_gemm(d, attn_map(a.P, d), TE_L_MN, head_rows(dctx, d.D, d.N, d.dh), TE_L_MN,
+                         head_rows(dqkv + 2 * d.D, 3 * d.D, d.N, d.dh), none, d.N, d.dh, d.N, 1.f, TE_EPI_STORE, st));  // dV = P^T dctx
+        TE_TRY(te_launch_softmax_bwd(a.P, a.G, dS, (long long)d.B * d.H * d.N, d.N, d.NP, scale, st));
+        TE_TRY(head_gemm(d, attn_map(dS, d), TE_L_K, k, TE_L_MN, head_rows(dqkv, 3 * d.D, d.N, d.dh), none, d.N, d.dh,
+                         d.N, 1.f, TE_EPI_STORE, st));                              // dQ = dS k
+        TE_TRY(head_gemm(d, attn_map(dS, d), TE_L_MN, q, TE_L_MN, head_rows(dqkv + d.D, 3 * d.D, d.N, d.dh), none, d.N,
+                         d.dh, d.N, 1.f, TE_EPI_STORE, st));                        // dK = dS^T q
+        TE_TRY(linear_bwd(dqkv, bw.qkvw, dxn, nullptr, d.M, d.D, 3 * d.D, TE_EPI_STORE, st));
+        TE_TRY(te_launch_layernorm_bwd(dxn, a.x_in, bw.n1w, a.mean1, a.rstd1, dxb, dxa, d.M, d.D, st));
+    }
+
+    // ---- relprop  (VisionTransformer.relprop :324-331) --------------------------------------------
+    float* R = ws.tD[0]; float* R1 = ws.tD[1]; float* R2 = ws.tD[2]; float* R3 = ws.tD[3];
+    float* RF = ws.tF[0]; float* SF = ws.tF[1]; float* S = ws.t3D[0]; float* Rqkv = ws.t3D[1]; float* S1 = ws.tA;
+    // head.relprop (z+), pool.relprop (IndexSelect), norm.relprop (identity)
+    TE_TRY(te_zplus_linear_relprop(ws.xf, (long long)d.N * d.D, w.headw, ws.seed, ws.rhead0, ws.shead, d.B, d.D, d.C,
+                                   false, st));
+    if (cfg->distilled)
+        TE_TRY(te_zplus_linear_relprop(ws.xf + d.D, (long long)d.N * d.D, w.headdw, ws.seed, ws.rhead1, ws.shead, d.B,
+                                       d.D, d.C, false, st));
+    TE_TRY(te_launch_index_select_relprop(ws.xf, ws.rhead0, cfg->distilled ? ws.rhead1 : nullptr, R, d.B, d.N, d.D, st));
+
+    for (int l = d.L - 1; l >= low; --l) {
+        LayerAct& a = ws.layer[l];
+        const BlockW& bw = w.blk[l];
+        const HeadOp q = head_rows(a.qkv, 3 * d.D, d.N, d.dh);
+        const HeadOp k = head_rows(a.qkv + d.D, 3 * d.D, d.N, d.dh);
+        const HeadOp v = head_rows(a.qkv + 2 * d.D, 3 * d.D, d.N, d.dh);
+        // Block.relprop :203-213
+        TE_TRY(te_launch_add_relprop(a.x_mid, a.mlp_out, R, R1, R2, ws.addpart, d.B, (long long)d.N * d.D, st));   // add2
+        TE_TRY(te_zplus_linear_relprop(a.g, d.F, bw.fc2w, R2, RF, S, d.M, d.F, d.D, tc, st));                       // fc2 ; GELU id
+        TE_TRY(te_zplus_linear_relprop(a.xn2, d.D, bw.fc1w, RF, R2, SF, d.M, d.D, d.F, tc, st));                    // fc1 ; norm2 id
+        TE_TRY(te_launch_clone_relprop(a.x_mid, R1, R2, nullptr, R, MD, st));                                      // clone2
+        TE_TRY(te_launch_add_relprop(a.x_in, a.attn_out, R, R1, R2, ws.addpart, d.B, (long long)d.N * d.D, st));    // add1
+        // Attention.relprop :154-177
+        TE_TRY(te_zplus_linear_relprop(a.ctx, d.D, bw.projw, R2, R3, S, d.M, d.D, d.D, tc, st));                    // proj
+        // matmul2 rule: Z = attn v is the saved ctx itself (bit-identical recomputation in the reference)
+        TE_TRY(te_launch_sd(R3, a.ctx, S, MD, st));
+        TE_TRY(head_gemm(d, head_rows(S, d.D, d.N, d.dh), TE_L_K, v, TE_L_K, attn_map(a.cam, d), attn_map(a.P, d), d.N,
+                         d.N, d.dh, 0.5f, TE_EPI_MUL, st));                         // attn_cam = (P * (S v^T)) / 2   :160-165
+        if (l == low) break;                                                        // nothing below is consumed
+        TE_TRY(head_gemm(d, attn_map(a.P, d), TE_L_MN, head_rows(S, d.D, d.N, d.dh), TE_L_MN,
+                         head_rows(Rqkv + 2 * d.D, 3 * d.D, d.N, d.dh), v, d.N, d.dh, d.N, 0.5f, TE_EPI_MUL, st));   // cam_v
+        // matmul1 rule (unscaled Z = q k^T)  :170-173
+        TE_TRY(head_gemm(d, q, TE_L_K, k, TE_L_K, attn_map(S1, d), attn_map(a.cam, d), d.N, d.N, d.dh, 1.f, TE_EPI_SD, st));
+        TE_TRY(head_gemm(d, attn_map(S1, d), TE_L_K, k, TE_L_MN, head_rows(Rqkv, 3 * d.D, d.N, d.dh), q, d.N, d.dh, d.N,
+                         0.5f, TE_EPI_MUL, st));                                    // cam_q
+        TE_TRY(head_gemm(d, attn_map(S1, d), TE_L_MN, q, TE_L_MN, head_rows(Rqkv + d.D, 3 * d.D, d.N, d.dh), k, d.N,
+                         d.dh, d.N, 0.5f, TE_EPI_MUL, st));                         // cam_k
+        TE_TRY(te_zplus_linear_relprop(a.xn1, d.D, bw.qkvw, Rqkv, R2, S, d.M, d.D, 3 * d.D, tc, st));               // qkv ; norm1 id
+        TE_TRY(te_launch_clone_relprop(a.x_in, R1, R2, nullptr, R, MD, st));                                       // clone1
+    }
+
+    // ---- aggregation + rollout  (:357-368) ---------------------------------------------------------
+    TE_TRY(te_rollout_layers(ws.layer[0].G, ws.layer[0].cam,
+                             d.L > 1 ? (long long)(ws.layer[1].G - ws.layer[0].G) : 0, d.L, d.B, d.H, d.N, d.NP, d.NP,
+                             start_layer, /*normalize=*/0, flags, ws.mats, ws.joint[0], ws.joint[1], nullptr, maps,
+                             d.prefix, /*bert_fix=*/0, st));
+    return TE_OK;
+}
+
+extern "C" int te_vit_explain(const te_vit_config* cfg, const float* weights, const float* images, int batch,
+                              int* index, int start_layer, unsigned flags, float* maps, float* logits,
+                              void* workspace, long long workspace_bytes, void* stream) {
+    TE_TRY(te_vit_forward(cfg, weights, images, batch, logits, workspace, workspace_bytes, stream));
+    return te_vit_attribute(cfg, weights, batch, index, start_layer, flags, maps, workspace, workspace_bytes, stream);
+}
+
+extern "C" int te_vit_tensor(const te_vit_config* cfg, int batch, void* workspace, const char* name, int layer,
+                             float** ptr, long long dims[4], long long strides[4]) {
+    Dims d; Workspace ws;
+    if (!workspace || !name || !ptr) return TE_ERR_ARG;
+    if (batch <= 0 || !make_dims(cfg, batch, d)) return TE_ERR_ARG;
+    carve(d, reinterpret_cast<char*>(workspace), ws);
+    const std::string n(name);
+    auto set = [&](float* p, long long d0, long long d1, long long d2, long long d3, long long s0, long long s1,
+                   long long s2, long long s3) {
+        *ptr = p; dims[0] = d0; dims[1] = d1; dims[2] = d2; dims[3] = d3;
+        strides[0] = s0; strides[1] = s1; strides[2] = s2; strides[3] = s3;
+        return TE_OK;
+    };
+    if (n == "logits") return set(ws.logits, d.B, d.C, 1, 1, d.C, 1, 1, 1);
+    if (n == "rollout_mats") return set(ws.mats, d.L, d.B, d.N, d.N, (long long)d.B * d.N * d.NP, (long long)d.N * d.NP, d.NP, 1);
+    if (layer < 0 || layer >= d.L) { te_set_last_error("te_vit_tensor: layer out of range"); return TE_ERR_ARG; }
+    LayerAct& a = ws.layer[layer];
+    const long long hs = (long long)d.N * d.NP, bs = hs * d.H;
+    if (n == "attn") return set(a.P, d.B, d.H, d.N, d.N, bs, hs, d.NP, 1);
+    if (n == "attn_grad") return set(a.G, d.B, d.H, d.N, d.N, bs, hs, d.NP, 1);
+    if (n == "attn_cam") return set(a.cam, d.B, d.H, d.N, d.N, bs, hs, d.NP, 1);
+    if (n == "qkv") return set(a.qkv, d.B, d.N, 3LL * d.D, 1, (long long)d.N * 3 * d.D, 3LL * d.D, 1, 1);
+    if (n == "x_in") return set(a.x_in, d.B, d.N, d.D, 1, (long long)d.N * d.D, d.D, 1, 1);
+    if (n == "ctx") return set(a.ctx, d.B, d.N, d.D, 1, (long long)d.N * d.D, d.D, 1, 1);
+    te_set_last_error("te_vit_tensor: unknown tensor name");
+    return TE_ERR_ARG;
+}

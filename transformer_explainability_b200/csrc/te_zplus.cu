@@ -1,0 +1,27 @@
+// z+ Linear rule driver: fp32 SIMT path (te_gemm.cu) or tcgen05 tensor-core path (te_gemm_tc.cu).
+#include "te_zplus.h"
+#include "te_gemm.cuh"
+#include "te_gemm_tc.h"
+#include <string.h>
+
+int te_zplus_linear_relprop(const float* x, long long ldx, const float* w, const float* r, float* out,
+                            float* s_scratch, long long rows, int in_features, int out_features, bool use_tc,
+                            cudaStream_t st) {
+    if (rows <= 0) return TE_OK;
+    if (rows > 0x7fffffffLL || ldx > 0x7fffffffLL) { te_set_last_error("zplus: rows/ldx overflow int"); return TE_ERR_ARG; }
+    if (use_tc && te_tc_zplus_supported(rows, in_features, out_features, ldx))
+        return te_tc_zplus_linear_relprop(x, ldx, w, r, out, s_scratch, rows, in_features, out_features, st);
+    TeGemm p;
+    memset(&p, 0, sizeof(p));
+    p.nb1 = p.nb2 = 1; p.alpha = 1.f;
+    // S = sd(R, x+ W+^T + x- W-^T)
+    p.A = x; p.lda = (int)ldx; p.B = w; p.ldb = in_features; p.C = s_scratch; p.ldc = out_features;
+    p.E0 = r; p.lde0 = out_features; p.M = (int)rows; p.N = out_features; p.K = in_features;
+    TE_TRY(te_gemm_launch(p, TE_L_K, TE_L_K, TE_XF_AB_POSNEG, TE_EPI_SD, st));
+    // R_in = x+ * (S W+) + x- * (S W-)
+    p.A = s_scratch; p.lda = out_features; p.B = w; p.ldb = in_features; p.C = out; p.ldc = in_features;
+    p.E0 = x; p.lde0 = (int)ldx; p.M = (int)rows; p.N = in_features; p.K = out_features;
+    TE_TRY(te_gemm_launch(p, TE_L_K, TE_L_MN, TE_XF_B_POS, TE_EPI_MULPOS, st));
+    TE_TRY(te_gemm_launch(p, TE_L_K, TE_L_MN, TE_XF_B_NEG, TE_EPI_MULNEG_ACC, st));
+    return TE_OK;
+}

@@ -1,0 +1,11 @@
+// z+ rule of Linear.relprop (modules/layers_ours.py:207-230, alpha=1):
+//   Z = x+ W+^T + x- W-^T ; S = safe_divide(R, Z) ; R_in = x+ * (S W+) + x- * (S W-)
+#pragma once
+#include "te_common.cuh"
+
+// x [rows, in] with row stride ldx ; w [out, in] ; r [rows, out] ; out [rows, in] ; s_scratch [rows, out].
+// use_tc: run both contractions on tcgen05 tensor cores (TF32 inputs, fp32 accumulate) when the shape
+// qualifies; otherwise (and as the checker) the fp32 SIMT path.
+int te_zplus_linear_relprop(const float* x, long long ldx, const float* w, const float* r, float* out,
+                            float* s_scratch, long long rows, int in_features, int out_features, bool use_tc,
+                            cudaStream_t st);

@@ -1,0 +1,163 @@
+"""Host-side engine objects: flat frozen-weight buffer, workspace, and the explain call.
+
+The engine is the B200 replacement for the stateful hook machinery of the reference
+(``modules/layers_ours.py:16-27`` forward hooks, ``retain_graph=True`` autograd graph): it owns one
+flat fp32 weight buffer (the unit of the single NCCL broadcast) and one activation workspace per
+stream, and issues O(1) launches per block per BATCH through the C ABI.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import TeVitConfig, check, ptr
+
+
+def vit_config(img_size=224, patch_size=16, in_chans=3, num_classes=1000, embed_dim=768, depth=12, num_heads=12,
+               mlp_ratio=4., distilled=False, eps_block=1e-6, eps_final=1e-5):
+    return TeVitConfig(img_size, patch_size, in_chans, num_classes, embed_dim, depth, num_heads,
+                       int(embed_dim * mlp_ratio), int(bool(distilled)), eps_block, eps_final)
+
+
+class ViTEngine:
+    """Runs ``generate_LRP(method='transformer_attribution')`` for batches of independent inputs."""
+
+    def __init__(self, cfg, state_dict=None, device=None, flags=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("transformer_explainability_b200 needs a CUDA device (B200, sm_100a); "
+                               "there is no CPU fallback")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.flags = flags
+        n = check(self.lib.te_vit_num_weights(ctypes.byref(cfg)), "te_vit_num_weights")
+        self.weight_table = []
+        for i in range(n):
+            self.weight_table.append((self.lib.te_vit_weight_name(ctypes.byref(cfg), i).decode(),
+                                      self.lib.te_vit_weight_numel(ctypes.byref(cfg), i),
+                                      self.lib.te_vit_weight_offset(ctypes.byref(cfg), i)))
+        total = check(self.lib.te_vit_weight_total(ctypes.byref(cfg)), "te_vit_weight_total")
+        self.weights = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self._ws = None
+        self._ws_batch = 0
+        self.tokens = (cfg.img_size // cfg.patch_size) ** 2 + (2 if cfg.distilled else 1)
+        self.prefix = 2 if cfg.distilled else 1
+        self.last_batch = 0
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+
+    # ---- weights ------------------------------------------------------------------------------
+    def load_state_dict(self, sd):
+        """Pack a reference-keyed ``state_dict`` (timm ViT names) into the flat device buffer."""
+        host = torch.zeros(self.weights.numel(), dtype=torch.float32)
+        for name, numel, off in self.weight_table:
+            if name not in sd:
+                if name.endswith("qkv.bias"):
+                    continue                          # qkv_bias=False models: zeros
+                raise KeyError("state_dict is missing %r" % name)
+            t = sd[name].detach().to(torch.float32).reshape(-1).cpu()
+            if t.numel() != numel:
+                raise ValueError("%s: expected %d values, got %d" % (name, numel, t.numel()))
+            host[off:off + numel] = t
+        self.weights.copy_(host, non_blocking=False)
+
+    def broadcast_weights(self, src=0, group=None):
+        """The one collective of the path: NCCL broadcast of the flat frozen-weight buffer."""
+        import torch.distributed as dist
+        dist.broadcast(self.weights, src=src, group=group)
+
+    # ---- workspace ----------------------------------------------------------------------------
+    def workspace_bytes(self, batch):
+        return check(self.lib.te_vit_workspace_bytes(ctypes.byref(self.cfg), batch), "te_vit_workspace_bytes")
+
+    def _workspace(self, batch):
+        if self._ws is None or self._ws_batch != batch:
+            self._ws = None
+            nbytes = self.workspace_bytes(batch)
+            self._ws = torch.empty(nbytes // 4, dtype=torch.float32, device=self.device)
+            self._ws_batch = batch
+        return self._ws
+
+    def max_chunk(self, limit=None, reserve_bytes=4 << 30):
+        """Largest per-call batch whose workspace fits in free HBM (activations of all blocks are kept)."""
+        free, _ = torch.cuda.mem_get_info(self.device)
+        if self._ws is not None:
+            free += self._ws.numel() * 4
+        per = self.workspace_bytes(2) - self.workspace_bytes(1)
+        b = max(1, int((free - reserve_bytes) // max(per, 1)))
+        return min(b, limit) if limit else b
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- the three calls ------------------------------------------------------------------------
+    def forward(self, images):
+        """``model(x)``: logits [B,C]; leaves the activations in the workspace."""
+        images = images.to(self.device, torch.float32).contiguous()
+        b = images.shape[0]
+        ws = self._workspace(b)
+        logits = torch.empty(b, self.cfg.num_classes, dtype=torch.float32, device=self.device)
+        check(self.lib.te_vit_forward(ctypes.byref(self.cfg), ptr(self.weights), ptr(images), b, ptr(logits), ptr(ws),
+                                      ws.numel() * 4, self._stream()), "te_vit_forward")
+        self.last_batch = b
+        return logits
+
+    def attribute(self, index=None, start_layer=0, flags=None):
+        """Backward + relprop + rollout on the activations of the last ``forward``.
+        Returns (maps [B,N-prefix], index [B] int32)."""
+        b = self.last_batch
+        if b <= 0:
+            raise RuntimeError("attribute() needs a preceding forward()")
+        ws = self._workspace(b)
+        idx = self._index_tensor(index, b)
+        maps = torch.empty(b, self.tokens - self.prefix, dtype=torch.float32, device=self.device)
+        check(self.lib.te_vit_attribute(ctypes.byref(self.cfg), ptr(self.weights), b, ptr(idx), int(start_layer),
+                                        self.flags if flags is None else flags, ptr(maps), ptr(ws), ws.numel() * 4,
+                                        self._stream()), "te_vit_attribute")
+        return maps, idx
+
+    def explain(self, images, index=None, start_layer=0, flags=None, chunk=None, return_logits=False):
+        """``LRP.generate_LRP`` for a batch of independent inputs (device-resident in, device-resident out)."""
+        images = images.to(self.device, torch.float32).contiguous()
+        B = images.shape[0]
+        chunk = min(B, chunk or self.max_chunk(limit=B))
+        maps = torch.empty(B, self.tokens - self.prefix, dtype=torch.float32, device=self.device)
+        idx_all = self._index_tensor(index, B)
+        logits = torch.empty(B, self.cfg.num_classes, dtype=torch.float32, device=self.device) if return_logits else None
+        fl = self.flags if flags is None else flags
+        for s in range(0, B, chunk):
+            e = min(B, s + chunk)
+            ws = self._workspace(chunk if e - s == chunk else e - s)
+            check(self.lib.te_vit_explain(ctypes.byref(self.cfg), ptr(self.weights), ptr(images[s:e]), e - s,
+                                          ptr(idx_all[s:e]), int(start_layer), fl, ptr(maps[s:e]),
+                                          ptr(logits[s:e]) if logits is not None else None, ptr(ws), ws.numel() * 4,
+                                          self._stream()), "te_vit_explain")
+            self.last_batch = e - s
+        if return_logits:
+            return maps, idx_all, logits
+        return maps, idx_all
+
+    def _index_tensor(self, index, b):
+        if index is None:
+            return torch.full((b,), -1, dtype=torch.int32, device=self.device)
+        t = torch.as_tensor(index, device=self.device).reshape(-1).to(torch.int32)
+        if t.numel() == 1 and b > 1:
+            t = t.expand(b)
+        if t.numel() != b:
+            raise ValueError("index must have one entry per sample")
+        return t.contiguous().clone()
+
+    # ---- accessors (get_attn / get_attn_gradients / get_attn_cam ..., ViT_LRP.py:102-130) ---------
+    def tensor(self, name, layer=0):
+        b = self.last_batch
+        ws = self._workspace(b)
+        p = ctypes.c_void_p()
+        dims = (ctypes.c_longlong * 4)()
+        strides = (ctypes.c_longlong * 4)()
+        check(self.lib.te_vit_tensor(ctypes.byref(self.cfg), b, ptr(ws), name.encode(), layer, ctypes.byref(p), dims,
+                                     strides), "te_vit_tensor")
+        off = (p.value - ws.data_ptr()) // 4
+        nd = 4
+        while nd > 2 and dims[nd - 1] == 1:
+            nd -= 1
+        return torch.as_strided(ws, [int(dims[i]) for i in range(nd)], [int(strides[i]) for i in range(nd)], off)

@@ -1,0 +1,132 @@
+"""Stand-alone LRP rules and rollout on CUDA tensors (thin wrappers over the C ABI).
+
+Each function is the CUDA counterpart of one ``relprop`` of the reference's
+``modules/layers_ours.py`` (alpha=1); see ``include/te_b200.h`` for the citations.
+All inputs must be contiguous fp32 CUDA tensors; there is no CPU path.
+"""
+import torch
+
+from . import _lib
+from ._lib import check, ptr
+
+
+def _stream():
+    return _lib.ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError("te_b200 ops need contiguous fp32 CUDA tensors (no CPU fallback)")
+
+
+def _workspace(nbytes, device):
+    return torch.empty((nbytes + 255) // 256 * 64, dtype=torch.float32, device=device)   # 256-byte multiple
+
+
+def linear_forward(x, w, bias=None):
+    _req(x, w, bias)
+    rows = x.numel() // x.shape[-1]
+    y = torch.empty(*x.shape[:-1], w.shape[0], device=x.device, dtype=torch.float32)
+    check(_lib.load().te_linear_forward(ptr(x), ptr(w), ptr(bias), ptr(y), rows, x.shape[-1], w.shape[0], _stream()),
+          "te_linear_forward")
+    return y
+
+
+def linear_relprop(x, w, r, tensor_cores=False):
+    """``Linear.relprop`` (layers_ours.py:207-230): x [...,in], w [out,in], r [...,out] -> [...,in]."""
+    _req(x, w, r)
+    rows = x.numel() // x.shape[-1]
+    out = torch.empty_like(x)
+    scratch = torch.empty(rows * w.shape[0], device=x.device, dtype=torch.float32)
+    flags = _lib.FLAG_ZPLUS_TENSOR_CORES if tensor_cores else 0
+    check(_lib.load().te_linear_relprop(ptr(x), ptr(w), ptr(r), ptr(out), ptr(scratch), rows, x.shape[-1], w.shape[0],
+                                        flags, _stream()), "te_linear_relprop")
+    return out
+
+
+def add_relprop(x1, x2, r):
+    """``Add.relprop`` (layers_ours.py:97-120), sums per sample (dim 0)."""
+    _req(x1, x2, r)
+    b = x1.shape[0]
+    r1, r2 = torch.empty_like(x1), torch.empty_like(x1)
+    scratch = torch.empty(b * 48, device=x1.device, dtype=torch.float64)
+    check(_lib.load().te_add_relprop(ptr(x1), ptr(x2), ptr(r), ptr(r1), ptr(r2), ptr(scratch), b, x1.numel() // b,
+                                     _stream()), "te_add_relprop")
+    return r1, r2
+
+
+def clone_relprop(x, rs):
+    """``Clone.relprop`` (layers_ours.py:151-169) for 2 or 3 branches."""
+    rs = list(rs)
+    _req(x, *rs)
+    out = torch.empty_like(x)
+    r3 = rs[2] if len(rs) > 2 else None
+    check(_lib.load().te_clone_relprop(ptr(x), ptr(rs[0]), ptr(rs[1]), ptr(r3), ptr(out), x.numel(), _stream()),
+          "te_clone_relprop")
+    return out
+
+
+def index_select_relprop(x, r):
+    """``IndexSelect.relprop`` (layers_ours.py:129-147), dim=1, index 0: x [B,N,D], r [B,1,D]|[B,D]."""
+    r = r.reshape(x.shape[0], x.shape[2]).contiguous()
+    _req(x, r)
+    out = torch.empty_like(x)
+    check(_lib.load().te_index_select_relprop(ptr(x), ptr(r), ptr(out), x.shape[0], x.shape[1], x.shape[2], _stream()),
+          "te_index_select_relprop")
+    return out
+
+
+def matmul_av_relprop(p, v, r):
+    """``einsum('bhij,bhjd->bhid').relprop``: returns UN-halved (R_attn, R_v)."""
+    _req(p, v, r)
+    b, h, n, d = v.shape
+    rp, rv = torch.empty_like(p), torch.empty_like(v)
+    scratch = torch.empty(b * h * n * d, device=p.device, dtype=torch.float32)
+    check(_lib.load().te_matmul_av_relprop(ptr(p), ptr(v), ptr(r), ptr(rp), ptr(rv), ptr(scratch), b * h, n, d,
+                                           _stream()), "te_matmul_av_relprop")
+    return rp, rv
+
+
+def matmul_qk_relprop(q, k, r):
+    """``einsum('bhid,bhjd->bhij').relprop``: returns UN-halved (R_q, R_k)."""
+    _req(q, k, r)
+    b, h, n, d = q.shape
+    rq, rk = torch.empty_like(q), torch.empty_like(k)
+    scratch = torch.empty(b * h * n * n, device=q.device, dtype=torch.float32)
+    check(_lib.load().te_matmul_qk_relprop(ptr(q), ptr(k), ptr(r), ptr(rq), ptr(rk), ptr(scratch), b * h, n, d,
+                                           _stream()), "te_matmul_qk_relprop")
+    return rq, rk
+
+
+def attribution_rollout(grad, cam, start_layer=0, normalize=False, fused=False, want_joint=True):
+    """grad, cam [L,B,H,N,N] -> (joint [B,N,N] or None, row0 [B,N]).
+    ``ViT_LRP.py:357-368`` (normalize=False) / ``ExplanationGenerator.py:47-57`` (normalize=True)."""
+    _req(grad, cam)
+    L, B, H, N, ld = grad.shape
+    lib = _lib.load()
+    nbytes = check(lib.te_rollout_workspace_bytes(L, B, N), "te_rollout_workspace_bytes")
+    ws = _workspace(nbytes, grad.device)
+    joint = torch.empty(B, N, N, device=grad.device, dtype=torch.float32) if want_joint else None
+    row0 = torch.empty(B, N, device=grad.device, dtype=torch.float32)
+    flags = _lib.FLAG_ROLLOUT_FUSED if fused else 0
+    check(lib.te_attribution_rollout(ptr(grad), ptr(cam), L, B, H, N, ld, start_layer, int(normalize), flags, ptr(joint),
+                                     ptr(row0), ptr(ws), ws.numel() * 4, _stream()), "te_attribution_rollout")
+    return joint, row0
+
+
+def compute_rollout_attention(all_layer_matrices, start_layer=0, normalize=False):
+    """``compute_rollout_attention`` (ViT_LRP.py:38-49; BERT variant with normalize=True,
+    ExplanationGenerator.py:7-18): list of [B,N,N] -> [B,N,N]."""
+    mats = torch.stack([m.to(torch.float32) for m in all_layer_matrices]).contiguous()
+    _req(mats)
+    L, B, N, _ = mats.shape
+    lib = _lib.load()
+    nbytes = check(lib.te_rollout_workspace_bytes(L, B, N), "te_rollout_workspace_bytes")
+    ws = _workspace(nbytes, mats.device)
+    joint = torch.empty(B, N, N, device=mats.device, dtype=torch.float32)
+    check(lib.te_compute_rollout_attention(ptr(mats), L, B, N, start_layer, int(normalize), ptr(joint), ptr(ws),
+                                           ws.numel() * 4, _stream()), "te_compute_rollout_attention")
+    return joint
