@@ -41,6 +41,8 @@ extern "C" {
 
 TE_API const char* te_last_error(void);
 TE_API int te_version(void);
+/* number of kernels this library has launched in this process (bench.py reports the delta as gpu_launches) */
+TE_API long long te_kernel_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * ViT / DeiT model description  (baselines/ViT/ViT_LRP.py:247-303 VisionTransformer.__init__)
@@ -68,6 +70,12 @@ TE_API long long te_vit_weight_numel(const te_vit_config* cfg, int i);
 TE_API long long te_vit_weight_offset(const te_vit_config* cfg, int i);
 TE_API long long te_vit_weight_total(const te_vit_config* cfg); /* floats */
 
+/* Tensor-core copies of the frozen Linear weights (W+, W-, W+^T, W-^T rounded to TF32, all K-major) used by
+ * the z+ rule when TE_FLAG_ZPLUS_TENSOR_CORES is set: te_vit_derived_total() floats, filled once per weight
+ * load by te_vit_prepare_derived().  `derived` may be NULL when the flag is not used. */
+TE_API long long te_vit_derived_total(const te_vit_config* cfg);
+TE_API int te_vit_prepare_derived(const te_vit_config* cfg, const float* weights, float* derived, void* stream);
+
 /* Scratch for `batch` samples processed together (activations of every block are kept for the
  * relprop, like the reference's forward hooks, modules/layers_ours.py:16-27). */
 TE_API long long te_vit_workspace_bytes(const te_vit_config* cfg, int batch);
@@ -82,12 +90,13 @@ TE_API int te_vit_forward(const te_vit_config* cfg, const float* weights, const 
  * arg-max (where index[b] < 0), one-hot, class gradient of every attention map, LRP relprop through
  * every block >= start_layer, relu(grad*cam) head-mean, +I, rollout, row 0 without the prefix token(s).
  * index [batch] int32 in/out (device); maps [batch, tokens-prefix] (device). */
-TE_API int te_vit_attribute(const te_vit_config* cfg, const float* weights, int batch, int* index, int start_layer,
-                     unsigned flags, float* maps, void* workspace, long long workspace_bytes, void* stream);
+TE_API int te_vit_attribute(const te_vit_config* cfg, const float* weights, const float* derived, int batch, int* index,
+                     int start_layer, unsigned flags, float* maps, void* workspace, long long workspace_bytes,
+                     void* stream);
 
 /* te_vit_forward + te_vit_attribute: one call per batch = LRP.generate_LRP for `batch` independent inputs. */
-TE_API int te_vit_explain(const te_vit_config* cfg, const float* weights, const float* images, int batch, int* index,
-                   int start_layer, unsigned flags, float* maps, float* logits, void* workspace,
+TE_API int te_vit_explain(const te_vit_config* cfg, const float* weights, const float* derived, const float* images,
+                   int batch, int* index, int start_layer, unsigned flags, float* maps, float* logits, void* workspace,
                    long long workspace_bytes, void* stream);
 
 /* Accessors into the workspace — get_attn / get_attn_gradients / get_attn_cam / get_v ...
@@ -101,7 +110,7 @@ TE_API int te_vit_tensor(const te_vit_config* cfg, int batch, void* workspace, c
  * that each rule can be parity-tested against the reference layer class it replaces.
  * ---------------------------------------------------------------------------------------------- */
 /* Linear.relprop, alpha=1 (layers_ours.py:207-230): x [rows,in], w [out,in], r [rows,out] -> out [rows,in].
- * scratch: rows*out floats. */
+ * scratch: rows*out floats; with TE_FLAG_ZPLUS_TENSOR_CORES: round_up(rows*out,64) + 4*in*out floats. */
 TE_API int te_linear_relprop(const float* x, const float* w, const float* r, float* out, float* scratch, int rows,
                       int in_features, int out_features, unsigned flags, void* stream);
 /* Add.relprop (layers_ours.py:97-120) per sample: x1,x2,r [batch,per_sample] -> r1,r2.

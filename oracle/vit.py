@@ -101,7 +101,7 @@ def attention_gradients(cache, seed):
     return list(torch.autograd.grad(loss, attns, retain_graph=True))
 
 
-def relprop(params, cache, seed, start_layer=0):
+def relprop(params, cache, seed, start_layer=0, taps=None):
     """LRP pass; returns list (per block) of attn_cam [B,H,N,N] (``ViT_LRP.py:165``).
 
     Blocks below ``start_layer`` are never consumed by the rollout and are returned as None.
@@ -123,14 +123,30 @@ def relprop(params, cache, seed, start_layer=0):
     for i in reversed(range(max(start_layer, 0), cfg.depth)):
         pre = "blocks.%d." % i
         c = cache["blocks"][i]
+        t = {} if taps is not None else None
+        if t is not None:
+            taps[i] = t
+            t["r_in"] = r
         # Block.relprop :203-213
         r1, r2 = rules.add_relprop(c["x_mid"], c["mlp_out"], r)                 # add2
+        if t is not None:
+            t["add2_r1"], t["add2_r2"] = r1, r2
         r2 = rules.linear_relprop(c["g"], p[pre + "mlp.fc2.weight"], r2)        # fc2 ; GELU identity
+        if t is not None:
+            t["fc2"] = r2
         r2 = rules.linear_relprop(c["xn2"], p[pre + "mlp.fc1.weight"], r2)      # fc1 ; norm2 identity
+        if t is not None:
+            t["fc1"] = r2
         r = rules.clone_relprop(c["x_mid"], (r1, r2))                           # clone2
+        if t is not None:
+            t["clone2"] = r
         r1, r2 = rules.add_relprop(c["x_in"], c["attn_out"], r)                 # add1
+        if t is not None:
+            t["add1_r1"], t["add1_r2"] = r1, r2
         # Attention.relprop :154-177
         r2 = rules.linear_relprop(c["ctx"], p[pre + "attn.proj.weight"], r2)
+        if t is not None:
+            t["proj"] = r2
         r2 = _split_heads(r2, cfg.heads)
         cam1, cam_v = rules.matmul_av_relprop(c["attn"], c["v"], r2)
         cam1 = cam1 / 2
@@ -144,6 +160,8 @@ def relprop(params, cache, seed, start_layer=0):
         r_qkv = torch.cat([_merge_heads(cam_q), _merge_heads(cam_k), _merge_heads(cam_v)], dim=-1)
         r2 = rules.linear_relprop(c["xn1"], p[pre + "attn.qkv.weight"], r_qkv)  # norm1 identity
         r = rules.clone_relprop(c["x_in"], (r1, r2))                            # clone1
+        if t is not None:
+            t["r_qkv"], t["qkv"], t["clone1"] = r_qkv, r2, r
     return cams
 
 
@@ -161,7 +179,8 @@ def explain(params, x, num_heads, index=None, start_layer=0, return_taps=False):
     with torch.no_grad():
         cache_d = {"cfg": cache["cfg"], "x_final_norm": cache["x_final_norm"].detach(),
                    "blocks": [{k: v.detach() for k, v in c.items()} for c in cache["blocks"]]}
-        cams = relprop(params, cache_d, seed, start_layer)
+        rtaps = {} if return_taps else None
+        cams = relprop(params, cache_d, seed, start_layer, taps=rtaps)
         mats = [rules.aggregate(g, c) if c is not None else torch.zeros_like(g[:, 0])
                 for g, c in zip(grads, cams)]
         joint = rules.rollout(mats, start_layer=start_layer, normalize=False)
@@ -169,7 +188,7 @@ def explain(params, x, num_heads, index=None, start_layer=0, return_taps=False):
         out = joint[:, 0, first:]
     if return_taps:
         return out, index, {"logits": logits.detach(), "grads": grads, "cams": cams, "mats": mats,
-                            "joint": joint, "cache": cache_d}
+                            "joint": joint, "cache": cache_d, "relprop": rtaps}
     return out, index
 
 

@@ -1,0 +1,67 @@
+"""GPU: the tcgen05 (TF32 tensor-core) z+ Linear rule against the fp32 SIMT path and the fp64 oracle.
+
+Tolerance: TF32 operands carry a 10-bit mantissa (rna), accumulation is fp32, Z is a sum of non-negative
+products -> relative error of a few 1e-4 on Z/S and on the output (stated: 2e-3 of the tensor maximum)."""
+import pytest
+import torch
+
+from oracle import rules
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    b = b.double()
+    return ((a.double().cpu() - b.cpu()).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("rows,inf,outf", [(128, 256, 256), (394, 768, 3072), (1000, 3072, 768), (77, 768, 2304),
+                                           (256, 1024, 1024)])
+def test_tc_linear_relprop_matches_simt_and_oracle(rows, inf, outf):
+    from transformer_explainability_b200 import ops
+    g = torch.Generator().manual_seed(rows)
+    x = torch.randn(rows, inf, generator=g)
+    w = torch.randn(outf, inf, generator=g) * 0.05
+    r = torch.rand(rows, outf, generator=g)
+    xd, wd, rd = x.cuda(), w.cuda(), r.cuda()
+    simt = ops.linear_relprop(xd, wd, rd, tensor_cores=False)
+    tc = ops.linear_relprop(xd, wd, rd, tensor_cores=True)
+    torch.cuda.synchronize()
+    ref = rules.linear_relprop(x.double(), w.double(), r.double())
+    assert rel(simt, ref) < 2e-5
+    assert rel(tc, ref) < 2e-3, "tcgen05 path: rel err %g" % rel(tc, ref)
+    # conservation of relevance survives the reduced-precision operands
+    assert abs(tc.double().sum().item() - r.double().sum().item()) < 2e-3 * r.sum().item()
+
+
+def test_tc_engine_vit_base_vs_simt_and_oracle():
+    """ViT-B/16: engine with the tensor-core z+ path vs the fp32 SIMT engine and the fp64 oracle; medians over
+    1e-7-perturbed copies (see tests/test_gpu_vit.py::_noise_trials for why)."""
+    from oracle import cpu as ocpu
+    from oracle import vit as ovit
+    from transformer_explainability_b200 import _lib
+    from transformer_explainability_b200.baselines.ViT.ViT_LRP import vit_base_patch16_224
+    from test_gpu_vit import _noise_trials
+    trials = 8
+    params, heads = ovit.init_params("vit_base_patch16_224", seed=0)
+    xs = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(100))
+    m = vit_base_patch16_224()
+    m.load_state_dict(params)
+    m = m.cuda().eval()
+    eng = m.engine()
+    xb = torch.cat([_noise_trials(xs[s:s + 1], trials) for s in range(2)]).cuda()
+    simt, idx0 = eng.explain(xb, flags=0)
+    tc, idx1 = eng.explain(xb, flags=_lib.FLAG_ZPLUS_TENSOR_CORES)
+    torch.cuda.synchronize()
+    assert torch.equal(idx0, idx1)
+    ocpu.set_torch_threads()
+    for s in range(2):
+        ref, ridx = ovit.explain({k: v.double() for k, v in params.items()}, xs[s:s + 1].double(), heads)
+        scale = ref.abs().max().item()
+        med = {}
+        for name, out in (("simt", simt), ("tc", tc)):
+            errs = sorted((out[s * trials + k].cpu().double() - ref[0]).abs().max().item() for k in range(trials))
+            med[name] = 0.5 * (errs[trials // 2 - 1] + errs[trials // 2])
+            print("sample %d %s: L_inf/max over trials %s" % (s, name, ["%.1e" % (e / scale) for e in errs]))
+        assert med["tc"] <= 1e-4                                    # BASELINE tolerance on raw maps
+        assert med["tc"] <= max(10 * med["simt"], 5e-2 * scale)     # same noise class as the fp32 path

@@ -8,6 +8,7 @@ import pytest
 import torch
 
 from oracle import ref_harness, rules
+from oracle import cpu as ocpu
 from oracle import vit as ovit
 
 
@@ -75,7 +76,7 @@ def test_vit_base_matches_reference(golden_dir):
     if abs(wsum - float(g["w_checksum"])) > 1e-6 * abs(float(g["w_checksum"])) or \
             not np.allclose(xs.double().sum(dim=(1, 2, 3)).numpy(), g["x_checksum"], rtol=1e-9):
         pytest.skip("seeded weights/inputs do not reproduce on this machine")
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    ocpu.set_torch_threads()
     s = 1                                   # one sample keeps the CPU suite short
     out, idx = ovit.explain(params, xs[s:s + 1], heads)
     assert int(idx) == int(g["f32.index"][s]) == int(g["f64.index"][s])

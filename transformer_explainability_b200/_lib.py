@@ -31,6 +31,7 @@ _CFG = ctypes.POINTER(TeVitConfig)
 PROTOTYPES = {
     "te_last_error": (c_char_p, []),
     "te_version": (c_int, []),
+    "te_kernel_launch_count": (c_ll, []),
     "te_vit_num_weights": (c_int, [_CFG]),
     "te_vit_weight_name": (c_char_p, [_CFG, c_int]),
     "te_vit_weight_numel": (c_ll, [_CFG, c_int]),
@@ -38,8 +39,10 @@ PROTOTYPES = {
     "te_vit_weight_total": (c_ll, [_CFG]),
     "te_vit_workspace_bytes": (c_ll, [_CFG, c_int]),
     "te_vit_forward": (c_int, [_CFG, _P, _P, c_int, _P, _P, c_ll, _P]),
-    "te_vit_attribute": (c_int, [_CFG, _P, c_int, _P, c_int, c_uint, _P, _P, c_ll, _P]),
-    "te_vit_explain": (c_int, [_CFG, _P, _P, c_int, _P, c_int, c_uint, _P, _P, _P, c_ll, _P]),
+    "te_vit_derived_total": (c_ll, [_CFG]),
+    "te_vit_prepare_derived": (c_int, [_CFG, _P, _P, _P]),
+    "te_vit_attribute": (c_int, [_CFG, _P, _P, c_int, _P, c_int, c_uint, _P, _P, c_ll, _P]),
+    "te_vit_explain": (c_int, [_CFG, _P, _P, _P, c_int, _P, c_int, c_uint, _P, _P, _P, c_ll, _P]),
     "te_vit_tensor": (c_int, [_CFG, c_int, _P, c_char_p, c_int, ctypes.POINTER(_P), ctypes.POINTER(c_ll),
                               ctypes.POINTER(c_ll)]),
     "te_linear_relprop": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_uint, _P]),

@@ -1,14 +1,20 @@
 // C-ABI wrappers for the stand-alone rules and rollout entry points declared in include/te_b200.h.
 #include <string.h>
+#include <atomic>
 #include <string>
 
 #include "../../include/te_b200.h"
 #include "te_kernels.h"
 #include "te_rollout.h"
 #include "te_zplus.h"
+#include "te_gemm_tc.h"
 
 static thread_local std::string g_last_error;
 void te_set_last_error(const char* msg) { g_last_error = msg ? msg : ""; }
+
+static std::atomic<long long> g_launches{0};
+void te_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" long long te_kernel_launch_count(void) { return g_launches.load(); }
 
 extern "C" const char* te_last_error(void) { return g_last_error.c_str(); }
 extern "C" int te_version(void) { return 100; }
@@ -35,8 +41,15 @@ extern "C" int te_linear_forward(const float* x, const float* w, const float* bi
 extern "C" int te_linear_relprop(const float* x, const float* w, const float* r, float* out, float* scratch, int rows,
                                  int in_features, int out_features, unsigned flags, void* stream) {
     REQ(x && w && r && out && scratch && rows > 0 && in_features > 0 && out_features > 0, "te_linear_relprop: bad argument");
-    return te_zplus_linear_relprop(x, in_features, w, r, out, scratch, rows, in_features, out_features,
-                                   (flags & TE_FLAG_ZPLUS_TENSOR_CORES) != 0, ST(stream));
+    const float* derived = nullptr;
+    if ((flags & TE_FLAG_ZPLUS_TENSOR_CORES) && te_tc_zplus_supported(rows, in_features, out_features, in_features)) {
+        // scratch layout with the flag: [rows*out S | 4*in*out derived weight copies]
+        float* d = scratch + (((long long)rows * out_features + 63) & ~63LL);
+        TE_TRY(te_tc_prepare_weights(w, d, in_features, out_features, ST(stream)));
+        derived = d;
+    }
+    return te_zplus_linear_relprop(x, in_features, w, derived, r, out, scratch, rows, in_features, out_features,
+                                   ST(stream));
 }
 
 extern "C" int te_add_relprop(const float* x1, const float* x2, const float* r, float* r1, float* r2, void* scratch,

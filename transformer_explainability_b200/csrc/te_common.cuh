@@ -11,6 +11,7 @@
 
 #define TE_CUDA_CHECK_LAUNCH()                                   \
     do {                                                         \
+        te_count_launch();                                       \
         cudaError_t e__ = cudaGetLastError();                    \
         if (e__ != cudaSuccess) { te_set_last_error(cudaGetErrorString(e__)); return TE_ERR_CUDA; } \
     } while (0)
@@ -19,6 +20,7 @@
     do { int r__ = (x); if (r__ != TE_OK) return r__; } while (0)
 
 void te_set_last_error(const char* msg);
+void te_count_launch();
 
 // safe_divide of the reference (modules/layers_ours.py:10-13):
 //   den = clamp(b,min=eps) + clamp(b,max=eps)  ( == b + eps ) ; den += eps where den == 0 ;

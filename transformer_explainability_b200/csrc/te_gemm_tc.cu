@@ -1,8 +1,402 @@
-// placeholder until the tcgen05 kernel lands: reports "unsupported" so callers use the fp32 SIMT path.
+// tcgen05 path of the z+ Linear rule (modules/layers_ours.py:207-230, alpha=1) for sm_100a.
+//
+//   kernel 1 (MODE_S):   S    = safe_divide(R, x+ W+^T + x- W-^T)            [rows, out]
+//   kernel 2 (MODE_R):   R_in = x+ * (S W+) + x- * (S W-)                     [rows, in]
+//
+// Both are "two-pass" 128x256 tiled GEMMs on the 5th-generation tensor cores:
+//   * operands are K-major fp32 tiles of 128 B rows (32 floats) staged by TMA (SWIZZLE_128B) into a
+//     4-stage shared-memory ring; tcgen05.mma.kind::tf32 (M=128, N=256, K=8) is issued by one thread,
+//     accumulators live in TMEM (256 columns for kernel 1, 2 x 256 for kernel 2);
+//   * pass 0 multiplies by W+ (pre-clamped, pre-rounded to TF32, K-major copy made once per frozen
+//     weight by te_tc_prepare_weights), pass 1 by W-;
+//   * kernel 1 clamps the activation tile IN PLACE in shared memory between the TMA arrival and the
+//     MMA (max(.,0) in pass 0, min(.,0) in pass 1, round-to-nearest TF32) — an elementwise pass that
+//     is independent of the swizzled layout — done by the four warps that later run the epilogue;
+//   * epilogue: tcgen05.ld 32 lanes x 32 columns per warp, fused safe_divide / x+- recombination,
+//     128-bit global stores.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = tile transform
+// (kernel 1) and epilogue.  Pipelines: full[s] (TMA -> transform/MMA), xf[s] (transform -> MMA),
+// empty[s] (tcgen05.commit -> TMA), accum (last commit -> epilogue).
+//
+// Numerics: TF32 (10-bit mantissa) operands, fp32 accumulation.  Z is a sum of non-negative products,
+// so this is well conditioned; SURVEY.md §7b measured TF32 on exactly these GEMMs as indistinguishable
+// from the fp32 reference's own noise.  Everything that feeds an ill-conditioned denominator stays on
+// the fp32 SIMT path.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <string.h>
+
 #include "te_gemm_tc.h"
-bool te_tc_zplus_supported(long long, int, int, long long) { return false; }
-int te_tc_zplus_linear_relprop(const float*, long long, const float*, const float*, float*, float*, long long, int,
-                               int, cudaStream_t) {
-    te_set_last_error("tcgen05 z+ path not built");
-    return TE_ERR_UNSUPPORTED;
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 32;                 // BK floats = 128 bytes = one swizzle row
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 4;                       // 16 KiB
+constexpr int B_BYTES = BN * BK * 4;                       // 32 KiB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;             // 48 KiB
+constexpr int NUM_THREADS = 192;
+constexpr int XF_THREADS = 128;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int MODE_S = 1, MODE_R = 2;
+
+struct TcParams {
+    int M, N, K;                 // C[M,N] = sum over two passes of A[M,K] * B_pass[N,K]^T
+    const float* E; long long lde;   // MODE_S: R [M,N] ; MODE_R: x [M,N]
+    float* C; long long ldc;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//  [0,14) start address >> 4 ; [16,30) leading byte offset >> 4 (unused for swizzled K-major, 1) ;
+//  [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B) ; [46,48) version = 1 ; [61,64) layout = 2.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format TF32 [7,10)/[10,13)=2,
+// a/b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+                   const __grid_constant__ CUtensorMap tmB1, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bars = smem_base + STAGES * STAGE_BYTES;            // 8-byte barriers
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto xf_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+    const uint32_t accum_bar = bars + 8u * (3 * STAGES);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 1));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kb = p.K / BK, iters = 2 * kb;
+    constexpr uint32_t TMEM_COLS = (MODE == MODE_S) ? 256u : 512u;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB0) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB1) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(xf_bar(s), XF_THREADS);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_arrive_expect_tx(full_bar(s), STAGE_BYTES);
+                const int pass = (it >= kb) ? 1 : 0;
+                const int k0 = (it - pass * kb) * BK;
+                const uint32_t sa = smem_base + s * STAGE_BYTES;
+                tma_load_2d(sa, &tmA, full_bar(s), k0, m0);
+                tma_load_2d(sa + A_BYTES, pass ? &tmB1 : &tmB0, full_bar(s), k0, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1u;
+                mbar_wait(MODE == MODE_S ? xf_bar(s) : full_bar(s), ph);
+                tcgen05_fence_after();
+                const int pass = (it >= kb) ? 1 : 0;
+                const uint32_t sa = smem_base + s * STAGE_BYTES;
+                const uint64_t adesc = make_smem_desc(sa);
+                const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
+                const uint32_t d = tmem_base + ((MODE == MODE_R && pass) ? (uint32_t)BN : 0u);
+                const bool first = (MODE == MODE_S) ? (it == 0) : (it == 0 || it == kb);
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    // advance 8 tf32 (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
+                    umma_tf32(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc, (first && k == 0) ? 0u : 1u);
+                }
+                umma_commit(empty_bar(s));          // frees the smem stage when these MMAs retire
+            }
+            umma_commit(accum_bar);                 // accumulators complete
+        }
+        __syncwarp();
+    } else {
+        // ================= tile transform (kernel 1) + epilogue: warps 2..5 =================
+        const int et = threadIdx.x - 64;            // 0..127
+        if (MODE == MODE_S) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1u;
+                mbar_wait(full_bar(s), ph);
+                const int pass = (it >= kb) ? 1 : 0;
+                float4* a4 = reinterpret_cast<float4*>(smem_al + s * STAGE_BYTES);
+#pragma unroll
+                for (int i = 0; i < A_BYTES / 16 / XF_THREADS; ++i) {
+                    float4 v = a4[et + i * XF_THREADS];
+                    if (pass == 0) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    else { v.x = fminf(v.x, 0.f); v.y = fminf(v.y, 0.f); v.z = fminf(v.z, 0.f); v.w = fminf(v.w, 0.f); }
+                    v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+                    a4[et + i * XF_THREADS] = v;
+                }
+                fence_proxy_async();                // generic-proxy writes -> visible to the tensor-core (async) proxy
+                mbar_arrive(xf_bar(s));
+            }
+        }
+        mbar_wait(accum_bar, 0);
+        tcgen05_fence_after();
+        const int q = warp & 3;                     // TMEM lane quarter this warp may read
+        const int row = m0 + q * 32 + lane;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool live = row < p.M;
+        const float* erow = p.E + (long long)row * p.lde + n0;
+        float* crow = p.C + (long long)row * p.ldc + n0;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t acc[32];
+            tmem_ld32(tlane + (uint32_t)(c * 32), acc);
+            if (MODE == MODE_S) {
+                tmem_ld_wait();
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 r = *reinterpret_cast<const float4*>(erow + c * 32 + j);
+                        float4 o;
+                        o.x = to_tf32(te_sd(r.x, __uint_as_float(acc[j + 0])));
+                        o.y = to_tf32(te_sd(r.y, __uint_as_float(acc[j + 1])));
+                        o.z = to_tf32(te_sd(r.z, __uint_as_float(acc[j + 2])));
+                        o.w = to_tf32(te_sd(r.w, __uint_as_float(acc[j + 3])));
+                        *reinterpret_cast<float4*>(crow + c * 32 + j) = o;
+                    }
+                }
+            } else {
+                uint32_t accn[32];
+                tmem_ld32(tlane + (uint32_t)(BN + c * 32), accn);
+                tmem_ld_wait();
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 x = *reinterpret_cast<const float4*>(erow + c * 32 + j);
+                        float4 o;
+                        o.x = fmaxf(x.x, 0.f) * __uint_as_float(acc[j + 0]) + fminf(x.x, 0.f) * __uint_as_float(accn[j + 0]);
+                        o.y = fmaxf(x.y, 0.f) * __uint_as_float(acc[j + 1]) + fminf(x.y, 0.f) * __uint_as_float(accn[j + 1]);
+                        o.z = fmaxf(x.z, 0.f) * __uint_as_float(acc[j + 2]) + fminf(x.z, 0.f) * __uint_as_float(accn[j + 2]);
+                        o.w = fmaxf(x.w, 0.f) * __uint_as_float(acc[j + 3]) + fminf(x.w, 0.f) * __uint_as_float(accn[j + 3]);
+                        *reinterpret_cast<float4*>(crow + c * 32 + j) = o;
+                    }
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- weight preparation: W [out,in] -> W+ , W- (K-major for kernel 1) and W+^T , W-^T (K-major for kernel 2),
+//      all rounded to TF32 once (weights are frozen) -------------------------------------------------------
+__global__ void prepare_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, float* __restrict__ wn,
+                                       float* __restrict__ wpt, float* __restrict__ wnt, int out_f, int in_f) {
+    __shared__ float tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;      // bx: in index, by: out index
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int o = by + i, c = bx + threadIdx.x;
+        float v = 0.f;
+        if (o < out_f && c < in_f) {
+            v = w[(long long)o * in_f + c];
+            wp[(long long)o * in_f + c] = to_tf32(fmaxf(v, 0.f));
+            wn[(long long)o * in_f + c] = to_tf32(fminf(v, 0.f));
+        }
+        tile[i][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = bx + i, o = by + threadIdx.x;
+        if (o < out_f && c < in_f) {
+            const float v = tile[threadIdx.x][i];
+            wpt[(long long)c * out_f + o] = to_tf32(fmaxf(v, 0.f));
+            wnt[(long long)c * out_f + o] = to_tf32(fminf(v, 0.f));
+        }
+    }
+}
+
+// ---- host: tensor maps ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// fp32 row-major [rows, cols] with row stride ld (floats); box = [box_rows, 32 floats], 128-byte swizzle
+bool make_map(CUtensorMap* m, const float* base, long long rows, long long cols, long long ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int MODE>
+int launch(const float* A, long long lda, const float* B0, const float* B1, const float* E, long long lde, float* C,
+           long long ldc, long long M, int N, int K, cudaStream_t st) {
+    CUtensorMap tmA, tmB0, tmB1;
+    if (!make_map(&tmA, A, M, K, lda, BM) || !make_map(&tmB0, B0, N, K, K, BN) || !make_map(&tmB1, B1, N, K, K, BN)) {
+        te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed");
+        return TE_ERR_CUDA;
+    }
+    static bool attr_set[3] = {false, false, false};
+    if (!attr_set[MODE]) {
+        if (cudaFuncSetAttribute(te_tc_zplus_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+            te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
+            return TE_ERR_CUDA;
+        }
+        attr_set[MODE] = true;
+    }
+    TcParams p;
+    p.M = (int)M; p.N = N; p.K = K; p.E = E; p.lde = lde; p.C = C; p.ldc = ldc;
+    dim3 grid(N / BN, (unsigned)((M + BM - 1) / BM));
+    te_tc_zplus_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB0, tmB1, p);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+
+inline bool a16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+}  // namespace
+
+bool te_tc_zplus_supported(long long rows, int in_features, int out_features, long long ldx) {
+    return rows > 0 && rows < (1LL << 31) && in_features % BN == 0 && out_features % BN == 0 && ldx % 4 == 0 &&
+           get_encode() != nullptr;
+}
+
+long long te_tc_derived_floats(int in_features, int out_features) { return 4LL * in_features * out_features; }
+
+int te_tc_prepare_weights(const float* w, float* derived, int in_features, int out_features, cudaStream_t st) {
+    const long long n = (long long)in_features * out_features;
+    dim3 grid((in_features + 31) / 32, (out_features + 31) / 32), block(32, 8);
+    prepare_weights_kernel<<<grid, block, 0, st>>>(w, derived, derived + n, derived + 2 * n, derived + 3 * n, out_features,
+                                                  in_features);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+
+int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* derived, const float* r, float* out,
+                               float* s_scratch, long long rows, int in_features, int out_features, cudaStream_t st) {
+    if (!a16(x) || !a16(derived) || !a16(r) || !a16(out) || !a16(s_scratch)) {
+        te_set_last_error("te_gemm_tc: operands must be 16-byte aligned");
+        return TE_ERR_ARG;
+    }
+    const long long n = (long long)in_features * out_features;
+    const float *wp = derived, *wn = derived + n, *wpt = derived + 2 * n, *wnt = derived + 3 * n;
+    // S = sd(R, x+ W+^T + x- W-^T)          A = x [rows, in] ; B = W+/- [out, in]
+    TE_TRY(launch<MODE_S>(x, ldx, wp, wn, r, out_features, s_scratch, out_features, rows, out_features, in_features, st));
+    // R_in = x+ (S W+) + x- (S W-)          A = S [rows, out] ; B = W+/-^T [in, out]
+    TE_TRY(launch<MODE_R>(s_scratch, out_features, wpt, wnt, x, ldx, out, in_features, rows, in_features, out_features, st));
+    return TE_OK;
 }

@@ -13,6 +13,7 @@
 #include "te_kernels.h"
 #include "te_rollout.h"
 #include "te_zplus.h"
+#include "te_gemm_tc.h"
 
 namespace {
 
@@ -108,6 +109,23 @@ static void bind_weights(const te_vit_config* c, const float* base, Weights& w) 
     w.normw = next(); w.normb = next(); w.headw = next(); w.headb = next();
     w.headdw = c->distilled ? next() : nullptr;
     w.headdb = c->distilled ? next() : nullptr;
+}
+
+// ---- derived (tensor-core) weight copies: per block qkv | proj | fc1 | fc2, 4 copies each ---------
+struct DerivedW { const float *qkv, *proj, *fc1, *fc2; };
+static long long derived_block_floats(const Dims& d) {
+    return te_tc_derived_floats(d.D, 3 * d.D) + te_tc_derived_floats(d.D, d.D) + te_tc_derived_floats(d.D, d.F) +
+           te_tc_derived_floats(d.F, d.D);
+}
+static DerivedW bind_derived(const Dims& d, const float* base, int l) {
+    DerivedW w = {nullptr, nullptr, nullptr, nullptr};
+    if (!base) return w;
+    const float* p = base + (long long)l * derived_block_floats(d);
+    w.qkv = p;  p += te_tc_derived_floats(d.D, 3 * d.D);
+    w.proj = p; p += te_tc_derived_floats(d.D, d.D);
+    w.fc1 = p;  p += te_tc_derived_floats(d.D, d.F);
+    w.fc2 = p;
+    return w;
 }
 
 // ---- workspace ---------------------------------------------------------------------------------
@@ -317,8 +335,31 @@ extern "C" int te_vit_forward(const te_vit_config* cfg, const float* weights, co
 // ================================================================================================
 // attribute = class-gradient backward + relprop + aggregation + rollout
 // ================================================================================================
-extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, int batch, int* index,
-                                int start_layer, unsigned flags, float* maps, void* workspace,
+extern "C" long long te_vit_derived_total(const te_vit_config* cfg) {
+    Dims d;
+    if (!make_dims(cfg, 1, d)) return TE_ERR_ARG;
+    return (long long)d.L * derived_block_floats(d);
+}
+
+extern "C" int te_vit_prepare_derived(const te_vit_config* cfg, const float* weights, float* derived, void* stream) {
+    Dims d;
+    if (!make_dims(cfg, 1, d)) return TE_ERR_ARG;
+    if (!weights || !derived) { te_set_last_error("te_vit_prepare_derived: null pointer"); return TE_ERR_ARG; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Weights w;
+    bind_weights(cfg, weights, w);
+    for (int l = 0; l < d.L; ++l) {
+        const DerivedW dw = bind_derived(d, derived, l);
+        TE_TRY(te_tc_prepare_weights(w.blk[l].qkvw, const_cast<float*>(dw.qkv), d.D, 3 * d.D, st));
+        TE_TRY(te_tc_prepare_weights(w.blk[l].projw, const_cast<float*>(dw.proj), d.D, d.D, st));
+        TE_TRY(te_tc_prepare_weights(w.blk[l].fc1w, const_cast<float*>(dw.fc1), d.D, d.F, st));
+        TE_TRY(te_tc_prepare_weights(w.blk[l].fc2w, const_cast<float*>(dw.fc2), d.F, d.D, st));
+    }
+    return TE_OK;
+}
+
+extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, const float* derived, int batch,
+                                int* index, int start_layer, unsigned flags, float* maps, void* workspace,
                                 long long workspace_bytes, void* stream) {
     Dims d; Workspace ws;
     TE_TRY(check_ws(cfg, batch, workspace, workspace_bytes, d, ws));
@@ -331,7 +372,11 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
     const HeadOp none = {nullptr, 0, 0, 0};
     const long long MD = d.M * d.D;
     const int low = (flags & TE_FLAG_KEEP_ALL_CAMS) ? 0 : start_layer;   // lowest block the relprop must reach
-    const bool tc = (flags & TE_FLAG_ZPLUS_TENSOR_CORES) != 0;
+    const float* dbase = (flags & TE_FLAG_ZPLUS_TENSOR_CORES) ? derived : nullptr;
+    if ((flags & TE_FLAG_ZPLUS_TENSOR_CORES) && !derived) {
+        te_set_last_error("te_vit_attribute: TE_FLAG_ZPLUS_TENSOR_CORES needs the derived weight buffer");
+        return TE_ERR_ARG;
+    }
 
     // ---- class index and seeds  (ViT_explanation_generator.py:28-35) ---------------------------
     TE_TRY(te_launch_argmax(ws.logits, index, d.B, d.C, /*only_negative=*/1, st));
@@ -383,27 +428,28 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
     float* R = ws.tD[0]; float* R1 = ws.tD[1]; float* R2 = ws.tD[2]; float* R3 = ws.tD[3];
     float* RF = ws.tF[0]; float* SF = ws.tF[1]; float* S = ws.t3D[0]; float* Rqkv = ws.t3D[1]; float* S1 = ws.tA;
     // head.relprop (z+), pool.relprop (IndexSelect), norm.relprop (identity)
-    TE_TRY(te_zplus_linear_relprop(ws.xf, (long long)d.N * d.D, w.headw, ws.seed, ws.rhead0, ws.shead, d.B, d.D, d.C,
-                                   false, st));
+    TE_TRY(te_zplus_linear_relprop(ws.xf, (long long)d.N * d.D, w.headw, nullptr, ws.seed, ws.rhead0, ws.shead, d.B, d.D,
+                                   d.C, st));
     if (cfg->distilled)
-        TE_TRY(te_zplus_linear_relprop(ws.xf + d.D, (long long)d.N * d.D, w.headdw, ws.seed, ws.rhead1, ws.shead, d.B,
-                                       d.D, d.C, false, st));
+        TE_TRY(te_zplus_linear_relprop(ws.xf + d.D, (long long)d.N * d.D, w.headdw, nullptr, ws.seed, ws.rhead1, ws.shead,
+                                       d.B, d.D, d.C, st));
     TE_TRY(te_launch_index_select_relprop(ws.xf, ws.rhead0, cfg->distilled ? ws.rhead1 : nullptr, R, d.B, d.N, d.D, st));
 
     for (int l = d.L - 1; l >= low; --l) {
         LayerAct& a = ws.layer[l];
         const BlockW& bw = w.blk[l];
+        const DerivedW dw = bind_derived(d, dbase, l);
         const HeadOp q = head_rows(a.qkv, 3 * d.D, d.N, d.dh);
         const HeadOp k = head_rows(a.qkv + d.D, 3 * d.D, d.N, d.dh);
         const HeadOp v = head_rows(a.qkv + 2 * d.D, 3 * d.D, d.N, d.dh);
         // Block.relprop :203-213
         TE_TRY(te_launch_add_relprop(a.x_mid, a.mlp_out, R, R1, R2, ws.addpart, d.B, (long long)d.N * d.D, st));   // add2
-        TE_TRY(te_zplus_linear_relprop(a.g, d.F, bw.fc2w, R2, RF, S, d.M, d.F, d.D, tc, st));                       // fc2 ; GELU id
-        TE_TRY(te_zplus_linear_relprop(a.xn2, d.D, bw.fc1w, RF, R2, SF, d.M, d.D, d.F, tc, st));                    // fc1 ; norm2 id
+        TE_TRY(te_zplus_linear_relprop(a.g, d.F, bw.fc2w, dw.fc2, R2, RF, S, d.M, d.F, d.D, st));                       // fc2 ; GELU id
+        TE_TRY(te_zplus_linear_relprop(a.xn2, d.D, bw.fc1w, dw.fc1, RF, R2, SF, d.M, d.D, d.F, st));                    // fc1 ; norm2 id
         TE_TRY(te_launch_clone_relprop(a.x_mid, R1, R2, nullptr, R, MD, st));                                      // clone2
         TE_TRY(te_launch_add_relprop(a.x_in, a.attn_out, R, R1, R2, ws.addpart, d.B, (long long)d.N * d.D, st));    // add1
         // Attention.relprop :154-177
-        TE_TRY(te_zplus_linear_relprop(a.ctx, d.D, bw.projw, R2, R3, S, d.M, d.D, d.D, tc, st));                    // proj
+        TE_TRY(te_zplus_linear_relprop(a.ctx, d.D, bw.projw, dw.proj, R2, R3, S, d.M, d.D, d.D, st));                    // proj
         // matmul2 rule: Z = attn v is the saved ctx itself (bit-identical recomputation in the reference)
         TE_TRY(te_launch_sd(R3, a.ctx, S, MD, st));
         TE_TRY(head_gemm(d, head_rows(S, d.D, d.N, d.dh), TE_L_K, v, TE_L_K, attn_map(a.cam, d), attn_map(a.P, d), d.N,
@@ -417,7 +463,7 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
                          0.5f, TE_EPI_MUL, st));                                    // cam_q
         TE_TRY(head_gemm(d, attn_map(S1, d), TE_L_MN, q, TE_L_MN, head_rows(Rqkv + d.D, 3 * d.D, d.N, d.dh), k, d.N,
                          d.dh, d.N, 0.5f, TE_EPI_MUL, st));                         // cam_k
-        TE_TRY(te_zplus_linear_relprop(a.xn1, d.D, bw.qkvw, Rqkv, R2, S, d.M, d.D, 3 * d.D, tc, st));               // qkv ; norm1 id
+        TE_TRY(te_zplus_linear_relprop(a.xn1, d.D, bw.qkvw, dw.qkv, Rqkv, R2, S, d.M, d.D, 3 * d.D, st));               // qkv ; norm1 id
         TE_TRY(te_launch_clone_relprop(a.x_in, R1, R2, nullptr, R, MD, st));                                       // clone1
     }
 
@@ -429,11 +475,12 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
     return TE_OK;
 }
 
-extern "C" int te_vit_explain(const te_vit_config* cfg, const float* weights, const float* images, int batch,
-                              int* index, int start_layer, unsigned flags, float* maps, float* logits,
+extern "C" int te_vit_explain(const te_vit_config* cfg, const float* weights, const float* derived, const float* images,
+                              int batch, int* index, int start_layer, unsigned flags, float* maps, float* logits,
                               void* workspace, long long workspace_bytes, void* stream) {
     TE_TRY(te_vit_forward(cfg, weights, images, batch, logits, workspace, workspace_bytes, stream));
-    return te_vit_attribute(cfg, weights, batch, index, start_layer, flags, maps, workspace, workspace_bytes, stream);
+    return te_vit_attribute(cfg, weights, derived, batch, index, start_layer, flags, maps, workspace, workspace_bytes,
+                            stream);
 }
 
 extern "C" int te_vit_tensor(const te_vit_config* cfg, int batch, void* workspace, const char* name, int layer,
@@ -451,6 +498,13 @@ extern "C" int te_vit_tensor(const te_vit_config* cfg, int batch, void* workspac
     };
     if (n == "logits") return set(ws.logits, d.B, d.C, 1, 1, d.C, 1, 1, 1);
     if (n == "rollout_mats") return set(ws.mats, d.L, d.B, d.N, d.N, (long long)d.B * d.N * d.NP, (long long)d.N * d.NP, d.NP, 1);
+    // scratch of the last attribute() call (debug / diagnostics): tmp_d0..3 [B,N,D], tmp_f0..1 [B,N,F], tmp_3d0..1 [B,N,3D]
+    if (n.rfind("tmp_d", 0) == 0 && n.size() == 6 && n[5] >= '0' && n[5] <= '3')
+        return set(ws.tD[n[5] - '0'], d.B, d.N, d.D, 1, (long long)d.N * d.D, d.D, 1, 1);
+    if (n.rfind("tmp_f", 0) == 0 && n.size() == 6 && n[5] >= '0' && n[5] <= '1')
+        return set(ws.tF[n[5] - '0'], d.B, d.N, d.F, 1, (long long)d.N * d.F, d.F, 1, 1);
+    if (n.rfind("tmp_3d", 0) == 0 && n.size() == 7 && n[6] >= '0' && n[6] <= '1')
+        return set(ws.t3D[n[6] - '0'], d.B, d.N, 3LL * d.D, 1, (long long)d.N * 3 * d.D, 3LL * d.D, 1, 1);
     if (layer < 0 || layer >= d.L) { te_set_last_error("te_vit_tensor: layer out of range"); return TE_ERR_ARG; }
     LayerAct& a = ws.layer[layer];
     const long long hs = (long long)d.N * d.NP, bs = hs * d.H;

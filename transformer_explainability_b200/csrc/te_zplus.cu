@@ -4,13 +4,13 @@
 #include "te_gemm_tc.h"
 #include <string.h>
 
-int te_zplus_linear_relprop(const float* x, long long ldx, const float* w, const float* r, float* out,
-                            float* s_scratch, long long rows, int in_features, int out_features, bool use_tc,
+int te_zplus_linear_relprop(const float* x, long long ldx, const float* w, const float* w_derived, const float* r,
+                            float* out, float* s_scratch, long long rows, int in_features, int out_features,
                             cudaStream_t st) {
     if (rows <= 0) return TE_OK;
     if (rows > 0x7fffffffLL || ldx > 0x7fffffffLL) { te_set_last_error("zplus: rows/ldx overflow int"); return TE_ERR_ARG; }
-    if (use_tc && te_tc_zplus_supported(rows, in_features, out_features, ldx))
-        return te_tc_zplus_linear_relprop(x, ldx, w, r, out, s_scratch, rows, in_features, out_features, st);
+    if (w_derived && te_tc_zplus_supported(rows, in_features, out_features, ldx))
+        return te_tc_zplus_linear_relprop(x, ldx, w_derived, r, out, s_scratch, rows, in_features, out_features, st);
     TeGemm p;
     memset(&p, 0, sizeof(p));
     p.nb1 = p.nb2 = 1; p.alpha = 1.f;

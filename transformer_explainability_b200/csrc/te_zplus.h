@@ -4,8 +4,9 @@
 #include "te_common.cuh"
 
 // x [rows, in] with row stride ldx ; w [out, in] ; r [rows, out] ; out [rows, in] ; s_scratch [rows, out].
-// use_tc: run both contractions on tcgen05 tensor cores (TF32 inputs, fp32 accumulate) when the shape
-// qualifies; otherwise (and as the checker) the fp32 SIMT path.
-int te_zplus_linear_relprop(const float* x, long long ldx, const float* w, const float* r, float* out,
-                            float* s_scratch, long long rows, int in_features, int out_features, bool use_tc,
+// w_derived: the te_tc_prepare_weights() copies of w, or NULL.  When given (and the shape qualifies) both
+// contractions run on tcgen05 tensor cores (TF32 inputs, fp32 accumulate); otherwise — and as the checker —
+// the fp32 SIMT path.
+int te_zplus_linear_relprop(const float* x, long long ldx, const float* w, const float* w_derived, const float* r,
+                            float* out, float* s_scratch, long long rows, int in_features, int out_features,
                             cudaStream_t st);

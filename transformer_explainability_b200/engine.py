@@ -38,6 +38,7 @@ class ViTEngine:
                                       self.lib.te_vit_weight_offset(ctypes.byref(cfg), i)))
         total = check(self.lib.te_vit_weight_total(ctypes.byref(cfg)), "te_vit_weight_total")
         self.weights = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.derived = None                      # tensor-core weight copies, built on demand
         self._ws = None
         self._ws_batch = 0
         self.tokens = (cfg.img_size // cfg.patch_size) ** 2 + (2 if cfg.distilled else 1)
@@ -60,6 +61,18 @@ class ViTEngine:
                 raise ValueError("%s: expected %d values, got %d" % (name, numel, t.numel()))
             host[off:off + numel] = t
         self.weights.copy_(host, non_blocking=False)
+        self.derived = None
+
+    def _derived(self, flags):
+        """W+/W-/W+^T/W-^T TF32 copies for the tcgen05 z+ path (built once per weight load)."""
+        if not (flags & _lib.FLAG_ZPLUS_TENSOR_CORES):
+            return None
+        if self.derived is None:
+            n = check(self.lib.te_vit_derived_total(ctypes.byref(self.cfg)), "te_vit_derived_total")
+            self.derived = torch.empty(n, dtype=torch.float32, device=self.device)
+            check(self.lib.te_vit_prepare_derived(ctypes.byref(self.cfg), ptr(self.weights), ptr(self.derived),
+                                                  self._stream()), "te_vit_prepare_derived")
+        return self.derived
 
     def broadcast_weights(self, src=0, group=None):
         """The one collective of the path: NCCL broadcast of the flat frozen-weight buffer."""
@@ -111,9 +124,10 @@ class ViTEngine:
         ws = self._workspace(b)
         idx = self._index_tensor(index, b)
         maps = torch.empty(b, self.tokens - self.prefix, dtype=torch.float32, device=self.device)
-        check(self.lib.te_vit_attribute(ctypes.byref(self.cfg), ptr(self.weights), b, ptr(idx), int(start_layer),
-                                        self.flags if flags is None else flags, ptr(maps), ptr(ws), ws.numel() * 4,
-                                        self._stream()), "te_vit_attribute")
+        fl = self.flags if flags is None else flags
+        check(self.lib.te_vit_attribute(ctypes.byref(self.cfg), ptr(self.weights), ptr(self._derived(fl)), b, ptr(idx),
+                                        int(start_layer), fl, ptr(maps), ptr(ws), ws.numel() * 4, self._stream()),
+              "te_vit_attribute")
         return maps, idx
 
     def explain(self, images, index=None, start_layer=0, flags=None, chunk=None, return_logits=False):
@@ -125,10 +139,11 @@ class ViTEngine:
         idx_all = self._index_tensor(index, B)
         logits = torch.empty(B, self.cfg.num_classes, dtype=torch.float32, device=self.device) if return_logits else None
         fl = self.flags if flags is None else flags
+        derived = self._derived(fl)
         for s in range(0, B, chunk):
             e = min(B, s + chunk)
             ws = self._workspace(chunk if e - s == chunk else e - s)
-            check(self.lib.te_vit_explain(ctypes.byref(self.cfg), ptr(self.weights), ptr(images[s:e]), e - s,
+            check(self.lib.te_vit_explain(ctypes.byref(self.cfg), ptr(self.weights), ptr(derived), ptr(images[s:e]), e - s,
                                           ptr(idx_all[s:e]), int(start_layer), fl, ptr(maps[s:e]),
                                           ptr(logits[s:e]) if logits is not None else None, ptr(ws), ws.numel() * 4,
                                           self._stream()), "te_vit_explain")

@@ -40,7 +40,10 @@ def linear_relprop(x, w, r, tensor_cores=False):
     _req(x, w, r)
     rows = x.numel() // x.shape[-1]
     out = torch.empty_like(x)
-    scratch = torch.empty(rows * w.shape[0], device=x.device, dtype=torch.float32)
+    nscratch = rows * w.shape[0]
+    if tensor_cores:
+        nscratch = (nscratch + 63) // 64 * 64 + 4 * w.numel()
+    scratch = torch.empty(nscratch, device=x.device, dtype=torch.float32)
     flags = _lib.FLAG_ZPLUS_TENSOR_CORES if tensor_cores else 0
     check(_lib.load().te_linear_relprop(ptr(x), ptr(w), ptr(r), ptr(out), ptr(scratch), rows, x.shape[-1], w.shape[0],
                                         flags, _stream()), "te_linear_relprop")
