@@ -38,6 +38,8 @@ extern "C" {
 #define TE_FLAG_ZPLUS_TENSOR_CORES 1u /* z+ Linear-rule GEMMs on tcgen05 (TF32 in, fp32 acc) instead of fp32 SIMT */
 #define TE_FLAG_ROLLOUT_FUSED 2u      /* single fused aggregation+rollout kernel instead of aggregate + bmm chain */
 #define TE_FLAG_KEEP_ALL_CAMS 4u      /* run the relprop below start_layer too (accessor parity with the reference) */
+#define TE_FLAG_RELPROP_TO_INPUT 8u   /* finish the lowest block as well: relevance at the encoder input (what
+                                         model.relprop() returns in the reference) is left in tensor "relevance_in" */
 
 TE_API const char* te_last_error(void);
 TE_API int te_version(void);
@@ -104,6 +106,54 @@ TE_API int te_vit_explain(const te_vit_config* cfg, const float* weights, const 
  * Returns a device pointer, 4 dims and 4 element strides (unused dims are 1). */
 TE_API int te_vit_tensor(const te_vit_config* cfg, int batch, void* workspace, const char* name, int layer,
                   float** ptr, long long dims[4], long long strides[4]);
+
+/* ------------------------------------------------------------------------------------------------
+ * BERT sequence classifier  (BERT_explainability/modules/BERT/BertForSequenceClassification.py:12-88,
+ * BERT.py:533-651; transformers.BertConfig fields)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct te_bert_config {
+    int vocab_size;       /* 30522 */
+    int max_position;     /* 512 */
+    int type_vocab;       /* 2 */
+    int hidden;           /* 768 */
+    int layers;           /* 12 */
+    int heads;            /* 12 */
+    int intermediate;     /* 3072 */
+    int num_labels;       /* 2 */
+    float layer_norm_eps; /* 1e-12 */
+} te_bert_config;
+
+/* flat fp32 weight buffer keyed by the HF state_dict names (query|key|value of a layer are adjacent and are
+ * used as one packed [3*hidden, hidden] weight); derived = tensor-core copies as for ViT. */
+TE_API int te_bert_num_weights(const te_bert_config* cfg);
+TE_API const char* te_bert_weight_name(const te_bert_config* cfg, int i);
+TE_API long long te_bert_weight_numel(const te_bert_config* cfg, int i);
+TE_API long long te_bert_weight_offset(const te_bert_config* cfg, int i);
+TE_API long long te_bert_weight_total(const te_bert_config* cfg);
+TE_API long long te_bert_derived_total(const te_bert_config* cfg);
+TE_API int te_bert_prepare_derived(const te_bert_config* cfg, const float* weights, float* derived, void* stream);
+TE_API long long te_bert_workspace_bytes(const te_bert_config* cfg, int batch, int seq);
+
+/* model(input_ids, attention_mask)[0]: ids / mask are int64 [batch, seq] (device); token_type_ids = 0,
+ * position_ids = arange(seq) as in BERT.py:69-75; logits [batch, num_labels] (may be NULL). */
+TE_API int te_bert_forward(const te_bert_config* cfg, const float* weights, const long long* input_ids,
+                    const long long* attention_mask, int batch, int seq, float* logits, void* workspace,
+                    long long workspace_bytes, void* stream);
+/* The rest of Generator.generate_LRP (ExplanationGenerator.py:33-59): arg-max (index[b] < 0), one-hot, class
+ * gradient of every attention_probs, relprop (BertForSequenceClassification.relprop), relu(grad*cam) head mean,
+ * +I, row-normalised rollout from start_layer, row 0 with element 0 replaced by the row minimum.
+ * maps [batch, seq]. */
+TE_API int te_bert_attribute(const te_bert_config* cfg, const float* weights, const float* derived, int batch, int seq,
+                      int* index, int start_layer, unsigned flags, float* maps, void* workspace,
+                      long long workspace_bytes, void* stream);
+TE_API int te_bert_explain(const te_bert_config* cfg, const float* weights, const float* derived,
+                    const long long* input_ids, const long long* attention_mask, int batch, int seq, int* index,
+                    int start_layer, unsigned flags, float* maps, float* logits, void* workspace,
+                    long long workspace_bytes, void* stream);
+/* get_attn / get_attn_gradients / get_attn_cam of BertSelfAttention (BERT.py:281-297):
+ * name in {"attn","attn_grad","attn_cam","hidden","logits"}. */
+TE_API int te_bert_tensor(const te_bert_config* cfg, int batch, int seq, void* workspace, const char* name, int layer,
+                   float** ptr, long long dims[4], long long strides[4]);
 
 /* ------------------------------------------------------------------------------------------------
  * Stand-alone LRP rules (modules/layers_ours.py) — the same kernels the engine chains, exported so

@@ -184,29 +184,66 @@ def _prepare_bert_imports():
 def build_bert(seed=0, dtype=torch.float32, state_dict=None, **cfg_over):
     _prepare_bert_imports()
     from transformers import BertConfig
-    with _ref_imports():
+    with _ref_imports():          # transformers 5.x looks the model class's module up in sys.modules at construction
         from BERT_explainability.modules.BERT.BertForSequenceClassification import BertForSequenceClassification
-    cfg = BertConfig(num_labels=2, return_dict=False, **cfg_over)     # shim 7
-    torch.manual_seed(seed)
-    old = torch.get_default_dtype()
-    model = BertForSequenceClassification(cfg)
-    if state_dict is not None:
-        model.load_state_dict(state_dict, strict=False)
-    model = model.to(dtype).eval()
-    torch.set_default_dtype(old)
+        cfg = BertConfig(num_labels=2, return_dict=False, **cfg_over)     # shim 7
+        torch.manual_seed(seed)
+        model = BertForSequenceClassification(cfg)
+        if state_dict is not None:
+            model.load_state_dict(state_dict, strict=False)
+        model = model.to(dtype).eval()
     return model
 
 
 def bert_generate_lrp(model, input_ids, attention_mask, index=None, start_layer=11, taps=False):
     _prepare_bert_imports()
+    assert input_ids.shape[0] == 1
     with _ref_imports():
         from BERT_explainability.modules.BERT.ExplanationGenerator import Generator
-    assert input_ids.shape[0] == 1
-    with _cpu_cuda_shim():
-        out = Generator(model).generate_LRP(input_ids, attention_mask, index=index, start_layer=start_layer)
+        with _cpu_cuda_shim():
+            if next(model.parameters()).dtype == torch.float64:
+                out = _bert_generate_lrp_any_dtype(Generator, model, input_ids, attention_mask, index, start_layer)
+            else:
+                out = Generator(model).generate_LRP(input_ids, attention_mask, index=index, start_layer=start_layer)
     res = {"map": out.detach()}
     if taps:
         layers = model.bert.encoder.layer
         res["grads"] = [l.attention.self.get_attn_gradients().detach() for l in layers]
         res["cams"] = [l.attention.self.get_attn_cam().detach() for l in layers]
+        res["attn"] = [l.attention.self.get_attn().detach() for l in layers]
     return res
+
+
+def _bert_generate_lrp_any_dtype(Generator, model, input_ids, attention_mask, index, start_layer):
+    """``Generator.generate_LRP`` (``ExplanationGenerator.py:28-59``) with the one-hot built in the model dtype
+    (the reference hard-codes float32 numpy); model / relprop / rollout calls are the reference's own code."""
+    import numpy as np
+    import sys as _sys
+    mod = _sys.modules[Generator.__module__]
+    output = model(input_ids=input_ids, attention_mask=attention_mask)[0]
+    if index is None:
+        index = np.argmax(output.cpu().data.numpy(), axis=-1)
+    one_hot = np.zeros((1, output.size()[-1]), dtype=np.float64)
+    one_hot[0, index] = 1
+    oh = torch.from_numpy(one_hot).to(output.dtype)
+    loss = torch.sum(oh * output)
+    model.zero_grad()
+    loss.backward(retain_graph=True)
+    model.relprop(oh.clone(), alpha=1)
+    cams = []
+    for blk in model.bert.encoder.layer:
+        grad = blk.attention.self.get_attn_gradients()
+        cam = blk.attention.self.get_attn_cam()
+        cam = cam[0].reshape(-1, cam.shape[-1], cam.shape[-1])
+        grad = grad[0].reshape(-1, grad.shape[-1], grad.shape[-1])
+        cam = (grad * cam).clamp(min=0).mean(dim=0)
+        cams.append(cam.unsqueeze(0))
+    rollout = mod.compute_rollout_attention(cams, start_layer=start_layer)
+    rollout[:, 0, 0] = rollout[:, 0].min()
+    return rollout[:, 0]
+
+
+def bert_logits(model, input_ids, attention_mask):
+    with _ref_imports():
+        with torch.enable_grad():
+            return model(input_ids=input_ids, attention_mask=attention_mask)[0].detach()

@@ -100,3 +100,27 @@ def test_oracle_bit_equal_to_live_reference():
     for l in range(3):
         assert torch.equal(taps["cams"][l], r["cams"][l])
         assert torch.equal(taps["grads"][l], r["grads"][l])
+
+
+@pytest.mark.parametrize("tag,dtype", [("f32", torch.float32), ("f64", torch.float64)])
+def test_bert_tiny_matches_reference(golden_dir, tag, dtype):
+    """BERT oracle vs the reference's Generator.generate_LRP (incl. a padded sequence: -10000 mask path)."""
+    from oracle import bert as obert
+    g = np.load(os.path.join(golden_dir, "bert_tiny.npz"))
+    params = {k[len("param."):]: T(g[k]).to(dtype) for k in g.files if k.startswith("param.")}
+    heads = int(g["heads"])
+    ids, mask = T(g["ids"]), T(g["mask"])
+    for s in range(2):
+        for sl in (0, 1, 2):
+            out, idx, taps = obert.explain(params, ids[s:s + 1], mask[s:s + 1], heads, start_layer=sl, return_taps=True)
+            assert torch.equal(out, T(g["%s.s%d.map.sl%d" % (tag, s, sl)]))
+            if sl == 0:
+                assert torch.equal(taps["logits"], T(g["%s.s%d.logits" % (tag, s)]))
+                for l in range(3):
+                    assert torch.equal(taps["grads"][l], T(g["%s.s%d.grad.%d" % (tag, s, l)]))
+                    assert torch.equal(taps["cams"][l], T(g["%s.s%d.cam.%d" % (tag, s, l)]))
+    out, _ = obert.explain(params, ids[0:1], mask[0:1], heads, index=0, start_layer=0)
+    assert torch.equal(out, T(g["%s.s0.map.index0" % tag]))
+    # padded tokens receive exactly zero relevance (SURVEY.md §8c invariant)
+    out, _ = obert.explain(params, ids[1:2], mask[1:2], heads, start_layer=0)
+    assert float(out[0, 18:].abs().max()) == 0.0

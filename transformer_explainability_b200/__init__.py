@@ -34,6 +34,8 @@ def install_aliases(extra=True):
             names.update({
                 "BERT_explainability": "transformer_explainability_b200.BERT_explainability",
                 "BERT_explainability.modules": "transformer_explainability_b200.BERT_explainability.modules",
+                "BERT_explainability.modules.layers_ours":
+                    "transformer_explainability_b200.BERT_explainability.modules.layers_ours",
                 "BERT_explainability.modules.BERT": "transformer_explainability_b200.BERT_explainability.modules.BERT",
                 "BERT_explainability.modules.BERT.ExplanationGenerator":
                     "transformer_explainability_b200.BERT_explainability.modules.BERT.ExplanationGenerator",

@@ -20,12 +20,21 @@ class TeVitConfig(ctypes.Structure):
                 ("eps_block", c_float), ("eps_final", c_float)]
 
 
+class TeBertConfig(ctypes.Structure):
+    """``te_bert_config`` of include/te_b200.h."""
+    _fields_ = [("vocab_size", c_int), ("max_position", c_int), ("type_vocab", c_int), ("hidden", c_int),
+                ("layers", c_int), ("heads", c_int), ("intermediate", c_int), ("num_labels", c_int),
+                ("layer_norm_eps", c_float)]
+
+
 FLAG_ZPLUS_TENSOR_CORES = 1
 FLAG_ROLLOUT_FUSED = 2
 FLAG_KEEP_ALL_CAMS = 4
+FLAG_RELPROP_TO_INPUT = 8
 
 _P = c_void_p
 _CFG = ctypes.POINTER(TeVitConfig)
+_BCFG = ctypes.POINTER(TeBertConfig)
 
 # name -> (restype, argtypes)   — exactly the prototypes of include/te_b200.h
 PROTOTYPES = {
@@ -45,6 +54,19 @@ PROTOTYPES = {
     "te_vit_explain": (c_int, [_CFG, _P, _P, _P, c_int, _P, c_int, c_uint, _P, _P, _P, c_ll, _P]),
     "te_vit_tensor": (c_int, [_CFG, c_int, _P, c_char_p, c_int, ctypes.POINTER(_P), ctypes.POINTER(c_ll),
                               ctypes.POINTER(c_ll)]),
+    "te_bert_num_weights": (c_int, [_BCFG]),
+    "te_bert_weight_name": (c_char_p, [_BCFG, c_int]),
+    "te_bert_weight_numel": (c_ll, [_BCFG, c_int]),
+    "te_bert_weight_offset": (c_ll, [_BCFG, c_int]),
+    "te_bert_weight_total": (c_ll, [_BCFG]),
+    "te_bert_derived_total": (c_ll, [_BCFG]),
+    "te_bert_prepare_derived": (c_int, [_BCFG, _P, _P, _P]),
+    "te_bert_workspace_bytes": (c_ll, [_BCFG, c_int, c_int]),
+    "te_bert_forward": (c_int, [_BCFG, _P, _P, _P, c_int, c_int, _P, _P, c_ll, _P]),
+    "te_bert_attribute": (c_int, [_BCFG, _P, _P, c_int, c_int, _P, c_int, c_uint, _P, _P, c_ll, _P]),
+    "te_bert_explain": (c_int, [_BCFG, _P, _P, _P, _P, c_int, c_int, _P, c_int, c_uint, _P, _P, _P, c_ll, _P]),
+    "te_bert_tensor": (c_int, [_BCFG, c_int, c_int, _P, c_char_p, c_int, ctypes.POINTER(_P), ctypes.POINTER(c_ll),
+                               ctypes.POINTER(c_ll)]),
     "te_linear_relprop": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_uint, _P]),
     "te_add_relprop": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_ll, _P]),
     "te_clone_relprop": (c_int, [_P, _P, _P, _P, _P, c_ll, _P]),

@@ -14,9 +14,9 @@ reference does not contain.
 import torch
 import torch.nn as nn
 
-from ... import ops
-from ... import _lib
-from ...engine import ViTEngine, vit_config
+from transformer_explainability_b200 import ops
+from transformer_explainability_b200 import _lib
+from transformer_explainability_b200.engine import ViTEngine, vit_config
 
 __all__ = ["VisionTransformer", "compute_rollout_attention", "vit_base_patch16_224", "vit_large_patch16_224",
            "deit_base_patch16_224", "deit_base_distilled_patch16_224"]

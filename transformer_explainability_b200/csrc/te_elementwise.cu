@@ -163,11 +163,16 @@ __global__ void layernorm_bwd_strided_kernel(const float* __restrict__ dy, long 
 // ------------------------------------------------------------------------------------------------
 // softmax over the last dim (row length N, row stride ld >= N, pad columns zeroed)
 // ------------------------------------------------------------------------------------------------
-__global__ void softmax_kernel(float* __restrict__ s, long long rows, int N, int ld) {
+__global__ void softmax_kernel(float* __restrict__ s, long long rows, int N, int ld,
+                               const float* __restrict__ keymask, long long rows_per_batch) {
     const int lane = threadIdx.x & 31;
     const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     float* r = s + row * ld;
+    if (keymask) {                                   // scores + extended attention mask  (BERT.py:342)
+        const float* mk = keymask + (row / rows_per_batch) * N;
+        for (int j = lane; j < N; j += 32) r[j] = r[j] + mk[j];
+    }
     float m = -INFINITY;
     for (int j = lane; j < N; j += 32) m = fmaxf(m, r[j]);
     m = te_warp_max(m);
@@ -422,6 +427,108 @@ __global__ void average2_kernel(const float* __restrict__ a, const float* __rest
          t += (long long)gridDim.x * blockDim.x) out[t] = (a[t] + b[t]) / 2.0f;
 }
 
+// ------------------------------------------------------------------------------------------------
+// BERT extras: embeddings, additive mask, tanh, elementwise add, Add rule with a key-broadcast operand
+// ------------------------------------------------------------------------------------------------
+// (token_type + position) + word   (BertEmbeddings.forward, BERT.py:80-81; token_type_ids = 0, position_ids = arange)
+__global__ void bert_embed_kernel(const long long* __restrict__ ids, const float* __restrict__ word,
+                                  const float* __restrict__ pos, const float* __restrict__ type0,
+                                  float* __restrict__ out, int B, int S, int D) {
+    const int d4 = D / 4;
+    const long long total = (long long)B * S * d4;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(t % d4);
+        const long long rt = t / d4;
+        const int s = (int)(rt % S);
+        const long long id = ids[rt];
+        const float4 w = *reinterpret_cast<const float4*>(word + id * D + q * 4);
+        const float4 p = *reinterpret_cast<const float4*>(pos + (long long)s * D + q * 4);
+        const float4 ty = *reinterpret_cast<const float4*>(type0 + q * 4);
+        *reinterpret_cast<float4*>(out + rt * D + q * 4) =
+            make_float4((ty.x + p.x) + w.x, (ty.y + p.y) + w.y, (ty.z + p.z) + w.z, (ty.w + p.w) + w.w);
+    }
+}
+// transformers 3.5.1 get_extended_attention_mask: (1 - mask) * -10000   (call site BERT.py:598)
+__global__ void bert_mask_kernel(const long long* __restrict__ mask, float* __restrict__ out, long long n) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        out[t] = (1.0f - (float)mask[t]) * -10000.0f;
+}
+__global__ void tanh_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        y[t] = tanhf(x[t]);
+}
+__global__ void tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx,
+                                long long n) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        dx[t] = dy[t] * (1.0f - y[t] * y[t]);
+}
+__global__ void add2_kernel(const float* a, const float* b, float* out, long long n4) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n4;
+         t += (long long)gridDim.x * blockDim.x) {
+        const float4 u = reinterpret_cast<const float4*>(a)[t], v = reinterpret_cast<const float4*>(b)[t];
+        reinterpret_cast<float4*>(out)[t] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+    }
+}
+
+// Add.relprop for add([scores, extended_mask]) (BERT.py:386-388): x1 [B,H,N,ld], x2[b,j] broadcast over (h,i).
+// pass 1: per-sample sums (a = x1*S, b = x2*S, rho = R) ; the mask's own relevance is discarded by the caller,
+// but its sum enters the renormalisation factors.
+__global__ void add_keymask_reduce_kernel(const float* __restrict__ x1, const float* __restrict__ mk,
+                                          const float* __restrict__ r, double* __restrict__ partial, int HN, int N,
+                                          int ld) {
+    const int b = blockIdx.y, sp = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const float* m = mk + (long long)b * N;
+    double sa = 0.0, sb = 0.0, sr = 0.0;
+    for (int row = sp * nw + wid; row < HN; row += TE_ADD_SPLIT * nw) {
+        const float* xr = x1 + ((long long)b * HN + row) * ld;
+        const float* rr = r + ((long long)b * HN + row) * ld;
+        for (int j = lane; j < N; j += 32) {
+            const float a = xr[j], c = m[j], rv = rr[j];
+            const float s = te_sd(rv, a + c);
+            sa += (double)(a * s); sb += (double)(c * s); sr += (double)rv;
+        }
+    }
+    __shared__ double red[3][kThreads / 32];
+    sa = te_warp_sum(sa); sb = te_warp_sum(sb); sr = te_warp_sum(sr);
+    if (lane == 0) { red[0][wid] = sa; red[1][wid] = sb; red[2][wid] = sr; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ta = 0, tb = 0, tr = 0;
+        for (int i = 0; i < nw; ++i) { ta += red[0][i]; tb += red[1][i]; tr += red[2][i]; }
+        double* o = partial + ((long long)b * TE_ADD_SPLIT + sp) * 3;
+        o[0] = ta; o[1] = tb; o[2] = tr;
+    }
+}
+__global__ void add_keymask_scale_kernel(const float* __restrict__ x1, const float* __restrict__ mk,
+                                         const float* __restrict__ r, float* __restrict__ r1,
+                                         const double* __restrict__ partial, int HN, int N, int ld) {
+    const int b = blockIdx.y;
+    __shared__ float fa_s;
+    if (threadIdx.x == 0) {
+        double A = 0, Bs = 0, rho = 0;
+        const double* q = partial + (long long)b * TE_ADD_SPLIT * 3;
+        for (int i = 0; i < TE_ADD_SPLIT; ++i) { A += q[i * 3]; Bs += q[i * 3 + 1]; rho += q[i * 3 + 2]; }
+        const double den = fabs(A) + fabs(Bs);
+        fa_s = (float)te_sd(te_sd(fabs(A), den) * rho, A);
+    }
+    __syncthreads();
+    const float fa = fa_s;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const float* m = mk + (long long)b * N;
+    for (int row = blockIdx.x * nw + wid; row < HN; row += gridDim.x * nw) {
+        const float* xr = x1 + ((long long)b * HN + row) * ld;
+        const float* rr = r + ((long long)b * HN + row) * ld;
+        float* o = r1 + ((long long)b * HN + row) * ld;
+        for (int j = lane; j < ld; j += 32) {
+            float v = 0.f;
+            if (j < N) { const float a = xr[j]; v = a * te_sd(rr[j], a + m[j]) * fa; }
+            o[j] = v;
+        }
+    }
+}
+
 __global__ void fill_kernel(float* __restrict__ p, float v, long long n) {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n;
          t += (long long)gridDim.x * blockDim.x) p[t] = v;
@@ -480,8 +587,12 @@ int te_launch_layernorm_bwd_strided(const float* dy, long long dy_stride, const 
     return TE_OK;
 }
 int te_launch_softmax(float* s, long long rows, int N, int ld, cudaStream_t st) {
+    return te_launch_softmax_masked(s, rows, N, ld, nullptr, 1, st);
+}
+int te_launch_softmax_masked(float* s, long long rows, int N, int ld, const float* keymask, long long rows_per_batch,
+                             cudaStream_t st) {
     if (rows <= 0) return TE_OK;
-    softmax_kernel<<<warp_rows_grid(rows), kThreads, 0, st>>>(s, rows, N, ld);
+    softmax_kernel<<<warp_rows_grid(rows), kThreads, 0, st>>>(s, rows, N, ld, keymask, rows_per_batch);
     TE_CUDA_CHECK_LAUNCH();
     return TE_OK;
 }
@@ -556,6 +667,45 @@ int te_launch_extract_row(const float* joint, float* out, int B, int N, int ld, 
 }
 int te_launch_average2(const float* a, const float* b, float* out, long long n, cudaStream_t st) {
     average2_kernel<<<flat_grid(n), kThreads, 0, st>>>(a, b, out, n);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_bert_embed(const long long* ids, const float* word, const float* pos, const float* type0, float* out,
+                         int B, int S, int D, cudaStream_t st) {
+    TE_REQ(D % 4 == 0, "bert_embed: D % 4 != 0");
+    bert_embed_kernel<<<flat_grid((long long)B * S * (D / 4)), kThreads, 0, st>>>(ids, word, pos, type0, out, B, S, D);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_bert_mask(const long long* mask, float* out, long long n, cudaStream_t st) {
+    bert_mask_kernel<<<flat_grid(n), kThreads, 0, st>>>(mask, out, n);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_tanh(const float* x, float* y, long long n, cudaStream_t st) {
+    tanh_kernel<<<flat_grid(n), kThreads, 0, st>>>(x, y, n);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_tanh_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream_t st) {
+    tanh_bwd_kernel<<<flat_grid(n), kThreads, 0, st>>>(dy, y, dx, n);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_add2(const float* a, const float* b, float* out, long long n, cudaStream_t st) {
+    TE_REQ(n % 4 == 0, "add2: n % 4 != 0");
+    add2_kernel<<<flat_grid(n / 4), kThreads, 0, st>>>(a, b, out, n / 4);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_add_relprop_keymask(const float* x1, const float* keymask, const float* r, float* r1, double* partial,
+                                  int B, int H, int N, int ld, cudaStream_t st) {
+    TE_REQ(B <= 65535, "add_relprop_keymask: batch too large for one launch");
+    add_keymask_reduce_kernel<<<dim3(TE_ADD_SPLIT, B), kThreads, 0, st>>>(x1, keymask, r, partial, H * N, N, ld);
+    TE_CUDA_CHECK_LAUNCH();
+    int gx = (H * N + 7) / 8;
+    gx = gx > 64 ? 64 : gx;
+    add_keymask_scale_kernel<<<dim3(gx, B), kThreads, 0, st>>>(x1, keymask, r, r1, partial, H * N, N, ld);
     TE_CUDA_CHECK_LAUNCH();
     return TE_OK;
 }

@@ -1,0 +1,52 @@
+// Host-side helpers shared by the model engines: GEMM parameter builders over packed activations.
+#pragma once
+#include <string.h>
+
+#include "te_gemm.cuh"
+
+namespace te_util {
+
+static inline TeGemm gemm0() {
+    TeGemm p;
+    memset(&p, 0, sizeof(p));
+    p.nb1 = 1; p.nb2 = 1; p.alpha = 1.f;
+    return p;
+}
+
+// y[M,out] = x[M,in] * W[out,in]^T  (+ epilogue);  y2 / e0 share y's row stride
+static inline int linear_fwd(const float* x, int lda, const float* w, const float* bias, float* y, float* y2,
+                             const float* e0, long long M, int in, int out, int epi, cudaStream_t st) {
+    TeGemm p = gemm0();
+    p.A = x; p.lda = lda; p.B = w; p.ldb = in; p.C = y; p.ldc = out; p.C2 = y2; p.ldc2 = out; p.E0 = e0; p.lde0 = out;
+    p.bias = bias; p.M = (int)M; p.N = out; p.K = in;
+    return te_gemm_launch(p, TE_L_K, TE_L_K, TE_XF_NONE, epi, st);
+}
+// dx[M,in] = dy[M,out] * W[out,in]
+static inline int linear_bwd(const float* dy, const float* w, float* dx, const float* e0, long long M, int in, int out,
+                             int epi, cudaStream_t st) {
+    TeGemm p = gemm0();
+    p.A = dy; p.lda = out; p.B = w; p.ldb = in; p.C = dx; p.ldc = in; p.E0 = e0; p.lde0 = in;
+    p.M = (int)M; p.N = in; p.K = out;
+    return te_gemm_launch(p, TE_L_K, TE_L_MN, TE_XF_NONE, epi, st);
+}
+
+// one operand of a (batch, head)-batched attention-shaped GEMM
+struct HeadOp { const float* ptr; int ld; long long s1, s2; };
+static inline HeadOp head_rows(const float* base, int ld, int N, int dh) {        // [b, n, (h d)] slice, rows = tokens
+    return {base, ld, (long long)N * ld, (long long)dh};
+}
+static inline HeadOp attn_map(const float* base, int H, int N, int NP) {          // [b, h, n, NP]
+    return {base, NP, (long long)H * N * NP, (long long)N * NP};
+}
+static inline int head_gemm(int B, int H, HeadOp A, int alay, HeadOp Bm, int blay, HeadOp C, HeadOp E, int M, int N,
+                            int K, float alpha, int epi, cudaStream_t st) {
+    TeGemm p = gemm0();
+    p.A = A.ptr; p.lda = A.ld; p.sA1 = A.s1; p.sA2 = A.s2;
+    p.B = Bm.ptr; p.ldb = Bm.ld; p.sB1 = Bm.s1; p.sB2 = Bm.s2;
+    p.C = const_cast<float*>(C.ptr); p.ldc = C.ld; p.sC1 = C.s1; p.sC2 = C.s2;
+    p.E0 = E.ptr; p.lde0 = E.ld; p.sE1 = E.s1; p.sE2 = E.s2;
+    p.M = M; p.N = N; p.K = K; p.nb1 = B; p.nb2 = H; p.alpha = alpha;
+    return te_gemm_launch(p, alay, blay, TE_XF_NONE, epi, st);
+}
+
+}  // namespace te_util

@@ -386,8 +386,8 @@ int te_tc_prepare_weights(const float* w, float* derived, int in_features, int o
     return TE_OK;
 }
 
-int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* derived, const float* r, float* out,
-                               float* s_scratch, long long rows, int in_features, int out_features, cudaStream_t st) {
+int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* derived, const float* r, long long ldr,
+                               float* out, float* s_scratch, long long rows, int in_features, int out_features, cudaStream_t st) {
     if (!a16(x) || !a16(derived) || !a16(r) || !a16(out) || !a16(s_scratch)) {
         te_set_last_error("te_gemm_tc: operands must be 16-byte aligned");
         return TE_ERR_ARG;
@@ -395,7 +395,7 @@ int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* deriv
     const long long n = (long long)in_features * out_features;
     const float *wp = derived, *wn = derived + n, *wpt = derived + 2 * n, *wnt = derived + 3 * n;
     // S = sd(R, x+ W+^T + x- W-^T)          A = x [rows, in] ; B = W+/- [out, in]
-    TE_TRY(launch<MODE_S>(x, ldx, wp, wn, r, out_features, s_scratch, out_features, rows, out_features, in_features, st));
+    TE_TRY(launch<MODE_S>(x, ldx, wp, wn, r, ldr, s_scratch, out_features, rows, out_features, in_features, st));
     // R_in = x+ (S W+) + x- (S W-)          A = S [rows, out] ; B = W+/-^T [in, out]
     TE_TRY(launch<MODE_R>(s_scratch, out_features, wpt, wnt, x, ldx, out, in_features, rows, in_features, out_features, st));
     return TE_OK;

@@ -8,5 +8,6 @@ bool te_tc_zplus_supported(long long rows, int in_features, int out_features, lo
 // rounded to TF32: 4*in*out floats
 long long te_tc_derived_floats(int in_features, int out_features);
 int te_tc_prepare_weights(const float* w, float* derived, int in_features, int out_features, cudaStream_t st);
-int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* derived, const float* r, float* out,
+int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* derived, const float* r, long long ldr,
+                               float* out,
                                float* s_scratch, long long rows, int in_features, int out_features, cudaStream_t st);

@@ -45,3 +45,15 @@ int te_launch_prep_mats(const float* in, float* out, long long rows, int N, int 
 int te_launch_extract_row(const float* joint, float* out, int B, int N, int ld, int first, int bert_fix,
                           cudaStream_t st);
 int te_launch_fill(float* p, float v, long long n, cudaStream_t st);
+// ---- BERT extras -------------------------------------------------------------------------------
+int te_launch_softmax_masked(float* s, long long rows, int N, int ld, const float* keymask, long long rows_per_batch,
+                             cudaStream_t st);
+int te_launch_bert_embed(const long long* ids, const float* word, const float* pos, const float* type0, float* out,
+                         int B, int S, int D, cudaStream_t st);
+int te_launch_bert_mask(const long long* mask, float* out, long long n, cudaStream_t st);
+int te_launch_tanh(const float* x, float* y, long long n, cudaStream_t st);
+int te_launch_tanh_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream_t st);
+int te_launch_add2(const float* a, const float* b, float* out, long long n, cudaStream_t st);
+// Add.relprop for add([scores, key-broadcast mask]); only the scores' relevance is produced.
+int te_launch_add_relprop_keymask(const float* x1, const float* keymask, const float* r, float* r1, double* partial,
+                                  int B, int H, int N, int ld, cudaStream_t st);

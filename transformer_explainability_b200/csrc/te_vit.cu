@@ -371,7 +371,7 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
     const float scale = 1.0f / sqrtf((float)d.dh);
     const HeadOp none = {nullptr, 0, 0, 0};
     const long long MD = d.M * d.D;
-    const int low = (flags & TE_FLAG_KEEP_ALL_CAMS) ? 0 : start_layer;   // lowest block the relprop must reach
+    const int low = (flags & (TE_FLAG_KEEP_ALL_CAMS | TE_FLAG_RELPROP_TO_INPUT)) ? 0 : start_layer;   // lowest block the relprop must reach
     const float* dbase = (flags & TE_FLAG_ZPLUS_TENSOR_CORES) ? derived : nullptr;
     if ((flags & TE_FLAG_ZPLUS_TENSOR_CORES) && !derived) {
         te_set_last_error("te_vit_attribute: TE_FLAG_ZPLUS_TENSOR_CORES needs the derived weight buffer");
@@ -454,7 +454,7 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
         TE_TRY(te_launch_sd(R3, a.ctx, S, MD, st));
         TE_TRY(head_gemm(d, head_rows(S, d.D, d.N, d.dh), TE_L_K, v, TE_L_K, attn_map(a.cam, d), attn_map(a.P, d), d.N,
                          d.N, d.dh, 0.5f, TE_EPI_MUL, st));                         // attn_cam = (P * (S v^T)) / 2   :160-165
-        if (l == low) break;                                                        // nothing below is consumed
+        if (l == low && !(flags & TE_FLAG_RELPROP_TO_INPUT)) break;                                                        // nothing below is consumed
         TE_TRY(head_gemm(d, attn_map(a.P, d), TE_L_MN, head_rows(S, d.D, d.N, d.dh), TE_L_MN,
                          head_rows(Rqkv + 2 * d.D, 3 * d.D, d.N, d.dh), v, d.N, d.dh, d.N, 0.5f, TE_EPI_MUL, st));   // cam_v
         // matmul1 rule (unscaled Z = q k^T)  :170-173
@@ -497,6 +497,7 @@ extern "C" int te_vit_tensor(const te_vit_config* cfg, int batch, void* workspac
         return TE_OK;
     };
     if (n == "logits") return set(ws.logits, d.B, d.C, 1, 1, d.C, 1, 1, 1);
+    if (n == "relevance_in") return set(ws.tD[0], d.B, d.N, d.D, 1, (long long)d.N * d.D, d.D, 1, 1);
     if (n == "rollout_mats") return set(ws.mats, d.L, d.B, d.N, d.N, (long long)d.B * d.N * d.NP, (long long)d.N * d.NP, d.NP, 1);
     // scratch of the last attribute() call (debug / diagnostics): tmp_d0..3 [B,N,D], tmp_f0..1 [B,N,F], tmp_3d0..1 [B,N,3D]
     if (n.rfind("tmp_d", 0) == 0 && n.size() == 6 && n[5] >= '0' && n[5] <= '3')

@@ -7,16 +7,23 @@
 int te_zplus_linear_relprop(const float* x, long long ldx, const float* w, const float* w_derived, const float* r,
                             float* out, float* s_scratch, long long rows, int in_features, int out_features,
                             cudaStream_t st) {
+    return te_zplus_linear_relprop_ldr(x, ldx, w, w_derived, r, out_features, out, s_scratch, rows, in_features,
+                                       out_features, st);
+}
+
+int te_zplus_linear_relprop_ldr(const float* x, long long ldx, const float* w, const float* w_derived, const float* r,
+                                long long ldr, float* out, float* s_scratch, long long rows, int in_features,
+                                int out_features, cudaStream_t st) {
     if (rows <= 0) return TE_OK;
     if (rows > 0x7fffffffLL || ldx > 0x7fffffffLL) { te_set_last_error("zplus: rows/ldx overflow int"); return TE_ERR_ARG; }
-    if (w_derived && te_tc_zplus_supported(rows, in_features, out_features, ldx))
-        return te_tc_zplus_linear_relprop(x, ldx, w_derived, r, out, s_scratch, rows, in_features, out_features, st);
+    if (w_derived && ldr % 4 == 0 && te_tc_zplus_supported(rows, in_features, out_features, ldx))
+        return te_tc_zplus_linear_relprop(x, ldx, w_derived, r, ldr, out, s_scratch, rows, in_features, out_features, st);
     TeGemm p;
     memset(&p, 0, sizeof(p));
     p.nb1 = p.nb2 = 1; p.alpha = 1.f;
     // S = sd(R, x+ W+^T + x- W-^T)
     p.A = x; p.lda = (int)ldx; p.B = w; p.ldb = in_features; p.C = s_scratch; p.ldc = out_features;
-    p.E0 = r; p.lde0 = out_features; p.M = (int)rows; p.N = out_features; p.K = in_features;
+    p.E0 = r; p.lde0 = (int)ldr; p.M = (int)rows; p.N = out_features; p.K = in_features;
     TE_TRY(te_gemm_launch(p, TE_L_K, TE_L_K, TE_XF_AB_POSNEG, TE_EPI_SD, st));
     // R_in = x+ * (S W+) + x- * (S W-)
     p.A = s_scratch; p.lda = out_features; p.B = w; p.ldb = in_features; p.C = out; p.ldc = in_features;

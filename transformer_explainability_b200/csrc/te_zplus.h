@@ -10,3 +10,7 @@
 int te_zplus_linear_relprop(const float* x, long long ldx, const float* w, const float* w_derived, const float* r,
                             float* out, float* s_scratch, long long rows, int in_features, int out_features,
                             cudaStream_t st);
+// same with an explicit row stride for r (a column slice of a packed [rows, 3*out] relevance tensor)
+int te_zplus_linear_relprop_ldr(const float* x, long long ldx, const float* w, const float* w_derived, const float* r,
+                                long long ldr, float* out, float* s_scratch, long long rows, int in_features,
+                                int out_features, cudaStream_t st);

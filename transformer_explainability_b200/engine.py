@@ -176,3 +176,149 @@ class ViTEngine:
         while nd > 2 and dims[nd - 1] == 1:
             nd -= 1
         return torch.as_strided(ws, [int(dims[i]) for i in range(nd)], [int(strides[i]) for i in range(nd)], off)
+
+
+def bert_config(vocab_size=30522, max_position_embeddings=512, type_vocab_size=2, hidden_size=768,
+                num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072, num_labels=2,
+                layer_norm_eps=1e-12):
+    from ._lib import TeBertConfig
+    return TeBertConfig(vocab_size, max_position_embeddings, type_vocab_size, hidden_size, num_hidden_layers,
+                        num_attention_heads, intermediate_size, num_labels, layer_norm_eps)
+
+
+class BertEngine:
+    """``Generator.generate_LRP`` (BERT_explainability/modules/BERT/ExplanationGenerator.py:28-59) for batches of
+    independent sequences of one length."""
+
+    def __init__(self, cfg, state_dict=None, device=None, flags=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("transformer_explainability_b200 needs a CUDA device (B200, sm_100a); "
+                               "there is no CPU fallback")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.flags = flags
+        n = check(self.lib.te_bert_num_weights(ctypes.byref(cfg)), "te_bert_num_weights")
+        self.weight_table = [(self.lib.te_bert_weight_name(ctypes.byref(cfg), i).decode(),
+                              self.lib.te_bert_weight_numel(ctypes.byref(cfg), i),
+                              self.lib.te_bert_weight_offset(ctypes.byref(cfg), i)) for i in range(n)]
+        total = check(self.lib.te_bert_weight_total(ctypes.byref(cfg)), "te_bert_weight_total")
+        self.weights = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.derived = None
+        self._ws = None
+        self._ws_key = None
+        self.last = (0, 0)
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+
+    def load_state_dict(self, sd):
+        host = torch.zeros(self.weights.numel(), dtype=torch.float32)
+        for name, numel, off in self.weight_table:
+            if name not in sd:
+                raise KeyError("state_dict is missing %r" % name)
+            t = sd[name].detach().to(torch.float32).reshape(-1).cpu()
+            if t.numel() != numel:
+                raise ValueError("%s: expected %d values, got %d" % (name, numel, t.numel()))
+            host[off:off + numel] = t
+        self.weights.copy_(host)
+        self.derived = None
+
+    def broadcast_weights(self, src=0, group=None):
+        import torch.distributed as dist
+        dist.broadcast(self.weights, src=src, group=group)
+
+    def _derived(self, flags):
+        if not (flags & _lib.FLAG_ZPLUS_TENSOR_CORES):
+            return None
+        if self.derived is None:
+            n = check(self.lib.te_bert_derived_total(ctypes.byref(self.cfg)), "te_bert_derived_total")
+            self.derived = torch.empty(n, dtype=torch.float32, device=self.device)
+            check(self.lib.te_bert_prepare_derived(ctypes.byref(self.cfg), ptr(self.weights), ptr(self.derived),
+                                                   self._stream()), "te_bert_prepare_derived")
+        return self.derived
+
+    def workspace_bytes(self, batch, seq):
+        return check(self.lib.te_bert_workspace_bytes(ctypes.byref(self.cfg), batch, seq), "te_bert_workspace_bytes")
+
+    def _workspace(self, batch, seq):
+        if self._ws is None or self._ws_key != (batch, seq):
+            self._ws = None
+            self._ws = torch.empty(self.workspace_bytes(batch, seq) // 4, dtype=torch.float32, device=self.device)
+            self._ws_key = (batch, seq)
+        return self._ws
+
+    def max_chunk(self, seq, limit=None, reserve_bytes=4 << 30):
+        free, _ = torch.cuda.mem_get_info(self.device)
+        if self._ws is not None:
+            free += self._ws.numel() * 4
+        per = self.workspace_bytes(2, seq) - self.workspace_bytes(1, seq)
+        b = max(1, int((free - reserve_bytes) // max(per, 1)))
+        return min(b, limit) if limit else b
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ids(self, input_ids, attention_mask):
+        ids = input_ids.to(self.device, torch.int64).contiguous()
+        if attention_mask is None:
+            attention_mask = torch.ones_like(ids)
+        return ids, attention_mask.to(self.device, torch.int64).contiguous()
+
+    def forward(self, input_ids, attention_mask=None):
+        ids, mask = self._ids(input_ids, attention_mask)
+        b, s = ids.shape
+        ws = self._workspace(b, s)
+        logits = torch.empty(b, self.cfg.num_labels, dtype=torch.float32, device=self.device)
+        check(self.lib.te_bert_forward(ctypes.byref(self.cfg), ptr(self.weights), ptr(ids), ptr(mask), b, s, ptr(logits),
+                                       ptr(ws), ws.numel() * 4, self._stream()), "te_bert_forward")
+        self.last = (b, s)
+        return logits
+
+    def attribute(self, index=None, start_layer=11, flags=None):
+        b, s = self.last
+        if b <= 0:
+            raise RuntimeError("attribute() needs a preceding forward()")
+        ws = self._workspace(b, s)
+        idx = ViTEngine._index_tensor(self, index, b)
+        maps = torch.empty(b, s, dtype=torch.float32, device=self.device)
+        fl = self.flags if flags is None else flags
+        check(self.lib.te_bert_attribute(ctypes.byref(self.cfg), ptr(self.weights), ptr(self._derived(fl)), b, s, ptr(idx),
+                                         int(start_layer), fl, ptr(maps), ptr(ws), ws.numel() * 4, self._stream()),
+              "te_bert_attribute")
+        return maps, idx
+
+    def explain(self, input_ids, attention_mask=None, index=None, start_layer=11, flags=None, chunk=None,
+                return_logits=False):
+        ids, mask = self._ids(input_ids, attention_mask)
+        B, S = ids.shape
+        chunk = min(B, chunk or self.max_chunk(S, limit=B))
+        maps = torch.empty(B, S, dtype=torch.float32, device=self.device)
+        idx_all = ViTEngine._index_tensor(self, index, B)
+        logits = torch.empty(B, self.cfg.num_labels, dtype=torch.float32, device=self.device) if return_logits else None
+        fl = self.flags if flags is None else flags
+        derived = self._derived(fl)
+        for s0 in range(0, B, chunk):
+            e = min(B, s0 + chunk)
+            ws = self._workspace(e - s0, S)
+            check(self.lib.te_bert_explain(ctypes.byref(self.cfg), ptr(self.weights), ptr(derived), ptr(ids[s0:e]),
+                                           ptr(mask[s0:e]), e - s0, S, ptr(idx_all[s0:e]), int(start_layer), fl,
+                                           ptr(maps[s0:e]), ptr(logits[s0:e]) if logits is not None else None, ptr(ws),
+                                           ws.numel() * 4, self._stream()), "te_bert_explain")
+            self.last = (e - s0, S)
+        if return_logits:
+            return maps, idx_all, logits
+        return maps, idx_all
+
+    def tensor(self, name, layer=0):
+        b, s = self.last
+        ws = self._workspace(b, s)
+        p = ctypes.c_void_p()
+        dims = (ctypes.c_longlong * 4)()
+        strides = (ctypes.c_longlong * 4)()
+        check(self.lib.te_bert_tensor(ctypes.byref(self.cfg), b, s, ptr(ws), name.encode(), layer, ctypes.byref(p), dims,
+                                      strides), "te_bert_tensor")
+        off = (p.value - ws.data_ptr()) // 4
+        nd = 4
+        while nd > 2 and dims[nd - 1] == 1:
+            nd -= 1
+        return torch.as_strided(ws, [int(dims[i]) for i in range(nd)], [int(strides[i]) for i in range(nd)], off)

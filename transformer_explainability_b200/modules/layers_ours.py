@@ -11,7 +11,7 @@ in ``relprop`` — they are out of scope.
 import torch
 import torch.nn as nn
 
-from .. import ops
+from transformer_explainability_b200 import ops
 
 __all__ = ['forward_hook', 'Clone', 'Add', 'Cat', 'ReLU', 'GELU', 'Dropout', 'BatchNorm2d', 'Linear', 'MaxPool2d',
            'AdaptiveAvgPool2d', 'AvgPool2d', 'Conv2d', 'Sequential', 'safe_divide', 'einsum', 'Softmax', 'IndexSelect',
