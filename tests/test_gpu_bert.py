@@ -98,8 +98,13 @@ def test_bert_tiny_batched_and_relprop_api(golden_dir):
 @pytest.mark.parametrize("seq,start", [(128, 0), (512, 11)])
 def test_bert_base_vs_oracle(seq, start):
     """BERT-base (BASELINE configs[4] shape; S=512 with the pipeline default start_layer=11, S=128 with the notebook's
-    start_layer=0), SIMT and tcgen05 z+ paths, median over 1e-7-equivalent perturbations is not available for integer
-    inputs, so three different sequences are used and the median relative error is bounded."""
+    start_layer=0), fp32 SIMT and tcgen05 z+ paths.
+
+    At random init the reference itself is badly conditioned on this model: its fp32 result (== oracle fp32, bit-equal)
+    deviates from its fp64 result by 2e-2 ... 7e-1 of the map maximum depending on the thread count (measured,
+    DESIGN.md §2).  So: class index bit-exact; logits, attention gradients and the top layer's attn_cam (one block of
+    relprop, little amplification) tight; final maps judged against the reference's own fp32-vs-fp64 error
+    measured on this box: median(err_new) <= max(5e-2, 3 * median(err_ref))."""
     from transformer_explainability_b200 import _lib
     params, heads = obert.init_params(seed=0, rand_affine=True)
     model = make_model(params, heads)
@@ -111,10 +116,20 @@ def test_bert_base_vs_oracle(seq, start):
     mask = torch.ones(n, seq, dtype=torch.long)
     ocpu.set_torch_threads()
     p64 = {k: v.double() for k, v in params.items()}
-    ref, ridx = obert.explain(p64, ids, mask, heads, start_layer=start)
+    ref, ridx, taps = obert.explain(p64, ids, mask, heads, start_layer=start, return_taps=True)
+    ref32, _ = obert.explain(params, ids, mask, heads, start_layer=start)
+    err_ref = sorted(rel(ref32[s], ref[s]) for s in range(n))
+    top = len(taps["cams"]) - 1
     for flags in (0, _lib.FLAG_ZPLUS_TENSOR_CORES):
-        maps, idx = eng.explain(ids.cuda(), mask.cuda(), start_layer=start, flags=flags)
+        maps, idx, logits = eng.explain(ids.cuda(), mask.cuda(), start_layer=start, flags=flags, return_logits=True)
         assert torch.equal(idx.cpu().long(), ridx)
+        assert rel(logits, taps["logits"]) < 1e-4
+        layers = model.bert.encoder.layer
+        assert rel(layers[top].attention.self.get_attn_gradients(), taps["grads"][top]) < 1e-3
+        assert rel(layers[start].attention.self.get_attn_gradients(), taps["grads"][start]) < 1e-3
+        cam_err = sorted(rel(layers[top].attention.self.get_attn_cam()[s], taps["cams"][top][s]) for s in range(n))
         errs = sorted(rel(maps[s], ref[s]) for s in range(n))
-        print("bert-base S=%d start=%d flags=%d rel errs %s" % (seq, start, flags, ["%.1e" % e for e in errs]))
-        assert errs[n // 2] < 5e-2
+        print("bert-base S=%d start=%d flags=%d: top-cam rel %s | map rel %s | reference fp32-vs-fp64 %s" % (
+            seq, start, flags, ["%.1e" % e for e in cam_err], ["%.1e" % e for e in errs], ["%.1e" % e for e in err_ref]))
+        assert cam_err[n // 2] < 5e-2
+        assert errs[n // 2] <= max(5e-2, 3 * err_ref[n // 2])
