@@ -361,7 +361,7 @@ def main():
 
 def default_flags():
     """Best validated kernel selection: updated as faster paths pass parity."""
-    return 0
+    return 3   # tcgen05 z+ rule + fused row-only rollout (validated: tests/test_gpu_tc.py, test_gpu_rules.py)
 
 
 if __name__ == "__main__":

@@ -107,7 +107,7 @@ def test_attention_matmul_rules(ops, b, h, n, d):
 
 
 @pytest.mark.parametrize("L,B,H,N,normalize", [(12, 2, 12, 197, False), (3, 3, 4, 17, False), (4, 1, 12, 512, True),
-                                               (12, 2, 12, 198, False)])
+                                               (12, 2, 12, 198, False), (2, 40, 16, 197, True), (12, 300, 2, 30, False)])
 def test_aggregation_rollout(ops, L, B, H, N, normalize):
     g = torch.Generator().manual_seed(N + L)
     grad = torch.randn(L, B, H, N, N, generator=g) * 0.05
@@ -118,6 +118,10 @@ def test_aggregation_rollout(ops, L, B, H, N, normalize):
         joint, row0 = ops.attribution_rollout(dev(grad), dev(cam), start_layer=start, normalize=normalize)
         assert rel_err(joint, ref) < 1e-5
         assert rel_err(row0, ref[:, 0]) < 1e-5
+        # fused single-kernel row-only path (what generate_LRP consumes)
+        _, row_f = ops.attribution_rollout(dev(grad), dev(cam), start_layer=start, normalize=normalize, fused=True,
+                                           want_joint=False)
+        assert rel_err(row_f, ref[:, 0]) < 1e-5
         # public compute_rollout_attention on pre-aggregated matrices
         j2 = ops.compute_rollout_attention([dev(m.float()) for m in mats], start_layer=start, normalize=normalize)
         assert rel_err(j2, ref) < 1e-5

@@ -84,6 +84,18 @@ def test_tiny_batched_equals_single(golden_dir):
     assert torch.allclose(chunked, batched, rtol=1e-5, atol=1e-9)
 
 
+def test_fused_rollout_flag_matches_composed_path():
+    from transformer_explainability_b200 import _lib
+    params, heads = ovit.init_params("vit_tiny_test", seed=6, rand_affine=True)
+    model = make_model(params, heads, **TINY)
+    x = torch.randn(7, 3, 32, 32, generator=torch.Generator().manual_seed(3)).cuda()
+    eng = model.engine()
+    for sl in (0, 2):
+        a, _ = eng.explain(x, start_layer=sl, flags=0)
+        b, _ = eng.explain(x, start_layer=sl, flags=_lib.FLAG_ROLLOUT_FUSED)
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-12)
+
+
 def test_distilled_extension_vs_oracle():
     params, heads = ovit.init_params("vit_tiny_test", seed=4, rand_affine=True, distilled=True)
     model = make_model(params, heads, distilled=True, **TINY)

@@ -33,9 +33,10 @@ int te_rollout_layers(const float* G0, const float* cam0, long long layer_stride
                       float* joint_out, float* row_out, int first, int bert_fix, cudaStream_t st) {
     if (start_layer < 0 || start_layer >= L) { te_set_last_error("rollout: start_layer out of range"); return TE_ERR_ARG; }
     const float* joint = nullptr;
-    if ((flags & 2u) && te_rollout_fused_supported(N, ld_in, ld)) {
-        TE_TRY(te_rollout_fused(G0, cam0, layer_stride, L, B, H, N, ld_in, ld, start_layer, normalize, joint_a, st));
-        joint = joint_a;
+    if ((flags & 2u) && !joint_out && row_out && te_rollout_fused_supported(N, ld_in, ld)) {
+        // row-only consumer (generate_LRP): fused single kernel, G / cam streamed once, nothing else in HBM
+        return te_rollout_fused_row(G0, cam0, layer_stride, L, B, H, N, ld_in, start_layer, normalize, row_out, first,
+                                    bert_fix, st);
     } else {
         const long long ms = (long long)B * N * ld;
         for (int l = start_layer; l < L; ++l)
