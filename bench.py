@@ -361,7 +361,7 @@ def main():
 
 def default_flags():
     """Best validated kernel selection: updated as faster paths pass parity."""
-    return 3   # tcgen05 z+ rule + fused row-only rollout (validated: tests/test_gpu_tc.py, test_gpu_rules.py)
+    return 19  # tcgen05 z+ rule (1) + fused row-only rollout (2) + 3xTF32 tcgen05 forward/backward Linears (16)
 
 
 if __name__ == "__main__":

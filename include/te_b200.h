@@ -38,6 +38,7 @@ extern "C" {
 #define TE_FLAG_ZPLUS_TENSOR_CORES 1u /* z+ Linear-rule GEMMs on tcgen05 (TF32 in, fp32 acc) instead of fp32 SIMT */
 #define TE_FLAG_ROLLOUT_FUSED 2u      /* single fused aggregation+rollout kernel instead of aggregate + bmm chain */
 #define TE_FLAG_KEEP_ALL_CAMS 4u      /* run the relprop below start_layer too (accessor parity with the reference) */
+#define TE_FLAG_LINEAR_TENSOR_CORES 16u /* forward / backward Linear GEMMs on tcgen05 with the fp32-grade 3xTF32 split */
 #define TE_FLAG_RELPROP_TO_INPUT 8u   /* finish the lowest block as well: relevance at the encoder input (what
                                          model.relprop() returns in the reference) is left in tensor "relevance_in" */
 
@@ -84,8 +85,8 @@ TE_API long long te_vit_workspace_bytes(const te_vit_config* cfg, int batch);
 
 /* model(x): VisionTransformer.forward (ViT_LRP.py:305-322).  images [batch,in_chans,img,img];
  * logits [batch,num_classes] (may be NULL).  Leaves every saved activation in `workspace`. */
-TE_API int te_vit_forward(const te_vit_config* cfg, const float* weights, const float* images, int batch,
-                   float* logits, void* workspace, long long workspace_bytes, void* stream);
+TE_API int te_vit_forward(const te_vit_config* cfg, const float* weights, const float* derived, const float* images,
+                   int batch, unsigned flags, float* logits, void* workspace, long long workspace_bytes, void* stream);
 
 /* The rest of LRP.generate_LRP (ViT_explanation_generator.py:27-41) + VisionTransformer.relprop with
  * method="transformer_attribution" (ViT_LRP.py:324-369) on the activations te_vit_forward left behind:
@@ -136,9 +137,9 @@ TE_API long long te_bert_workspace_bytes(const te_bert_config* cfg, int batch, i
 
 /* model(input_ids, attention_mask)[0]: ids / mask are int64 [batch, seq] (device); token_type_ids = 0,
  * position_ids = arange(seq) as in BERT.py:69-75; logits [batch, num_labels] (may be NULL). */
-TE_API int te_bert_forward(const te_bert_config* cfg, const float* weights, const long long* input_ids,
-                    const long long* attention_mask, int batch, int seq, float* logits, void* workspace,
-                    long long workspace_bytes, void* stream);
+TE_API int te_bert_forward(const te_bert_config* cfg, const float* weights, const float* derived,
+                    const long long* input_ids, const long long* attention_mask, int batch, int seq, unsigned flags,
+                    float* logits, void* workspace, long long workspace_bytes, void* stream);
 /* The rest of Generator.generate_LRP (ExplanationGenerator.py:33-59): arg-max (index[b] < 0), one-hot, class
  * gradient of every attention_probs, relprop (BertForSequenceClassification.relprop), relu(grad*cam) head mean,
  * +I, row-normalised rollout from start_layer, row 0 with element 0 replaced by the row minimum.
@@ -160,7 +161,7 @@ TE_API int te_bert_tensor(const te_bert_config* cfg, int batch, int seq, void* w
  * that each rule can be parity-tested against the reference layer class it replaces.
  * ---------------------------------------------------------------------------------------------- */
 /* Linear.relprop, alpha=1 (layers_ours.py:207-230): x [rows,in], w [out,in], r [rows,out] -> out [rows,in].
- * scratch: rows*out floats; with TE_FLAG_ZPLUS_TENSOR_CORES: round_up(rows*out,64) + 4*in*out floats. */
+ * scratch: rows*out floats; with TE_FLAG_ZPLUS_TENSOR_CORES: round_up(rows*out,64) + 8*in*out floats. */
 TE_API int te_linear_relprop(const float* x, const float* w, const float* r, float* out, float* scratch, int rows,
                       int in_features, int out_features, unsigned flags, void* stream);
 /* Add.relprop (layers_ours.py:97-120) per sample: x1,x2,r [batch,per_sample] -> r1,r2.
@@ -195,9 +196,14 @@ TE_API int te_attribution_rollout(const float* grad, const float* cam, int layer
 TE_API int te_compute_rollout_attention(const float* mats, int layers, int batch, int n, int start_layer, int normalize,
                                  float* joint, void* workspace, long long workspace_bytes, void* stream);
 
-/* Plain fp32 GEMM C[m,n] = A[m,k] * W[n,k]^T (+bias) — exported for kernel unit tests only. */
+/* Plain Linear GEMMs — exported for kernel unit tests only.  flags & TE_FLAG_LINEAR_TENSOR_CORES selects the
+ * tcgen05 3xTF32 path (scratch: 8*in*out floats for the derived weight copies; may be NULL otherwise). */
 TE_API int te_linear_forward(const float* x, const float* w, const float* bias, float* y, int rows, int in_features,
                       int out_features, void* stream);
+TE_API int te_linear_forward_ex(const float* x, const float* w, const float* bias, float* y, float* scratch, int rows,
+                         int in_features, int out_features, unsigned flags, void* stream);
+TE_API int te_linear_backward_ex(const float* dy, const float* w, float* dx, float* scratch, int rows, int in_features,
+                          int out_features, unsigned flags, void* stream);
 
 #ifdef __cplusplus
 }

@@ -65,3 +65,66 @@ def test_tc_engine_vit_base_vs_simt_and_oracle():
             print("sample %d %s: L_inf/max over trials %s" % (s, name, ["%.1e" % (e / scale) for e in errs]))
         assert med["tc"] <= 1e-4                                    # BASELINE tolerance on raw maps
         assert med["tc"] <= max(10 * med["simt"], 5e-2 * scale)     # same noise class as the fp32 path
+
+
+@pytest.mark.parametrize("rows,inf,outf", [(128, 256, 256), (394, 768, 3072), (1000, 3072, 768), (77, 768, 2304)])
+def test_tc_3xtf32_linear_is_fp32_grade(rows, inf, outf):
+    """Forward / backward Linear GEMMs on tcgen05 with the error-compensated 3xTF32 split.  The split removes the
+    TF32 operand rounding (1e-3 -> 1e-6); what remains is the tensor core's own fp32 accumulation, which truncates
+    (round-toward-zero) at every MMA, so the error grows linearly with the reduction length: measured 7e-9 * K
+    (K = 3072: 2e-5) against 5e-7 for the fp32 SIMT kernel.  Stated bound: 1.5e-8 * K + 2e-6."""
+    from transformer_explainability_b200 import ops
+    g = torch.Generator().manual_seed(rows + 1)
+    x = torch.randn(rows, inf, generator=g)
+    w = torch.randn(outf, inf, generator=g) * 0.05
+    b = torch.randn(outf, generator=g)
+    dy = torch.randn(rows, outf, generator=g)
+    ref_y = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    ref_dx = dy.double() @ w.double()
+    for tc in (False, True):
+        y = ops.linear_forward(x.cuda(), w.cuda(), b.cuda(), tensor_cores=tc)
+        dx = ops.linear_backward(dy.cuda(), w.cuda(), tensor_cores=tc)
+        torch.cuda.synchronize()
+        ey, edx = rel(y, ref_y), rel(dx, ref_dx)
+        print("rows %d in %d out %d tc=%s: fwd %.2e bwd %.2e" % (rows, inf, outf, tc, ey, edx))
+        if tc:
+            assert ey < 1.5e-8 * inf + 2e-6 and edx < 1.5e-8 * outf + 2e-6
+        else:
+            assert ey < 3e-6 and edx < 3e-6
+
+
+def test_tc_linear_engine_vit_base():
+    """ViT-B/16 with every Linear GEMM (forward, backward, z+ rule) on tensor cores vs the fp32 SIMT engine and the
+    fp64 oracle: class index bit-exact, logits at fp32 accuracy, maps in the same noise class (medians)."""
+    from oracle import cpu as ocpu
+    from oracle import vit as ovit
+    from transformer_explainability_b200 import _lib
+    from transformer_explainability_b200.baselines.ViT.ViT_LRP import vit_base_patch16_224
+    from test_gpu_vit import _noise_trials
+    trials = 8
+    params, heads = ovit.init_params("vit_base_patch16_224", seed=0)
+    xs = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(100))
+    m = vit_base_patch16_224()
+    m.load_state_dict(params)
+    m = m.cuda().eval()
+    eng = m.engine()
+    xb = torch.cat([_noise_trials(xs[s:s + 1], trials) for s in range(2)]).cuda()
+    simt, idx0, lg0 = eng.explain(xb, flags=0, return_logits=True)
+    full = _lib.FLAG_TENSOR_CORES | _lib.FLAG_ROLLOUT_FUSED
+    tc, idx1, lg1 = eng.explain(xb, flags=full, return_logits=True)
+    torch.cuda.synchronize()
+    assert torch.equal(idx0, idx1)
+    ocpu.set_torch_threads()
+    for s in range(2):
+        ref, ridx, taps = ovit.explain({k: v.double() for k, v in params.items()}, xs[s:s + 1].double(), heads,
+                                       return_taps=True)
+        assert int(idx1[s * trials]) == int(ridx)
+        assert rel(lg1[s * trials], taps["logits"][0]) < 1e-5
+        scale = ref.abs().max().item()
+        med = {}
+        for name, out in (("simt", simt), ("tc", tc)):
+            errs = sorted((out[s * trials + k].cpu().double() - ref[0]).abs().max().item() for k in range(trials))
+            med[name] = 0.5 * (errs[trials // 2 - 1] + errs[trials // 2])
+            print("sample %d %s: L_inf/max over trials %s" % (s, name, ["%.1e" % (e / scale) for e in errs]))
+        assert med["tc"] <= 1e-4
+        assert med["tc"] <= max(10 * med["simt"], 5e-2 * scale)

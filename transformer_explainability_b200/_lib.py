@@ -31,6 +31,8 @@ FLAG_ZPLUS_TENSOR_CORES = 1
 FLAG_ROLLOUT_FUSED = 2
 FLAG_KEEP_ALL_CAMS = 4
 FLAG_RELPROP_TO_INPUT = 8
+FLAG_LINEAR_TENSOR_CORES = 16
+FLAG_TENSOR_CORES = FLAG_ZPLUS_TENSOR_CORES | FLAG_LINEAR_TENSOR_CORES
 
 _P = c_void_p
 _CFG = ctypes.POINTER(TeVitConfig)
@@ -47,7 +49,7 @@ PROTOTYPES = {
     "te_vit_weight_offset": (c_ll, [_CFG, c_int]),
     "te_vit_weight_total": (c_ll, [_CFG]),
     "te_vit_workspace_bytes": (c_ll, [_CFG, c_int]),
-    "te_vit_forward": (c_int, [_CFG, _P, _P, c_int, _P, _P, c_ll, _P]),
+    "te_vit_forward": (c_int, [_CFG, _P, _P, _P, c_int, c_uint, _P, _P, c_ll, _P]),
     "te_vit_derived_total": (c_ll, [_CFG]),
     "te_vit_prepare_derived": (c_int, [_CFG, _P, _P, _P]),
     "te_vit_attribute": (c_int, [_CFG, _P, _P, c_int, _P, c_int, c_uint, _P, _P, c_ll, _P]),
@@ -62,7 +64,7 @@ PROTOTYPES = {
     "te_bert_derived_total": (c_ll, [_BCFG]),
     "te_bert_prepare_derived": (c_int, [_BCFG, _P, _P, _P]),
     "te_bert_workspace_bytes": (c_ll, [_BCFG, c_int, c_int]),
-    "te_bert_forward": (c_int, [_BCFG, _P, _P, _P, c_int, c_int, _P, _P, c_ll, _P]),
+    "te_bert_forward": (c_int, [_BCFG, _P, _P, _P, _P, c_int, c_int, c_uint, _P, _P, c_ll, _P]),
     "te_bert_attribute": (c_int, [_BCFG, _P, _P, c_int, c_int, _P, c_int, c_uint, _P, _P, c_ll, _P]),
     "te_bert_explain": (c_int, [_BCFG, _P, _P, _P, _P, c_int, c_int, _P, c_int, c_uint, _P, _P, _P, c_ll, _P]),
     "te_bert_tensor": (c_int, [_BCFG, c_int, c_int, _P, c_char_p, c_int, ctypes.POINTER(_P), ctypes.POINTER(c_ll),
@@ -78,6 +80,8 @@ PROTOTYPES = {
                                        c_ll, _P]),
     "te_compute_rollout_attention": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_ll, _P]),
     "te_linear_forward": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "te_linear_forward_ex": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_uint, _P]),
+    "te_linear_backward_ex": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_uint, _P]),
 }
 
 _lib = None

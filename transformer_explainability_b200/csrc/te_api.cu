@@ -38,12 +38,36 @@ extern "C" int te_linear_forward(const float* x, const float* w, const float* bi
     return te_gemm_launch(p, TE_L_K, TE_L_K, TE_XF_NONE, TE_EPI_BIAS, ST(stream));
 }
 
+extern "C" int te_linear_forward_ex(const float* x, const float* w, const float* bias, float* y, float* scratch, int rows,
+                                    int in_features, int out_features, unsigned flags, void* stream) {
+    REQ(x && w && y && rows > 0 && in_features > 0 && out_features > 0, "te_linear_forward_ex: bad argument");
+    if ((flags & TE_FLAG_LINEAR_TENSOR_CORES) && scratch && te_tc_gemm3x_supported(rows, in_features, out_features, in_features)) {
+        TE_TRY(te_tc_prepare_weights(w, scratch, in_features, out_features, ST(stream)));
+        return te_tc_linear_fwd(x, in_features, scratch, in_features, out_features, bias, y, nullptr, nullptr, rows,
+                                TE_TC_EPI_BIAS, ST(stream));
+    }
+    return te_linear_forward(x, w, bias, y, rows, in_features, out_features, stream);
+}
+
+extern "C" int te_linear_backward_ex(const float* dy, const float* w, float* dx, float* scratch, int rows, int in_features,
+                                     int out_features, unsigned flags, void* stream) {
+    REQ(dy && w && dx && rows > 0 && in_features > 0 && out_features > 0, "te_linear_backward_ex: bad argument");
+    if ((flags & TE_FLAG_LINEAR_TENSOR_CORES) && scratch && te_tc_gemm3x_supported(rows, out_features, in_features, out_features)) {
+        TE_TRY(te_tc_prepare_weights(w, scratch, in_features, out_features, ST(stream)));
+        return te_tc_linear_bwd(dy, scratch, in_features, out_features, dx, nullptr, rows, TE_TC_EPI_STORE, ST(stream));
+    }
+    TeGemm p = g0(1);
+    p.A = dy; p.lda = out_features; p.B = w; p.ldb = in_features; p.C = dx; p.ldc = in_features;
+    p.M = rows; p.N = in_features; p.K = out_features;
+    return te_gemm_launch(p, TE_L_K, TE_L_MN, TE_XF_NONE, TE_EPI_STORE, ST(stream));
+}
+
 extern "C" int te_linear_relprop(const float* x, const float* w, const float* r, float* out, float* scratch, int rows,
                                  int in_features, int out_features, unsigned flags, void* stream) {
     REQ(x && w && r && out && scratch && rows > 0 && in_features > 0 && out_features > 0, "te_linear_relprop: bad argument");
     const float* derived = nullptr;
     if ((flags & TE_FLAG_ZPLUS_TENSOR_CORES) && te_tc_zplus_supported(rows, in_features, out_features, in_features)) {
-        // scratch layout with the flag: [rows*out S | 4*in*out derived weight copies]
+        // scratch layout with the flag: [rows*out S | 8*in*out derived weight copies]
         float* d = scratch + (((long long)rows * out_features + 63) & ~63LL);
         TE_TRY(te_tc_prepare_weights(w, d, in_features, out_features, ST(stream)));
         derived = d;

@@ -116,18 +116,21 @@ static void bind_weights(const te_bert_config* c, const float* base, Weights& w)
 }
 
 // ---- derived tensor-core copies: per layer q | k | v | o | w1 | w2 ---------------------------------------
-struct DerivedW { const float *q, *k, *v, *o, *w1, *w2; };
+// (q, k, v: operands of their three z+ rules; qkv: the packed [3D, D] weight for the forward / backward GEMMs)
+struct DerivedW { const float *q, *k, *v, *o, *w1, *w2, *qkv; };
 static long long derived_layer_floats(const Dims& d) {
-    return 4 * te_tc_derived_floats(d.D, d.D) + te_tc_derived_floats(d.D, d.F) + te_tc_derived_floats(d.F, d.D);
+    return 4 * te_tc_derived_floats(d.D, d.D) + te_tc_derived_floats(d.D, d.F) + te_tc_derived_floats(d.F, d.D) +
+           te_tc_derived_floats(d.D, 3 * d.D);
 }
 static DerivedW bind_derived(const Dims& d, const float* base, int l) {
-    DerivedW w = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    DerivedW w = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (!base) return w;
     const float* p = base + (long long)l * derived_layer_floats(d);
     const long long dd = te_tc_derived_floats(d.D, d.D);
     w.q = p; w.k = p + dd; w.v = p + 2 * dd; w.o = p + 3 * dd;
     w.w1 = p + 4 * dd;
     w.w2 = w.w1 + te_tc_derived_floats(d.D, d.F);
+    w.qkv = w.w2 + te_tc_derived_floats(d.F, d.D);
     return w;
 }
 
@@ -242,6 +245,7 @@ extern "C" int te_bert_prepare_derived(const te_bert_config* cfg, const float* w
         TE_TRY(te_tc_prepare_weights(w.layer[l].ow, const_cast<float*>(dw.o), d.D, d.D, st));
         TE_TRY(te_tc_prepare_weights(w.layer[l].w1, const_cast<float*>(dw.w1), d.D, d.F, st));
         TE_TRY(te_tc_prepare_weights(w.layer[l].w2, const_cast<float*>(dw.w2), d.F, d.D, st));
+        TE_TRY(te_tc_prepare_weights(w.layer[l].qkvw, const_cast<float*>(dw.qkv), d.D, 3 * d.D, st));
     }
     return TE_OK;
 }
@@ -249,12 +253,17 @@ extern "C" int te_bert_prepare_derived(const te_bert_config* cfg, const float* w
 // =====================================================================================================
 // forward  (BertForSequenceClassification.forward -> BertModel.forward)
 // =====================================================================================================
-extern "C" int te_bert_forward(const te_bert_config* cfg, const float* weights, const long long* input_ids,
-                               const long long* attention_mask, int batch, int seq, float* logits, void* workspace,
-                               long long workspace_bytes, void* stream) {
+extern "C" int te_bert_forward(const te_bert_config* cfg, const float* weights, const float* derived,
+                               const long long* input_ids, const long long* attention_mask, int batch, int seq,
+                               unsigned flags, float* logits, void* workspace, long long workspace_bytes, void* stream) {
     Dims d; Workspace ws;
     TE_TRY(check_ws(cfg, batch, seq, workspace, workspace_bytes, d, ws));
     if (!weights || !input_ids || !attention_mask) { te_set_last_error("te_bert_forward: null pointer"); return TE_ERR_ARG; }
+    if ((flags & TE_FLAG_LINEAR_TENSOR_CORES) && !derived) {
+        te_set_last_error("te_bert_forward: TE_FLAG_LINEAR_TENSOR_CORES needs the derived weight buffer");
+        return TE_ERR_ARG;
+    }
+    const float* lbase = (flags & TE_FLAG_LINEAR_TENSOR_CORES) ? derived : nullptr;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     Weights w;
     bind_weights(cfg, weights, w);
@@ -269,7 +278,8 @@ extern "C" int te_bert_forward(const te_bert_config* cfg, const float* weights, 
         LayerAct& a = ws.layer[l];
         const LayerW& lw = w.layer[l];
         float* h_next = (l + 1 < d.L) ? ws.layer[l + 1].h : ws.h_last;
-        TE_TRY(linear_fwd(a.h, d.D, lw.qkvw, lw.qkvb, a.qkv, nullptr, nullptr, d.M, d.D, 3 * d.D, TE_EPI_BIAS, st));
+        const DerivedW tw = bind_derived(d, lbase, l);
+        TE_TRY(linear_fwd_tc(tw.qkv, a.h, d.D, lw.qkvw, lw.qkvb, a.qkv, nullptr, nullptr, d.M, d.D, 3 * d.D, TE_EPI_BIAS, st));
         const HeadOp q = head_rows(a.qkv, 3 * d.D, d.N, d.dh);
         const HeadOp k = head_rows(a.qkv + d.D, 3 * d.D, d.N, d.dh);
         const HeadOp v = head_rows(a.qkv + 2 * d.D, 3 * d.D, d.N, d.dh);
@@ -280,11 +290,11 @@ extern "C" int te_bert_forward(const te_bert_config* cfg, const float* weights, 
         TE_TRY(head_gemm(d.B, d.H, attn_map(a.P, d.H, d.N, d.NP), TE_L_K, v, TE_L_MN, head_rows(a.ctx, d.D, d.N, d.dh),
                          none, d.N, d.dh, d.N, 1.f, TE_EPI_STORE, st));
         // BertSelfOutput: dense -> add([dense, input]) -> LayerNorm
-        TE_TRY(linear_fwd(a.ctx, d.D, lw.ow, lw.ob, a.d1, a.s1, a.h, d.M, d.D, d.D, TE_EPI_BIAS_ADD, st));
+        TE_TRY(linear_fwd_tc(tw.o, a.ctx, d.D, lw.ow, lw.ob, a.d1, a.s1, a.h, d.M, d.D, d.D, TE_EPI_BIAS_ADD, st));
         TE_TRY(te_launch_layernorm(a.s1, lw.ln1w, lw.ln1b, a.ao, a.mean1, a.rstd1, d.M, d.D, d.eps, st));
         // BertIntermediate (dense + GELU), BertOutput (dense -> add -> LayerNorm)
-        TE_TRY(linear_fwd(a.ao, d.D, lw.w1, lw.b1, a.hpre, a.g, nullptr, d.M, d.D, d.F, TE_EPI_BIAS_GELU, st));
-        TE_TRY(linear_fwd(a.g, d.F, lw.w2, lw.b2, a.d2, a.s2, a.ao, d.M, d.F, d.D, TE_EPI_BIAS_ADD, st));
+        TE_TRY(linear_fwd_tc(tw.w1, a.ao, d.D, lw.w1, lw.b1, a.hpre, a.g, nullptr, d.M, d.D, d.F, TE_EPI_BIAS_GELU, st));
+        TE_TRY(linear_fwd_tc(tw.w2, a.g, d.F, lw.w2, lw.b2, a.d2, a.s2, a.ao, d.M, d.F, d.D, TE_EPI_BIAS_ADD, st));
         TE_TRY(te_launch_layernorm(a.s2, lw.ln2w, lw.ln2b, h_next, a.mean2, a.rstd2, d.M, d.D, d.eps, st));
     }
     // pooler (first token -> dense -> tanh), classifier
@@ -308,10 +318,11 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
     TE_TRY(check_ws(cfg, batch, seq, workspace, workspace_bytes, d, ws));
     if (!weights || !index || !maps) { te_set_last_error("te_bert_attribute: null pointer"); return TE_ERR_ARG; }
     if (start_layer < 0 || start_layer >= d.L) { te_set_last_error("te_bert_attribute: start_layer out of range"); return TE_ERR_ARG; }
-    if ((flags & TE_FLAG_ZPLUS_TENSOR_CORES) && !derived) {
-        te_set_last_error("te_bert_attribute: TE_FLAG_ZPLUS_TENSOR_CORES needs the derived weight buffer");
+    if ((flags & (TE_FLAG_ZPLUS_TENSOR_CORES | TE_FLAG_LINEAR_TENSOR_CORES)) && !derived) {
+        te_set_last_error("te_bert_attribute: tensor-core flags need the derived weight buffer");
         return TE_ERR_ARG;
     }
+    const float* lbase = (flags & TE_FLAG_LINEAR_TENSOR_CORES) ? derived : nullptr;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     Weights w;
     bind_weights(cfg, weights, w);
@@ -344,11 +355,12 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
         const HeadOp k = head_rows(a.qkv + d.D, 3 * d.D, d.N, d.dh);
         const HeadOp v = head_rows(a.qkv + 2 * d.D, 3 * d.D, d.N, d.dh);
         TE_TRY(te_launch_layernorm_bwd(dxa, a.s2, lw.ln2w, a.mean2, a.rstd2, nullptr, dsx, d.M, d.D, st));    // d s2
-        TE_TRY(linear_bwd(dsx, lw.w2, dF, a.hpre, d.M, d.F, d.D, TE_EPI_GELU_BWD, st));
-        TE_TRY(linear_bwd(dF, lw.w1, dxn, nullptr, d.M, d.D, d.F, TE_EPI_STORE, st));
+        const DerivedW tw = bind_derived(d, lbase, l);
+        TE_TRY(linear_bwd_tc(tw.w2, dsx, lw.w2, dF, a.hpre, d.M, d.F, d.D, TE_EPI_GELU_BWD, st));
+        TE_TRY(linear_bwd_tc(tw.w1, dF, lw.w1, dxn, nullptr, d.M, d.D, d.F, TE_EPI_STORE, st));
         TE_TRY(te_launch_add2(dxn, dsx, dxn, MD, st));                                                          // d ao
         TE_TRY(te_launch_layernorm_bwd(dxn, a.s1, lw.ln1w, a.mean1, a.rstd1, nullptr, dsx, d.M, d.D, st));    // d s1
-        TE_TRY(linear_bwd(dsx, lw.ow, dctx, nullptr, d.M, d.D, d.D, TE_EPI_STORE, st));
+        TE_TRY(linear_bwd_tc(tw.o, dsx, lw.ow, dctx, nullptr, d.M, d.D, d.D, TE_EPI_STORE, st));
         TE_TRY(head_gemm(d.B, d.H, head_rows(dctx, d.D, d.N, d.dh), TE_L_K, v, TE_L_K, amap(a.G), none, d.N, d.N, d.dh,
                          1.f, TE_EPI_STORE, st));                                                               // G = dctx v^T
         if (l == start_layer) break;
@@ -359,7 +371,7 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
                          1.f, TE_EPI_STORE, st));
         TE_TRY(head_gemm(d.B, d.H, amap(dS), TE_L_MN, q, TE_L_MN, head_rows(dqkv + d.D, 3 * d.D, d.N, d.dh), none, d.N,
                          d.dh, d.N, 1.f, TE_EPI_STORE, st));
-        TE_TRY(linear_bwd(dqkv, lw.qkvw, dxn, nullptr, d.M, d.D, 3 * d.D, TE_EPI_STORE, st));
+        TE_TRY(linear_bwd_tc(tw.qkv, dqkv, lw.qkvw, dxn, nullptr, d.M, d.D, 3 * d.D, TE_EPI_STORE, st));
         TE_TRY(te_launch_add2(dxn, dsx, dxa, MD, st));                                                          // d h
     }
 
@@ -422,7 +434,8 @@ extern "C" int te_bert_explain(const te_bert_config* cfg, const float* weights, 
                                const long long* input_ids, const long long* attention_mask, int batch, int seq,
                                int* index, int start_layer, unsigned flags, float* maps, float* logits, void* workspace,
                                long long workspace_bytes, void* stream) {
-    TE_TRY(te_bert_forward(cfg, weights, input_ids, attention_mask, batch, seq, logits, workspace, workspace_bytes, stream));
+    TE_TRY(te_bert_forward(cfg, weights, derived, input_ids, attention_mask, batch, seq, flags, logits, workspace,
+                           workspace_bytes, stream));
     return te_bert_attribute(cfg, weights, derived, batch, seq, index, start_layer, flags, maps, workspace, workspace_bytes,
                              stream);
 }

@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "te_gemm.cuh"
+#include "te_gemm_tc.h"
 
 namespace te_util {
 
@@ -28,6 +29,20 @@ static inline int linear_bwd(const float* dy, const float* w, float* dx, const f
     p.A = dy; p.lda = out; p.B = w; p.ldb = in; p.C = dx; p.ldc = in; p.E0 = e0; p.lde0 = in;
     p.M = (int)M; p.N = in; p.K = out;
     return te_gemm_launch(p, TE_L_K, TE_L_MN, TE_XF_NONE, epi, st);
+}
+
+// tensor-core (3xTF32) variants when the derived weight copies are supplied and the shape qualifies
+static inline int linear_fwd_tc(const float* dw, const float* x, int lda, const float* w, const float* bias, float* y,
+                                float* y2, const float* e0, long long M, int in, int out, int epi, cudaStream_t st) {
+    if (dw && te_tc_gemm3x_supported(M, in, out, lda))
+        return te_tc_linear_fwd(x, lda, dw, in, out, bias, y, y2, e0, M, epi, st);      // epilogue ids coincide
+    return linear_fwd(x, lda, w, bias, y, y2, e0, M, in, out, epi, st);
+}
+static inline int linear_bwd_tc(const float* dw, const float* dy, const float* w, float* dx, const float* e0, long long M,
+                                int in, int out, int epi, cudaStream_t st) {
+    if (dw && te_tc_gemm3x_supported(M, out, in, out))
+        return te_tc_linear_bwd(dy, dw, in, out, dx, e0, M, epi, st);
+    return linear_bwd(dy, w, dx, e0, M, in, out, epi, st);
 }
 
 // one operand of a (batch, head)-batched attention-shaped GEMM

@@ -104,6 +104,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float to_tf32(float x) {
@@ -285,17 +293,24 @@ te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
 // ---- weight preparation: W [out,in] -> W+ , W- (K-major for kernel 1) and W+^T , W-^T (K-major for kernel 2),
 //      all rounded to TF32 once (weights are frozen) -------------------------------------------------------
-__global__ void prepare_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, float* __restrict__ wn,
-                                       float* __restrict__ wpt, float* __restrict__ wnt, int out_f, int in_f) {
+__global__ void prepare_weights_kernel(const float* __restrict__ w, float* __restrict__ d, int out_f, int in_f) {
+    // d = [ W+ | W- | W+^T | W-^T | W_hi | W_lo | W^T_hi | W^T_lo ], each in*out floats
+    const long long n = (long long)out_f * in_f;
+    float *wp = d, *wn = d + n, *wpt = d + 2 * n, *wnt = d + 3 * n, *wh = d + 4 * n, *wl = d + 5 * n, *wth = d + 6 * n,
+          *wtl = d + 7 * n;
     __shared__ float tile[32][33];
     const int bx = blockIdx.x * 32, by = blockIdx.y * 32;      // bx: in index, by: out index
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int o = by + i, c = bx + threadIdx.x;
         float v = 0.f;
         if (o < out_f && c < in_f) {
-            v = w[(long long)o * in_f + c];
-            wp[(long long)o * in_f + c] = to_tf32(fmaxf(v, 0.f));
-            wn[(long long)o * in_f + c] = to_tf32(fminf(v, 0.f));
+            const long long idx = (long long)o * in_f + c;
+            v = w[idx];
+            wp[idx] = to_tf32(fmaxf(v, 0.f));
+            wn[idx] = to_tf32(fminf(v, 0.f));
+            const float hi = to_tf32(v);
+            wh[idx] = hi;
+            wl[idx] = to_tf32(v - hi);
         }
         tile[i][threadIdx.x] = v;
     }
@@ -304,9 +319,220 @@ __global__ void prepare_weights_kernel(const float* __restrict__ w, float* __res
         const int c = bx + i, o = by + threadIdx.x;
         if (o < out_f && c < in_f) {
             const float v = tile[threadIdx.x][i];
-            wpt[(long long)c * out_f + o] = to_tf32(fmaxf(v, 0.f));
-            wnt[(long long)c * out_f + o] = to_tf32(fminf(v, 0.f));
+            const long long idx = (long long)c * out_f + o;
+            wpt[idx] = to_tf32(fmaxf(v, 0.f));
+            wnt[idx] = to_tf32(fminf(v, 0.f));
+            const float hi = to_tf32(v);
+            wth[idx] = hi;
+            wtl[idx] = to_tf32(v - hi);
         }
+    }
+}
+
+// =====================================================================================================================
+// fp32-grade Linear GEMM on tensor cores: 3xTF32 error-compensated split
+//   C = A B^T  ~=  A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T ,  x_hi = tf32(x), x_lo = tf32(x - x_hi)
+// A (activations) is split in shared memory by the transform warps; B (frozen weights) is pre-split.
+// Tile 128 x 256 x 32, 2 stages of [A_hi 16K | A_lo 16K | B_hi 32K | B_lo 32K], 12 MMAs per k-block.
+// =====================================================================================================================
+constexpr int STAGES3 = 2;
+constexpr int STAGE3_BYTES = 2 * A_BYTES + 2 * B_BYTES;          // 96 KiB
+constexpr int SMEM3_BYTES = STAGES3 * STAGE3_BYTES + 1024 + 256;
+constexpr int NUM_THREADS3 = 320;                                // TMA, MMA, 4 transform+drain warps, 4 drain warps
+constexpr int DRAIN_THREADS = 256;
+constexpr int CHUNK = 4;                                         // k-blocks (of 32) accumulated inside the tensor core
+enum { EP_STORE = 0, EP_BIAS = 1, EP_BIAS_GELU = 2, EP_BIAS_ADD = 3, EP_GELU_BWD = 4 };
+
+struct Tc3Params {
+    int M, N, K;
+    const float* bias; const float* E; long long lde;
+    float* C; long long ldc; float* C2; long long ldc2;
+};
+
+// The tensor core accumulates in fp32 with truncation (round-toward-zero) at every MMA, so a long reduction drifts
+// by ~7e-9*K relative (measured: 2e-5 at K = 3072).  To stay at fp32 grade the reduction is cut into chunks of
+// CHUNK*32 = 128 elements: each chunk accumulates in one of two TMEM accumulators (2 x 256 columns), and while the
+// MMAs of the next chunk run, 8 warps drain the finished accumulator with tcgen05.ld and add it into fp32 register
+// sums with round-to-nearest CUDA-core adds (128 sums per thread: one row x half of the 256 columns).
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS3, 1)      // 10 warps are register-allocated as 12: 168 regs / thread
+te_tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                    const __grid_constant__ CUtensorMap tmBl, const Tc3Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bars = smem_base + STAGES3 * STAGE3_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto xf_bar = [&](int s) { return bars + 8u * (2 + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (4 + s); };
+    auto accfull_bar = [&](int b) { return bars + 8u * (6 + b); };
+    auto accfree_bar = [&](int b) { return bars + 8u * (8 + b); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + STAGES3 * STAGE3_BYTES + 8 * 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kb = p.K / BK;
+    const int nchunks = (kb + CHUNK - 1) / CHUNK;
+    constexpr uint32_t TMEM_COLS = 512u;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBl) : "memory");
+        for (int s = 0; s < STAGES3; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(xf_bar(s), XF_THREADS);
+            mbar_init(empty_bar(s), 1);
+            mbar_init(accfull_bar(s), 1);
+            mbar_init(accfree_bar(s), DRAIN_THREADS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < kb; ++it) {
+                const int s = it % STAGES3;
+                const uint32_t ph = (it / STAGES3) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_arrive_expect_tx(full_bar(s), A_BYTES + 2 * B_BYTES);
+                const uint32_t sa = smem_base + s * STAGE3_BYTES;
+                tma_load_2d(sa, &tmA, full_bar(s), it * BK, m0);                         // raw A -> A_hi slot
+                tma_load_2d(sa + 2 * A_BYTES, &tmBh, full_bar(s), it * BK, n0);
+                tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &tmBl, full_bar(s), it * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int it = 0; it < kb; ++it) {
+                const int c = it / CHUNK, b = c & 1;
+                const bool chunk_start = (it % CHUNK) == 0;
+                if (chunk_start && c >= 2) {                        // accumulator b must have been drained (chunk c-2)
+                    mbar_wait(accfree_bar(b), (uint32_t)(((c >> 1) & 1) ^ 1));
+                    tcgen05_fence_after();
+                }
+                const int s = it % STAGES3;
+                const uint32_t ph = (it / STAGES3) & 1u;
+                mbar_wait(xf_bar(s), ph);
+                tcgen05_fence_after();
+                const uint32_t sa = smem_base + s * STAGE3_BYTES;
+                const uint64_t ah = make_smem_desc(sa), al = make_smem_desc(sa + A_BYTES);
+                const uint64_t bh = make_smem_desc(sa + 2 * A_BYTES), bl = make_smem_desc(sa + 2 * A_BYTES + B_BYTES);
+                const uint32_t d = tmem_base + (uint32_t)(b * BN);
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    const uint64_t o = (uint64_t)(2 * k);
+                    umma_tf32(d, al + o, bh + o, kIdesc, (chunk_start && k == 0) ? 0u : 1u);        // small terms first
+                    umma_tf32(d, ah + o, bl + o, kIdesc, 1u);
+                    umma_tf32(d, ah + o, bh + o, kIdesc, 1u);
+                }
+                umma_commit(empty_bar(s));
+                if ((it % CHUNK) == CHUNK - 1 || it == kb - 1) umma_commit(accfull_bar(b));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- warps 2..9: row = lane quarter (warp & 3), column half = 0 for warps 2-5, 1 for warps 6-9 ----
+        const int q = warp & 3;
+        const int half = (warp >= 6) ? 1 : 0;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
+        float sum[128];
+#pragma unroll
+        for (int j = 0; j < 128; ++j) sum[j] = 0.f;
+
+        auto drain = [&](int c) {
+            const int b = c & 1;
+            mbar_wait(accfull_bar(b), (uint32_t)((c >> 1) & 1));
+            tcgen05_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+                uint32_t v[16];
+                tmem_ld16(tlane + (uint32_t)(b * BN + cc * 16), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sum[cc * 16 + j] += __uint_as_float(v[j]);
+            }
+            tcgen05_fence_before();
+            mbar_arrive(accfree_bar(b));
+        };
+
+        if (warp < 6) {
+            const int et = threadIdx.x - 64;                        // 0..127: the four transform warps
+            for (int it = 0; it < kb; ++it) {
+                const int s = it % STAGES3;
+                const uint32_t ph = (it / STAGES3) & 1u;
+                mbar_wait(full_bar(s), ph);
+                float4* a4 = reinterpret_cast<float4*>(smem_al + s * STAGE3_BYTES);
+                float4* l4 = reinterpret_cast<float4*>(smem_al + s * STAGE3_BYTES + A_BYTES);
+#pragma unroll
+                for (int i = 0; i < A_BYTES / 16 / XF_THREADS; ++i) {
+                    const float4 v = a4[et + i * XF_THREADS];
+                    float4 h, l;
+                    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+                    l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+                    a4[et + i * XF_THREADS] = h;
+                    l4[et + i * XF_THREADS] = l;
+                }
+                fence_proxy_async();
+                mbar_arrive(xf_bar(s));
+                // the last stage of chunk c has just been handed to the MMA warp: drain chunk c-1 meanwhile
+                if (((it % CHUNK) == CHUNK - 1 || it == kb - 1) && it / CHUNK >= 1) drain(it / CHUNK - 1);
+            }
+            drain(nchunks - 1);
+        } else {
+            for (int c = 0; c < nchunks; ++c) drain(c);
+        }
+
+        // ---- epilogue from the register sums ----
+        const int row = m0 + q * 32 + lane;
+        if (row < p.M) {
+            const int cbase = n0 + half * 128;
+            const float* erow = p.E ? p.E + (long long)row * p.lde + cbase : nullptr;
+            float* crow = p.C + (long long)row * p.ldc + cbase;
+            float* c2row = p.C2 ? p.C2 + (long long)row * p.ldc2 + cbase : nullptr;
+#pragma unroll
+            for (int j = 0; j < 128; j += 4) {
+                float o[4], o2[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
+                if (EPI == EP_BIAS || EPI == EP_BIAS_GELU || EPI == EP_BIAS_ADD) {
+                    if (p.bias) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
+                        bb[0] = t.x; bb[1] = t.y; bb[2] = t.z; bb[3] = t.w;
+                    }
+                }
+                if (EPI == EP_BIAS_ADD || EPI == EP_GELU_BWD) {
+                    const float4 t = *reinterpret_cast<const float4*>(erow + j);
+                    e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float a = sum[j + u];
+                    if (EPI == EP_STORE) o[u] = a;
+                    else if (EPI == EP_BIAS) o[u] = a + bb[u];
+                    else if (EPI == EP_BIAS_GELU) { o[u] = a + bb[u]; o2[u] = te_gelu(o[u]); }
+                    else if (EPI == EP_BIAS_ADD) { o[u] = a + bb[u]; o2[u] = e[u] + o[u]; }
+                    else o[u] = a * te_gelu_grad(e[u]);
+                }
+                *reinterpret_cast<float4*>(crow + j) = make_float4(o[0], o[1], o[2], o[3]);
+                if (EPI == EP_BIAS_GELU || EPI == EP_BIAS_ADD)
+                    *reinterpret_cast<float4*>(c2row + j) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -375,15 +601,72 @@ bool te_tc_zplus_supported(long long rows, int in_features, int out_features, lo
            get_encode() != nullptr;
 }
 
-long long te_tc_derived_floats(int in_features, int out_features) { return 4LL * in_features * out_features; }
+long long te_tc_derived_floats(int in_features, int out_features) { return 8LL * in_features * out_features; }
 
 int te_tc_prepare_weights(const float* w, float* derived, int in_features, int out_features, cudaStream_t st) {
-    const long long n = (long long)in_features * out_features;
     dim3 grid((in_features + 31) / 32, (out_features + 31) / 32), block(32, 8);
-    prepare_weights_kernel<<<grid, block, 0, st>>>(w, derived, derived + n, derived + 2 * n, derived + 3 * n, out_features,
-                                                  in_features);
+    prepare_weights_kernel<<<grid, block, 0, st>>>(w, derived, out_features, in_features);
     TE_CUDA_CHECK_LAUNCH();
     return TE_OK;
+}
+
+bool te_tc_gemm3x_supported(long long rows, int K, int N, long long lda) {
+    return rows > 0 && rows < (1LL << 31) && K % BK == 0 && N % BN == 0 && lda % 4 == 0 && get_encode() != nullptr;
+}
+
+namespace {
+template <int EPI>
+int launch3(const float* A, long long lda, const float* Bh, const float* Bl, const Tc3Params& p, cudaStream_t st) {
+    CUtensorMap tmA, tmBh, tmBl;
+    if (!make_map(&tmA, A, p.M, p.K, lda, BM) || !make_map(&tmBh, Bh, p.N, p.K, p.K, BN) ||
+        !make_map(&tmBl, Bl, p.N, p.K, p.K, BN)) {
+        te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed");
+        return TE_ERR_CUDA;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(te_tc_gemm3x_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) != cudaSuccess) {
+            te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
+            return TE_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    dim3 grid(p.N / BN, (unsigned)((p.M + BM - 1) / BM));
+    te_tc_gemm3x_kernel<EPI><<<grid, NUM_THREADS3, SMEM3_BYTES, st>>>(tmA, tmBh, tmBl, p);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+
+int dispatch3(int epi, const float* A, long long lda, const float* Bh, const float* Bl, const Tc3Params& p, cudaStream_t st) {
+    switch (epi) {
+        case TE_TC_EPI_STORE: return launch3<EP_STORE>(A, lda, Bh, Bl, p, st);
+        case TE_TC_EPI_BIAS: return launch3<EP_BIAS>(A, lda, Bh, Bl, p, st);
+        case TE_TC_EPI_BIAS_GELU: return launch3<EP_BIAS_GELU>(A, lda, Bh, Bl, p, st);
+        case TE_TC_EPI_BIAS_ADD: return launch3<EP_BIAS_ADD>(A, lda, Bh, Bl, p, st);
+        case TE_TC_EPI_GELU_BWD: return launch3<EP_GELU_BWD>(A, lda, Bh, Bl, p, st);
+    }
+    te_set_last_error("te_gemm_tc: unsupported epilogue");
+    return TE_ERR_UNSUPPORTED;
+}
+}  // namespace
+
+// y[rows,out] = x[rows,in] W^T (+ epilogue)   — fp32-grade (3xTF32) on tcgen05
+int te_tc_linear_fwd(const float* x, long long ldx, const float* derived, int in_features, int out_features,
+                     const float* bias, float* y, float* y2, const float* e0, long long rows, int epi, cudaStream_t st) {
+    const long long n = (long long)in_features * out_features;
+    Tc3Params p;
+    p.M = (int)rows; p.N = out_features; p.K = in_features; p.bias = bias; p.E = e0; p.lde = out_features;
+    p.C = y; p.ldc = out_features; p.C2 = y2; p.ldc2 = out_features;
+    return dispatch3(epi, x, ldx, derived + 4 * n, derived + 5 * n, p, st);
+}
+// dx[rows,in] = dy[rows,out] W (+ epilogue)
+int te_tc_linear_bwd(const float* dy, const float* derived, int in_features, int out_features, float* dx, const float* e0,
+                     long long rows, int epi, cudaStream_t st) {
+    const long long n = (long long)in_features * out_features;
+    Tc3Params p;
+    p.M = (int)rows; p.N = in_features; p.K = out_features; p.bias = nullptr; p.E = e0; p.lde = in_features;
+    p.C = dx; p.ldc = in_features; p.C2 = nullptr; p.ldc2 = 0;
+    return dispatch3(epi, dy, out_features, derived + 6 * n, derived + 7 * n, p, st);
 }
 
 int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* derived, const float* r, long long ldr,

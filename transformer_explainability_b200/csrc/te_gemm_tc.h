@@ -4,10 +4,21 @@
 
 // shapes the tensor-core path accepts (in/out multiples of 256, 16-byte aligned rows)
 bool te_tc_zplus_supported(long long rows, int in_features, int out_features, long long ldx);
-// derived copies of one frozen weight W [out,in]: W+, W- (K-major for S-kernel), W+^T, W-^T (K-major for R-kernel),
-// rounded to TF32: 4*in*out floats
+// derived copies of one frozen weight W [out,in], all K-major and rounded to TF32:
+//   [ W+ | W- | W+^T | W-^T ]        operands of the z+ rule kernels
+//   [ W_hi | W_lo | W^T_hi | W^T_lo ] error-compensated split (x_hi = tf32(x), x_lo = tf32(x - x_hi)) for the
+//                                     fp32-grade 3xTF32 forward / backward Linear GEMMs
+// = 8*in*out floats
 long long te_tc_derived_floats(int in_features, int out_features);
 int te_tc_prepare_weights(const float* w, float* derived, int in_features, int out_features, cudaStream_t st);
 int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* derived, const float* r, long long ldr,
                                float* out,
                                float* s_scratch, long long rows, int in_features, int out_features, cudaStream_t st);
+
+// fp32-grade (3xTF32 split) Linear GEMMs on tcgen05; epilogues mirror the SIMT ones
+enum { TE_TC_EPI_STORE = 0, TE_TC_EPI_BIAS = 1, TE_TC_EPI_BIAS_GELU = 2, TE_TC_EPI_BIAS_ADD = 3, TE_TC_EPI_GELU_BWD = 4 };
+bool te_tc_gemm3x_supported(long long rows, int K, int N, long long lda);
+int te_tc_linear_fwd(const float* x, long long ldx, const float* derived, int in_features, int out_features,
+                     const float* bias, float* y, float* y2, const float* e0, long long rows, int epi, cudaStream_t st);
+int te_tc_linear_bwd(const float* dy, const float* derived, int in_features, int out_features, float* dx, const float* e0,
+                     long long rows, int epi, cudaStream_t st);

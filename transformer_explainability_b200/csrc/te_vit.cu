@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/te_b200.h"
+#include "te_engine_util.h"
 #include "te_kernels.h"
 #include "te_rollout.h"
 #include "te_zplus.h"
@@ -274,11 +275,17 @@ extern "C" long long te_vit_workspace_bytes(const te_vit_config* cfg, int batch)
 // ================================================================================================
 // forward   (ViT_LRP.py:305-322)
 // ================================================================================================
-extern "C" int te_vit_forward(const te_vit_config* cfg, const float* weights, const float* images, int batch,
-                              float* logits, void* workspace, long long workspace_bytes, void* stream) {
+extern "C" int te_vit_forward(const te_vit_config* cfg, const float* weights, const float* derived, const float* images,
+                              int batch, unsigned flags, float* logits, void* workspace, long long workspace_bytes,
+                              void* stream) {
     Dims d; Workspace ws;
     TE_TRY(check_ws(cfg, batch, workspace, workspace_bytes, d, ws));
     if (!weights || !images) { te_set_last_error("te_vit_forward: null pointer"); return TE_ERR_ARG; }
+    if ((flags & TE_FLAG_LINEAR_TENSOR_CORES) && !derived) {
+        te_set_last_error("te_vit_forward: TE_FLAG_LINEAR_TENSOR_CORES needs the derived weight buffer");
+        return TE_ERR_ARG;
+    }
+    const float* lbase = (flags & TE_FLAG_LINEAR_TENSOR_CORES) ? derived : nullptr;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     Weights w;
     bind_weights(cfg, weights, w);
@@ -296,8 +303,10 @@ extern "C" int te_vit_forward(const te_vit_config* cfg, const float* weights, co
         LayerAct& a = ws.layer[l];
         const BlockW& bw = w.blk[l];
         float* x_next = (l + 1 < d.L) ? ws.layer[l + 1].x_in : ws.x_last;
+        const DerivedW lw = bind_derived(d, lbase, l);
         TE_TRY(te_launch_layernorm(a.x_in, bw.n1w, bw.n1b, a.xn1, a.mean1, a.rstd1, d.M, d.D, cfg->eps_block, st));
-        TE_TRY(linear_fwd(a.xn1, d.D, bw.qkvw, bw.qkvb, a.qkv, nullptr, nullptr, d.M, d.D, 3 * d.D, TE_EPI_BIAS, st));
+        TE_TRY(te_util::linear_fwd_tc(lw.qkv, a.xn1, d.D, bw.qkvw, bw.qkvb, a.qkv, nullptr, nullptr, d.M, d.D, 3 * d.D,
+                                      TE_EPI_BIAS, st));
         const HeadOp q = head_rows(a.qkv, 3 * d.D, d.N, d.dh);
         const HeadOp k = head_rows(a.qkv + d.D, 3 * d.D, d.N, d.dh);
         const HeadOp v = head_rows(a.qkv + 2 * d.D, 3 * d.D, d.N, d.dh);
@@ -309,11 +318,13 @@ extern "C" int te_vit_forward(const te_vit_config* cfg, const float* weights, co
         TE_TRY(head_gemm(d, attn_map(a.P, d), TE_L_K, v, TE_L_MN, head_rows(a.ctx, d.D, d.N, d.dh), none, d.N, d.dh,
                          d.N, 1.f, TE_EPI_STORE, st));
         // proj + residual add1                                  (:150, :198)
-        TE_TRY(linear_fwd(a.ctx, d.D, bw.projw, bw.projb, a.attn_out, a.x_mid, a.x_in, d.M, d.D, d.D,
-                          TE_EPI_BIAS_ADD, st));
+        TE_TRY(te_util::linear_fwd_tc(lw.proj, a.ctx, d.D, bw.projw, bw.projb, a.attn_out, a.x_mid, a.x_in, d.M, d.D, d.D,
+                                      TE_EPI_BIAS_ADD, st));
         TE_TRY(te_launch_layernorm(a.x_mid, bw.n2w, bw.n2b, a.xn2, a.mean2, a.rstd2, d.M, d.D, cfg->eps_block, st));
-        TE_TRY(linear_fwd(a.xn2, d.D, bw.fc1w, bw.fc1b, a.h, a.g, nullptr, d.M, d.D, d.F, TE_EPI_BIAS_GELU, st));
-        TE_TRY(linear_fwd(a.g, d.F, bw.fc2w, bw.fc2b, a.mlp_out, x_next, a.x_mid, d.M, d.F, d.D, TE_EPI_BIAS_ADD, st));
+        TE_TRY(te_util::linear_fwd_tc(lw.fc1, a.xn2, d.D, bw.fc1w, bw.fc1b, a.h, a.g, nullptr, d.M, d.D, d.F,
+                                      TE_EPI_BIAS_GELU, st));
+        TE_TRY(te_util::linear_fwd_tc(lw.fc2, a.g, d.F, bw.fc2w, bw.fc2b, a.mlp_out, x_next, a.x_mid, d.M, d.F, d.D,
+                                      TE_EPI_BIAS_ADD, st));
     }
     // final norm, pool token 0 (and 1), head(s)                (:318-321)
     TE_TRY(te_launch_layernorm(ws.x_last, w.normw, w.normb, ws.xf, nullptr, nullptr, d.M, d.D, cfg->eps_final, st));
@@ -373,10 +384,11 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
     const long long MD = d.M * d.D;
     const int low = (flags & (TE_FLAG_KEEP_ALL_CAMS | TE_FLAG_RELPROP_TO_INPUT)) ? 0 : start_layer;   // lowest block the relprop must reach
     const float* dbase = (flags & TE_FLAG_ZPLUS_TENSOR_CORES) ? derived : nullptr;
-    if ((flags & TE_FLAG_ZPLUS_TENSOR_CORES) && !derived) {
-        te_set_last_error("te_vit_attribute: TE_FLAG_ZPLUS_TENSOR_CORES needs the derived weight buffer");
+    if ((flags & (TE_FLAG_ZPLUS_TENSOR_CORES | TE_FLAG_LINEAR_TENSOR_CORES)) && !derived) {
+        te_set_last_error("te_vit_attribute: tensor-core flags need the derived weight buffer");
         return TE_ERR_ARG;
     }
+    const float* lbase = (flags & TE_FLAG_LINEAR_TENSOR_CORES) ? derived : nullptr;
 
     // ---- class index and seeds  (ViT_explanation_generator.py:28-35) ---------------------------
     TE_TRY(te_launch_argmax(ws.logits, index, d.B, d.C, /*only_negative=*/1, st));
@@ -404,12 +416,13 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
         const HeadOp q = head_rows(a.qkv, 3 * d.D, d.N, d.dh);
         const HeadOp k = head_rows(a.qkv + d.D, 3 * d.D, d.N, d.dh);
         const HeadOp v = head_rows(a.qkv + 2 * d.D, 3 * d.D, d.N, d.dh);
+        const DerivedW lw = bind_derived(d, lbase, l);
         // mlp branch
-        TE_TRY(linear_bwd(dxa, bw.fc2w, dF, a.h, d.M, d.F, d.D, TE_EPI_GELU_BWD, st));
-        TE_TRY(linear_bwd(dF, bw.fc1w, dxn, nullptr, d.M, d.D, d.F, TE_EPI_STORE, st));
+        TE_TRY(te_util::linear_bwd_tc(lw.fc2, dxa, bw.fc2w, dF, a.h, d.M, d.F, d.D, TE_EPI_GELU_BWD, st));
+        TE_TRY(te_util::linear_bwd_tc(lw.fc1, dF, bw.fc1w, dxn, nullptr, d.M, d.D, d.F, TE_EPI_STORE, st));
         TE_TRY(te_launch_layernorm_bwd(dxn, a.x_mid, bw.n2w, a.mean2, a.rstd2, dxa, dxb, d.M, d.D, st));
         // attention branch
-        TE_TRY(linear_bwd(dxb, bw.projw, dctx, nullptr, d.M, d.D, d.D, TE_EPI_STORE, st));
+        TE_TRY(te_util::linear_bwd_tc(lw.proj, dxb, bw.projw, dctx, nullptr, d.M, d.D, d.D, TE_EPI_STORE, st));
         TE_TRY(head_gemm(d, head_rows(dctx, d.D, d.N, d.dh), TE_L_K, v, TE_L_K, attn_map(a.G, d), none, d.N, d.N, d.dh,
                          1.f, TE_EPI_STORE, st));                                   // G = dctx v^T
         if (l == start_layer) break;                                                // lower gradients are never read
@@ -420,7 +433,7 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
                          d.N, 1.f, TE_EPI_STORE, st));                              // dQ = dS k
         TE_TRY(head_gemm(d, attn_map(dS, d), TE_L_MN, q, TE_L_MN, head_rows(dqkv + d.D, 3 * d.D, d.N, d.dh), none, d.N,
                          d.dh, d.N, 1.f, TE_EPI_STORE, st));                        // dK = dS^T q
-        TE_TRY(linear_bwd(dqkv, bw.qkvw, dxn, nullptr, d.M, d.D, 3 * d.D, TE_EPI_STORE, st));
+        TE_TRY(te_util::linear_bwd_tc(lw.qkv, dqkv, bw.qkvw, dxn, nullptr, d.M, d.D, 3 * d.D, TE_EPI_STORE, st));
         TE_TRY(te_launch_layernorm_bwd(dxn, a.x_in, bw.n1w, a.mean1, a.rstd1, dxb, dxa, d.M, d.D, st));
     }
 
@@ -478,7 +491,7 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
 extern "C" int te_vit_explain(const te_vit_config* cfg, const float* weights, const float* derived, const float* images,
                               int batch, int* index, int start_layer, unsigned flags, float* maps, float* logits,
                               void* workspace, long long workspace_bytes, void* stream) {
-    TE_TRY(te_vit_forward(cfg, weights, images, batch, logits, workspace, workspace_bytes, stream));
+    TE_TRY(te_vit_forward(cfg, weights, derived, images, batch, flags, logits, workspace, workspace_bytes, stream));
     return te_vit_attribute(cfg, weights, derived, batch, index, start_layer, flags, maps, workspace, workspace_bytes,
                             stream);
 }

@@ -65,7 +65,7 @@ class ViTEngine:
 
     def _derived(self, flags):
         """W+/W-/W+^T/W-^T TF32 copies for the tcgen05 z+ path (built once per weight load)."""
-        if not (flags & _lib.FLAG_ZPLUS_TENSOR_CORES):
+        if not (flags & _lib.FLAG_TENSOR_CORES):
             return None
         if self.derived is None:
             n = check(self.lib.te_vit_derived_total(ctypes.byref(self.cfg)), "te_vit_derived_total")
@@ -104,14 +104,15 @@ class ViTEngine:
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ---- the three calls ------------------------------------------------------------------------
-    def forward(self, images):
+    def forward(self, images, flags=None):
         """``model(x)``: logits [B,C]; leaves the activations in the workspace."""
         images = images.to(self.device, torch.float32).contiguous()
         b = images.shape[0]
         ws = self._workspace(b)
+        fl = self.flags if flags is None else flags
         logits = torch.empty(b, self.cfg.num_classes, dtype=torch.float32, device=self.device)
-        check(self.lib.te_vit_forward(ctypes.byref(self.cfg), ptr(self.weights), ptr(images), b, ptr(logits), ptr(ws),
-                                      ws.numel() * 4, self._stream()), "te_vit_forward")
+        check(self.lib.te_vit_forward(ctypes.byref(self.cfg), ptr(self.weights), ptr(self._derived(fl)), ptr(images), b,
+                                      fl, ptr(logits), ptr(ws), ws.numel() * 4, self._stream()), "te_vit_forward")
         self.last_batch = b
         return logits
 
@@ -228,7 +229,7 @@ class BertEngine:
         dist.broadcast(self.weights, src=src, group=group)
 
     def _derived(self, flags):
-        if not (flags & _lib.FLAG_ZPLUS_TENSOR_CORES):
+        if not (flags & _lib.FLAG_TENSOR_CORES):
             return None
         if self.derived is None:
             n = check(self.lib.te_bert_derived_total(ctypes.byref(self.cfg)), "te_bert_derived_total")
@@ -264,13 +265,15 @@ class BertEngine:
             attention_mask = torch.ones_like(ids)
         return ids, attention_mask.to(self.device, torch.int64).contiguous()
 
-    def forward(self, input_ids, attention_mask=None):
+    def forward(self, input_ids, attention_mask=None, flags=None):
         ids, mask = self._ids(input_ids, attention_mask)
         b, s = ids.shape
         ws = self._workspace(b, s)
+        fl = self.flags if flags is None else flags
         logits = torch.empty(b, self.cfg.num_labels, dtype=torch.float32, device=self.device)
-        check(self.lib.te_bert_forward(ctypes.byref(self.cfg), ptr(self.weights), ptr(ids), ptr(mask), b, s, ptr(logits),
-                                       ptr(ws), ws.numel() * 4, self._stream()), "te_bert_forward")
+        check(self.lib.te_bert_forward(ctypes.byref(self.cfg), ptr(self.weights), ptr(self._derived(fl)), ptr(ids),
+                                       ptr(mask), b, s, fl, ptr(logits), ptr(ws), ws.numel() * 4, self._stream()),
+              "te_bert_forward")
         self.last = (b, s)
         return logits
 

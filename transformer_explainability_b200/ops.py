@@ -26,13 +26,28 @@ def _workspace(nbytes, device):
     return torch.empty((nbytes + 255) // 256 * 64, dtype=torch.float32, device=device)   # 256-byte multiple
 
 
-def linear_forward(x, w, bias=None):
+def linear_forward(x, w, bias=None, tensor_cores=False):
+    """y = x W^T + b.  tensor_cores: fp32-grade 3xTF32 split on tcgen05 (shapes that do not qualify fall back)."""
     _req(x, w, bias)
     rows = x.numel() // x.shape[-1]
     y = torch.empty(*x.shape[:-1], w.shape[0], device=x.device, dtype=torch.float32)
-    check(_lib.load().te_linear_forward(ptr(x), ptr(w), ptr(bias), ptr(y), rows, x.shape[-1], w.shape[0], _stream()),
-          "te_linear_forward")
+    scratch = torch.empty(8 * w.numel(), device=x.device, dtype=torch.float32) if tensor_cores else None
+    check(_lib.load().te_linear_forward_ex(ptr(x), ptr(w), ptr(bias), ptr(y), ptr(scratch), rows, x.shape[-1], w.shape[0],
+                                           _lib.FLAG_LINEAR_TENSOR_CORES if tensor_cores else 0, _stream()),
+          "te_linear_forward_ex")
     return y
+
+
+def linear_backward(dy, w, tensor_cores=False):
+    """dx = dy W  (activation gradient of a Linear; no dW on this path)."""
+    _req(dy, w)
+    rows = dy.numel() // dy.shape[-1]
+    dx = torch.empty(*dy.shape[:-1], w.shape[1], device=dy.device, dtype=torch.float32)
+    scratch = torch.empty(8 * w.numel(), device=dy.device, dtype=torch.float32) if tensor_cores else None
+    check(_lib.load().te_linear_backward_ex(ptr(dy), ptr(w), ptr(dx), ptr(scratch), rows, w.shape[1], w.shape[0],
+                                            _lib.FLAG_LINEAR_TENSOR_CORES if tensor_cores else 0, _stream()),
+          "te_linear_backward_ex")
+    return dx
 
 
 def linear_relprop(x, w, r, tensor_cores=False):
@@ -42,7 +57,7 @@ def linear_relprop(x, w, r, tensor_cores=False):
     out = torch.empty_like(x)
     nscratch = rows * w.shape[0]
     if tensor_cores:
-        nscratch = (nscratch + 63) // 64 * 64 + 4 * w.numel()
+        nscratch = (nscratch + 63) // 64 * 64 + 8 * w.numel()
     scratch = torch.empty(nscratch, device=x.device, dtype=torch.float32)
     flags = _lib.FLAG_ZPLUS_TENSOR_CORES if tensor_cores else 0
     check(_lib.load().te_linear_relprop(ptr(x), ptr(w), ptr(r), ptr(out), ptr(scratch), rows, x.shape[-1], w.shape[0],
