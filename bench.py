@@ -32,10 +32,21 @@ import torch                                                     # noqa: E402
 import torch.distributed as dist                                 # noqa: E402
 
 WORKLOADS = {
-    "vit_base": dict(factory="vit_base_patch16_224", oracle="vit_base_patch16_224", batch=256, tokens=197, dim=768,
-                     depth=12, heads=12, mlp=3072, label="ViT-B/16 transformer_attribution, batch 256, 224x224, start_layer 0"),
-    "vit_large": dict(factory="vit_large_patch16_224", oracle="vit_large_patch16_224", batch=128, tokens=197, dim=1024,
-                      depth=24, heads=16, mlp=4096, label="ViT-L/16 transformer_attribution, batch 128, 224x224, start_layer 0"),
+    "vit_base": dict(kind="vit", factory="vit_base_patch16_224", oracle="vit_base_patch16_224", batch=256, tokens=197,
+                     dim=768, depth=12, heads=12, mlp=3072,
+                     label="ViT-B/16 transformer_attribution, batch 256, 224x224, start_layer 0"),
+    "vit_large": dict(kind="vit", factory="vit_large_patch16_224", oracle="vit_large_patch16_224", batch=128, tokens=197,
+                      dim=1024, depth=24, heads=16, mlp=4096,
+                      label="ViT-L/16 transformer_attribution, batch 128, 224x224, start_layer 0"),
+    "deit_base": dict(kind="vit", factory="deit_base_patch16_224", oracle="deit_base_patch16_224", batch=256, tokens=197,
+                      dim=768, depth=12, heads=12, mlp=3072,
+                      label="DeiT-B/16 (reference 197-token model) transformer_attribution, batch 256, start_layer 0"),
+    "deit_base_distilled": dict(kind="vit", factory="deit_base_distilled_patch16_224",
+                                oracle="deit_base_distilled_patch16_224", batch=256, tokens=198, dim=768, depth=12,
+                                heads=12, mlp=3072,
+                                label="DeiT-B distilled (198 tokens) transformer_attribution, batch 256, start_layer 0"),
+    "bert_base": dict(kind="bert", batch=64, tokens=512, dim=768, depth=12, heads=12, mlp=3072,
+                      label="BERT-base seq_len 512 Generator.generate_LRP, batch 64, start_layer 0"),
 }
 
 
@@ -62,6 +73,16 @@ def peaks():
         return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained"),
                     source="measured (MEASURED_PEAKS.json)")
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def measured_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch (group) from the committed ncu --set full capture of the
+    same kernel at the same shape (profiles/ncu_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(key, {}).get("bytes")
+    except (OSError, ValueError):
+        return None
 
 
 class ClockSampler:
@@ -117,15 +138,38 @@ class ClockSampler:
 
 
 def make_model(w, device):
-    from transformer_explainability_b200.baselines.ViT import ViT_LRP
     torch.manual_seed(0)
-    model = getattr(ViT_LRP, w["factory"])(pretrained=False)
+    if w["kind"] == "bert":
+        from transformers import BertConfig
+        from transformer_explainability_b200.BERT_explainability.modules.BERT.BertForSequenceClassification import \
+            BertForSequenceClassification
+        model = BertForSequenceClassification(BertConfig(num_labels=2))
+    else:
+        from transformer_explainability_b200.baselines.ViT import ViT_LRP
+        model = getattr(ViT_LRP, w["factory"])(pretrained=False)
     return model.to(device).eval()
 
 
 def synthetic_images(batch, seed):
     g = torch.Generator().manual_seed(seed)
     return torch.randn(batch, 3, 224, 224, generator=g)
+
+
+def synthetic_inputs(w, batch, seed):
+    """ViT: randn images.  BERT: ids ~ U{1000..4999}, [CLS]=101 first, [SEP]=102 last, mask all ones (movies documents
+    are truncated to 512 and unpadded, bert_pipeline.py:262-271)."""
+    if w["kind"] == "bert":
+        g = torch.Generator().manual_seed(seed)
+        ids = torch.randint(1000, 5000, (batch, w["tokens"]), generator=g)
+        ids[:, 0], ids[:, -1] = 101, 102
+        return ids
+    return synthetic_images(batch, seed)
+
+
+def explain_call(w, eng, x, batch):
+    if w["kind"] == "bert":
+        return eng.explain(x, None, start_layer=0, chunk=batch)
+    return eng.explain(x, chunk=batch)
 
 
 def timed_steps(fn, steps, warmup, world):
@@ -177,9 +221,10 @@ def roofline_zplus(w, batch, flags, pk):
     # TF32 dense peak = half the measured bf16 peak (nominal 1.1 vs 2.25 PF); the fp32 SIMT path is judged
     # against the same tensor roof: it is the baseline the tcgen05 path replaces.
     peak = pk["bf16_tflops"] / 2.0
+    traffic = measured_traffic("zplus_tc" if tc else "zplus_simt")
     return {"kernel": "zplus_linear_relprop[%s] rows=%d in=%d out=%d" % ("tcgen05-tf32" if tc else "simt-fp32", rows, inf, outf),
             "bound": "tensor", "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s",
-            "frac": round(achieved / peak, 4), "traffic": None, "ms_per_launch_group": round(ms, 3),
+            "frac": round(achieved / peak, 4), "traffic": traffic, "ms_per_launch_group": round(ms, 3),
             "peak_source": pk["source"] + "; TF32 dense taken as bf16/2"}
 
 
@@ -209,7 +254,8 @@ def roofline_rollout(w, flags, pk):
     achieved = nbytes / (ms * 1e-3) / 1e9
     return {"kernel": "attribution_rollout[%s] L=%d B=%d H=%d N=%d" % ("fused" if fused else "aggregate+bmm", L, B, H, N),
             "bound": "hbm", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
-            "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": None, "ms": round(ms, 3), "peak_source": pk["source"]}
+            "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": measured_traffic("rollout_fused" if fused else "rollout"),
+            "algorithmic_bytes": nbytes, "ms": round(ms, 3), "peak_source": pk["source"]}
 
 
 def cpu_baseline(w, state_dict, n_samples):
@@ -219,9 +265,15 @@ def cpu_baseline(w, state_dict, n_samples):
     from oracle import vit as ovit
     from oracle import cpu as ocpu
     ocpu.set_torch_threads(cap=256)
-    xs = synthetic_images(n_samples + 2, seed=1234)
+    xs = synthetic_inputs(w, n_samples + 2, seed=1234)
     sd = {k: v.detach().float().cpu() for k, v in state_dict.items()}
-    if ref_harness.available():
+    if w["kind"] == "bert":
+        from oracle import bert as obert
+        sd = {k: v for k, v in sd.items() if "position_ids" not in k}
+        kind = "port"
+        ones = torch.ones(1, w["tokens"], dtype=torch.long)
+        run = lambda x: obert.explain(sd, x, ones, w["heads"], start_layer=0)[0]      # noqa: E731
+    elif ref_harness.available():
         kind = "reference"
         model = ref_harness.build_vit(w["oracle"], state_dict=sd)
         run = lambda x: ref_harness.vit_generate_lrp(model, x)["map"]      # noqa: E731
@@ -307,17 +359,23 @@ def main():
         if rank != 0:
             eng.weights.zero_()
         parallel.broadcast_flat_weights(eng.weights, src=0)          # the one collective of the path
-    lrp = LRP(model)
+    if w["kind"] == "bert":
+        from transformer_explainability_b200.BERT_explainability.modules.BERT.ExplanationGenerator import Generator
+        gen = Generator(model)
+        public_call = lambda xd: gen.generate_LRP_batched(xd, None, start_layer=0, chunk=batch)      # noqa: E731
+    else:
+        lrp = LRP(model)
+        public_call = lambda xd: lrp.generate_LRP_batched(xd, chunk=batch)                           # noqa: E731
 
-    host = synthetic_images(batch, seed=100 + rank).pin_memory()
+    host = synthetic_inputs(w, batch, seed=100 + rank).pin_memory()
     x_dev = host.to(dev)
-    eng.explain(x_dev[:min(batch, 8)])                               # allocator / module warm-up (untimed)
+    explain_call(w, eng, x_dev[:min(batch, 8)], min(batch, 8))       # allocator / module warm-up (untimed)
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
     l0 = lib.te_kernel_launch_count()
     sampler.start()
-    ms = timed_steps(lambda: eng.explain(x_dev, chunk=batch), args.steps, args.warmup, world)
+    ms = timed_steps(lambda: explain_call(w, eng, x_dev, batch), args.steps, args.warmup, world)
     clocks = sampler.stop()
     launches = (lib.te_kernel_launch_count() - l0) // max(1, (args.steps + args.warmup)) * args.steps
     value = world * batch * args.steps / (ms * 1e-3)
@@ -326,7 +384,7 @@ def main():
 
     def e2e_step():
         xd = host.to(dev, non_blocking=True)                          # H2D of this step's inputs (pinned)
-        maps = lrp.generate_LRP_batched(xd, chunk=batch)              # public API
+        maps = public_call(xd)                                        # public API
         sink["maps"] = maps.cpu()                                     # D2H read of the step's result
 
     ms_e2e = timed_steps(e2e_step, args.steps, 1, world)
@@ -338,10 +396,11 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["label"], "per_gpu_batch": batch, "global_batch": batch * world,
                        "weights": "random-init (reference constructor distributions)", "engine_flags": flags,
-                       "l2": "inputs exceed L2: 154 MB of images and >50 GB of saved activations per step",
+                       "l2": "working set exceeds L2 by orders of magnitude: >50 GB of saved activations are written and "
+                             "re-read every step (126 MB L2)",
                        "outputs_finite": finite},
             "clocks": clocks,
-            "e2e": {"value": round(e2e, 2), "unit": "expl/s", "h2d_bytes_per_step": host.numel() * 4,
+            "e2e": {"value": round(e2e, 2), "unit": "expl/s", "h2d_bytes_per_step": host.numel() * host.element_size(),
                     "d2h_bytes_per_step": sink["maps"].numel() * 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
             "gpu_launches": int(launches)}
     if rank == 0:
