@@ -420,7 +420,7 @@ def main():
 
 def default_flags():
     """Best validated kernel selection: updated as faster paths pass parity."""
-    return 19  # tcgen05 z+ rule (1) + fused row-only rollout (2) + 3xTF32 tcgen05 forward/backward Linears (16)
+    return 51  # tcgen05 z+ rule (1) + fused row-only rollout (2) + 3xTF32 tcgen05 Linears (16) + N x N attention contractions (32)
 
 
 if __name__ == "__main__":

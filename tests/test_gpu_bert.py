@@ -120,7 +120,7 @@ def test_bert_base_vs_oracle(seq, start):
     ref32, _ = obert.explain(params, ids, mask, heads, start_layer=start)
     err_ref = sorted(rel(ref32[s], ref[s]) for s in range(n))
     top = len(taps["cams"]) - 1
-    for flags in (0, _lib.FLAG_ZPLUS_TENSOR_CORES):
+    for flags in (0, _lib.FLAG_ZPLUS_TENSOR_CORES, _lib.FLAG_ALL_FAST):
         maps, idx, logits = eng.explain(ids.cuda(), mask.cuda(), start_layer=start, flags=flags, return_logits=True)
         assert torch.equal(idx.cpu().long(), ridx)
         assert rel(logits, taps["logits"]) < 1e-4

@@ -115,3 +115,34 @@ def test_tc_linear_engine_vit_base():
         assert int(idx1[s * trials]) == int(ridx)
         assert rel(lg1[s * trials], taps["logits"][0]) < 1e-5
         check_parity(tc[s * trials:(s + 1) * trials], ref[0], "sample %d all-tensor-core" % s)
+
+
+def test_tc_attention_contractions_engine():
+    """QK^T, dctx V^T and both attention-rule N x N contractions on tcgen05 (3xTF32): attention probabilities,
+    attention gradients and the top-layer attn_cam stay at fp32 accuracy; maps in the same noise class."""
+    from oracle import cpu as ocpu
+    from oracle import vit as ovit
+    from transformer_explainability_b200 import _lib
+    from transformer_explainability_b200.baselines.ViT.ViT_LRP import vit_base_patch16_224
+    from test_gpu_vit import _noise_trials, check_parity
+    trials = 16
+    params, heads = ovit.init_params("vit_base_patch16_224", seed=0)
+    xs = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(100))
+    m = vit_base_patch16_224()
+    m.load_state_dict(params)
+    m = m.cuda().eval()
+    eng = m.engine()
+    ocpu.set_torch_threads()
+    p64 = {k: v.double() for k, v in params.items()}
+    ref, ridx, taps = ovit.explain(p64, xs[0:1].double(), heads, return_taps=True)
+    maps, idx = eng.explain(xs[0:1].cuda(), flags=_lib.FLAG_ALL_FAST)
+    assert int(idx[0]) == int(ridx)
+    for l in (0, 6, 11):
+        assert rel(m.blocks[l].attn.get_attn()[0], taps["cache"]["blocks"][l]["attn"][0]) < 1e-5
+        assert rel(m.blocks[l].attn.get_attn_gradients()[0], taps["grads"][l][0]) < 1e-4
+    assert rel(m.blocks[11].attn.get_attn_cam()[0], taps["cams"][11][0]) < 2e-2
+    xb = torch.cat([_noise_trials(xs[s:s + 1], trials) for s in range(2)]).cuda()
+    fast, idx1 = eng.explain(xb, flags=_lib.FLAG_ALL_FAST)
+    for s in range(2):
+        r, _ = ovit.explain(p64, xs[s:s + 1].double(), heads)
+        check_parity(fast[s * trials:(s + 1) * trials], r[0], "sample %d all-fast" % s)

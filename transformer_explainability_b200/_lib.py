@@ -32,7 +32,9 @@ FLAG_ROLLOUT_FUSED = 2
 FLAG_KEEP_ALL_CAMS = 4
 FLAG_RELPROP_TO_INPUT = 8
 FLAG_LINEAR_TENSOR_CORES = 16
-FLAG_TENSOR_CORES = FLAG_ZPLUS_TENSOR_CORES | FLAG_LINEAR_TENSOR_CORES
+FLAG_ATTN_TENSOR_CORES = 32
+FLAG_TENSOR_CORES = FLAG_ZPLUS_TENSOR_CORES | FLAG_LINEAR_TENSOR_CORES      # the ones that need derived weights
+FLAG_ALL_FAST = FLAG_TENSOR_CORES | FLAG_ATTN_TENSOR_CORES | FLAG_ROLLOUT_FUSED
 
 _P = c_void_p
 _CFG = ctypes.POINTER(TeVitConfig)

@@ -284,8 +284,8 @@ extern "C" int te_bert_forward(const te_bert_config* cfg, const float* weights, 
         const HeadOp k = head_rows(a.qkv + d.D, 3 * d.D, d.N, d.dh);
         const HeadOp v = head_rows(a.qkv + 2 * d.D, 3 * d.D, d.N, d.dh);
         // scores = q k^T / sqrt(d) ; + extended mask ; softmax      (:338-345)
-        TE_TRY(head_gemm(d.B, d.H, q, TE_L_K, k, TE_L_K, attn_map(a.P, d.H, d.N, d.NP), none, d.N, d.N, d.dh, scale,
-                         TE_EPI_STORE, st));
+        TE_TRY(attn_nn((flags & TE_FLAG_ATTN_TENSOR_CORES) != 0, d.B, d.H, d.N, d.NP, d.dh, a.qkv, 3 * d.D, a.qkv + d.D,
+                       3 * d.D, a.P, nullptr, scale, TE_EPI_STORE, st));
         TE_TRY(te_launch_softmax_masked(a.P, (long long)d.B * d.H * d.N, d.N, d.NP, ws.maskadd, (long long)d.H * d.N, st));
         TE_TRY(head_gemm(d.B, d.H, attn_map(a.P, d.H, d.N, d.NP), TE_L_K, v, TE_L_MN, head_rows(a.ctx, d.D, d.N, d.dh),
                          none, d.N, d.dh, d.N, 1.f, TE_EPI_STORE, st));
@@ -323,6 +323,7 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
         return TE_ERR_ARG;
     }
     const float* lbase = (flags & TE_FLAG_LINEAR_TENSOR_CORES) ? derived : nullptr;
+    const bool atc = (flags & TE_FLAG_ATTN_TENSOR_CORES) != 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     Weights w;
     bind_weights(cfg, weights, w);
@@ -361,8 +362,8 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
         TE_TRY(te_launch_add2(dxn, dsx, dxn, MD, st));                                                          // d ao
         TE_TRY(te_launch_layernorm_bwd(dxn, a.s1, lw.ln1w, a.mean1, a.rstd1, nullptr, dsx, d.M, d.D, st));    // d s1
         TE_TRY(linear_bwd_tc(tw.o, dsx, lw.ow, dctx, nullptr, d.M, d.D, d.D, TE_EPI_STORE, st));
-        TE_TRY(head_gemm(d.B, d.H, head_rows(dctx, d.D, d.N, d.dh), TE_L_K, v, TE_L_K, amap(a.G), none, d.N, d.N, d.dh,
-                         1.f, TE_EPI_STORE, st));                                                               // G = dctx v^T
+        TE_TRY(attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, dctx, d.D, a.qkv + 2 * d.D, 3 * d.D, a.G, nullptr, 1.f,
+                       TE_EPI_STORE, st));                                                                      // G = dctx v^T
         if (l == start_layer) break;
         TE_TRY(head_gemm(d.B, d.H, amap(a.P), TE_L_MN, head_rows(dctx, d.D, d.N, d.dh), TE_L_MN,
                          head_rows(dqkv + 2 * d.D, 3 * d.D, d.N, d.dh), none, d.N, d.dh, d.N, 1.f, TE_EPI_STORE, st));
@@ -401,16 +402,18 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
         TE_TRY(te_zplus_linear_relprop(a.ctx, d.D, lw.ow, dw.o, R1, R3, S, d.M, d.D, d.D, st));
         // BertSelfAttention.relprop :367-409
         TE_TRY(te_launch_sd(R3, a.ctx, S, MD, st));                                       // matmul2: Z == saved ctx
-        TE_TRY(head_gemm(d.B, d.H, head_rows(S, d.D, d.N, d.dh), TE_L_K, v, TE_L_K, amap(a.cam), amap(a.P), d.N, d.N, d.dh,
-                         0.5f, TE_EPI_MUL, st));                                          // attn_cam   :380
+        TE_TRY(attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, S, d.D, a.qkv + 2 * d.D, 3 * d.D, a.cam, a.P, 0.5f, TE_EPI_MUL,
+                       st));                                                              // attn_cam   :380
         if (l == low && !(flags & TE_FLAG_RELPROP_TO_INPUT)) break;
         TE_TRY(head_gemm(d.B, d.H, amap(a.P), TE_L_MN, head_rows(S, d.D, d.N, d.dh), TE_L_MN,
                          head_rows(Rqkv + 2 * d.D, 3 * d.D, d.N, d.dh), v, d.N, d.dh, d.N, 0.5f, TE_EPI_MUL, st));
         // add([scores, mask]).relprop : scores = q k^T / sqrt(d) recomputed ; relevance renormalised  :386-388
-        TE_TRY(head_gemm(d.B, d.H, q, TE_L_K, k, TE_L_K, amap(ws.tA[0]), none, d.N, d.N, d.dh, scale, TE_EPI_STORE, st));
+        TE_TRY(attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, a.qkv, 3 * d.D, a.qkv + d.D, 3 * d.D, ws.tA[0], nullptr, scale,
+                       TE_EPI_STORE, st));
         TE_TRY(te_launch_add_relprop_keymask(ws.tA[0], ws.maskadd, a.cam, ws.tA[1], ws.addpart, d.B, d.H, d.N, d.NP, st));
         // matmul1 rule on the unscaled product
-        TE_TRY(head_gemm(d.B, d.H, q, TE_L_K, k, TE_L_K, amap(ws.tA[0]), amap(ws.tA[1]), d.N, d.N, d.dh, 1.f, TE_EPI_SD, st));
+        TE_TRY(attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, a.qkv, 3 * d.D, a.qkv + d.D, 3 * d.D, ws.tA[0], ws.tA[1], 1.f,
+                       TE_EPI_SD, st));
         TE_TRY(head_gemm(d.B, d.H, amap(ws.tA[0]), TE_L_K, k, TE_L_MN, head_rows(Rqkv, 3 * d.D, d.N, d.dh), q, d.N, d.dh,
                          d.N, 0.5f, TE_EPI_MUL, st));
         TE_TRY(head_gemm(d.B, d.H, amap(ws.tA[0]), TE_L_MN, q, TE_L_MN, head_rows(Rqkv + d.D, 3 * d.D, d.N, d.dh), k, d.N,

@@ -536,6 +536,182 @@ te_tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
+// =====================================================================================================================
+// Attention-shaped N x N contractions on tensor cores (fp32-grade 3xTF32):
+//   out[b,h,i,j] = epi( alpha * sum_d A[b,i,h,d] * B[b,j,h,d] )        (Q K^T, dctx V^T, S2 V^T: K = head_dim)
+// A and B are head slices of packed [batch*N, ld] activations, addressed in place by 2-D tensor maps
+// (column = h*dh + kblock*32, row = b*N + tile row).  Rows of a tile that fall into the next sample (N is not a
+// multiple of 128 / 256) only produce output rows / columns that the epilogue masks.  Both operands are activations,
+// so both are split into hi/lo in shared memory.  One CTA per (b, h, 128-row tile): the whole K (<= 64) is resident,
+// 6 MMAs per 8-wide k-step, one 128 x 256 fp32 accumulator in TMEM, fused epilogue (scale / multiply by E / safe_divide).
+// =====================================================================================================================
+constexpr int AT_KB = 2;                                          // max k-blocks (head_dim <= 64)
+constexpr int AT_SMEM = 2 * (AT_KB * A_BYTES + AT_KB * B_BYTES) + 1024 + 256;   // hi + lo of A and B
+enum { AT_STORE = 0, AT_MUL = 1, AT_SD = 2 };
+
+struct AtParams {
+    int N, H, dh, ld_out;            // tokens, heads, head_dim, row stride of out / E
+    const float* E; float* out; float alpha;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const AtParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    // layout: A_hi[kb] | B_hi[kb] | A_lo[kb] | B_lo[kb]
+    constexpr uint32_t OFF_AH = 0, OFF_BH = AT_KB * A_BYTES, OFF_AL = OFF_BH + AT_KB * B_BYTES, OFF_BL = OFF_AL + AT_KB * A_BYTES;
+    constexpr uint32_t TOTAL = OFF_BL + AT_KB * B_BYTES;
+    const uint32_t bars = smem_base + TOTAL;
+    const uint32_t full_bar = bars, xf_bar = bars + 8, accum_bar = bars + 16;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + TOTAL + 32);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
+    const int m0 = blockIdx.x * BM;
+    const int kb = p.dh / BK;
+    constexpr uint32_t TMEM_COLS = 256u;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        mbar_init(full_bar, 1);
+        mbar_init(xf_bar, XF_THREADS);
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(full_bar, (uint32_t)(kb * (A_BYTES + B_BYTES)));
+            for (int k = 0; k < kb; ++k) {
+                tma_load_2d(smem_base + OFF_AH + k * A_BYTES, &tmA, full_bar, h * p.dh + k * BK, b * p.N + m0);
+                tma_load_2d(smem_base + OFF_BH + k * B_BYTES, &tmB, full_bar, h * p.dh + k * BK, b * p.N);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            mbar_wait(xf_bar, 0);
+            tcgen05_fence_after();
+            for (int kk = 0; kk < kb; ++kk) {
+                const uint64_t ah = make_smem_desc(smem_base + OFF_AH + kk * A_BYTES), al = make_smem_desc(smem_base + OFF_AL + kk * A_BYTES);
+                const uint64_t bh_ = make_smem_desc(smem_base + OFF_BH + kk * B_BYTES), bl = make_smem_desc(smem_base + OFF_BL + kk * B_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    const uint64_t o = (uint64_t)(2 * k);
+                    umma_tf32(tmem_base, al + o, bh_ + o, kIdesc, (kk == 0 && k == 0) ? 0u : 1u);
+                    umma_tf32(tmem_base, ah + o, bl + o, kIdesc, 1u);
+                    umma_tf32(tmem_base, ah + o, bh_ + o, kIdesc, 1u);
+                }
+            }
+            umma_commit(accum_bar);
+        }
+        __syncwarp();
+    } else {
+        const int et = threadIdx.x - 64;
+        mbar_wait(full_bar, 0);
+        // split A (kb*16 KiB) and B (kb*32 KiB): hi in place, lo to the *_lo regions (same swizzled offsets)
+        {
+            float4* a4 = reinterpret_cast<float4*>(smem_al + OFF_AH);
+            float4* l4 = reinterpret_cast<float4*>(smem_al + OFF_AL);
+            const int na = kb * A_BYTES / 16;
+            for (int i = et; i < na; i += XF_THREADS) {
+                const float4 v = a4[i];
+                float4 hh, l;
+                hh.x = to_tf32(v.x); hh.y = to_tf32(v.y); hh.z = to_tf32(v.z); hh.w = to_tf32(v.w);
+                l.x = to_tf32(v.x - hh.x); l.y = to_tf32(v.y - hh.y); l.z = to_tf32(v.z - hh.z); l.w = to_tf32(v.w - hh.w);
+                a4[i] = hh; l4[i] = l;
+            }
+            float4* b4 = reinterpret_cast<float4*>(smem_al + OFF_BH);
+            float4* m4 = reinterpret_cast<float4*>(smem_al + OFF_BL);
+            const int nb = kb * B_BYTES / 16;
+            for (int i = et; i < nb; i += XF_THREADS) {
+                const float4 v = b4[i];
+                float4 hh, l;
+                hh.x = to_tf32(v.x); hh.y = to_tf32(v.y); hh.z = to_tf32(v.z); hh.w = to_tf32(v.w);
+                l.x = to_tf32(v.x - hh.x); l.y = to_tf32(v.y - hh.y); l.z = to_tf32(v.z - hh.z); l.w = to_tf32(v.w - hh.w);
+                b4[i] = hh; m4[i] = l;
+            }
+        }
+        fence_proxy_async();
+        mbar_arrive(xf_bar);
+
+        const int q = warp & 3;
+        const int i = m0 + q * 32 + lane;                       // query row inside the sample
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool live = i < p.N;
+        const long long rowoff = ((long long)bh * p.N + i) * p.ld_out;
+        const int nchunks = (p.N + 31) / 32;
+        // E (attention probabilities / attn_cam) comes from HBM: its loads are issued one 32-column chunk ahead so
+        // that their latency overlaps the TMEM read, the math and the stores of the previous chunk.  Reading a
+        // full float4 whose tail lies in the row padding is memory-safe (ld_out % 4 == 0); the tail is masked.
+        float4 ebuf[2][8];
+        auto load_e = [&](int c, float4 (&buf)[8]) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int col = c * 32 + j * 4;
+                buf[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (EPI != AT_STORE && live && col < p.N) buf[j] = __ldcs(reinterpret_cast<const float4*>(p.E + rowoff + col));
+            }
+        };
+        load_e(0, ebuf[0]);
+        mbar_wait(accum_bar, 0);
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < nchunks; c += 2) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int cc = c + half;
+                if (cc < nchunks) {
+                    if (cc + 1 < nchunks) load_e(cc + 1, ebuf[half ^ 1]);
+                    uint32_t acc[32];
+                    tmem_ld32(tlane + (uint32_t)(cc * 32), acc);
+                    tmem_ld_wait();
+                    if (live) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int col = cc * 32 + j * 4;
+                            if (col < p.N) {
+                                const float e[4] = {ebuf[half][j].x, ebuf[half][j].y, ebuf[half][j].z, ebuf[half][j].w};
+                                float o[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const float a = __uint_as_float(acc[j * 4 + u]);
+                                    if (EPI == AT_STORE) o[u] = p.alpha * a;
+                                    else if (EPI == AT_MUL) o[u] = p.alpha * a * e[u];
+                                    else o[u] = te_sd(e[u], p.alpha * a);
+                                }
+                                if (col + 3 < p.N) *reinterpret_cast<float4*>(p.out + rowoff + col) = make_float4(o[0], o[1], o[2], o[3]);
+                                else {
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) if (col + u < p.N) p.out[rowoff + col + u] = o[u];
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // ---- host: tensor maps ------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -649,6 +825,50 @@ int dispatch3(int epi, const float* A, long long lda, const float* Bh, const flo
     return TE_ERR_UNSUPPORTED;
 }
 }  // namespace
+
+bool te_tc_attn_supported(int N, int dh, long long lda, long long ldb, int ld_out) {
+    return N >= 1 && N <= BN && (dh == 32 || dh == 64) && lda % 4 == 0 && ldb % 4 == 0 && ld_out % 4 == 0 && get_encode() != nullptr;
+}
+
+namespace {
+template <int EPI>
+int launch_attn(const float* A, long long lda, const float* B, long long ldb, long long total_rows, const AtParams& p,
+                int batch, cudaStream_t st) {
+    CUtensorMap tmA, tmB;
+    if (!make_map(&tmA, A, total_rows, (long long)p.H * p.dh, lda, BM) || !make_map(&tmB, B, total_rows, (long long)p.H * p.dh, ldb, BN)) {
+        te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed (attention)");
+        return TE_ERR_CUDA;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(te_tc_attn_nn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) {
+            te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
+            return TE_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    dim3 grid((p.N + BM - 1) / BM, batch * p.H);
+    if (grid.y > 65535) { te_set_last_error("te_gemm_tc: batch*heads too large for one launch"); return TE_ERR_ARG; }
+    te_tc_attn_nn_kernel<EPI><<<grid, NUM_THREADS, AT_SMEM, st>>>(tmA, tmB, p);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+}  // namespace
+
+// out[b,h,i,j] = epi(alpha * sum_d A[b*N+i, h*dh+d] * B[b*N+j, h*dh+d]);  out / E are [batch,H,N,ld_out]
+int te_tc_attn_nn(const float* A, long long lda, const float* B, long long ldb, int batch, int H, int N, int dh,
+                  float* out, int ld_out, const float* E, float alpha, int epi, cudaStream_t st) {
+    AtParams p;
+    p.N = N; p.H = H; p.dh = dh; p.ld_out = ld_out; p.E = E; p.out = out; p.alpha = alpha;
+    const long long rows = (long long)batch * N;
+    switch (epi) {
+        case TE_TC_ATTN_STORE: return launch_attn<AT_STORE>(A, lda, B, ldb, rows, p, batch, st);
+        case TE_TC_ATTN_MUL: return launch_attn<AT_MUL>(A, lda, B, ldb, rows, p, batch, st);
+        case TE_TC_ATTN_SD: return launch_attn<AT_SD>(A, lda, B, ldb, rows, p, batch, st);
+    }
+    te_set_last_error("te_gemm_tc: unsupported attention epilogue");
+    return TE_ERR_UNSUPPORTED;
+}
 
 // y[rows,out] = x[rows,in] W^T (+ epilogue)   — fp32-grade (3xTF32) on tcgen05
 int te_tc_linear_fwd(const float* x, long long ldx, const float* derived, int in_features, int out_features,

@@ -312,7 +312,8 @@ extern "C" int te_vit_forward(const te_vit_config* cfg, const float* weights, co
         const HeadOp v = head_rows(a.qkv + 2 * d.D, 3 * d.D, d.N, d.dh);
         const HeadOp none = {nullptr, 0, 0, 0};
         // dots = q k^T * scale ; attn = softmax(dots)        (:139-141)
-        TE_TRY(head_gemm(d, q, TE_L_K, k, TE_L_K, attn_map(a.P, d), none, d.N, d.N, d.dh, scale, TE_EPI_STORE, st));
+        TE_TRY(te_util::attn_nn((flags & TE_FLAG_ATTN_TENSOR_CORES) != 0, d.B, d.H, d.N, d.NP, d.dh, a.qkv, 3 * d.D,
+                                a.qkv + d.D, 3 * d.D, a.P, nullptr, scale, TE_EPI_STORE, st));
         TE_TRY(te_launch_softmax(a.P, (long long)d.B * d.H * d.N, d.N, d.NP, st));
         // out = attn v -> 'b h n d -> b n (h d)'              (:147-148)
         TE_TRY(head_gemm(d, attn_map(a.P, d), TE_L_K, v, TE_L_MN, head_rows(a.ctx, d.D, d.N, d.dh), none, d.N, d.dh,
@@ -389,6 +390,7 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
         return TE_ERR_ARG;
     }
     const float* lbase = (flags & TE_FLAG_LINEAR_TENSOR_CORES) ? derived : nullptr;
+    const bool atc = (flags & TE_FLAG_ATTN_TENSOR_CORES) != 0;
 
     // ---- class index and seeds  (ViT_explanation_generator.py:28-35) ---------------------------
     TE_TRY(te_launch_argmax(ws.logits, index, d.B, d.C, /*only_negative=*/1, st));
@@ -423,8 +425,8 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
         TE_TRY(te_launch_layernorm_bwd(dxn, a.x_mid, bw.n2w, a.mean2, a.rstd2, dxa, dxb, d.M, d.D, st));
         // attention branch
         TE_TRY(te_util::linear_bwd_tc(lw.proj, dxb, bw.projw, dctx, nullptr, d.M, d.D, d.D, TE_EPI_STORE, st));
-        TE_TRY(head_gemm(d, head_rows(dctx, d.D, d.N, d.dh), TE_L_K, v, TE_L_K, attn_map(a.G, d), none, d.N, d.N, d.dh,
-                         1.f, TE_EPI_STORE, st));                                   // G = dctx v^T
+        TE_TRY(te_util::attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, dctx, d.D, a.qkv + 2 * d.D, 3 * d.D, a.G, nullptr, 1.f,
+                                TE_EPI_STORE, st));                                 // G = dctx v^T
         if (l == start_layer) break;                                                // lower gradients are never read
         TE_TRY(head_gemm(d, attn_map(a.P, d), TE_L_MN, head_rows(dctx, d.D, d.N, d.dh), TE_L_MN,
                          head_rows(dqkv + 2 * d.D, 3 * d.D, d.N, d.dh), none, d.N, d.dh, d.N, 1.f, TE_EPI_STORE, st));  // dV = P^T dctx
@@ -465,13 +467,14 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
         TE_TRY(te_zplus_linear_relprop(a.ctx, d.D, bw.projw, dw.proj, R2, R3, S, d.M, d.D, d.D, st));                    // proj
         // matmul2 rule: Z = attn v is the saved ctx itself (bit-identical recomputation in the reference)
         TE_TRY(te_launch_sd(R3, a.ctx, S, MD, st));
-        TE_TRY(head_gemm(d, head_rows(S, d.D, d.N, d.dh), TE_L_K, v, TE_L_K, attn_map(a.cam, d), attn_map(a.P, d), d.N,
-                         d.N, d.dh, 0.5f, TE_EPI_MUL, st));                         // attn_cam = (P * (S v^T)) / 2   :160-165
+        TE_TRY(te_util::attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, S, d.D, a.qkv + 2 * d.D, 3 * d.D, a.cam, a.P, 0.5f,
+                                TE_EPI_MUL, st));                                   // attn_cam = (P * (S v^T)) / 2   :160-165
         if (l == low && !(flags & TE_FLAG_RELPROP_TO_INPUT)) break;                                                        // nothing below is consumed
         TE_TRY(head_gemm(d, attn_map(a.P, d), TE_L_MN, head_rows(S, d.D, d.N, d.dh), TE_L_MN,
                          head_rows(Rqkv + 2 * d.D, 3 * d.D, d.N, d.dh), v, d.N, d.dh, d.N, 0.5f, TE_EPI_MUL, st));   // cam_v
         // matmul1 rule (unscaled Z = q k^T)  :170-173
-        TE_TRY(head_gemm(d, q, TE_L_K, k, TE_L_K, attn_map(S1, d), attn_map(a.cam, d), d.N, d.N, d.dh, 1.f, TE_EPI_SD, st));
+        TE_TRY(te_util::attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, a.qkv, 3 * d.D, a.qkv + d.D, 3 * d.D, S1, a.cam, 1.f,
+                                TE_EPI_SD, st));
         TE_TRY(head_gemm(d, attn_map(S1, d), TE_L_K, k, TE_L_MN, head_rows(Rqkv, 3 * d.D, d.N, d.dh), q, d.N, d.dh, d.N,
                          0.5f, TE_EPI_MUL, st));                                    // cam_q
         TE_TRY(head_gemm(d, attn_map(S1, d), TE_L_MN, q, TE_L_MN, head_rows(Rqkv + d.D, 3 * d.D, d.N, d.dh), k, d.N,
