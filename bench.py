@@ -205,14 +205,16 @@ def roofline_zplus(w, batch, flags, pk):
     wt = torch.randn(outf, inf, device="cuda", generator=g) * 0.02
     r = torch.rand(rows, outf, device="cuda", generator=g)
     tc = bool(flags & _lib.FLAG_ZPLUS_TENSOR_CORES)
+    bias = torch.randn(outf, device="cuda", generator=g) * 0.02
+    y = ops.linear_forward(x, wt, bias) if tc else None          # the engine hands the saved forward output to the rule
     for _ in range(2):
-        ops.linear_relprop(x, wt, r, tensor_cores=tc)
+        ops.linear_relprop(x, wt, r, tensor_cores=tc, y=y, bias=bias if tc else None)
     torch.cuda.synchronize()
     reps = 5
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        ops.linear_relprop(x, wt, r, tensor_cores=tc)
+        ops.linear_relprop(x, wt, r, tensor_cores=tc, y=y, bias=bias if tc else None)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
@@ -225,6 +227,11 @@ def roofline_zplus(w, batch, flags, pk):
     return {"kernel": "zplus_linear_relprop[%s] rows=%d in=%d out=%d" % ("tcgen05-tf32" if tc else "simt-fp32", rows, inf, outf),
             "bound": "tensor", "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s",
             "frac": round(achieved / peak, 4), "traffic": traffic, "ms_per_launch_group": round(ms, 3),
+            "algorithmic_flops": flops,
+            "executed_flops": (6.0 if tc else 8.0) * rows * inf * outf,
+            "note": ("algorithmic = 8*rows*in*out (SURVEY 8a); the tcgen05 path executes 6*rows*in*out: the denominator is "
+                     "formed in one pass from the saved forward output, ((y-b) + |x||W|^T)/2; each launch also derives "
+                     "the TF32 weight copies (prepare kernel, <1% of the time)") if tc else "fp32 SIMT reference path",
             "peak_source": pk["source"] + "; TF32 dense taken as bf16/2"}
 
 

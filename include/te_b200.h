@@ -162,9 +162,15 @@ TE_API int te_bert_tensor(const te_bert_config* cfg, int batch, int seq, void* w
  * that each rule can be parity-tested against the reference layer class it replaces.
  * ---------------------------------------------------------------------------------------------- */
 /* Linear.relprop, alpha=1 (layers_ours.py:207-230): x [rows,in], w [out,in], r [rows,out] -> out [rows,in].
- * scratch: rows*out floats; with TE_FLAG_ZPLUS_TENSOR_CORES: round_up(rows*out,64) + 8*in*out floats. */
+ * scratch: rows*out floats; with TE_FLAG_ZPLUS_TENSOR_CORES: round_up(rows*out,64) + 9*in*out floats. */
 TE_API int te_linear_relprop(const float* x, const float* w, const float* r, float* out, float* scratch, int rows,
                       int in_features, int out_features, unsigned flags, void* stream);
+/* Same rule with the Linear's saved forward output y = x W^T + bias [rows,out] supplied (what the engines do): with
+ * TE_FLAG_ZPLUS_TENSOR_CORES the denominator is then formed in ONE tensor-core pass through the exact identity
+ * x+ W+^T + x- W-^T == ((y - bias) + |x| |W|^T) / 2.  bias may be NULL (no bias).  scratch as above. */
+TE_API int te_linear_relprop_ex(const float* x, const float* w, const float* bias, const float* y, const float* r,
+                         float* out, float* scratch, int rows, int in_features, int out_features, unsigned flags,
+                         void* stream);
 /* Add.relprop (layers_ours.py:97-120) per sample: x1,x2,r [batch,per_sample] -> r1,r2.
  * scratch: batch*48 doubles. */
 TE_API int te_add_relprop(const float* x1, const float* x2, const float* r, float* r1, float* r2, void* scratch,
@@ -198,7 +204,7 @@ TE_API int te_compute_rollout_attention(const float* mats, int layers, int batch
                                  float* joint, void* workspace, long long workspace_bytes, void* stream);
 
 /* Plain Linear GEMMs — exported for kernel unit tests only.  flags & TE_FLAG_LINEAR_TENSOR_CORES selects the
- * tcgen05 3xTF32 path (scratch: 8*in*out floats for the derived weight copies; may be NULL otherwise). */
+ * tcgen05 3xTF32 path (scratch: 9*in*out floats for the derived weight copies; may be NULL otherwise). */
 TE_API int te_linear_forward(const float* x, const float* w, const float* bias, float* y, int rows, int in_features,
                       int out_features, void* stream);
 TE_API int te_linear_forward_ex(const float* x, const float* w, const float* bias, float* y, float* scratch, int rows,

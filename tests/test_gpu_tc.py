@@ -32,6 +32,11 @@ def test_tc_linear_relprop_matches_simt_and_oracle(rows, inf, outf):
     assert rel(tc, ref) < 2e-3, "tcgen05 path: rel err %g" % rel(tc, ref)
     # conservation of relevance survives the reduced-precision operands
     assert abs(tc.double().sum().item() - r.double().sum().item()) < 2e-3 * r.sum().item()
+    # single-pass variant fed with the saved forward output: Z = ((y - b) + |x||W|^T)/2 (what the engines run)
+    b = torch.randn(outf, generator=g)
+    y = ops.linear_forward(xd, wd, b.cuda())
+    tc1 = ops.linear_relprop(xd, wd, rd, tensor_cores=True, y=y, bias=b.cuda())
+    assert rel(tc1, ref) < 3e-3, "single-pass tcgen05 path: rel err %g" % rel(tc1, ref)
 
 
 def test_tc_engine_vit_base_vs_simt_and_oracle():

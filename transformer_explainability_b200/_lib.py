@@ -72,6 +72,7 @@ PROTOTYPES = {
     "te_bert_tensor": (c_int, [_BCFG, c_int, c_int, _P, c_char_p, c_int, ctypes.POINTER(_P), ctypes.POINTER(c_ll),
                                ctypes.POINTER(c_ll)]),
     "te_linear_relprop": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_uint, _P]),
+    "te_linear_relprop_ex": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_uint, _P]),
     "te_add_relprop": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_ll, _P]),
     "te_clone_relprop": (c_int, [_P, _P, _P, _P, _P, c_ll, _P]),
     "te_matmul_av_relprop": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),

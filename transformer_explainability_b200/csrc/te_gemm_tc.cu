@@ -38,12 +38,13 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;             // 48 KiB
 constexpr int NUM_THREADS = 192;
 constexpr int XF_THREADS = 128;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int MODE_S = 1, MODE_R = 2;
+constexpr int MODE_S = 1, MODE_R = 2, MODE_S1 = 3;   // MODE_S1: single-pass S kernel using the saved forward output
 
 struct TcParams {
     int M, N, K;                 // C[M,N] = sum over two passes of A[M,K] * B_pass[N,K]^T
-    const float* E; long long lde;   // MODE_S: R [M,N] ; MODE_R: x [M,N]
+    const float* E; long long lde;   // MODE_S / MODE_S1: R [M,N] ; MODE_R: x [M,N]
     float* C; long long ldc;
+    const float* Y; long long ldy; const float* bias;   // MODE_S1: forward output y = x W^T + bias
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -151,8 +152,8 @@ te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int kb = p.K / BK, iters = 2 * kb;
-    constexpr uint32_t TMEM_COLS = (MODE == MODE_S) ? 256u : 512u;
+    const int kb = p.K / BK, iters = (MODE == MODE_S1) ? kb : 2 * kb;
+    constexpr uint32_t TMEM_COLS = (MODE == MODE_R) ? 512u : 256u;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -198,14 +199,14 @@ te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             for (int it = 0; it < iters; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
-                mbar_wait(MODE == MODE_S ? xf_bar(s) : full_bar(s), ph);
+                mbar_wait(MODE != MODE_R ? xf_bar(s) : full_bar(s), ph);
                 tcgen05_fence_after();
                 const int pass = (it >= kb) ? 1 : 0;
                 const uint32_t sa = smem_base + s * STAGE_BYTES;
                 const uint64_t adesc = make_smem_desc(sa);
                 const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
                 const uint32_t d = tmem_base + ((MODE == MODE_R && pass) ? (uint32_t)BN : 0u);
-                const bool first = (MODE == MODE_S) ? (it == 0) : (it == 0 || it == kb);
+                const bool first = (MODE != MODE_R) ? (it == 0) : (it == 0 || it == kb);
 #pragma unroll
                 for (int k = 0; k < BK / 8; ++k) {
                     // advance 8 tf32 (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
@@ -219,7 +220,7 @@ te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     } else {
         // ================= tile transform (kernel 1) + epilogue: warps 2..5 =================
         const int et = threadIdx.x - 64;            // 0..127
-        if (MODE == MODE_S) {
+        if (MODE != MODE_R) {
             for (int it = 0; it < iters; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1u;
@@ -229,7 +230,8 @@ te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < A_BYTES / 16 / XF_THREADS; ++i) {
                     float4 v = a4[et + i * XF_THREADS];
-                    if (pass == 0) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    if (MODE == MODE_S1) { v.x = fabsf(v.x); v.y = fabsf(v.y); v.z = fabsf(v.z); v.w = fabsf(v.w); }
+                    else if (pass == 0) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                     else { v.x = fminf(v.x, 0.f); v.y = fminf(v.y, 0.f); v.z = fminf(v.z, 0.f); v.w = fminf(v.w, 0.f); }
                     v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
                     a4[et + i * XF_THREADS] = v;
@@ -250,17 +252,27 @@ te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int c = 0; c < BN / 32; ++c) {
             uint32_t acc[32];
             tmem_ld32(tlane + (uint32_t)(c * 32), acc);
-            if (MODE == MODE_S) {
+            if (MODE != MODE_R) {
                 tmem_ld_wait();
                 if (live) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 r = *reinterpret_cast<const float4*>(erow + c * 32 + j);
+                        float z[4] = {__uint_as_float(acc[j + 0]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
+                                      __uint_as_float(acc[j + 3])};
+                        if (MODE == MODE_S1) {
+                            // x+ W+^T + x- W-^T == ( x W^T + |x| |W|^T ) / 2 ,  x W^T = y - bias (saved forward output)
+                            const float4 y = *reinterpret_cast<const float4*>(p.Y + (long long)row * p.ldy + n0 + c * 32 + j);
+                            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c * 32 + j));
+                            z[0] = 0.5f * ((y.x - bb.x) + z[0]); z[1] = 0.5f * ((y.y - bb.y) + z[1]);
+                            z[2] = 0.5f * ((y.z - bb.z) + z[2]); z[3] = 0.5f * ((y.w - bb.w) + z[3]);
+                        }
                         float4 o;
-                        o.x = to_tf32(te_sd(r.x, __uint_as_float(acc[j + 0])));
-                        o.y = to_tf32(te_sd(r.y, __uint_as_float(acc[j + 1])));
-                        o.z = to_tf32(te_sd(r.z, __uint_as_float(acc[j + 2])));
-                        o.w = to_tf32(te_sd(r.w, __uint_as_float(acc[j + 3])));
+                        o.x = to_tf32(te_sd(r.x, z[0]));
+                        o.y = to_tf32(te_sd(r.y, z[1]));
+                        o.z = to_tf32(te_sd(r.z, z[2]));
+                        o.w = to_tf32(te_sd(r.w, z[3]));
                         *reinterpret_cast<float4*>(crow + c * 32 + j) = o;
                     }
                 }
@@ -294,10 +306,10 @@ te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // ---- weight preparation: W [out,in] -> W+ , W- (K-major for kernel 1) and W+^T , W-^T (K-major for kernel 2),
 //      all rounded to TF32 once (weights are frozen) -------------------------------------------------------
 __global__ void prepare_weights_kernel(const float* __restrict__ w, float* __restrict__ d, int out_f, int in_f) {
-    // d = [ W+ | W- | W+^T | W-^T | W_hi | W_lo | W^T_hi | W^T_lo ], each in*out floats
+    // d = [ W+ | W- | W+^T | W-^T | W_hi | W_lo | W^T_hi | W^T_lo | |W| ], each in*out floats
     const long long n = (long long)out_f * in_f;
     float *wp = d, *wn = d + n, *wpt = d + 2 * n, *wnt = d + 3 * n, *wh = d + 4 * n, *wl = d + 5 * n, *wth = d + 6 * n,
-          *wtl = d + 7 * n;
+          *wtl = d + 7 * n, *wa = d + 8 * n;
     __shared__ float tile[32][33];
     const int bx = blockIdx.x * 32, by = blockIdx.y * 32;      // bx: in index, by: out index
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -311,6 +323,7 @@ __global__ void prepare_weights_kernel(const float* __restrict__ w, float* __res
             const float hi = to_tf32(v);
             wh[idx] = hi;
             wl[idx] = to_tf32(v - hi);
+            wa[idx] = to_tf32(fabsf(v));
         }
         tile[i][threadIdx.x] = v;
     }
@@ -746,13 +759,14 @@ bool make_map(CUtensorMap* m, const float* base, long long rows, long long cols,
 
 template <int MODE>
 int launch(const float* A, long long lda, const float* B0, const float* B1, const float* E, long long lde, float* C,
-           long long ldc, long long M, int N, int K, cudaStream_t st) {
+           long long ldc, long long M, int N, int K, cudaStream_t st, const float* Y = nullptr, long long ldy = 0,
+           const float* bias = nullptr) {
     CUtensorMap tmA, tmB0, tmB1;
     if (!make_map(&tmA, A, M, K, lda, BM) || !make_map(&tmB0, B0, N, K, K, BN) || !make_map(&tmB1, B1, N, K, K, BN)) {
         te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed");
         return TE_ERR_CUDA;
     }
-    static bool attr_set[3] = {false, false, false};
+    static bool attr_set[4] = {false, false, false, false};
     if (!attr_set[MODE]) {
         if (cudaFuncSetAttribute(te_tc_zplus_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
             te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
@@ -761,7 +775,7 @@ int launch(const float* A, long long lda, const float* B0, const float* B1, cons
         attr_set[MODE] = true;
     }
     TcParams p;
-    p.M = (int)M; p.N = N; p.K = K; p.E = E; p.lde = lde; p.C = C; p.ldc = ldc;
+    p.M = (int)M; p.N = N; p.K = K; p.E = E; p.lde = lde; p.C = C; p.ldc = ldc; p.Y = Y; p.ldy = ldy; p.bias = bias;
     dim3 grid(N / BN, (unsigned)((M + BM - 1) / BM));
     te_tc_zplus_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB0, tmB1, p);
     TE_CUDA_CHECK_LAUNCH();
@@ -777,7 +791,7 @@ bool te_tc_zplus_supported(long long rows, int in_features, int out_features, lo
            get_encode() != nullptr;
 }
 
-long long te_tc_derived_floats(int in_features, int out_features) { return 8LL * in_features * out_features; }
+long long te_tc_derived_floats(int in_features, int out_features) { return 9LL * in_features * out_features; }
 
 int te_tc_prepare_weights(const float* w, float* derived, int in_features, int out_features, cudaStream_t st) {
     dim3 grid((in_features + 31) / 32, (out_features + 31) / 32), block(32, 8);
@@ -890,7 +904,8 @@ int te_tc_linear_bwd(const float* dy, const float* derived, int in_features, int
 }
 
 int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* derived, const float* r, long long ldr,
-                               float* out, float* s_scratch, long long rows, int in_features, int out_features, cudaStream_t st) {
+                               float* out, float* s_scratch, long long rows, int in_features, int out_features, cudaStream_t st,
+                               const float* y, long long ldy, const float* bias) {
     if (!a16(x) || !a16(derived) || !a16(r) || !a16(out) || !a16(s_scratch)) {
         te_set_last_error("te_gemm_tc: operands must be 16-byte aligned");
         return TE_ERR_ARG;
@@ -898,7 +913,14 @@ int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* deriv
     const long long n = (long long)in_features * out_features;
     const float *wp = derived, *wn = derived + n, *wpt = derived + 2 * n, *wnt = derived + 3 * n;
     // S = sd(R, x+ W+^T + x- W-^T)          A = x [rows, in] ; B = W+/- [out, in]
-    TE_TRY(launch<MODE_S>(x, ldx, wp, wn, r, ldr, s_scratch, out_features, rows, out_features, in_features, st));
+    if (y && a16(y) && ldy % 4 == 0 && (!bias || a16(bias))) {
+        // single pass: Z = ((y - bias) + |x| |W|^T) / 2 with the saved forward output y = x W^T + bias
+        const float* wabs = derived + 8 * n;
+        TE_TRY(launch<MODE_S1>(x, ldx, wabs, wabs, r, ldr, s_scratch, out_features, rows, out_features, in_features, st, y, ldy,
+                               bias));
+    } else {
+        TE_TRY(launch<MODE_S>(x, ldx, wp, wn, r, ldr, s_scratch, out_features, rows, out_features, in_features, st));
+    }
     // R_in = x+ (S W+) + x- (S W-)          A = S [rows, out] ; B = W+/-^T [in, out]
     TE_TRY(launch<MODE_R>(s_scratch, out_features, wpt, wnt, x, ldx, out, in_features, rows, in_features, out_features, st));
     return TE_OK;

@@ -11,6 +11,8 @@ int te_zplus_linear_relprop(const float* x, long long ldx, const float* w, const
                             float* out, float* s_scratch, long long rows, int in_features, int out_features,
                             cudaStream_t st);
 // same with an explicit row stride for r (a column slice of a packed [rows, 3*out] relevance tensor)
+// y / bias: the Linear's saved forward output and bias (optional; enables the single-pass tensor-core S kernel)
 int te_zplus_linear_relprop_ldr(const float* x, long long ldx, const float* w, const float* w_derived, const float* r,
                                 long long ldr, float* out, float* s_scratch, long long rows, int in_features,
-                                int out_features, cudaStream_t st);
+                                int out_features, cudaStream_t st, const float* y = nullptr, long long ldy = 0,
+                                const float* bias = nullptr);
