@@ -179,50 +179,15 @@ static void carve(const Dims& d, char* base, Workspace& ws) {
     ws.bytes = off;
 }
 
-// ---- GEMM parameter helpers --------------------------------------------------------------------
-static TeGemm gemm0() {
-    TeGemm p;
-    memset(&p, 0, sizeof(p));
-    p.nb1 = 1; p.nb2 = 1; p.alpha = 1.f;
-    return p;
-}
-
-// y[M,out] = x[M,in] * W[out,in]^T  (+ epilogue)
-static int linear_fwd(const float* x, int lda, const float* w, const float* bias, float* y, float* y2,
-                      const float* e0, long long M, int in, int out, int epi, cudaStream_t st) {
-    TeGemm p = gemm0();
-    p.A = x; p.lda = lda; p.B = w; p.ldb = in; p.C = y; p.ldc = out; p.C2 = y2; p.ldc2 = out; p.E0 = e0; p.lde0 = out;
-    p.bias = bias; p.M = (int)M; p.N = out; p.K = in;
-    return te_gemm_launch(p, TE_L_K, TE_L_K, TE_XF_NONE, epi, st);
-}
-// dx[M,in] = dy[M,out] * W[out,in]
-static int linear_bwd(const float* dy, const float* w, float* dx, const float* e0, long long M, int in, int out,
-                      int epi, cudaStream_t st) {
-    TeGemm p = gemm0();
-    p.A = dy; p.lda = out; p.B = w; p.ldb = in; p.C = dx; p.ldc = in; p.E0 = e0; p.lde0 = in;
-    p.M = (int)M; p.N = in; p.K = out;
-    return te_gemm_launch(p, TE_L_K, TE_L_MN, TE_XF_NONE, epi, st);
-}
-
-// head-batched attention-shaped GEMM over the packed activations
-struct HeadOp {
-    const float* ptr; int ld; long long s1, s2;
-};
-static HeadOp head_rows(const float* base, int ld, int N, int dh) {      // [b, n, (h d)] slice, rows = tokens
-    return {base, ld, (long long)N * ld, (long long)dh};
-}
-static HeadOp attn_map(const float* base, const Dims& d) {               // [b, h, n, NP]
-    return {base, d.NP, (long long)d.H * d.N * d.NP, (long long)d.N * d.NP};
-}
+// ---- GEMM parameter helpers (shared builders live in te_engine_util.h) ----------------------------
+using te_util::HeadOp;
+using te_util::head_rows;
+using te_util::linear_bwd;
+using te_util::linear_fwd;
+static HeadOp attn_map(const float* base, const Dims& d) { return te_util::attn_map(base, d.H, d.N, d.NP); }
 static int head_gemm(const Dims& d, HeadOp A, int alay, HeadOp B, int blay, HeadOp C, HeadOp E, int M, int N, int K,
                      float alpha, int epi, cudaStream_t st) {
-    TeGemm p = gemm0();
-    p.A = A.ptr; p.lda = A.ld; p.sA1 = A.s1; p.sA2 = A.s2;
-    p.B = B.ptr; p.ldb = B.ld; p.sB1 = B.s1; p.sB2 = B.s2;
-    p.C = const_cast<float*>(C.ptr); p.ldc = C.ld; p.sC1 = C.s1; p.sC2 = C.s2;
-    p.E0 = E.ptr; p.lde0 = E.ld; p.sE1 = E.s1; p.sE2 = E.s2;
-    p.M = M; p.N = N; p.K = K; p.nb1 = d.B; p.nb2 = d.H; p.alpha = alpha;
-    return te_gemm_launch(p, alay, blay, TE_XF_NONE, epi, st);
+    return te_util::head_gemm(d.B, d.H, A, alay, B, blay, C, E, M, N, K, alpha, epi, st);
 }
 
 static int check_ws(const te_vit_config* cfg, int batch, void* workspace, long long bytes, Dims& d, Workspace& ws) {
