@@ -151,3 +151,24 @@ def test_tc_attention_contractions_engine():
     for s in range(2):
         r, _ = ovit.explain(p64, xs[s:s + 1].double(), heads)
         check_parity(fast[s * trials:(s + 1) * trials], r[0], "sample %d all-fast" % s)
+
+
+@pytest.mark.parametrize("rows,inf,outf", [(394, 768, 3072), (1000, 3072, 768), (128, 256, 256)])
+def test_tc_bf16_second_contraction(rows, inf, outf):
+    """TE_FLAG_ZPLUS_BF16: S stored as bf16 and R_in = x+ (S W+) + x- (S W-) on tcgen05 kind::f16 with bf16 operands
+    (8-bit mantissa, fp32 accumulate).  Stated tolerance 1.5e-2 of the tensor maximum; relevance is conserved to 1e-2."""
+    from transformer_explainability_b200 import ops
+    g = torch.Generator().manual_seed(rows + 7)
+    x = torch.randn(rows, inf, generator=g)
+    w = torch.randn(outf, inf, generator=g) * 0.05
+    b = torch.randn(outf, generator=g)
+    r = torch.rand(rows, outf, generator=g)
+    xd, wd, rd, bd = x.cuda(), w.cuda(), r.cuda(), b.cuda()
+    y = ops.linear_forward(xd, wd, bd)
+    out = ops.linear_relprop(xd, wd, rd, tensor_cores=True, y=y, bias=bd, bf16=True)
+    torch.cuda.synchronize()
+    ref = rules.linear_relprop(x.double(), w.double(), r.double())
+    e = rel(out, ref)
+    print("bf16 R kernel rows %d in %d out %d: rel %.2e" % (rows, inf, outf, e))
+    assert e < 1.5e-2
+    assert abs(out.double().sum().item() - r.double().sum().item()) < 1e-2 * r.sum().item()

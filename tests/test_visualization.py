@@ -1,0 +1,41 @@
+"""generate_visualization (example.ipynb:55-66) pieces: 14x14 -> bilinear x16 -> per-sample min-max."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from transformer_explainability_b200.visualization import relevance_to_heatmap
+
+
+def _notebook_reference(row):
+    """The notebook's own sequence for one explanation (example.ipynb:57-60)."""
+    t = row.reshape(1, 1, 14, 14)
+    t = F.interpolate(t, scale_factor=16, mode='bilinear')
+    t = t.reshape(224, 224)
+    return (t - t.min()) / (t.max() - t.min())
+
+
+def test_heatmap_matches_notebook_sequence_per_sample():
+    g = torch.Generator().manual_seed(0)
+    maps = torch.rand(5, 196, generator=g) * 1e-4
+    heat = relevance_to_heatmap(maps)
+    assert heat.shape == (5, 224, 224)
+    for s in range(5):
+        assert torch.equal(heat[s], _notebook_reference(maps[s]))
+    assert float(heat.min()) == 0.0 and float(heat.max()) == 1.0
+
+
+@pytest.mark.gpu
+def test_generate_visualization_end_to_end_gpu():
+    cv2 = pytest.importorskip("cv2")
+    from oracle import vit as ovit
+    from transformer_explainability_b200.baselines.ViT.ViT_LRP import VisionTransformer
+    from transformer_explainability_b200.baselines.ViT.ViT_explanation_generator import LRP
+    from transformer_explainability_b200.visualization import generate_visualization
+    params, heads = ovit.init_params("vit_base_patch16_224", seed=0)
+    m = VisionTransformer(patch_size=16, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4, qkv_bias=True)
+    m.load_state_dict(params)
+    m = m.cuda().eval()
+    img = torch.rand(3, 224, 224, generator=torch.Generator().manual_seed(1))
+    vis = generate_visualization(LRP(m), img)
+    assert vis.shape == (224, 224, 3) and vis.dtype == np.uint8

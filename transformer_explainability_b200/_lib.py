@@ -33,6 +33,7 @@ FLAG_KEEP_ALL_CAMS = 4
 FLAG_RELPROP_TO_INPUT = 8
 FLAG_LINEAR_TENSOR_CORES = 16
 FLAG_ATTN_TENSOR_CORES = 32
+FLAG_ZPLUS_BF16 = 64
 FLAG_TENSOR_CORES = FLAG_ZPLUS_TENSOR_CORES | FLAG_LINEAR_TENSOR_CORES      # the ones that need derived weights
 FLAG_ALL_FAST = FLAG_TENSOR_CORES | FLAG_ATTN_TENSOR_CORES | FLAG_ROLLOUT_FUSED
 

@@ -67,7 +67,7 @@ extern "C" int te_linear_relprop(const float* x, const float* w, const float* r,
     REQ(x && w && r && out && scratch && rows > 0 && in_features > 0 && out_features > 0, "te_linear_relprop: bad argument");
     const float* derived = nullptr;
     if ((flags & TE_FLAG_ZPLUS_TENSOR_CORES) && te_tc_zplus_supported(rows, in_features, out_features, in_features)) {
-        // scratch layout with the flag: [rows*out S | 9*in*out derived weight copies]
+        // scratch layout with the flag: [rows*out S | 10*in*out derived weight copies]
         float* d = scratch + (((long long)rows * out_features + 63) & ~63LL);
         TE_TRY(te_tc_prepare_weights(w, d, in_features, out_features, ST(stream)));
         derived = d;
@@ -87,7 +87,7 @@ extern "C" int te_linear_relprop_ex(const float* x, const float* w, const float*
         derived = d;
     }
     return te_zplus_linear_relprop_ldr(x, in_features, w, derived, r, out_features, out, scratch, rows, in_features,
-                                       out_features, ST(stream), y, out_features, bias);
+                                       out_features, ST(stream), y, out_features, bias, (flags & TE_FLAG_ZPLUS_BF16) != 0);
 }
 
 extern "C" int te_add_relprop(const float* x1, const float* x2, const float* r, float* r1, float* r2, void* scratch,

@@ -324,6 +324,7 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
     }
     const float* lbase = (flags & TE_FLAG_LINEAR_TENSOR_CORES) ? derived : nullptr;
     const bool atc = (flags & TE_FLAG_ATTN_TENSOR_CORES) != 0;
+    const bool zb = (flags & TE_FLAG_ZPLUS_BF16) != 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     Weights w;
     bind_weights(cfg, weights, w);
@@ -394,12 +395,12 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
         const HeadOp v = head_rows(a.qkv + 2 * d.D, 3 * d.D, d.N, d.dh);
         // BertOutput.relprop :474-487 ; BertIntermediate.relprop :451-456 ; BertLayer.clone
         TE_TRY(te_launch_add_relprop(a.d2, a.ao, R, R1, R2, ws.addpart, d.B, (long long)d.N * d.D, st));
-        TE_TRY(te_zplus_linear_relprop_ldr(a.g, d.F, lw.w2, dw.w2, R1, d.D, RF, S, d.M, d.F, d.D, st, a.d2, d.D, lw.b2));
-        TE_TRY(te_zplus_linear_relprop_ldr(a.ao, d.D, lw.w1, dw.w1, RF, d.F, R1, SF, d.M, d.D, d.F, st, a.hpre, d.F, lw.b1));
+        TE_TRY(te_zplus_linear_relprop_ldr(a.g, d.F, lw.w2, dw.w2, R1, d.D, RF, S, d.M, d.F, d.D, st, a.d2, d.D, lw.b2, zb));
+        TE_TRY(te_zplus_linear_relprop_ldr(a.ao, d.D, lw.w1, dw.w1, RF, d.F, R1, SF, d.M, d.D, d.F, st, a.hpre, d.F, lw.b1, zb));
         TE_TRY(te_launch_clone_relprop(a.ao, R1, R2, nullptr, R, MD, st));
         // BertSelfOutput.relprop :427-434
         TE_TRY(te_launch_add_relprop(a.d1, a.h, R, R1, R2, ws.addpart, d.B, (long long)d.N * d.D, st));
-        TE_TRY(te_zplus_linear_relprop_ldr(a.ctx, d.D, lw.ow, dw.o, R1, d.D, R3, S, d.M, d.D, d.D, st, a.d1, d.D, lw.ob));
+        TE_TRY(te_zplus_linear_relprop_ldr(a.ctx, d.D, lw.ow, dw.o, R1, d.D, R3, S, d.M, d.D, d.D, st, a.d1, d.D, lw.ob, zb));
         // BertSelfAttention.relprop :367-409
         TE_TRY(te_launch_sd(R3, a.ctx, S, MD, st));                                       // matmul2: Z == saved ctx
         TE_TRY(attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, S, d.D, a.qkv + 2 * d.D, 3 * d.D, a.cam, a.P, 0.5f, TE_EPI_MUL,
@@ -419,11 +420,11 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
         TE_TRY(head_gemm(d.B, d.H, amap(ws.tA[0]), TE_L_MN, q, TE_L_MN, head_rows(Rqkv + d.D, 3 * d.D, d.N, d.dh), k, d.N,
                          d.dh, d.N, 0.5f, TE_EPI_MUL, st));
         // query / key / value z+ rules (separate Linears), Clone(3), Clone(2)
-        TE_TRY(te_zplus_linear_relprop_ldr(a.h, d.D, lw.qkvw, dw.q, Rqkv, 3 * d.D, R, S, d.M, d.D, d.D, st, a.qkv, 3 * d.D, lw.qkvb));
+        TE_TRY(te_zplus_linear_relprop_ldr(a.h, d.D, lw.qkvw, dw.q, Rqkv, 3 * d.D, R, S, d.M, d.D, d.D, st, a.qkv, 3 * d.D, lw.qkvb, zb));
         TE_TRY(te_zplus_linear_relprop_ldr(a.h, d.D, lw.qkvw + DD, dw.k, Rqkv + d.D, 3 * d.D, R1, S, d.M, d.D, d.D, st, a.qkv + d.D, 3 * d.D,
-                                           lw.qkvb + d.D));
+                                           lw.qkvb + d.D, zb));
         TE_TRY(te_zplus_linear_relprop_ldr(a.h, d.D, lw.qkvw + 2 * DD, dw.v, Rqkv + 2 * d.D, 3 * d.D, R3, S, d.M, d.D, d.D, st,
-                                           a.qkv + 2 * d.D, 3 * d.D, lw.qkvb + 2 * d.D));
+                                           a.qkv + 2 * d.D, 3 * d.D, lw.qkvb + 2 * d.D, zb));
         TE_TRY(te_launch_clone_relprop(a.h, R, R1, R3, SF, MD, st));                      // self.clone (3-way)
         TE_TRY(te_launch_clone_relprop(a.h, SF, R2, nullptr, R, MD, st));                 // attention.clone
     }

@@ -23,6 +23,7 @@
 // from the fp32 reference's own noise.  Everything that feeds an ill-conditioned denominator stays on
 // the fp32 SIMT path.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <string.h>
 
@@ -45,6 +46,7 @@ struct TcParams {
     const float* E; long long lde;   // MODE_S / MODE_S1: R [M,N] ; MODE_R: x [M,N]
     float* C; long long ldc;
     const float* Y; long long ldy; const float* bias;   // MODE_S1: forward output y = x W^T + bias
+    int out_bf16;                                        // MODE_S / MODE_S1: write S as bf16 (C is then a bf16 [M, ldc] buffer)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -87,6 +89,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
@@ -135,11 +147,16 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format TF32 [7,10)/[10,13)=2,
 // a/b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// same with BF16 operands (a/b format = 1), kind::f16: K = 16 elements (32 bytes) per MMA, 64 elements per 128-byte row
+constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-template <int MODE>
+// BF (MODE_R only): A (= S, written as bf16 by the S kernel) and B (bf16 weight copies) are 2-byte operands:
+// one 128-byte swizzle row holds 64 elements, tcgen05.mma.kind::f16, half the shared-memory traffic per flop.
+template <int MODE, bool BF = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                    const __grid_constant__ CUtensorMap tmB1, const TcParams p) {
+    constexpr int KELEMS = BF ? 64 : 32;              // elements per k-block (one 128-byte row)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -152,7 +169,7 @@ te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int kb = p.K / BK, iters = (MODE == MODE_S1) ? kb : 2 * kb;
+    const int kb = p.K / KELEMS, iters = (MODE == MODE_S1) ? kb : 2 * kb;
     constexpr uint32_t TMEM_COLS = (MODE == MODE_R) ? 512u : 256u;
 
     if (warp == 0 && lane == 0) {
@@ -187,7 +204,7 @@ te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 mbar_wait(empty_bar(s), ph ^ 1u);
                 mbar_arrive_expect_tx(full_bar(s), STAGE_BYTES);
                 const int pass = (it >= kb) ? 1 : 0;
-                const int k0 = (it - pass * kb) * BK;
+                const int k0 = (it - pass * kb) * KELEMS;
                 const uint32_t sa = smem_base + s * STAGE_BYTES;
                 tma_load_2d(sa, &tmA, full_bar(s), k0, m0);
                 tma_load_2d(sa + A_BYTES, pass ? &tmB1 : &tmB0, full_bar(s), k0, n0);
@@ -210,7 +227,8 @@ te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
                 for (int k = 0; k < BK / 8; ++k) {
                     // advance 8 tf32 (32 bytes) along K inside the 128-byte swizzle row: +2 in 16-byte units
-                    umma_tf32(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc, (first && k == 0) ? 0u : 1u);
+                    if (BF) umma_bf16(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdescBf16, (first && k == 0) ? 0u : 1u);
+                    else umma_tf32(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc, (first && k == 0) ? 0u : 1u);
                 }
                 umma_commit(empty_bar(s));          // frees the smem stage when these MMAs retire
             }
@@ -268,12 +286,22 @@ te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             z[0] = 0.5f * ((y.x - bb.x) + z[0]); z[1] = 0.5f * ((y.y - bb.y) + z[1]);
                             z[2] = 0.5f * ((y.z - bb.z) + z[2]); z[3] = 0.5f * ((y.w - bb.w) + z[3]);
                         }
-                        float4 o;
-                        o.x = to_tf32(te_sd(r.x, z[0]));
-                        o.y = to_tf32(te_sd(r.y, z[1]));
-                        o.z = to_tf32(te_sd(r.z, z[2]));
-                        o.w = to_tf32(te_sd(r.w, z[3]));
-                        *reinterpret_cast<float4*>(crow + c * 32 + j) = o;
+                        if (p.out_bf16) {
+                            __nv_bfloat162 lo = __floats2bfloat162_rn(te_sd(r.x, z[0]), te_sd(r.y, z[1]));
+                            __nv_bfloat162 hi = __floats2bfloat162_rn(te_sd(r.z, z[2]), te_sd(r.w, z[3]));
+                            uint2 pk;
+                            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                            __nv_bfloat16* cb = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + n0 + c * 32 + j;
+                            *reinterpret_cast<uint2*>(cb) = pk;
+                        } else {
+                            float4 o;
+                            o.x = to_tf32(te_sd(r.x, z[0]));
+                            o.y = to_tf32(te_sd(r.y, z[1]));
+                            o.z = to_tf32(te_sd(r.z, z[2]));
+                            o.w = to_tf32(te_sd(r.w, z[3]));
+                            *reinterpret_cast<float4*>(crow + c * 32 + j) = o;
+                        }
                     }
                 }
             } else {
@@ -306,7 +334,8 @@ te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // ---- weight preparation: W [out,in] -> W+ , W- (K-major for kernel 1) and W+^T , W-^T (K-major for kernel 2),
 //      all rounded to TF32 once (weights are frozen) -------------------------------------------------------
 __global__ void prepare_weights_kernel(const float* __restrict__ w, float* __restrict__ d, int out_f, int in_f) {
-    // d = [ W+ | W- | W+^T | W-^T | W_hi | W_lo | W^T_hi | W^T_lo | |W| ], each in*out floats
+    // d = [ W+ | W- | W+^T | W-^T | W_hi | W_lo | W^T_hi | W^T_lo | |W| ] (fp32, in*out floats each)
+    //     [ bf16(W+^T) | bf16(W-^T) ]  (2-byte elements: in*out/2 floats each)
     const long long n = (long long)out_f * in_f;
     float *wp = d, *wn = d + n, *wpt = d + 2 * n, *wnt = d + 3 * n, *wh = d + 4 * n, *wl = d + 5 * n, *wth = d + 6 * n,
           *wtl = d + 7 * n, *wa = d + 8 * n;
@@ -335,6 +364,9 @@ __global__ void prepare_weights_kernel(const float* __restrict__ w, float* __res
             const long long idx = (long long)c * out_f + o;
             wpt[idx] = to_tf32(fmaxf(v, 0.f));
             wnt[idx] = to_tf32(fminf(v, 0.f));
+            __nv_bfloat16* bp = reinterpret_cast<__nv_bfloat16*>(d + 9 * n);
+            bp[idx] = __float2bfloat16_rn(fmaxf(v, 0.f));
+            bp[n + idx] = __float2bfloat16_rn(fminf(v, 0.f));
             const float hi = to_tf32(v);
             wth[idx] = hi;
             wtl[idx] = to_tf32(v - hi);
@@ -744,23 +776,27 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// fp32 row-major [rows, cols] with row stride ld (floats); box = [box_rows, 32 floats], 128-byte swizzle
-bool make_map(CUtensorMap* m, const float* base, long long rows, long long cols, long long ld, int box_rows) {
+// row-major [rows, cols] with row stride ld (elements); box = [box_rows, one 128-byte row], 128-byte swizzle
+bool make_map_t(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_rows, bool bf16) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
+    const int esz = bf16 ? 2 : 4;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
+               strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+bool make_map(CUtensorMap* m, const float* base, long long rows, long long cols, long long ld, int box_rows) {
+    return make_map_t(m, base, rows, cols, ld, box_rows, false);
 }
 
 template <int MODE>
 int launch(const float* A, long long lda, const float* B0, const float* B1, const float* E, long long lde, float* C,
            long long ldc, long long M, int N, int K, cudaStream_t st, const float* Y = nullptr, long long ldy = 0,
-           const float* bias = nullptr) {
+           const float* bias = nullptr, int out_bf16 = 0) {
     CUtensorMap tmA, tmB0, tmB1;
     if (!make_map(&tmA, A, M, K, lda, BM) || !make_map(&tmB0, B0, N, K, K, BN) || !make_map(&tmB1, B1, N, K, K, BN)) {
         te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed");
@@ -776,8 +812,35 @@ int launch(const float* A, long long lda, const float* B0, const float* B1, cons
     }
     TcParams p;
     p.M = (int)M; p.N = N; p.K = K; p.E = E; p.lde = lde; p.C = C; p.ldc = ldc; p.Y = Y; p.ldy = ldy; p.bias = bias;
+    p.out_bf16 = out_bf16;
     dim3 grid(N / BN, (unsigned)((M + BM - 1) / BM));
     te_tc_zplus_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB0, tmB1, p);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+
+// R kernel with bf16 operands: A = S (bf16 [M, K], row stride K), B0/B1 = bf16 [N, K]
+int launch_r_bf16(const void* A, const void* B0, const void* B1, const float* E, long long lde, float* C, long long ldc,
+                  long long M, int N, int K, cudaStream_t st) {
+    CUtensorMap tmA, tmB0, tmB1;
+    if (!make_map_t(&tmA, A, M, K, K, BM, true) || !make_map_t(&tmB0, B0, N, K, K, BN, true) ||
+        !make_map_t(&tmB1, B1, N, K, K, BN, true)) {
+        te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed (bf16)");
+        return TE_ERR_CUDA;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(te_tc_zplus_kernel<MODE_R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+            te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
+            return TE_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = (int)M; p.N = N; p.K = K; p.E = E; p.lde = lde; p.C = C; p.ldc = ldc;
+    dim3 grid(N / BN, (unsigned)((M + BM - 1) / BM));
+    te_tc_zplus_kernel<MODE_R, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB0, tmB1, p);
     TE_CUDA_CHECK_LAUNCH();
     return TE_OK;
 }
@@ -791,7 +854,7 @@ bool te_tc_zplus_supported(long long rows, int in_features, int out_features, lo
            get_encode() != nullptr;
 }
 
-long long te_tc_derived_floats(int in_features, int out_features) { return 9LL * in_features * out_features; }
+long long te_tc_derived_floats(int in_features, int out_features) { return 10LL * in_features * out_features; }
 
 int te_tc_prepare_weights(const float* w, float* derived, int in_features, int out_features, cudaStream_t st) {
     dim3 grid((in_features + 31) / 32, (out_features + 31) / 32), block(32, 8);
@@ -905,7 +968,7 @@ int te_tc_linear_bwd(const float* dy, const float* derived, int in_features, int
 
 int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* derived, const float* r, long long ldr,
                                float* out, float* s_scratch, long long rows, int in_features, int out_features, cudaStream_t st,
-                               const float* y, long long ldy, const float* bias) {
+                               const float* y, long long ldy, const float* bias, bool bf16) {
     if (!a16(x) || !a16(derived) || !a16(r) || !a16(out) || !a16(s_scratch)) {
         te_set_last_error("te_gemm_tc: operands must be 16-byte aligned");
         return TE_ERR_ARG;
@@ -913,13 +976,19 @@ int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* deriv
     const long long n = (long long)in_features * out_features;
     const float *wp = derived, *wn = derived + n, *wpt = derived + 2 * n, *wnt = derived + 3 * n;
     // S = sd(R, x+ W+^T + x- W-^T)          A = x [rows, in] ; B = W+/- [out, in]
+    const bool rb = bf16 && (out_features % 64 == 0);          // S as bf16, R kernel with bf16 operands (kind::f16)
     if (y && a16(y) && ldy % 4 == 0 && (!bias || a16(bias))) {
         // single pass: Z = ((y - bias) + |x| |W|^T) / 2 with the saved forward output y = x W^T + bias
         const float* wabs = derived + 8 * n;
         TE_TRY(launch<MODE_S1>(x, ldx, wabs, wabs, r, ldr, s_scratch, out_features, rows, out_features, in_features, st, y, ldy,
-                               bias));
+                               bias, rb ? 1 : 0));
     } else {
-        TE_TRY(launch<MODE_S>(x, ldx, wp, wn, r, ldr, s_scratch, out_features, rows, out_features, in_features, st));
+        TE_TRY(launch<MODE_S>(x, ldx, wp, wn, r, ldr, s_scratch, out_features, rows, out_features, in_features, st, nullptr, 0,
+                              nullptr, rb ? 1 : 0));
+    }
+    if (rb) {
+        const __nv_bfloat16* wb = reinterpret_cast<const __nv_bfloat16*>(derived + 9 * n);
+        return launch_r_bf16(s_scratch, wb, wb + n, x, ldx, out, in_features, rows, in_features, out_features, st);
     }
     // R_in = x+ (S W+) + x- (S W-)          A = S [rows, out] ; B = W+/-^T [in, out]
     TE_TRY(launch<MODE_R>(s_scratch, out_features, wpt, wnt, x, ldx, out, in_features, rows, in_features, out_features, st));

@@ -9,7 +9,8 @@ bool te_tc_zplus_supported(long long rows, int in_features, int out_features, lo
 //   [ W_hi | W_lo | W^T_hi | W^T_lo ] error-compensated split (x_hi = tf32(x), x_lo = tf32(x - x_hi)) for the
 //                                     fp32-grade 3xTF32 forward / backward Linear GEMMs
 //   [ |W| ]                          operand of the single-pass S kernel
-// = 9*in*out floats
+//   [ bf16(W+^T) | bf16(W-^T) ]      2-byte operands of the bf16 R kernel (kind::f16)
+// = 10*in*out floats
 long long te_tc_derived_floats(int in_features, int out_features);
 int te_tc_prepare_weights(const float* w, float* derived, int in_features, int out_features, cudaStream_t st);
 // y / bias (optional): the Linear's saved forward output y = x W^T + bias [rows, out] (row stride ldy).  When given,
@@ -17,7 +18,7 @@ int te_tc_prepare_weights(const float* w, float* derived, int in_features, int o
 int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* derived, const float* r, long long ldr,
                                float* out,
                                float* s_scratch, long long rows, int in_features, int out_features, cudaStream_t st,
-                               const float* y = nullptr, long long ldy = 0, const float* bias = nullptr);
+                               const float* y = nullptr, long long ldy = 0, const float* bias = nullptr, bool bf16 = false);
 
 // fp32-grade (3xTF32 split) Linear GEMMs on tcgen05; epilogues mirror the SIMT ones
 enum { TE_TC_EPI_STORE = 0, TE_TC_EPI_BIAS = 1, TE_TC_EPI_BIAS_GELU = 2, TE_TC_EPI_BIAS_ADD = 3, TE_TC_EPI_GELU_BWD = 4 };

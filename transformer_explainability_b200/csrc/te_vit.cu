@@ -356,6 +356,7 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
     }
     const float* lbase = (flags & TE_FLAG_LINEAR_TENSOR_CORES) ? derived : nullptr;
     const bool atc = (flags & TE_FLAG_ATTN_TENSOR_CORES) != 0;
+    const bool zb = (flags & TE_FLAG_ZPLUS_BF16) != 0;
 
     // ---- class index and seeds  (ViT_explanation_generator.py:28-35) ---------------------------
     TE_TRY(te_launch_argmax(ws.logits, index, d.B, d.C, /*only_negative=*/1, st));
@@ -424,12 +425,12 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
         const HeadOp v = head_rows(a.qkv + 2 * d.D, 3 * d.D, d.N, d.dh);
         // Block.relprop :203-213
         TE_TRY(te_launch_add_relprop(a.x_mid, a.mlp_out, R, R1, R2, ws.addpart, d.B, (long long)d.N * d.D, st));   // add2
-        TE_TRY(te_zplus_linear_relprop_ldr(a.g, d.F, bw.fc2w, dw.fc2, R2, d.D, RF, S, d.M, d.F, d.D, st, a.mlp_out, d.D, bw.fc2b));                       // fc2 ; GELU id
-        TE_TRY(te_zplus_linear_relprop_ldr(a.xn2, d.D, bw.fc1w, dw.fc1, RF, d.F, R2, SF, d.M, d.D, d.F, st, a.h, d.F, bw.fc1b));                    // fc1 ; norm2 id
+        TE_TRY(te_zplus_linear_relprop_ldr(a.g, d.F, bw.fc2w, dw.fc2, R2, d.D, RF, S, d.M, d.F, d.D, st, a.mlp_out, d.D, bw.fc2b, zb));                       // fc2 ; GELU id
+        TE_TRY(te_zplus_linear_relprop_ldr(a.xn2, d.D, bw.fc1w, dw.fc1, RF, d.F, R2, SF, d.M, d.D, d.F, st, a.h, d.F, bw.fc1b, zb));                    // fc1 ; norm2 id
         TE_TRY(te_launch_clone_relprop(a.x_mid, R1, R2, nullptr, R, MD, st));                                      // clone2
         TE_TRY(te_launch_add_relprop(a.x_in, a.attn_out, R, R1, R2, ws.addpart, d.B, (long long)d.N * d.D, st));    // add1
         // Attention.relprop :154-177
-        TE_TRY(te_zplus_linear_relprop_ldr(a.ctx, d.D, bw.projw, dw.proj, R2, d.D, R3, S, d.M, d.D, d.D, st, a.attn_out, d.D, bw.projb));                    // proj
+        TE_TRY(te_zplus_linear_relprop_ldr(a.ctx, d.D, bw.projw, dw.proj, R2, d.D, R3, S, d.M, d.D, d.D, st, a.attn_out, d.D, bw.projb, zb));                    // proj
         // matmul2 rule: Z = attn v is the saved ctx itself (bit-identical recomputation in the reference)
         TE_TRY(te_launch_sd(R3, a.ctx, S, MD, st));
         TE_TRY(te_util::attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, S, d.D, a.qkv + 2 * d.D, 3 * d.D, a.cam, a.P, 0.5f,
@@ -444,7 +445,7 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
                          0.5f, TE_EPI_MUL, st));                                    // cam_q
         TE_TRY(head_gemm(d, attn_map(S1, d), TE_L_MN, q, TE_L_MN, head_rows(Rqkv + d.D, 3 * d.D, d.N, d.dh), k, d.N,
                          d.dh, d.N, 0.5f, TE_EPI_MUL, st));                         // cam_k
-        TE_TRY(te_zplus_linear_relprop_ldr(a.xn1, d.D, bw.qkvw, dw.qkv, Rqkv, 3 * d.D, R2, S, d.M, d.D, 3 * d.D, st, a.qkv, 3 * d.D, bw.qkvb));               // qkv ; norm1 id
+        TE_TRY(te_zplus_linear_relprop_ldr(a.xn1, d.D, bw.qkvw, dw.qkv, Rqkv, 3 * d.D, R2, S, d.M, d.D, 3 * d.D, st, a.qkv, 3 * d.D, bw.qkvb, zb));               // qkv ; norm1 id
         TE_TRY(te_launch_clone_relprop(a.x_in, R1, R2, nullptr, R, MD, st));                                       // clone1
     }
 

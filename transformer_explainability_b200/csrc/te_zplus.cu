@@ -13,12 +13,12 @@ int te_zplus_linear_relprop(const float* x, long long ldx, const float* w, const
 
 int te_zplus_linear_relprop_ldr(const float* x, long long ldx, const float* w, const float* w_derived, const float* r,
                                 long long ldr, float* out, float* s_scratch, long long rows, int in_features,
-                                int out_features, cudaStream_t st, const float* y, long long ldy, const float* bias) {
+                                int out_features, cudaStream_t st, const float* y, long long ldy, const float* bias, bool bf16) {
     if (rows <= 0) return TE_OK;
     if (rows > 0x7fffffffLL || ldx > 0x7fffffffLL) { te_set_last_error("zplus: rows/ldx overflow int"); return TE_ERR_ARG; }
     if (w_derived && ldr % 4 == 0 && te_tc_zplus_supported(rows, in_features, out_features, ldx))
         return te_tc_zplus_linear_relprop(x, ldx, w_derived, r, ldr, out, s_scratch, rows, in_features, out_features, st, y, ldy,
-                                          bias);
+                                          bias, bf16);
     TeGemm p;
     memset(&p, 0, sizeof(p));
     p.nb1 = p.nb2 = 1; p.alpha = 1.f;

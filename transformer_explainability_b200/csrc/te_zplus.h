@@ -15,4 +15,4 @@ int te_zplus_linear_relprop(const float* x, long long ldx, const float* w, const
 int te_zplus_linear_relprop_ldr(const float* x, long long ldx, const float* w, const float* w_derived, const float* r,
                                 long long ldr, float* out, float* s_scratch, long long rows, int in_features,
                                 int out_features, cudaStream_t st, const float* y = nullptr, long long ldy = 0,
-                                const float* bias = nullptr);
+                                const float* bias = nullptr, bool bf16 = false);

@@ -31,7 +31,7 @@ def linear_forward(x, w, bias=None, tensor_cores=False):
     _req(x, w, bias)
     rows = x.numel() // x.shape[-1]
     y = torch.empty(*x.shape[:-1], w.shape[0], device=x.device, dtype=torch.float32)
-    scratch = torch.empty(9 * w.numel(), device=x.device, dtype=torch.float32) if tensor_cores else None
+    scratch = torch.empty(10 * w.numel(), device=x.device, dtype=torch.float32) if tensor_cores else None
     check(_lib.load().te_linear_forward_ex(ptr(x), ptr(w), ptr(bias), ptr(y), ptr(scratch), rows, x.shape[-1], w.shape[0],
                                            _lib.FLAG_LINEAR_TENSOR_CORES if tensor_cores else 0, _stream()),
           "te_linear_forward_ex")
@@ -43,14 +43,14 @@ def linear_backward(dy, w, tensor_cores=False):
     _req(dy, w)
     rows = dy.numel() // dy.shape[-1]
     dx = torch.empty(*dy.shape[:-1], w.shape[1], device=dy.device, dtype=torch.float32)
-    scratch = torch.empty(9 * w.numel(), device=dy.device, dtype=torch.float32) if tensor_cores else None
+    scratch = torch.empty(10 * w.numel(), device=dy.device, dtype=torch.float32) if tensor_cores else None
     check(_lib.load().te_linear_backward_ex(ptr(dy), ptr(w), ptr(dx), ptr(scratch), rows, w.shape[1], w.shape[0],
                                             _lib.FLAG_LINEAR_TENSOR_CORES if tensor_cores else 0, _stream()),
           "te_linear_backward_ex")
     return dx
 
 
-def linear_relprop(x, w, r, tensor_cores=False, y=None, bias=None):
+def linear_relprop(x, w, r, tensor_cores=False, y=None, bias=None, bf16=False):
     """``Linear.relprop`` (layers_ours.py:207-230): x [...,in], w [out,in], r [...,out] -> [...,in].
     y / bias: the layer's saved forward output (and bias) — lets the tensor-core path form the denominator in one pass."""
     _req(x, w, r, y, bias)
@@ -58,9 +58,11 @@ def linear_relprop(x, w, r, tensor_cores=False, y=None, bias=None):
     out = torch.empty_like(x)
     nscratch = rows * w.shape[0]
     if tensor_cores:
-        nscratch = (nscratch + 63) // 64 * 64 + 9 * w.numel()
+        nscratch = (nscratch + 63) // 64 * 64 + 10 * w.numel()
     scratch = torch.empty(nscratch, device=x.device, dtype=torch.float32)
     flags = _lib.FLAG_ZPLUS_TENSOR_CORES if tensor_cores else 0
+    if bf16:
+        flags |= _lib.FLAG_ZPLUS_BF16
     if y is not None:
         check(_lib.load().te_linear_relprop_ex(ptr(x), ptr(w), ptr(bias), ptr(y), ptr(r), ptr(out), ptr(scratch), rows,
                                                x.shape[-1], w.shape[0], flags, _stream()), "te_linear_relprop_ex")
