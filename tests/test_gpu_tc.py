@@ -123,8 +123,10 @@ def test_tc_linear_engine_vit_base():
 
 
 def test_tc_attention_contractions_engine():
-    """QK^T, dctx V^T and both attention-rule N x N contractions on tcgen05 (3xTF32): attention probabilities,
-    attention gradients and the top-layer attn_cam stay at fp32 accuracy; maps in the same noise class."""
+    """Every attention-shaped contraction on tcgen05 (3xTF32): the N x N ones (QK^T, dctx V^T, attn_cam, S1; K-major
+    operands) and the N x d ones reduced over tokens (attn v, attn^T dctx, dS k, dS^T q, S1 k, S1^T q, attn^T S2; MN-major
+    tf32 operands in the SWIZZLE_128B_BASE32B layout).  Attention probabilities and attention gradients of every layer
+    stay at fp32 accuracy (they chain through all of these kernels); maps in the same noise class."""
     from oracle import cpu as ocpu
     from oracle import vit as ovit
     from transformer_explainability_b200 import _lib
@@ -145,7 +147,7 @@ def test_tc_attention_contractions_engine():
     for l in (0, 6, 11):
         assert rel(m.blocks[l].attn.get_attn()[0], taps["cache"]["blocks"][l]["attn"][0]) < 1e-5
         assert rel(m.blocks[l].attn.get_attn_gradients()[0], taps["grads"][l][0]) < 1e-4
-    assert rel(m.blocks[11].attn.get_attn_cam()[0], taps["cams"][11][0]) < 2e-2
+    assert rel(m.blocks[11].attn.get_attn_cam()[0], taps["cams"][11][0]) < 5e-2      # TF32 z+ rules feed this one
     xb = torch.cat([_noise_trials(xs[s:s + 1], trials) for s in range(2)]).cuda()
     fast, idx1 = eng.explain(xb, flags=_lib.FLAG_ALL_FAST)
     for s in range(2):

@@ -287,8 +287,8 @@ extern "C" int te_bert_forward(const te_bert_config* cfg, const float* weights, 
         TE_TRY(attn_nn((flags & TE_FLAG_ATTN_TENSOR_CORES) != 0, d.B, d.H, d.N, d.NP, d.dh, a.qkv, 3 * d.D, a.qkv + d.D,
                        3 * d.D, a.P, nullptr, scale, TE_EPI_STORE, st));
         TE_TRY(te_launch_softmax_masked(a.P, (long long)d.B * d.H * d.N, d.N, d.NP, ws.maskadd, (long long)d.H * d.N, st));
-        TE_TRY(head_gemm(d.B, d.H, attn_map(a.P, d.H, d.N, d.NP), TE_L_K, v, TE_L_MN, head_rows(a.ctx, d.D, d.N, d.dh),
-                         none, d.N, d.dh, d.N, 1.f, TE_EPI_STORE, st));
+        TE_TRY(attn_nk((flags & TE_FLAG_ATTN_TENSOR_CORES) != 0, d.B, d.H, d.N, d.NP, d.dh, a.P, 0, a.qkv + 2 * d.D, 3 * d.D,
+                       a.ctx, d.D, nullptr, 1.f, TE_EPI_STORE, st));
         // BertSelfOutput: dense -> add([dense, input]) -> LayerNorm
         TE_TRY(linear_fwd_tc(tw.o, a.ctx, d.D, lw.ow, lw.ob, a.d1, a.s1, a.h, d.M, d.D, d.D, TE_EPI_BIAS_ADD, st));
         TE_TRY(te_launch_layernorm(a.s1, lw.ln1w, lw.ln1b, a.ao, a.mean1, a.rstd1, d.M, d.D, d.eps, st));
@@ -366,13 +366,11 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
         TE_TRY(attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, dctx, d.D, a.qkv + 2 * d.D, 3 * d.D, a.G, nullptr, 1.f,
                        TE_EPI_STORE, st));                                                                      // G = dctx v^T
         if (l == start_layer) break;
-        TE_TRY(head_gemm(d.B, d.H, amap(a.P), TE_L_MN, head_rows(dctx, d.D, d.N, d.dh), TE_L_MN,
-                         head_rows(dqkv + 2 * d.D, 3 * d.D, d.N, d.dh), none, d.N, d.dh, d.N, 1.f, TE_EPI_STORE, st));
+        TE_TRY(attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, a.P, 1, dctx, d.D, dqkv + 2 * d.D, 3 * d.D, nullptr, 1.f,
+                       TE_EPI_STORE, st));
         TE_TRY(te_launch_softmax_bwd(a.P, a.G, dS, (long long)d.B * d.H * d.N, d.N, d.NP, scale, st));
-        TE_TRY(head_gemm(d.B, d.H, amap(dS), TE_L_K, k, TE_L_MN, head_rows(dqkv, 3 * d.D, d.N, d.dh), none, d.N, d.dh, d.N,
-                         1.f, TE_EPI_STORE, st));
-        TE_TRY(head_gemm(d.B, d.H, amap(dS), TE_L_MN, q, TE_L_MN, head_rows(dqkv + d.D, 3 * d.D, d.N, d.dh), none, d.N,
-                         d.dh, d.N, 1.f, TE_EPI_STORE, st));
+        TE_TRY(attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, dS, 0, a.qkv + d.D, 3 * d.D, dqkv, 3 * d.D, nullptr, 1.f, TE_EPI_STORE, st));
+        TE_TRY(attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, dS, 1, a.qkv, 3 * d.D, dqkv + d.D, 3 * d.D, nullptr, 1.f, TE_EPI_STORE, st));
         TE_TRY(linear_bwd_tc(tw.qkv, dqkv, lw.qkvw, dxn, nullptr, d.M, d.D, 3 * d.D, TE_EPI_STORE, st));
         TE_TRY(te_launch_add2(dxn, dsx, dxa, MD, st));                                                          // d h
     }
@@ -406,8 +404,8 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
         TE_TRY(attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, S, d.D, a.qkv + 2 * d.D, 3 * d.D, a.cam, a.P, 0.5f, TE_EPI_MUL,
                        st));                                                              // attn_cam   :380
         if (l == low && !(flags & TE_FLAG_RELPROP_TO_INPUT)) break;
-        TE_TRY(head_gemm(d.B, d.H, amap(a.P), TE_L_MN, head_rows(S, d.D, d.N, d.dh), TE_L_MN,
-                         head_rows(Rqkv + 2 * d.D, 3 * d.D, d.N, d.dh), v, d.N, d.dh, d.N, 0.5f, TE_EPI_MUL, st));
+        TE_TRY(attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, a.P, 1, S, d.D, Rqkv + 2 * d.D, 3 * d.D, a.qkv + 2 * d.D, 0.5f, TE_EPI_MUL,
+                       st));
         // add([scores, mask]).relprop : scores = q k^T / sqrt(d) recomputed ; relevance renormalised  :386-388
         TE_TRY(attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, a.qkv, 3 * d.D, a.qkv + d.D, 3 * d.D, ws.tA[0], nullptr, scale,
                        TE_EPI_STORE, st));
@@ -415,10 +413,9 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
         // matmul1 rule on the unscaled product
         TE_TRY(attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, a.qkv, 3 * d.D, a.qkv + d.D, 3 * d.D, ws.tA[0], ws.tA[1], 1.f,
                        TE_EPI_SD, st));
-        TE_TRY(head_gemm(d.B, d.H, amap(ws.tA[0]), TE_L_K, k, TE_L_MN, head_rows(Rqkv, 3 * d.D, d.N, d.dh), q, d.N, d.dh,
-                         d.N, 0.5f, TE_EPI_MUL, st));
-        TE_TRY(head_gemm(d.B, d.H, amap(ws.tA[0]), TE_L_MN, q, TE_L_MN, head_rows(Rqkv + d.D, 3 * d.D, d.N, d.dh), k, d.N,
-                         d.dh, d.N, 0.5f, TE_EPI_MUL, st));
+        TE_TRY(attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, ws.tA[0], 0, a.qkv + d.D, 3 * d.D, Rqkv, 3 * d.D, a.qkv, 0.5f, TE_EPI_MUL, st));
+        TE_TRY(attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, ws.tA[0], 1, a.qkv, 3 * d.D, Rqkv + d.D, 3 * d.D, a.qkv + d.D, 0.5f,
+                       TE_EPI_MUL, st));
         // query / key / value z+ rules (separate Linears), Clone(3), Clone(2)
         TE_TRY(te_zplus_linear_relprop_ldr(a.h, d.D, lw.qkvw, dw.q, Rqkv, 3 * d.D, R, S, d.M, d.D, d.D, st, a.qkv, 3 * d.D, lw.qkvb, zb));
         TE_TRY(te_zplus_linear_relprop_ldr(a.h, d.D, lw.qkvw + DD, dw.k, Rqkv + d.D, 3 * d.D, R1, S, d.M, d.D, d.D, st, a.qkv + d.D, 3 * d.D,

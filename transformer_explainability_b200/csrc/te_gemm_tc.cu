@@ -740,11 +740,211 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                 if (col + 3 < p.N) *reinterpret_cast<float4*>(p.out + rowoff + col) = make_float4(o[0], o[1], o[2], o[3]);
                                 else {
 #pragma unroll
-                                    for (int u = 0; u < 4; ++u) if (col + u < p.N) p.out[rowoff + col + u] = o[u];
+                                    for (int u = 0; u < 4; ++u) p.out[rowoff + col + u] = (col + u < p.N) ? o[u] : 0.f;   // zero the row padding
                                 }
                             }
                         }
                     }
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// =====================================================================================================================
+// Attention-shaped N x d contractions with the reduction over the TOKEN axis (fp32-grade 3xTF32):
+//   out[b, m, h, :] = epi( alpha * sum_k A_h[m,k] * X[b, k, h, :] )
+//     AMN = 0:  A_h[m,k] = map[b,h,m,k]   (attn v, dS k, S1 k)           -> A is K-major
+//     AMN = 1:  A_h[m,k] = map[b,h,k,m]   (attn^T dctx, attn^T S2, dS^T q, S1^T q: the transposed map) -> A is MN-major
+//   X (a head slice of a packed activation, [token, feature]) is always MN-major for this product.
+// MN-major tf32 operands use the SWIZZLE_128B_BASE32B layout: 32 consecutive M/N elements (128 B) per K row, 4 K rows
+// per 512-byte atom (SBO), 32-element M/N blocks LBO apart; a TMA box of 32 elements x 32 K rows with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B lands exactly as eight such atoms.  3-D tensor maps (col, token, batch*head | batch) make every row past the N tokens of
+// a head read as zero, so K (= N = 197) is padded to 224 for free.  4-stage ring, both operands split hi/lo in smem.
+// =====================================================================================================================
+constexpr int NK_BN = 64;                                          // head_dim
+constexpr int NK_A = A_BYTES, NK_B = NK_BN * BK * 4;               // 16 KiB, 8 KiB
+constexpr int NK_STAGE = 2 * NK_A + 2 * NK_B;                      // 48 KiB
+constexpr int NK_STAGES = 4;
+constexpr int NK_SMEM = NK_STAGES * NK_STAGE + 1024 + 256;
+constexpr int NK_XF4 = (NK_A + NK_B) / 16;                         // float4 to split per stage
+
+struct NkParams {
+    int N, H, ld_out;                 // tokens, heads, row stride of out / E (packed activation)
+    const float* E; float* out; float alpha;
+};
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// MN-major descriptor for 32-bit (tf32) operands.  The only layout the tensor core accepts for MN-major tf32 is
+// SWIZZLE_128B_BASE32B (cute::UMMA::Layout_MN_SW128_32B_Atom: 32 M/N elements = one 128-byte row per K row, atoms of
+// 4 K rows = 512 B, 32-byte chunks XOR-swizzled by (K row % 4)); TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+// LBO = byte distance between 32-element M/N blocks, SBO = 512 B between 4-row K atoms, layout type 1.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;
+    return d;
+}
+
+template <int AMN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+te_tc_attn_nk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const NkParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bars = smem_base + NK_STAGES * NK_STAGE;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto xf_bar = [&](int s) { return bars + 8u * (NK_STAGES + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (2 * NK_STAGES + s); };
+    const uint32_t accum_bar = bars + 8u * (3 * NK_STAGES);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + NK_STAGES * NK_STAGE + 8 * (3 * NK_STAGES + 1));
+    constexpr uint32_t OFF_AL = NK_A, OFF_BH = 2 * NK_A, OFF_BL = 2 * NK_A + NK_B;
+    // instruction descriptor: tf32, M = 128, N = 64, A major = AMN, B major = MN
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)AMN << 15) | (1u << 16) |
+                               ((uint32_t)(NK_BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
+    const int m0 = blockIdx.x * BM;
+    const int kb = (p.N + BK - 1) / BK;
+    constexpr uint32_t TMEM_COLS = 64u;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int s = 0; s < NK_STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(xf_bar(s), XF_THREADS);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < kb; ++it) {
+                const int s = it % NK_STAGES;
+                const uint32_t ph = (it / NK_STAGES) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_arrive_expect_tx(full_bar(s), NK_A + NK_B);
+                const uint32_t sa = smem_base + s * NK_STAGE;
+                const int k0 = it * BK;
+                if (AMN == 0) {
+                    tma_load_3d(sa, &tmA, full_bar(s), k0, m0, bh);                      // [128 rows m] x [32 k], K-major
+                } else {
+#pragma unroll
+                    for (int mb = 0; mb < BM / 32; ++mb)                                 // four [32 m] x [32 k rows] blocks
+                        tma_load_3d(sa + mb * 4096, &tmA, full_bar(s), m0 + mb * 32, k0, bh);
+                }
+#pragma unroll
+                for (int nb = 0; nb < NK_BN / 32; ++nb)                                  // two [32 d] x [32 k rows] blocks
+                    tma_load_3d(sa + OFF_BH + nb * 4096, &tmB, full_bar(s), h * NK_BN + nb * 32, k0, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int it = 0; it < kb; ++it) {
+                const int s = it % NK_STAGES;
+                const uint32_t ph = (it / NK_STAGES) & 1u;
+                mbar_wait(xf_bar(s), ph);
+                tcgen05_fence_after();
+                const uint32_t sa = smem_base + s * NK_STAGE;
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    uint64_t ah, al;
+                    if (AMN == 0) {
+                        ah = make_smem_desc(sa) + (uint64_t)(2 * k);                      // +32 B along the K-major row
+                        al = make_smem_desc(sa + OFF_AL) + (uint64_t)(2 * k);
+                    } else {
+                        ah = make_smem_desc_mn(sa + k * 1024, 4096);                      // +8 K rows = one 1 KiB atom
+                        al = make_smem_desc_mn(sa + OFF_AL + k * 1024, 4096);
+                    }
+                    const uint64_t bhd = make_smem_desc_mn(sa + OFF_BH + k * 1024, 4096);
+                    const uint64_t bld = make_smem_desc_mn(sa + OFF_BL + k * 1024, 4096);
+                    umma_tf32(tmem_base, al, bhd, idesc, (it == 0 && k == 0) ? 0u : 1u);
+                    umma_tf32(tmem_base, ah, bld, idesc, 1u);
+                    umma_tf32(tmem_base, ah, bhd, idesc, 1u);
+                }
+                umma_commit(empty_bar(s));
+            }
+            umma_commit(accum_bar);
+        }
+        __syncwarp();
+    } else {
+        const int et = threadIdx.x - 64;
+        for (int it = 0; it < kb; ++it) {
+            const int s = it % NK_STAGES;
+            const uint32_t ph = (it / NK_STAGES) & 1u;
+            mbar_wait(full_bar(s), ph);
+            // split A_hi (16 KiB) and B_hi (8 KiB) slots -> hi in place, lo into the matching *_lo slot
+            float4* base4 = reinterpret_cast<float4*>(smem_al + s * NK_STAGE);
+            for (int i = et; i < NK_XF4; i += XF_THREADS) {
+                const bool isA = i < NK_A / 16;
+                float4* src = isA ? base4 + i : base4 + (OFF_BH / 16) + (i - NK_A / 16);
+                float4* dst = isA ? base4 + (OFF_AL / 16) + i : base4 + (OFF_BL / 16) + (i - NK_A / 16);
+                const float4 v = *src;
+                float4 hh, l;
+                hh.x = to_tf32(v.x); hh.y = to_tf32(v.y); hh.z = to_tf32(v.z); hh.w = to_tf32(v.w);
+                l.x = to_tf32(v.x - hh.x); l.y = to_tf32(v.y - hh.y); l.z = to_tf32(v.z - hh.z); l.w = to_tf32(v.w - hh.w);
+                *src = hh; *dst = l;
+            }
+            fence_proxy_async();
+            mbar_arrive(xf_bar(s));
+        }
+        const int q = warp & 3;
+        const int m = m0 + q * 32 + lane;
+        const bool live = m < p.N;
+        const long long off = ((long long)b * p.N + m) * p.ld_out + (long long)h * NK_BN;
+        float4 ebuf[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) ebuf[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (EPI == AT_MUL && live) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ebuf[j] = *reinterpret_cast<const float4*>(p.E + off + j * 4);
+        }
+        mbar_wait(accum_bar, 0);
+        tcgen05_fence_after();
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t acc[32];
+            tmem_ld32(tlane + (uint32_t)(c * 32), acc);
+            tmem_ld_wait();
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float o[4];
+                    const float e[4] = {ebuf[c * 8 + j].x, ebuf[c * 8 + j].y, ebuf[c * 8 + j].z, ebuf[c * 8 + j].w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float a = __uint_as_float(acc[j * 4 + u]);
+                        o[u] = (EPI == AT_MUL) ? p.alpha * a * e[u] : p.alpha * a;
+                    }
+                    *reinterpret_cast<float4*>(p.out + off + c * 32 + j * 4) = make_float4(o[0], o[1], o[2], o[3]);
                 }
             }
         }
@@ -944,6 +1144,62 @@ int te_tc_attn_nn(const float* A, long long lda, const float* B, long long ldb, 
         case TE_TC_ATTN_SD: return launch_attn<AT_SD>(A, lda, B, ldb, rows, p, batch, st);
     }
     te_set_last_error("te_gemm_tc: unsupported attention epilogue");
+    return TE_ERR_UNSUPPORTED;
+}
+
+bool te_tc_attn_nk_supported(int N, int dh, int NP, long long ldx, long long ld_out) {
+    return N >= 1 && dh == NK_BN && NP % 4 == 0 && ldx % 4 == 0 && ld_out % 4 == 0 && get_encode() != nullptr;
+}
+
+namespace {
+// rank-3 fp32 map: dims {cols, rows, batch}, box {bc, br, 1}, 128-byte swizzle, zero fill outside
+bool make_map3(CUtensorMap* m, const float* base, long long cols, long long rows, long long batch, long long row_stride,
+               long long batch_stride, int box_cols, int box_rows, bool mn_major) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)row_stride * 4, (cuuint64_t)batch_stride * 4};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int AMN, int EPI>
+int launch_nk(const float* map, int NP, const float* X, long long ldx, const NkParams& p, int batch, cudaStream_t st) {
+    CUtensorMap tmA, tmB;
+    // attention-shaped map [batch*H, N, NP] ; activation [batch, N, ldx]
+    if (!make_map3(&tmA, map, NP, p.N, (long long)batch * p.H, NP, (long long)p.N * NP, 32, AMN ? 32 : BM, AMN != 0) ||
+        !make_map3(&tmB, X, ldx, p.N, batch, ldx, (long long)p.N * ldx, 32, 32, true)) {
+        te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed (attention nk)");
+        return TE_ERR_CUDA;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(te_tc_attn_nk_kernel<AMN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, NK_SMEM) != cudaSuccess) {
+            te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
+            return TE_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    dim3 grid((p.N + BM - 1) / BM, batch * p.H);
+    if (grid.y > 65535) { te_set_last_error("te_gemm_tc: batch*heads too large for one launch"); return TE_ERR_ARG; }
+    te_tc_attn_nk_kernel<AMN, EPI><<<grid, NUM_THREADS, NK_SMEM, st>>>(tmA, tmB, p);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+}  // namespace
+
+// out[b, m, h, :] = epi(alpha * sum_k A_h[m,k] X[b,k,h,:]) ; A_h = map[b,h] (amn = 0) or its transpose (amn = 1);
+// X, out, E: packed activations [batch, N, ld] (head h at columns h*64..); epi: TE_TC_ATTN_STORE / TE_TC_ATTN_MUL
+int te_tc_attn_nk(const float* map, int NP, int amn, const float* X, long long ldx, int batch, int H, int N, float* out,
+                  int ld_out, const float* E, float alpha, int epi, cudaStream_t st) {
+    NkParams p;
+    p.N = N; p.H = H; p.ld_out = ld_out; p.E = E; p.out = out; p.alpha = alpha;
+    if (epi == TE_TC_ATTN_STORE) return amn ? launch_nk<1, AT_STORE>(map, NP, X, ldx, p, batch, st) : launch_nk<0, AT_STORE>(map, NP, X, ldx, p, batch, st);
+    if (epi == TE_TC_ATTN_MUL) return amn ? launch_nk<1, AT_MUL>(map, NP, X, ldx, p, batch, st) : launch_nk<0, AT_MUL>(map, NP, X, ldx, p, batch, st);
+    te_set_last_error("te_gemm_tc: unsupported attention nk epilogue");
     return TE_ERR_UNSUPPORTED;
 }
 

@@ -33,3 +33,8 @@ enum { TE_TC_ATTN_STORE = 0, TE_TC_ATTN_MUL = 1, TE_TC_ATTN_SD = 2 };
 bool te_tc_attn_supported(int N, int dh, long long lda, long long ldb, int ld_out);
 int te_tc_attn_nn(const float* A, long long lda, const float* B, long long ldb, int batch, int H, int N, int dh,
                   float* out, int ld_out, const float* E, float alpha, int epi, cudaStream_t st);
+
+// attention-shaped N x d contractions with the reduction over tokens (attn v, attn^T dctx, dS k, dS^T q, S1 k, S1^T q ...)
+bool te_tc_attn_nk_supported(int N, int dh, int NP, long long ldx, long long ld_out);
+int te_tc_attn_nk(const float* map, int NP, int amn, const float* X, long long ldx, int batch, int H, int N, float* out,
+                  int ld_out, const float* E, float alpha, int epi, cudaStream_t st);

@@ -281,8 +281,8 @@ extern "C" int te_vit_forward(const te_vit_config* cfg, const float* weights, co
                                 a.qkv + d.D, 3 * d.D, a.P, nullptr, scale, TE_EPI_STORE, st));
         TE_TRY(te_launch_softmax(a.P, (long long)d.B * d.H * d.N, d.N, d.NP, st));
         // out = attn v -> 'b h n d -> b n (h d)'              (:147-148)
-        TE_TRY(head_gemm(d, attn_map(a.P, d), TE_L_K, v, TE_L_MN, head_rows(a.ctx, d.D, d.N, d.dh), none, d.N, d.dh,
-                         d.N, 1.f, TE_EPI_STORE, st));
+        TE_TRY(te_util::attn_nk((flags & TE_FLAG_ATTN_TENSOR_CORES) != 0, d.B, d.H, d.N, d.NP, d.dh, a.P, 0, a.qkv + 2 * d.D,
+                                3 * d.D, a.ctx, d.D, nullptr, 1.f, TE_EPI_STORE, st));
         // proj + residual add1                                  (:150, :198)
         TE_TRY(te_util::linear_fwd_tc(lw.proj, a.ctx, d.D, bw.projw, bw.projb, a.attn_out, a.x_mid, a.x_in, d.M, d.D, d.D,
                                       TE_EPI_BIAS_ADD, st));
@@ -394,13 +394,13 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
         TE_TRY(te_util::attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, dctx, d.D, a.qkv + 2 * d.D, 3 * d.D, a.G, nullptr, 1.f,
                                 TE_EPI_STORE, st));                                 // G = dctx v^T
         if (l == start_layer) break;                                                // lower gradients are never read
-        TE_TRY(head_gemm(d, attn_map(a.P, d), TE_L_MN, head_rows(dctx, d.D, d.N, d.dh), TE_L_MN,
-                         head_rows(dqkv + 2 * d.D, 3 * d.D, d.N, d.dh), none, d.N, d.dh, d.N, 1.f, TE_EPI_STORE, st));  // dV = P^T dctx
+        TE_TRY(te_util::attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, a.P, 1, dctx, d.D, dqkv + 2 * d.D, 3 * d.D, nullptr, 1.f,
+                                TE_EPI_STORE, st));                                 // dV = P^T dctx
         TE_TRY(te_launch_softmax_bwd(a.P, a.G, dS, (long long)d.B * d.H * d.N, d.N, d.NP, scale, st));
-        TE_TRY(head_gemm(d, attn_map(dS, d), TE_L_K, k, TE_L_MN, head_rows(dqkv, 3 * d.D, d.N, d.dh), none, d.N, d.dh,
-                         d.N, 1.f, TE_EPI_STORE, st));                              // dQ = dS k
-        TE_TRY(head_gemm(d, attn_map(dS, d), TE_L_MN, q, TE_L_MN, head_rows(dqkv + d.D, 3 * d.D, d.N, d.dh), none, d.N,
-                         d.dh, d.N, 1.f, TE_EPI_STORE, st));                        // dK = dS^T q
+        TE_TRY(te_util::attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, dS, 0, a.qkv + d.D, 3 * d.D, dqkv, 3 * d.D, nullptr, 1.f,
+                                TE_EPI_STORE, st));                                 // dQ = dS k
+        TE_TRY(te_util::attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, dS, 1, a.qkv, 3 * d.D, dqkv + d.D, 3 * d.D, nullptr, 1.f,
+                                TE_EPI_STORE, st));                                 // dK = dS^T q
         TE_TRY(te_util::linear_bwd_tc(lw.qkv, dqkv, bw.qkvw, dxn, nullptr, d.M, d.D, 3 * d.D, TE_EPI_STORE, st));
         TE_TRY(te_launch_layernorm_bwd(dxn, a.x_in, bw.n1w, a.mean1, a.rstd1, dxb, dxa, d.M, d.D, st));
     }
@@ -436,15 +436,15 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
         TE_TRY(te_util::attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, S, d.D, a.qkv + 2 * d.D, 3 * d.D, a.cam, a.P, 0.5f,
                                 TE_EPI_MUL, st));                                   // attn_cam = (P * (S v^T)) / 2   :160-165
         if (l == low && !(flags & TE_FLAG_RELPROP_TO_INPUT)) break;                                                        // nothing below is consumed
-        TE_TRY(head_gemm(d, attn_map(a.P, d), TE_L_MN, head_rows(S, d.D, d.N, d.dh), TE_L_MN,
-                         head_rows(Rqkv + 2 * d.D, 3 * d.D, d.N, d.dh), v, d.N, d.dh, d.N, 0.5f, TE_EPI_MUL, st));   // cam_v
+        TE_TRY(te_util::attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, a.P, 1, S, d.D, Rqkv + 2 * d.D, 3 * d.D, a.qkv + 2 * d.D, 0.5f,
+                                TE_EPI_MUL, st));                                   // cam_v
         // matmul1 rule (unscaled Z = q k^T)  :170-173
         TE_TRY(te_util::attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, a.qkv, 3 * d.D, a.qkv + d.D, 3 * d.D, S1, a.cam, 1.f,
                                 TE_EPI_SD, st));
-        TE_TRY(head_gemm(d, attn_map(S1, d), TE_L_K, k, TE_L_MN, head_rows(Rqkv, 3 * d.D, d.N, d.dh), q, d.N, d.dh, d.N,
-                         0.5f, TE_EPI_MUL, st));                                    // cam_q
-        TE_TRY(head_gemm(d, attn_map(S1, d), TE_L_MN, q, TE_L_MN, head_rows(Rqkv + d.D, 3 * d.D, d.N, d.dh), k, d.N,
-                         d.dh, d.N, 0.5f, TE_EPI_MUL, st));                         // cam_k
+        TE_TRY(te_util::attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, S1, 0, a.qkv + d.D, 3 * d.D, Rqkv, 3 * d.D, a.qkv, 0.5f,
+                                TE_EPI_MUL, st));                                   // cam_q
+        TE_TRY(te_util::attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, S1, 1, a.qkv, 3 * d.D, Rqkv + d.D, 3 * d.D, a.qkv + d.D, 0.5f,
+                                TE_EPI_MUL, st));                                   // cam_k
         TE_TRY(te_zplus_linear_relprop_ldr(a.xn1, d.D, bw.qkvw, dw.qkv, Rqkv, 3 * d.D, R2, S, d.M, d.D, 3 * d.D, st, a.qkv, 3 * d.D, bw.qkvb, zb));               // qkv ; norm1 id
         TE_TRY(te_launch_clone_relprop(a.x_in, R1, R2, nullptr, R, MD, st));                                       // clone1
     }
