@@ -42,6 +42,8 @@ extern "C" {
 #define TE_FLAG_ATTN_TENSOR_CORES 32u  /* the N x N attention contractions (QK^T, dctx V^T, S2 V^T) on tcgen05, 3xTF32 */
 #define TE_FLAG_ZPLUS_BF16 64u          /* with TE_FLAG_ZPLUS_TENSOR_CORES: S = R/Z stored as bf16 and the second z+ contraction
                                          (R_in = x+ (S W+) + x- (S W-)) on tcgen05 kind::f16 with bf16 operands */
+#define TE_FLAG_GRADIENTS_ONLY 128u    /* te_*_attribute stops after the class-gradient backward: only "attn_grad" of the layers
+                                         >= start_layer is produced (maps may be NULL) — the attention-GradCAM baselines */
 #define TE_FLAG_RELPROP_TO_INPUT 8u   /* finish the lowest block as well: relevance at the encoder input (what
                                          model.relprop() returns in the reference) is left in tensor "relevance_in" */
 
@@ -110,6 +112,14 @@ TE_API int te_vit_explain(const te_vit_config* cfg, const float* weights, const 
  * Returns a device pointer, 4 dims and 4 element strides (unused dims are 1). */
 TE_API int te_vit_tensor(const te_vit_config* cfg, int batch, void* workspace, const char* name, int layer,
                   float** ptr, long long dims[4], long long strides[4]);
+/* method="full" (ViT_LRP.py:337-343): relevance carried through ``self.add`` (tokens + pos_embed), ``[:, 1:]``,
+ * PatchEmbed.relprop (:238-242) and the z^B rule of the patch convolution (layers_ours.py:242-259).
+ * Call after te_vit_forward + te_vit_attribute(flags | TE_FLAG_RELPROP_TO_INPUT) on the same workspace and images.
+ * pixel_maps [batch, img, img] (channels summed — what relprop returns) and / or pixel_relevance
+ * [batch, in_chans, img, img] (Conv2d.relprop's own output) are written when non-NULL. */
+TE_API int te_vit_relprop_pixels(const te_vit_config* cfg, const float* weights, const float* images, int batch,
+                          float* pixel_maps, float* pixel_relevance, void* workspace, long long workspace_bytes,
+                          void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * BERT sequence classifier  (BERT_explainability/modules/BERT/BertForSequenceClassification.py:12-88,
@@ -190,6 +200,24 @@ TE_API int te_matmul_qk_relprop(const float* q, const float* k, const float* r, 
                          int bh, int n, int d, void* stream);
 /* IndexSelect.relprop for token 0 (layers_ours.py:129-147): x [b,n,d], r [b,d] -> out [b,n,d]. */
 TE_API int te_index_select_relprop(const float* x, const float* r, float* out, int batch, int n, int d, void* stream);
+/* Conv2d.relprop, 3-channel-input (z^B) branch (layers_ours.py:242-259) for a kernel == stride patch convolution, as
+ * called by PatchEmbed.relprop (ViT_LRP.py:238-242).  images [batch, in_chans, img, img]; weight [dim, in_chans*patch*patch];
+ * r [batch, (img/patch)^2, dim] (token-major: the ``cam`` PatchEmbed.relprop receives).  r_pixels [batch,in_chans,img,img]
+ * and / or r_sum [batch,img,img] (channel sum) are written when non-NULL.  Min / max are taken per sample. */
+TE_API long long te_patch_embed_relprop_workspace_bytes(int batch, int in_chans, int img_size, int patch_size, int dim);
+TE_API int te_patch_embed_relprop(const float* images, const float* weight, const float* r, int batch, int in_chans,
+                           int img_size, int patch_size, int dim, float* r_pixels, float* r_sum, void* workspace,
+                           long long workspace_bytes, void* stream);
+
+/* Head reductions of attention-shaped tensors [batch, heads, n, ld] -> out [batch, n, n] (contiguous), the building
+ * block of the secondary methods (ViT_LRP.py:345-398; ViT_explanation_generator.py:51-83; BERT
+ * ExplanationGenerator.py:61-155):   v_h = a_h (* g_h if g) (* head_w[b,h] if head_w);
+ *   mode 0: mean_h v_h          mode 1: mean_h relu(v_h)  ("clamp(min=0).mean")      mode 2: relu(mean_h v_h). */
+TE_API int te_head_reduce(const float* a, const float* g, const float* head_w, int batch, int heads, int n, int ld, int mode,
+                   float* out, void* stream);
+/* out[b,h] = mean of g[b,h, r0:r1, c0:c1]  (``grad.mean(dim=[1,2])`` of the GradCAM baselines). */
+TE_API int te_head_region_mean(const float* g, int batch, int heads, int n, int ld, int r0, int r1, int c0, int c1, float* out,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Aggregation + rollout  (ViT_LRP.py:357-368, :38-49 ; ExplanationGenerator.py:47-59, :7-18)

@@ -116,7 +116,7 @@ def vit_generate_lrp(model, x, index=None, start_layer=0, method="transformer_at
     return res
 
 
-def _generate_lrp_any_dtype(model, x, index, start_layer, method):
+def _generate_lrp_any_dtype(model, x, index, start_layer, method, is_ablation=False):
     """``generate_LRP`` (``ViT_explanation_generator.py:25-41``) with the one-hot built in the
     model's dtype — the reference hard-codes float32 numpy there, which cannot multiply an
     fp64 output.  Every model/relprop call is still the reference's own code."""
@@ -130,7 +130,7 @@ def _generate_lrp_any_dtype(model, x, index, start_layer, method):
     loss = torch.sum(oh * output)
     model.zero_grad()
     loss.backward(retain_graph=True)
-    return model.relprop(oh.clone(), method=method, is_ablation=False, start_layer=start_layer, alpha=1)
+    return model.relprop(oh.clone(), method=method, is_ablation=is_ablation, start_layer=start_layer, alpha=1)
 
 
 def vit_logits(model, x):

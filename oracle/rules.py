@@ -112,6 +112,30 @@ def matmul_qk_relprop(q, k, r):
     return q * (s @ k), k * (s.transpose(-1, -2) @ q)
 
 
+def conv_zb_relprop(x, w, r, stride):
+    """z^B ("box") rule of the first layer, ``Conv2d.relprop`` for a 3-channel input
+    (``layers_ours.py:242-259``), per sample.
+
+    x [B,3,H,W] image, w [O,3,P,P], r [B,O,H/P,W/P] -> [B,3,H,W].
+    L / H = per-sample min / max of the image (broadcast to the image shape);
+    Za = conv(x, W) - conv(L, W+) - conv(H, W-) + 1e-9 ; S = R / Za (plain division) ;
+    C = x * convT(S, W) - L * convT(S, W+) - H * convT(S, W-).
+    """
+    import torch.nn.functional as F
+    pw = w.clamp(min=0)
+    nw = w.clamp(max=0)
+    lo = x * 0 + x.amin(dim=(1, 2, 3), keepdim=True)
+    hi = x * 0 + x.amax(dim=(1, 2, 3), keepdim=True)
+    za = F.conv2d(x, w, None, stride=stride) - F.conv2d(lo, pw, None, stride=stride) - \
+        F.conv2d(hi, nw, None, stride=stride) + 1e-9
+    s = r / za
+
+    def back(wt):
+        return F.conv_transpose2d(s, wt, stride=stride)
+
+    return x * back(w) - lo * back(pw) - hi * back(nw)
+
+
 def aggregate(grad, cam):
     """``ViT_LRP.py:359-365`` / ``ExplanationGenerator.py:49-55``:
     grad, cam [B,H,N,N] -> mean_h relu(grad*cam) [B,N,N] (clamp THEN mean)."""

@@ -59,10 +59,11 @@ def forward(params, x, num_heads, need_grad=False):
     if cfg.distilled:
         toks.append(p["dist_token"].expand(B, -1, -1))
     t = torch.cat(toks + [t], dim=1)
+    tokens_pre_pos = t
     t = t + p["pos_embed"]
     if need_grad:
         t = t.detach().requires_grad_(True)     # puts every attn tensor on an autograd graph
-    cache = {"cfg": cfg, "blocks": []}
+    cache = {"cfg": cfg, "blocks": [], "tokens_pre_pos": tokens_pre_pos.detach(), "image": x}
     scale = (cfg.dim // cfg.heads) ** -0.5
     for i in range(cfg.depth):
         pre = "blocks.%d." % i
@@ -101,10 +102,12 @@ def attention_gradients(cache, seed):
     return list(torch.autograd.grad(loss, attns, retain_graph=True))
 
 
-def relprop(params, cache, seed, start_layer=0, taps=None):
+def relprop(params, cache, seed, start_layer=0, taps=None, to_input=False):
     """LRP pass; returns list (per block) of attn_cam [B,H,N,N] (``ViT_LRP.py:165``).
 
     Blocks below ``start_layer`` are never consumed by the rollout and are returned as None.
+    ``to_input=True`` runs every block to its end (what the reference always does, ``:331-332``) and
+    returns ``(cams, r)`` with ``r`` the relevance at the encoder input [B,N,D].
     """
     cfg = cache["cfg"]
     p = params
@@ -152,7 +155,7 @@ def relprop(params, cache, seed, start_layer=0, taps=None):
         cam1 = cam1 / 2
         cam_v = cam_v / 2
         cams[i] = cam1                                                          # save_attn_cam :165
-        if i == start_layer:
+        if i == start_layer and not to_input:
             break                                                               # nothing below is consumed
         cam_q, cam_k = rules.matmul_qk_relprop(c["q"], c["k"], cam1)
         cam_q = cam_q / 2
@@ -162,7 +165,54 @@ def relprop(params, cache, seed, start_layer=0, taps=None):
         r = rules.clone_relprop(c["x_in"], (r1, r2))                            # clone1
         if t is not None:
             t["r_qkv"], t["qkv"], t["clone1"] = r_qkv, r2, r
+    if to_input:
+        return cams, r
     return cams
+
+
+METHODS = ("transformer_attribution", "grad", "rollout", "full", "last_layer", "last_layer_attn", "second_layer")
+
+
+def explain_method(params, x, num_heads, method, index=None, start_layer=0, is_ablation=False):
+    """``LRP.generate_LRP(method=...)`` for every branch of ``VisionTransformer.relprop``
+    (``ViT_LRP.py:337-398``), batch = independent B=1 explanations.  Returns (map, index):
+    [B,N-1] for the token methods, [B,H,W] for ``full`` (relevance of every pixel, channels summed)."""
+    if method in ("transformer_attribution", "grad"):
+        return explain(params, x, num_heads, index=index, start_layer=start_layer)
+    with torch.enable_grad():
+        logits, cache = forward(params, x, num_heads, need_grad=True)
+        if index is None:
+            index = logits.argmax(dim=-1)
+        index = torch.as_tensor(index).reshape(-1).long()
+        seed = torch.zeros_like(logits)
+        seed[torch.arange(logits.shape[0]), index] = 1
+        grads = attention_gradients(cache, seed)
+    cfg = cache["cfg"]
+    first = 2 if cfg.distilled else 1
+    with torch.no_grad():
+        cache_d = {"cfg": cfg, "x_final_norm": cache["x_final_norm"].detach(),
+                   "blocks": [{k: v.detach() for k, v in c.items()} for c in cache["blocks"]]}
+        cams, r = relprop(params, cache_d, seed, 0, to_input=True)
+        if method == "full":                                                    # :337-343
+            pos = params["pos_embed"].expand_as(cache["tokens_pre_pos"])
+            r, _ = rules.add_relprop(cache["tokens_pre_pos"], pos, r)
+            r = r[:, first:]
+            g = x.shape[-1] // cfg.patch
+            r = r.transpose(1, 2).reshape(r.shape[0], cfg.dim, x.shape[-2] // cfg.patch, g)   # PatchEmbed.relprop :238-242
+            r = rules.conv_zb_relprop(x, params["patch_embed.proj.weight"], r, cfg.patch)
+            return r.sum(dim=1), index
+        if method == "rollout":                                                 # :345-354
+            mats = [c.clamp(min=0).mean(dim=1) for c in cams]
+            return rules.rollout(mats, start_layer=start_layer)[:, 0, first:], index
+        if method in ("last_layer", "second_layer"):                            # :371-380, :389-398
+            l = cfg.depth - 1 if method == "last_layer" else 1
+            c = cams[l]
+            if is_ablation:
+                c = grads[l] * c
+            return c.clamp(min=0).mean(dim=1)[:, 0, first:], index
+        if method == "last_layer_attn":                                         # :382-387
+            return cache_d["blocks"][-1]["attn"].clamp(min=0).mean(dim=1)[:, 0, first:], index
+    raise ValueError("unknown method %r" % (method,))
 
 
 def explain(params, x, num_heads, index=None, start_layer=0, return_taps=False):

@@ -106,8 +106,26 @@ def test_attention_matmul_rules(ops, b, h, n, d):
     assert rel_err(rq, oq) < 1e-4 and rel_err(rk, ok) < 1e-4
 
 
+@pytest.mark.parametrize("B,C,S,P,D", [(2, 3, 32, 8, 64), (3, 3, 224, 16, 768), (1, 3, 48, 16, 40)])
+def test_patch_embed_zb_rule(ops, B, C, S, P, D):
+    """Conv2d.relprop z^B branch behind PatchEmbed.relprop (layers_ours.py:242-259) vs the fp64 restatement."""
+    g = torch.Generator().manual_seed(S + D)
+    img = torch.randn(B, C, S, S, generator=g)
+    w = torch.randn(D, C, P, P, generator=g) * 0.05
+    r = torch.randn(B, (S // P) ** 2, D, generator=g)
+    ref = rules.conv_zb_relprop(img.double(), w.double(), r.transpose(1, 2).reshape(B, D, S // P, S // P).double(), P)
+    out = ops.patch_embed_relprop(dev(img), dev(w), dev(r))
+    assert out.shape == ref.shape
+    assert rel_err(out, ref) < 2e-5
+    out_sum = ops.patch_embed_relprop(dev(img), dev(w), dev(r), per_channel=False)
+    assert rel_err(out_sum, ref.sum(dim=1)) < 2e-5
+    # conservation: sum of the pixel relevance == sum of R * (Za - 1e-9) / Za ~= sum R
+    assert abs(out.double().sum().item() - r.double().sum().item()) < 1e-3 * r.abs().double().sum().item()
+
+
 @pytest.mark.parametrize("L,B,H,N,normalize", [(12, 2, 12, 197, False), (3, 3, 4, 17, False), (4, 1, 12, 512, True),
-                                               (12, 2, 12, 198, False), (2, 40, 16, 197, True), (12, 300, 2, 30, False)])
+                                               (12, 2, 12, 198, False), (2, 40, 16, 197, True), (12, 300, 2, 30, False),
+                                               (3, 3, 2, 301, True)])
 def test_aggregation_rollout(ops, L, B, H, N, normalize):
     g = torch.Generator().manual_seed(N + L)
     grad = torch.randn(L, B, H, N, N, generator=g) * 0.05
@@ -122,6 +140,13 @@ def test_aggregation_rollout(ops, L, B, H, N, normalize):
         _, row_f = ops.attribution_rollout(dev(grad), dev(cam), start_layer=start, normalize=normalize, fused=True,
                                            want_joint=False)
         assert rel_err(row_f, ref[:, 0]) < 1e-5
+        # dense joint with the fast flag: N x N x N chain on tcgen05 (3xTF32) when N <= 224, SIMT otherwise
+        joint_tc, row_tc = ops.attribution_rollout(dev(grad), dev(cam), start_layer=start, normalize=normalize,
+                                                   fused=True, want_joint=True)
+        assert rel_err(joint_tc, ref) < 1e-5 and rel_err(row_tc, ref[:, 0]) < 1e-5
+        assert (joint_tc.cpu().double() - ref).abs().max() < 2e-6 * max(1.0, ref.abs().max().item())
+        off = ~torch.eye(N, dtype=torch.bool)                    # the small off-diagonal entries, relative to themselves
+        assert ((joint_tc.cpu().double() - ref).abs()[:, off].max() / ref[:, off].abs().max()).item() < 2e-5
         # public compute_rollout_attention on pre-aggregated matrices
         j2 = ops.compute_rollout_attention([dev(m.float()) for m in mats], start_layer=start, normalize=normalize)
         assert rel_err(j2, ref) < 1e-5

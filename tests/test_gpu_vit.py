@@ -65,6 +65,38 @@ def test_tiny_vs_golden_reference(golden_dir):
     assert rel(out, T(g["f64.s0.map.index3"])) < 2e-2
 
 
+def test_tiny_other_methods_vs_golden_reference(golden_dir):
+    """method = rollout / full / last_layer(+ablation) / last_layer_attn / second_layer(+ablation) through the
+    reference-shaped generate_LRP, vs the UNMODIFIED reference's fp64 outputs."""
+    from transformer_explainability_b200.baselines.ViT.ViT_explanation_generator import LRP
+    g = np.load(os.path.join(golden_dir, "vit_tiny_methods.npz"))
+    params, heads = ovit.init_params("vit_tiny_test", seed=int(g["param_seed"]), rand_affine=True)
+    model = make_model(params, heads, **TINY)
+    lrp = LRP(model)
+    x = T(g["x"]).cuda()
+    for s in range(x.shape[0]):
+        for key in [k for k in g.files if k.startswith("f64.s%d." % s)]:
+            method, suffix = key.split(".")[2:4]
+            kw = {"is_ablation": True} if suffix == "ablation" else {"start_layer": int(suffix[2:])}
+            out = lrp.generate_LRP(x[s:s + 1], method=method, **kw)
+            ref = T(g[key])
+            if method == "full":
+                assert out.shape == (1, 32, 32)
+            ref = ref.reshape(out.shape)
+            tol = 1e-5 if method == "last_layer_attn" else 2e-2
+            assert rel(out, ref) < tol, "%s rel=%g" % (key, rel(out, ref))
+    # batched pixel relevance = per-sample calls
+    full = lrp.generate_LRP(x, method="full")
+    for s in range(x.shape[0]):
+        one = lrp.generate_LRP(x[s:s + 1], method="full")
+        assert torch.allclose(one[0], full[s], rtol=1e-4, atol=1e-9)
+    # conservation through the first layer: the pixel relevance sums to the relevance of the patch tokens
+    model(x)
+    per_channel = model.engine().relprop_pixels(per_channel=True)
+    assert per_channel.shape == (x.shape[0], 3, 32, 32)
+    assert torch.allclose(per_channel.sum(dim=1), full, rtol=1e-4, atol=1e-8)
+
+
 def test_tiny_batched_equals_single(golden_dir):
     """Batch = independent B=1 explanations: the batched call reproduces the per-sample calls."""
     from transformer_explainability_b200.baselines.ViT.ViT_explanation_generator import LRP

@@ -55,6 +55,28 @@ def test_vit_tiny_matches_reference(golden_dir, tag, dtype):
     assert torch.equal(out, T(g["%s.s0.map.index3" % tag]))
 
 
+@pytest.mark.parametrize("tag,dtype", [("f32", torch.float32), ("f64", torch.float64)])
+def test_vit_tiny_other_methods_match_reference(golden_dir, tag, dtype):
+    """Every other ``method`` branch of VisionTransformer.relprop (rollout, full, last_layer, ...), incl. the
+    first-layer z^B rule, is bit-equal to the unmodified reference."""
+    g = np.load(os.path.join(golden_dir, "vit_tiny_methods.npz"))
+    params, heads = ovit.init_params("vit_tiny_test", seed=int(g["param_seed"]), rand_affine=True)
+    params = {k: v.to(dtype) for k, v in params.items()}
+    x = T(g["x"]).to(dtype)
+    for s in range(x.shape[0]):
+        for key in [k for k in g.files if k.startswith("%s.s%d." % (tag, s))]:
+            method, suffix = key.split(".")[2:4]
+            kw = {"is_ablation": True} if suffix == "ablation" else {"start_layer": int(suffix[2:])}
+            out, _ = ovit.explain_method(params, x[s:s + 1], heads, method, **kw)
+            ref = T(g[key]).reshape(out.shape)
+            assert torch.equal(out, ref), key
+    # a batch is a set of independent B=1 explanations for these branches as well
+    out, _ = ovit.explain_method(params, x, heads, "full")
+    for s in range(x.shape[0]):
+        one, _ = ovit.explain_method(params, x[s:s + 1], heads, "full")
+        assert torch.allclose(out[s], one[0], rtol=1e-4 if dtype == torch.float32 else 1e-10, atol=0)
+
+
 def test_vit_tiny_batched_equals_per_sample(golden_dir):
     """A batch is a set of independent B=1 explanations (per-sample reductions)."""
     g = np.load(os.path.join(golden_dir, "vit_tiny.npz"))

@@ -21,6 +21,7 @@ _ALIASES = {
     "baselines": "transformer_explainability_b200.baselines",
     "baselines.ViT": "transformer_explainability_b200.baselines.ViT",
     "baselines.ViT.ViT_LRP": "transformer_explainability_b200.baselines.ViT.ViT_LRP",
+    "baselines.ViT.ViT_new": "transformer_explainability_b200.baselines.ViT.ViT_new",
     "baselines.ViT.ViT_explanation_generator": "transformer_explainability_b200.baselines.ViT.ViT_explanation_generator",
 }
 

@@ -31,6 +31,7 @@ FLAG_ZPLUS_TENSOR_CORES = 1
 FLAG_ROLLOUT_FUSED = 2
 FLAG_KEEP_ALL_CAMS = 4
 FLAG_RELPROP_TO_INPUT = 8
+FLAG_GRADIENTS_ONLY = 128
 FLAG_LINEAR_TENSOR_CORES = 16
 FLAG_ATTN_TENSOR_CORES = 32
 FLAG_ZPLUS_BF16 = 64
@@ -59,6 +60,7 @@ PROTOTYPES = {
     "te_vit_explain": (c_int, [_CFG, _P, _P, _P, c_int, _P, c_int, c_uint, _P, _P, _P, c_ll, _P]),
     "te_vit_tensor": (c_int, [_CFG, c_int, _P, c_char_p, c_int, ctypes.POINTER(_P), ctypes.POINTER(c_ll),
                               ctypes.POINTER(c_ll)]),
+    "te_vit_relprop_pixels": (c_int, [_CFG, _P, _P, c_int, _P, _P, _P, c_ll, _P]),
     "te_bert_num_weights": (c_int, [_BCFG]),
     "te_bert_weight_name": (c_char_p, [_BCFG, c_int]),
     "te_bert_weight_numel": (c_ll, [_BCFG, c_int]),
@@ -79,6 +81,10 @@ PROTOTYPES = {
     "te_matmul_av_relprop": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "te_matmul_qk_relprop": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "te_index_select_relprop": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
+    "te_patch_embed_relprop_workspace_bytes": (c_ll, [c_int, c_int, c_int, c_int, c_int]),
+    "te_patch_embed_relprop": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_ll, _P]),
+    "te_head_reduce": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "te_head_region_mean": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "te_rollout_workspace_bytes": (c_ll, [c_int, c_int, c_int]),
     "te_attribution_rollout": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_uint, _P, _P, _P,
                                        c_ll, _P]),

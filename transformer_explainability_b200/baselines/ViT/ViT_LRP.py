@@ -89,7 +89,7 @@ class VisionTransformer(nn.Module):
 
     def __init__(self, img_size=224, patch_size=16, in_chans=3, num_classes=1000, embed_dim=768, depth=12,
                  num_heads=12, mlp_ratio=4., qkv_bias=False, mlp_head=False, drop_rate=0., attn_drop_rate=0.,
-                 distilled=False):
+                 distilled=False, norm_eps=None):
         super().__init__()
         if mlp_head:
             raise NotImplementedError("mlp_head=True is not used by any reference factory")
@@ -105,6 +105,10 @@ class VisionTransformer(nn.Module):
             self.dist_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
         self.blocks = nn.ModuleList([_Block(embed_dim, num_heads, mlp_ratio, qkv_bias) for _ in range(depth)])
         self.norm = nn.LayerNorm(embed_dim)
+        if norm_eps is not None:               # ViT_new passes one norm_layer (one epsilon) to every LayerNorm
+            self.norm.eps = norm_eps
+            for blk in self.blocks:
+                blk.norm1.eps = blk.norm2.eps = norm_eps
         self.head = nn.Linear(embed_dim, num_classes)
         if distilled:
             self.head_dist = nn.Linear(embed_dim, num_classes)
@@ -112,7 +116,7 @@ class VisionTransformer(nn.Module):
             blk.attn._owner = (self,)          # tuple: keep the back-reference out of the module tree
             blk.attn._layer = i
         self._cfg = vit_config(img_size, patch_size, in_chans, num_classes, embed_dim, depth, num_heads, mlp_ratio,
-                               distilled, 1e-6, self.norm.eps)
+                               distilled, self.blocks[0].norm1.eps, self.norm.eps)
         self._engine = None
         self._weights_version = None
         self.engine_flags = 0
@@ -181,20 +185,22 @@ class VisionTransformer(nn.Module):
         if method in ("transformer_attribution", "grad"):
             maps, _ = eng.attribute(index=index, start_layer=start_layer)
             return maps
-        # secondary methods: served from the saved per-block tensors (run the relprop through every block)
-        eng.attribute(index=index, start_layer=0, flags=eng.flags | _lib.FLAG_KEEP_ALL_CAMS)
-        if method == "rollout":
-            cams = [blk.attn.get_attn_cam().clamp(min=0).mean(dim=1) for blk in self.blocks]
+        if method == "full":                                   # :337-343: relevance of every pixel, channels summed
+            return eng.relprop_pixels(index=index)
+        # secondary methods (:345-398): head reductions of the saved per-block tensors
+        if method == "rollout":                                # attn_cam of every block -> rollout
+            eng.attribute(index=index, start_layer=0, flags=eng.flags | _lib.FLAG_KEEP_ALL_CAMS)
+            cams = [ops.head_reduce(blk.attn.get_attn_cam(), mode="relu_mean") for blk in self.blocks]
             return compute_rollout_attention(cams, start_layer=start_layer)[:, 0, first:]
         if method in ("last_layer", "second_layer"):
-            blk = self.blocks[-1] if method == "last_layer" else self.blocks[1]
-            c = blk.attn.get_attn_cam()
-            if is_ablation:
-                c = blk.attn.get_attn_gradients() * c
-            return c.clamp(min=0).mean(dim=1)[:, 0, first:]
+            l = len(self.blocks) - 1 if method == "last_layer" else 1
+            eng.attribute(index=index, start_layer=l)          # the relprop stops at attn_cam of block l
+            attn = self.blocks[l].attn
+            c = ops.head_reduce(attn.get_attn_cam(), attn.get_attn_gradients() if is_ablation else None, mode="relu_mean")
+            return c[:, 0, first:]
         if method == "last_layer_attn":
-            return self.blocks[-1].attn.get_attn().clamp(min=0).mean(dim=1)[:, 0, first:]
-        raise NotImplementedError("method=%r (pixel-level 'full' LRP) is outside the attribution hot path" % method)
+            return ops.head_reduce(self.blocks[-1].attn.get_attn(), mode="relu_mean")[:, 0, first:]
+        raise ValueError("unknown method %r" % (method,))
 
 
 def _conv_filter(state_dict, patch_size=16):

@@ -2,9 +2,13 @@
 
 ``generate_LRP`` keeps the reference signature and return shape ([1, 196]); ``generate_LRP_batched`` is the
 batched addition: B independent explanations per call, device-resident in and out.
-The ``Baselines`` class (raw-attention rollout / attention GradCAM on the hook-free ViT) is out of scope.
+``Baselines`` (raw-attention rollout / attention GradCAM, reference ``:45-83``) runs on the same engine: it needs
+the forward pass (+ the class-gradient of the last block's attention) only.
 """
 import torch
+
+from transformer_explainability_b200 import _lib, ops
+from transformer_explainability_b200.baselines.ViT.ViT_LRP import compute_rollout_attention
 
 
 class LRP:
@@ -26,3 +30,36 @@ class LRP:
         """B independent ``transformer_attribution`` explanations in one engine call: [B,3,H,W] -> [B,196]."""
         maps, idx = self.model.engine().explain(input, index=index, start_layer=start_layer, chunk=chunk)
         return (maps, idx) if return_index else maps
+
+
+class Baselines:
+    """``ViT_explanation_generator.py:45-83`` for a ``baselines.ViT.ViT_new`` (or ``ViT_LRP``) model."""
+
+    def __init__(self, model):
+        self.model = model
+        self.model.eval()
+
+    def generate_cam_attn(self, input, index=None):
+        """``:50-71``: CLS-row attention of the last block, weighted per head by the mean of its gradient over the
+        patch positions, relu(mean over heads), min-max normalised -> [g,g] (B = 1) or [B,g,g]."""
+        eng = self.model.engine()
+        eng.forward(input)
+        eng.attribute(index=index, start_layer=self.model._cfg.depth - 1, flags=eng.flags | _lib.FLAG_GRADIENTS_ONLY)
+        attn = self.model.blocks[-1].attn
+        n = eng.tokens
+        first = eng.prefix
+        w = ops.head_region_mean(attn.get_attn_gradients(), rows=(0, 1), cols=(first, n))
+        cam = ops.head_reduce(attn.get_attn(), head_weight=w, mode="mean_relu")[:, 0, first:]
+        lo = cam.amin(dim=1, keepdim=True)
+        hi = cam.amax(dim=1, keepdim=True)
+        cam = (cam - lo) / (hi - lo)
+        g = int(round((n - first) ** 0.5))
+        cam = cam.reshape(-1, g, g)
+        return cam[0] if cam.shape[0] == 1 else cam
+
+    def generate_rollout(self, input, start_layer=0):
+        """``:73-83``: rollout of the head-averaged raw attention maps, CLS row -> [B,N-1]."""
+        eng = self.model.engine()
+        eng.forward(input)
+        mats = [ops.head_reduce(blk.attn.get_attn(), mode="mean") for blk in self.model.blocks]
+        return compute_rollout_attention(mats, start_layer=start_layer)[:, 0, eng.prefix:]

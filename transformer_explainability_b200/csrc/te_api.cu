@@ -156,17 +156,30 @@ extern "C" int te_matmul_qk_relprop(const float* q, const float* k, const float*
     return TE_OK;
 }
 
+// ---- head reductions of the secondary methods ------------------------------------------------------------
+extern "C" int te_head_reduce(const float* a, const float* g, const float* head_w, int batch, int heads, int n, int ld,
+                              int mode, float* out, void* stream) {
+    REQ(a && out && batch > 0 && heads > 0 && n > 0 && ld >= n && mode >= 0 && mode <= 2, "te_head_reduce: bad argument");
+    return te_launch_head_reduce(a, g, head_w, out, batch, heads, n, ld, mode, ST(stream));
+}
+extern "C" int te_head_region_mean(const float* g, int batch, int heads, int n, int ld, int r0, int r1, int c0, int c1,
+                                   float* out, void* stream) {
+    REQ(g && out && batch > 0 && heads > 0 && n > 0 && ld >= n, "te_head_region_mean: bad argument");
+    return te_launch_head_region_mean(g, out, batch * heads, n, ld, r0, r1, c0, c1, ST(stream));
+}
+
 // ---- rollout -------------------------------------------------------------------------------------
 static long long ro_align(long long bytes) { return ((bytes + 255) / 256) * 256; }
 
 extern "C" long long te_rollout_workspace_bytes(int layers, int batch, int n) {
     if (layers <= 0 || batch <= 0 || n <= 0) return TE_ERR_ARG;
     const long long ld = (n + 3) & ~3;
-    return ro_align((long long)layers * batch * n * ld * 4) + 2 * ro_align((long long)batch * n * ld * 4);
+    return ro_align((long long)layers * batch * n * ld * 4) + 2 * ro_align((long long)batch * n * ld * 4) +
+           ro_align((long long)layers * batch * n * 4);
 }
 
 static int ro_carve(void* workspace, long long bytes, int layers, int batch, int n, float** mats, float** ja,
-                    float** jb, int* ld) {
+                    float** jb, int* ld, float** diag = nullptr) {
     REQ(workspace && (((uintptr_t)workspace) & 255u) == 0, "rollout: workspace null or not 256-byte aligned");
     if (te_rollout_workspace_bytes(layers, batch, n) > bytes) { te_set_last_error("rollout: workspace too small"); return TE_ERR_WORKSPACE; }
     *ld = (n + 3) & ~3;
@@ -176,18 +189,38 @@ static int ro_carve(void* workspace, long long bytes, int layers, int batch, int
     *ja = reinterpret_cast<float*>(b);
     b += ro_align((long long)batch * n * (*ld) * 4);
     *jb = reinterpret_cast<float*>(b);
+    b += ro_align((long long)batch * n * (*ld) * 4);
+    if (diag) *diag = reinterpret_cast<float*>(b);
     return TE_OK;
+}
+
+// ---- first layer: Conv2d z^B rule / PatchEmbed.relprop (layers_ours.py:242-259, ViT_LRP.py:238-242) ----------------
+extern "C" long long te_patch_embed_relprop_workspace_bytes(int batch, int in_chans, int img_size, int patch_size, int dim) {
+    if (batch <= 0 || in_chans <= 0 || patch_size <= 0 || img_size % patch_size != 0 || dim <= 0) return TE_ERR_ARG;
+    return te_patch_relprop_scratch_floats(batch, in_chans, img_size, patch_size, dim) * 4 + 256;
+}
+extern "C" int te_patch_embed_relprop(const float* images, const float* weight, const float* r, int batch, int in_chans,
+                                      int img_size, int patch_size, int dim, float* r_pixels, float* r_sum, void* workspace,
+                                      long long workspace_bytes, void* stream) {
+    REQ(images && weight && r && (r_pixels || r_sum) && batch > 0, "te_patch_embed_relprop: bad argument");
+    REQ(workspace && (((uintptr_t)workspace) & 255u) == 0, "te_patch_embed_relprop: workspace null or not 256-byte aligned");
+    const long long need = te_patch_embed_relprop_workspace_bytes(batch, in_chans, img_size, patch_size, dim);
+    if (need < 0) { te_set_last_error("te_patch_embed_relprop: bad shape"); return TE_ERR_ARG; }
+    if (need > workspace_bytes) { te_set_last_error("te_patch_embed_relprop: workspace too small"); return TE_ERR_WORKSPACE; }
+    const long long np = (long long)(img_size / patch_size) * (img_size / patch_size);
+    return te_patch_relprop_run(images, weight, r, np * dim, batch, in_chans, img_size, patch_size, dim,
+                                reinterpret_cast<float*>(workspace), r_pixels, r_sum, ST(stream));
 }
 
 extern "C" int te_attribution_rollout(const float* grad, const float* cam, int layers, int batch, int heads, int n,
                                       int ld, int start_layer, int normalize, unsigned flags, float* joint,
                                       float* row0, void* workspace, long long workspace_bytes, void* stream) {
     REQ(grad && cam && layers > 0 && batch > 0 && heads > 0 && n > 0 && ld >= n, "te_attribution_rollout: bad argument");
-    float *mats, *ja, *jb;
+    float *mats, *ja, *jb, *diag;
     int ldw;
-    TE_TRY(ro_carve(workspace, workspace_bytes, layers, batch, n, &mats, &ja, &jb, &ldw));
+    TE_TRY(ro_carve(workspace, workspace_bytes, layers, batch, n, &mats, &ja, &jb, &ldw, &diag));
     return te_rollout_layers(grad, cam, (long long)batch * heads * n * ld, layers, batch, heads, n, ld, ldw, start_layer,
-                             normalize, flags, mats, ja, jb, joint, row0, /*first=*/0, /*bert_fix=*/0, ST(stream));
+                             normalize, flags, mats, ja, jb, joint, row0, /*first=*/0, /*bert_fix=*/0, ST(stream), diag);
 }
 
 extern "C" int te_compute_rollout_attention(const float* mats_in, int layers, int batch, int n, int start_layer,

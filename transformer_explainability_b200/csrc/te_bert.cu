@@ -316,7 +316,7 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
                                  long long workspace_bytes, void* stream) {
     Dims d; Workspace ws;
     TE_TRY(check_ws(cfg, batch, seq, workspace, workspace_bytes, d, ws));
-    if (!weights || !index || !maps) { te_set_last_error("te_bert_attribute: null pointer"); return TE_ERR_ARG; }
+    if (!weights || !index || (!maps && !(flags & TE_FLAG_GRADIENTS_ONLY))) { te_set_last_error("te_bert_attribute: null pointer"); return TE_ERR_ARG; }
     if (start_layer < 0 || start_layer >= d.L) { te_set_last_error("te_bert_attribute: start_layer out of range"); return TE_ERR_ARG; }
     if ((flags & (TE_FLAG_ZPLUS_TENSOR_CORES | TE_FLAG_LINEAR_TENSOR_CORES)) && !derived) {
         te_set_last_error("te_bert_attribute: tensor-core flags need the derived weight buffer");
@@ -374,6 +374,8 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
         TE_TRY(linear_bwd_tc(tw.qkv, dqkv, lw.qkvw, dxn, nullptr, d.M, d.D, 3 * d.D, TE_EPI_STORE, st));
         TE_TRY(te_launch_add2(dxn, dsx, dxa, MD, st));                                                          // d h
     }
+
+    if (flags & TE_FLAG_GRADIENTS_ONLY) return TE_OK;      // attention-GradCAM baseline: gradients are all it reads
 
     // ---- relprop -----------------------------------------------------------------------------------------------
     float* R = ws.tD[0]; float* R1 = ws.tD[1]; float* R2 = ws.tD[2]; float* R3 = ws.tD[3];

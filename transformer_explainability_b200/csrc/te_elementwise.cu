@@ -49,8 +49,10 @@ __global__ void assemble_tokens_kernel(const float* __restrict__ patch_out, cons
         float4 v;
         if (tok < n_prefix) v = *reinterpret_cast<const float4*>((tok == 0 ? cls : dist) + q * 4);
         else v = *reinterpret_cast<const float4*>(patch_out + ((long long)b * (N - n_prefix) + tok - n_prefix) * D + q * 4);
-        const float4 pe = *reinterpret_cast<const float4*>(pos + (long long)tok * D + q * 4);
-        v.x += pe.x; v.y += pe.y; v.z += pe.z; v.w += pe.w;
+        if (pos != nullptr) {                                   // pos == null: the tokens before ``self.add`` (:311)
+            const float4 pe = *reinterpret_cast<const float4*>(pos + (long long)tok * D + q * 4);
+            v.x += pe.x; v.y += pe.y; v.z += pe.z; v.w += pe.w;
+        }
         *reinterpret_cast<float4*>(x + rt * D + q * 4) = v;
     }
 }
@@ -269,12 +271,13 @@ __global__ void clone_relprop_kernel(const float* __restrict__ x, const float* _
 // Add.relprop (layers_ours.py:97-120), reductions PER SAMPLE (the reference is B=1), fp64 sums.
 // pass 1: partial[b][split] = (sum a, sum b, sum R),  a = x1*sd(R,x1+x2), b = x2*sd(R,x1+x2)
 __global__ void add_reduce_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
-                                  const float* __restrict__ r, double* __restrict__ partial, long long per4) {
+                                  const float* __restrict__ r, double* __restrict__ partial, long long per4,
+                                  long long x2s4) {
     const int b = blockIdx.y, sp = blockIdx.x;
     const long long chunk = (per4 + TE_ADD_SPLIT - 1) / TE_ADD_SPLIT;
     const long long lo = sp * chunk, hi = min(per4, lo + chunk);
     const float4* p1 = reinterpret_cast<const float4*>(x1) + b * per4;
-    const float4* p2 = reinterpret_cast<const float4*>(x2) + b * per4;
+    const float4* p2 = reinterpret_cast<const float4*>(x2) + b * x2s4;
     const float4* pr = reinterpret_cast<const float4*>(r) + b * per4;
     double sa = 0.0, sb = 0.0, sr = 0.0;
     for (long long t = lo + threadIdx.x; t < hi; t += blockDim.x) {
@@ -301,7 +304,7 @@ __global__ void add_reduce_kernel(const float* __restrict__ x1, const float* __r
 // pass 2: a *= sd( sd(|A|,|A|+|B|)*rho , A ) ; b likewise
 __global__ void add_scale_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
                                  const float* __restrict__ r, float* __restrict__ r1, float* __restrict__ r2,
-                                 const double* __restrict__ partial, long long per4) {
+                                 const double* __restrict__ partial, long long per4, long long x2s4) {
     const int b = blockIdx.y;
     __shared__ float fa_s, fb_s;
     if (threadIdx.x == 0) {
@@ -317,17 +320,17 @@ __global__ void add_scale_kernel(const float* __restrict__ x1, const float* __re
     __syncthreads();
     const float fa = fa_s, fb = fb_s;
     const float4* p1 = reinterpret_cast<const float4*>(x1) + b * per4;
-    const float4* p2 = reinterpret_cast<const float4*>(x2) + b * per4;
+    const float4* p2 = reinterpret_cast<const float4*>(x2) + b * x2s4;
     const float4* pr = reinterpret_cast<const float4*>(r) + b * per4;
     float4* o1 = reinterpret_cast<float4*>(r1) + b * per4;
-    float4* o2 = reinterpret_cast<float4*>(r2) + b * per4;
+    float4* o2 = r2 ? reinterpret_cast<float4*>(r2) + b * per4 : nullptr;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < per4;
          t += (long long)gridDim.x * blockDim.x) {
         const float4 a = p1[t], c = p2[t], rr = pr[t];
         const float s0 = te_sd(rr.x, a.x + c.x), s1 = te_sd(rr.y, a.y + c.y);
         const float s2 = te_sd(rr.z, a.z + c.z), s3 = te_sd(rr.w, a.w + c.w);
         o1[t] = make_float4(a.x * s0 * fa, a.y * s1 * fa, a.z * s2 * fa, a.w * s3 * fa);
-        o2[t] = make_float4(c.x * s0 * fb, c.y * s1 * fb, c.z * s2 * fb, c.w * s3 * fb);
+        if (o2) o2[t] = make_float4(c.x * s0 * fb, c.y * s1 * fb, c.z * s2 * fb, c.w * s3 * fb);
     }
 }
 
@@ -352,9 +355,11 @@ __global__ void index_select_relprop_kernel(const float* __restrict__ x, const f
 // ------------------------------------------------------------------------------------------------
 // aggregation: M = mean_h relu(G*cam) (+I) (/rowsum)      ViT_LRP.py:359-365 ; ExplanationGenerator.py:49-55,12-14
 // ------------------------------------------------------------------------------------------------
+// diag != null ("split" form for the tensor-core chain): the identity is NOT added into M; it still counts in the row
+// sum, and its weight after normalisation (1 / rowsum) goes to diag[row].
 __global__ void aggregate_kernel(const float* __restrict__ G, const float* __restrict__ cam,
                                  float* __restrict__ M, int B, int H, int N, int ld_in, int ld, int add_eye,
-                                 int normalize) {
+                                 int normalize, float* __restrict__ diag) {
     const int lane = threadIdx.x & 31;
     const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);   // b*N + i
     if (row >= (long long)B * N) return;
@@ -377,8 +382,49 @@ __global__ void aggregate_kernel(const float* __restrict__ G, const float* __res
     }
     if (normalize) {
         rs = te_warp_sum(rs);
+        if (diag != nullptr) rs += 1.0f;
         __syncwarp();
         for (int j = lane; j < N; j += 32) out[j] = out[j] / rs;
+        if (diag != nullptr && lane == 0) diag[row] = 1.0f / rs;
+    }
+}
+
+// head reductions for the secondary methods: one warp per output row
+__global__ void head_reduce_kernel(const float* __restrict__ A, const float* __restrict__ G,
+                                   const float* __restrict__ hw, float* __restrict__ out, int B, int H, int N, int ld,
+                                   int mode) {
+    const int lane = threadIdx.x & 31;
+    const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);   // b*N + i
+    if (row >= (long long)B * N) return;
+    const int b = (int)(row / N), i = (int)(row % N);
+    for (int j = lane; j < N; j += 32) {
+        float s = 0.f;
+        for (int h = 0; h < H; ++h) {
+            const long long o = (((long long)b * H + h) * N + i) * ld + j;
+            float v = A[o];
+            if (G != nullptr) v *= G[o];
+            if (hw != nullptr) v *= hw[b * H + h];
+            s += (mode == 1) ? fmaxf(v, 0.f) : v;
+        }
+        s /= (float)H;
+        out[row * N + j] = (mode == 2) ? fmaxf(s, 0.f) : s;
+    }
+}
+// out[b,h] = mean of G[b,h,r0:r1,c0:c1]; one block per (b,h)
+__global__ void head_region_mean_kernel(const float* __restrict__ G, float* __restrict__ out, int N, int ld, int r0, int r1,
+                                        int c0, int c1) {
+    const float* g = G + (long long)blockIdx.x * N * ld;
+    const int w = c1 - c0, total = (r1 - r0) * w;
+    double s = 0.0;
+    for (int t = threadIdx.x; t < total; t += blockDim.x) s += (double)g[(long long)(r0 + t / w) * ld + c0 + t % w];
+    __shared__ double red[kThreads / 32];
+    s = te_warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int i = 0; i < kThreads / 32; ++i) t += red[i];
+        out[blockIdx.x] = (float)(t / (double)total);
     }
 }
 
@@ -626,18 +672,22 @@ int te_launch_clone_relprop(const float* x, const float* r1, const float* r2, co
     TE_CUDA_CHECK_LAUNCH();
     return TE_OK;
 }
-int te_launch_add_relprop(const float* x1, const float* x2, const float* r, float* r1, float* r2, double* partial,
-                          int B, long long per_sample, cudaStream_t st) {
-    TE_REQ(per_sample % 4 == 0, "add_relprop: per-sample size % 4 != 0");
+int te_launch_add_relprop_ex(const float* x1, const float* x2, long long x2_sample_stride, const float* r, float* r1,
+                             float* r2, double* partial, int B, long long per_sample, cudaStream_t st) {
+    TE_REQ(per_sample % 4 == 0 && x2_sample_stride % 4 == 0, "add_relprop: per-sample size % 4 != 0");
     TE_REQ(B <= 65535, "add_relprop: batch too large for one launch");
-    const long long per4 = per_sample / 4;
-    add_reduce_kernel<<<dim3(TE_ADD_SPLIT, B), kThreads, 0, st>>>(x1, x2, r, partial, per4);
+    const long long per4 = per_sample / 4, x2s4 = x2_sample_stride / 4;
+    add_reduce_kernel<<<dim3(TE_ADD_SPLIT, B), kThreads, 0, st>>>(x1, x2, r, partial, per4, x2s4);
     TE_CUDA_CHECK_LAUNCH();
     int gx = (int)((per4 + kThreads - 1) / kThreads);
     gx = gx > 64 ? 64 : (gx < 1 ? 1 : gx);
-    add_scale_kernel<<<dim3(gx, B), kThreads, 0, st>>>(x1, x2, r, r1, r2, partial, per4);
+    add_scale_kernel<<<dim3(gx, B), kThreads, 0, st>>>(x1, x2, r, r1, r2, partial, per4, x2s4);
     TE_CUDA_CHECK_LAUNCH();
     return TE_OK;
+}
+int te_launch_add_relprop(const float* x1, const float* x2, const float* r, float* r1, float* r2, double* partial,
+                          int B, long long per_sample, cudaStream_t st) {
+    return te_launch_add_relprop_ex(x1, x2, per_sample, r, r1, r2, partial, B, per_sample, st);
 }
 int te_launch_index_select_relprop(const float* x, const float* r_tok0, const float* r_tok1, float* out, int B,
                                    int N, int D, cudaStream_t st) {
@@ -646,9 +696,22 @@ int te_launch_index_select_relprop(const float* x, const float* r_tok0, const fl
     return TE_OK;
 }
 int te_launch_aggregate(const float* G, const float* cam, float* M, int B, int H, int N, int ld_in, int ld_out,
-                        int add_eye, int normalize, cudaStream_t st) {
+                        int add_eye, int normalize, cudaStream_t st, float* diag) {
     aggregate_kernel<<<warp_rows_grid((long long)B * N), kThreads, 0, st>>>(G, cam, M, B, H, N, ld_in, ld_out, add_eye,
-                                                                          normalize);
+                                                                          normalize, diag);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_head_reduce(const float* a, const float* g, const float* hw, float* out, int B, int H, int N, int ld,
+                          int mode, cudaStream_t st) {
+    head_reduce_kernel<<<warp_rows_grid((long long)B * N), kThreads, 0, st>>>(a, g, hw, out, B, H, N, ld, mode);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_head_region_mean(const float* g, float* out, int BH, int N, int ld, int r0, int r1, int c0, int c1,
+                               cudaStream_t st) {
+    TE_REQ(BH > 0 && r0 >= 0 && r1 > r0 && r1 <= N && c0 >= 0 && c1 > c0 && c1 <= N, "head_region_mean: bad region");
+    head_region_mean_kernel<<<BH, kThreads, 0, st>>>(g, out, N, ld, r0, r1, c0, c1);
     TE_CUDA_CHECK_LAUNCH();
     return TE_OK;
 }

@@ -269,6 +269,9 @@ int te_gemm_launch(TeGemm p, int alay, int blay, int xf, int epi, cudaStream_t s
     TE_CASE(TE_L_MN, TE_L_MN, TE_XF_NONE, TE_EPI_MUL)
     TE_CASE(TE_L_K, TE_L_MN, TE_XF_NONE, TE_EPI_MUL)
     TE_CASE(TE_L_K, TE_L_MN, TE_XF_NONE, TE_EPI_ACCUM)
+    // first-layer z^B rule: S W+, S W-
+    TE_CASE(TE_L_K, TE_L_MN, TE_XF_B_POS, TE_EPI_STORE)
+    TE_CASE(TE_L_K, TE_L_MN, TE_XF_B_NEG, TE_EPI_STORE)
     te_set_last_error("te_gemm: unsupported (layout, transform, epilogue) combination");
     return TE_ERR_UNSUPPORTED;
 }

@@ -592,7 +592,7 @@ te_tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // =====================================================================================================================
 constexpr int AT_KB = 2;                                          // max k-blocks (head_dim <= 64)
 constexpr int AT_SMEM = 2 * (AT_KB * A_BYTES + AT_KB * B_BYTES) + 1024 + 256;   // hi + lo of A and B
-enum { AT_STORE = 0, AT_MUL = 1, AT_SD = 2 };
+enum { AT_STORE = 0, AT_MUL = 1, AT_SD = 2, AT_RESID = 3 };
 
 struct AtParams {
     int N, H, dh, ld_out;            // tokens, heads, head_dim, row stride of out / E
@@ -768,15 +768,29 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B lands exactly as eight such atoms.  3-D tensor maps (col, token, batch*head | batch) make every row past the N tokens of
 // a head read as zero, so K (= N = 197) is padded to 224 for free.  4-stage ring, both operands split hi/lo in smem.
 // =====================================================================================================================
-constexpr int NK_BN = 64;                                          // head_dim
-constexpr int NK_A = A_BYTES, NK_B = NK_BN * BK * 4;               // 16 KiB, 8 KiB
-constexpr int NK_STAGE = 2 * NK_A + 2 * NK_B;                      // 48 KiB
-constexpr int NK_STAGES = 4;
-constexpr int NK_SMEM = NK_STAGES * NK_STAGE + 1024 + 256;
-constexpr int NK_XF4 = (NK_A + NK_B) / 16;                         // float4 to split per stage
+// NB = number of 32-wide output-column blocks: 2 for the head_dim-64 attention products, 7 (N <= 224) for the dense
+// rollout product J <- (M_l + I) J, which is the same contraction with H = 1 (A = M_l K-major, B = J MN-major).
+constexpr int NK_A = A_BYTES;                                      // 16 KiB
+template <int NB> struct NkCfg {
+    static constexpr int BN = NB * 32;
+    static constexpr int B_BYTES_ = BN * BK * 4;                   // 4 KiB per block
+    static constexpr int STAGE = 2 * NK_A + 2 * B_BYTES_;
+    static constexpr int STAGES = (NB <= 2) ? 4 : 2;
+    static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+    static constexpr int XF4 = (NK_A + B_BYTES_) / 16;
+    // wide tiles (the dense rollout product) keep the lo*hi + hi*lo correction terms in a second accumulator at column
+    // 256: the tensor core truncates on every accumulate, so the fewer (and the smaller) the addends an accumulator
+    // sees after it holds a large value, the smaller the drift
+    static constexpr bool SPLIT_ACC = NB >= 7;
+    static constexpr uint32_t TMEM_COLS = SPLIT_ACC ? 512u : ((BN <= 64) ? 64u : (BN <= 128 ? 128u : 256u));
+};
 
 struct NkParams {
-    int N, H, ld_out;                 // tokens, heads, row stride of out / E (packed activation)
+    int N, H, ld_out;                 // tokens (= reduction length and output rows), heads, row stride of out / E
+    int n_out;                        // valid output columns of the whole row (all heads / column tiles); columns in
+    int n_pad;                        // [n_out, n_pad) are written as zero, columns >= n_pad are not touched
+    int a_shared;                     // 1: A is indexed by the batch only (dense product, "heads" are column tiles)
+    const float* rowscale;            // AT_RESID: out = acc + rowscale[b*N + m] * E  (null: 1)
     const float* E; float* out; float alpha;
 };
 
@@ -799,9 +813,11 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t l
     return d;
 }
 
-template <int AMN, int EPI>
+template <int AMN, int EPI, int NB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 te_tc_attn_nk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const NkParams p) {
+    using C = NkCfg<NB>;
+    constexpr int NK_BN = C::BN, NK_B = C::B_BYTES_, NK_STAGE = C::STAGE, NK_STAGES = C::STAGES, NK_XF4 = C::XF4;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -820,7 +836,7 @@ te_tc_attn_nk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
     const int m0 = blockIdx.x * BM;
     const int kb = (p.N + BK - 1) / BK;
-    constexpr uint32_t TMEM_COLS = 64u;
+    constexpr uint32_t TMEM_COLS = C::TMEM_COLS;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -854,11 +870,11 @@ te_tc_attn_nk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const uint32_t sa = smem_base + s * NK_STAGE;
                 const int k0 = it * BK;
                 if (AMN == 0) {
-                    tma_load_3d(sa, &tmA, full_bar(s), k0, m0, bh);                      // [128 rows m] x [32 k], K-major
+                    tma_load_3d(sa, &tmA, full_bar(s), k0, m0, p.a_shared ? b : bh);     // [128 rows m] x [32 k], K-major
                 } else {
 #pragma unroll
                     for (int mb = 0; mb < BM / 32; ++mb)                                 // four [32 m] x [32 k rows] blocks
-                        tma_load_3d(sa + mb * 4096, &tmA, full_bar(s), m0 + mb * 32, k0, bh);
+                        tma_load_3d(sa + mb * 4096, &tmA, full_bar(s), m0 + mb * 32, k0, p.a_shared ? b : bh);
                 }
 #pragma unroll
                 for (int nb = 0; nb < NK_BN / 32; ++nb)                                  // two [32 d] x [32 k rows] blocks
@@ -885,9 +901,16 @@ te_tc_attn_nk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     }
                     const uint64_t bhd = make_smem_desc_mn(sa + OFF_BH + k * 1024, 4096);
                     const uint64_t bld = make_smem_desc_mn(sa + OFF_BL + k * 1024, 4096);
-                    umma_tf32(tmem_base, al, bhd, idesc, (it == 0 && k == 0) ? 0u : 1u);
-                    umma_tf32(tmem_base, ah, bld, idesc, 1u);
-                    umma_tf32(tmem_base, ah, bhd, idesc, 1u);
+                    const uint32_t first = (it == 0 && k == 0) ? 0u : 1u;
+                    if (C::SPLIT_ACC) {
+                        umma_tf32(tmem_base + 256u, al, bhd, idesc, first);
+                        umma_tf32(tmem_base + 256u, ah, bld, idesc, 1u);
+                        umma_tf32(tmem_base, ah, bhd, idesc, first);
+                    } else {
+                        umma_tf32(tmem_base, al, bhd, idesc, first);
+                        umma_tf32(tmem_base, ah, bld, idesc, 1u);
+                        umma_tf32(tmem_base, ah, bhd, idesc, 1u);
+                    }
                 }
                 umma_commit(empty_bar(s));
             }
@@ -919,32 +942,60 @@ te_tc_attn_nk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int m = m0 + q * 32 + lane;
         const bool live = m < p.N;
         const long long off = ((long long)b * p.N + m) * p.ld_out + (long long)h * NK_BN;
-        float4 ebuf[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) ebuf[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 ebuf[(EPI == AT_MUL) ? NB * 8 : 1];
         if (EPI == AT_MUL && live) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) ebuf[j] = *reinterpret_cast<const float4*>(p.E + off + j * 4);
+            for (int j = 0; j < NB * 8; ++j) ebuf[j] = *reinterpret_cast<const float4*>(p.E + off + j * 4);
         }
         mbar_wait(accum_bar, 0);
         tcgen05_fence_after();
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const float rscale = (EPI == AT_RESID && live && p.rowscale) ? p.rowscale[(long long)b * p.N + m] : 1.f;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < NB; ++c) {
             uint32_t acc[32];
             tmem_ld32(tlane + (uint32_t)(c * 32), acc);
+            float4 rbuf[(EPI == AT_RESID) ? 8 : 1];
+            if (EPI == AT_RESID && live) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    rbuf[(EPI == AT_RESID) ? j : 0] = (h * NK_BN + c * 32 + j * 4 < p.n_pad)
+                                                         ? *reinterpret_cast<const float4*>(p.E + off + c * 32 + j * 4)
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             tmem_ld_wait();
+            if (C::SPLIT_ACC) {
+                uint32_t acc2[32];
+                tmem_ld32(tlane + 256u + (uint32_t)(c * 32), acc2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(acc2[j]));
+            }
             if (live) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    float o[4];
-                    const float e[4] = {ebuf[c * 8 + j].x, ebuf[c * 8 + j].y, ebuf[c * 8 + j].z, ebuf[c * 8 + j].w};
+                    const int col = c * 32 + j * 4;
+                    const int gcol = h * NK_BN + col;
+                    if (gcol < p.n_pad) {
+                        float o[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float a = __uint_as_float(acc[j * 4 + u]);
-                        o[u] = (EPI == AT_MUL) ? p.alpha * a * e[u] : p.alpha * a;
+                        for (int u = 0; u < 4; ++u) {
+                            const float a = __uint_as_float(acc[j * 4 + u]);
+                            float v = p.alpha * a;
+                            if (EPI == AT_MUL) {
+                                const float4 e4 = ebuf[(EPI == AT_MUL) ? c * 8 + j : 0];
+                                const float e = (u == 0) ? e4.x : (u == 1) ? e4.y : (u == 2) ? e4.z : e4.w;
+                                v *= e;
+                            }
+                            if (EPI == AT_RESID) {
+                                const float4 e4 = rbuf[(EPI == AT_RESID) ? j : 0];
+                                const float e = (u == 0) ? e4.x : (u == 1) ? e4.y : (u == 2) ? e4.z : e4.w;
+                                v += rscale * e;
+                            }
+                            o[u] = (gcol + u < p.n_out) ? v : 0.f;                    // zero the row padding
+                        }
+                        *reinterpret_cast<float4*>(p.out + off + col) = make_float4(o[0], o[1], o[2], o[3]);
                     }
-                    *reinterpret_cast<float4*>(p.out + off + c * 32 + j * 4) = make_float4(o[0], o[1], o[2], o[3]);
                 }
             }
         }
@@ -1148,8 +1199,9 @@ int te_tc_attn_nn(const float* A, long long lda, const float* B, long long ldb, 
 }
 
 bool te_tc_attn_nk_supported(int N, int dh, int NP, long long ldx, long long ld_out) {
-    return N >= 1 && dh == NK_BN && NP % 4 == 0 && ldx % 4 == 0 && ld_out % 4 == 0 && get_encode() != nullptr;
+    return N >= 1 && dh == 64 && NP % 4 == 0 && ldx % 4 == 0 && ld_out % 4 == 0 && get_encode() != nullptr;
 }
+bool te_tc_bmm_nk_supported(int N, int ld) { return N >= 1 && ld % 4 == 0 && ld >= N && get_encode() != nullptr; }
 
 namespace {
 // rank-3 fp32 map: dims {cols, rows, batch}, box {bc, br, 1}, 128-byte swizzle, zero fill outside
@@ -1166,18 +1218,20 @@ bool make_map3(CUtensorMap* m, const float* base, long long cols, long long rows
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int AMN, int EPI>
+template <int AMN, int EPI, int NB>
 int launch_nk(const float* map, int NP, const float* X, long long ldx, const NkParams& p, int batch, cudaStream_t st) {
+    constexpr int NK_SMEM = NkCfg<NB>::SMEM;
     CUtensorMap tmA, tmB;
     // attention-shaped map [batch*H, N, NP] ; activation [batch, N, ldx]
-    if (!make_map3(&tmA, map, NP, p.N, (long long)batch * p.H, NP, (long long)p.N * NP, 32, AMN ? 32 : BM, AMN != 0) ||
+    if (!make_map3(&tmA, map, NP, p.N, p.a_shared ? (long long)batch : (long long)batch * p.H, NP, (long long)p.N * NP, 32,
+                   AMN ? 32 : BM, AMN != 0) ||
         !make_map3(&tmB, X, ldx, p.N, batch, ldx, (long long)p.N * ldx, 32, 32, true)) {
         te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed (attention nk)");
         return TE_ERR_CUDA;
     }
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(te_tc_attn_nk_kernel<AMN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, NK_SMEM) != cudaSuccess) {
+        if (cudaFuncSetAttribute(te_tc_attn_nk_kernel<AMN, EPI, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, NK_SMEM) != cudaSuccess) {
             te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
             return TE_ERR_CUDA;
         }
@@ -1185,7 +1239,7 @@ int launch_nk(const float* map, int NP, const float* X, long long ldx, const NkP
     }
     dim3 grid((p.N + BM - 1) / BM, batch * p.H);
     if (grid.y > 65535) { te_set_last_error("te_gemm_tc: batch*heads too large for one launch"); return TE_ERR_ARG; }
-    te_tc_attn_nk_kernel<AMN, EPI><<<grid, NUM_THREADS, NK_SMEM, st>>>(tmA, tmB, p);
+    te_tc_attn_nk_kernel<AMN, EPI, NB><<<grid, NUM_THREADS, NK_SMEM, st>>>(tmA, tmB, p);
     TE_CUDA_CHECK_LAUNCH();
     return TE_OK;
 }
@@ -1196,11 +1250,31 @@ int launch_nk(const float* map, int NP, const float* X, long long ldx, const NkP
 int te_tc_attn_nk(const float* map, int NP, int amn, const float* X, long long ldx, int batch, int H, int N, float* out,
                   int ld_out, const float* E, float alpha, int epi, cudaStream_t st) {
     NkParams p;
-    p.N = N; p.H = H; p.ld_out = ld_out; p.E = E; p.out = out; p.alpha = alpha;
-    if (epi == TE_TC_ATTN_STORE) return amn ? launch_nk<1, AT_STORE>(map, NP, X, ldx, p, batch, st) : launch_nk<0, AT_STORE>(map, NP, X, ldx, p, batch, st);
-    if (epi == TE_TC_ATTN_MUL) return amn ? launch_nk<1, AT_MUL>(map, NP, X, ldx, p, batch, st) : launch_nk<0, AT_MUL>(map, NP, X, ldx, p, batch, st);
+    p.N = N; p.H = H; p.ld_out = ld_out; p.n_out = H * 64; p.n_pad = H * 64; p.a_shared = 0; p.rowscale = nullptr;
+    p.E = E; p.out = out; p.alpha = alpha;
+    if (epi == TE_TC_ATTN_STORE) return amn ? launch_nk<1, AT_STORE, 2>(map, NP, X, ldx, p, batch, st) : launch_nk<0, AT_STORE, 2>(map, NP, X, ldx, p, batch, st);
+    if (epi == TE_TC_ATTN_MUL) return amn ? launch_nk<1, AT_MUL, 2>(map, NP, X, ldx, p, batch, st) : launch_nk<0, AT_MUL, 2>(map, NP, X, ldx, p, batch, st);
     te_set_last_error("te_gemm_tc: unsupported attention nk epilogue");
     return TE_ERR_UNSUPPORTED;
+}
+
+// One step of the rollout chain in residual form: out[b] = A[b] * J[b] + diag(rowscale[b]) * J[b], all [batch, N, ld]
+// (fp32-grade 3xTF32; A K-major, J MN-major).  A is the layer matrix WITHOUT its identity part (mean_h relu(G*cam),
+// divided by the row sum for BERT) and rowscale the identity's weight (null: 1; BERT: 1 / rowsum) — the large I * J term
+// is added in fp32 in the epilogue instead of being pushed through the truncating tensor-core accumulator.
+// One 128 x 224 tile per CTA when N <= 224 (ViT / DeiT), 128 x 256 column tiles otherwise (BERT-512: 4 x 2 CTAs per
+// sample).  The padding columns of out are zeroed so that it can be the next J.
+int te_tc_bmm_nk_resid(const float* A, const float* J, const float* rowscale, float* out, int batch, int N, int ld,
+                       cudaStream_t st) {
+    NkParams p;
+    p.N = N; p.ld_out = ld; p.n_out = N; p.n_pad = ld; p.a_shared = 1; p.rowscale = rowscale; p.E = J; p.out = out;
+    p.alpha = 1.f;
+    if (ld <= 224) {
+        p.H = 1;
+        return launch_nk<0, AT_RESID, 7>(A, ld, J, ld, p, batch, st);
+    }
+    p.H = (ld + 255) / 256;
+    return launch_nk<0, AT_RESID, 8>(A, ld, J, ld, p, batch, st);
 }
 
 // y[rows,out] = x[rows,in] W^T (+ epilogue)   — fp32-grade (3xTF32) on tcgen05

@@ -38,3 +38,8 @@ int te_tc_attn_nn(const float* A, long long lda, const float* B, long long ldb, 
 bool te_tc_attn_nk_supported(int N, int dh, int NP, long long ldx, long long ld_out);
 int te_tc_attn_nk(const float* map, int NP, int amn, const float* X, long long ldx, int batch, int H, int N, float* out,
                   int ld_out, const float* E, float alpha, int epi, cudaStream_t st);
+
+// dense rollout product out[b] = A[b] * Bm[b] ([batch, N, ld], N <= 224) on tcgen05, fp32-grade 3xTF32
+bool te_tc_bmm_nk_supported(int N, int ld);
+int te_tc_bmm_nk_resid(const float* A, const float* J, const float* rowscale, float* out, int batch, int N, int ld,
+                       cudaStream_t st);

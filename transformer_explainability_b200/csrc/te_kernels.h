@@ -33,13 +33,28 @@ int te_launch_clone_relprop(const float* x, const float* r1, const float* r2, co
 #define TE_ADD_SPLIT 16
 int te_launch_add_relprop(const float* x1, const float* x2, const float* r, float* r1, float* r2, double* partial,
                           int B, long long per_sample, cudaStream_t st);
+// same with x2 addressed as x2 + b*x2_sample_stride (0: one tensor shared by every sample, e.g. pos_embed); r2 may be null
+int te_launch_add_relprop_ex(const float* x1, const float* x2, long long x2_sample_stride, const float* r, float* r1,
+                             float* r2, double* partial, int B, long long per_sample, cudaStream_t st);
+// ---- first layer: Conv2d z^B rule behind PatchEmbed.relprop (te_patch_relprop.cu) ------------------
+long long te_patch_relprop_scratch_floats(int B, int C, int img, int P, int D);
+// r: relevance of the patch tokens, row (b, p) at r + b*r_sample_stride + p*D.  r_pixels [B,C,img,img] and / or
+// r_sum [B,img,img] (channels summed) are written when non-null.
+int te_patch_relprop_run(const float* images, const float* weight, const float* r, long long r_sample_stride, int B,
+                         int C, int img, int P, int D, float* scratch, float* r_pixels, float* r_sum, cudaStream_t st);
 // IndexSelect rule: out[b,tok,:] = x*sd(r,x), zero elsewhere.  r is [B,D] per token slot.
 int te_launch_index_select_relprop(const float* x, const float* r_tok0, const float* r_tok1, float* out, int B,
                                    int N, int D, cudaStream_t st);
 // ---- aggregation / rollout ---------------------------------------------------------------------
 // M[b] = mean_h relu(G*cam) (+I) (row-normalised if normalize) ; G, cam [B,H,N,ld_in] ; M [B,N,ld_out]
+// diag (with add_eye = 0, normalize = 1): identity kept out of M, its normalised weight 1/rowsum written to diag [B*N]
 int te_launch_aggregate(const float* G, const float* cam, float* M, int B, int H, int N, int ld_in, int ld_out,
-                        int add_eye, int normalize, cudaStream_t st);
+                        int add_eye, int normalize, cudaStream_t st, float* diag = nullptr);
+// secondary methods: out[b,i,j] = reduce_h( a (* g) (* hw[b,h]) ); mode 0 mean, 1 mean of relu, 2 relu of mean
+int te_launch_head_reduce(const float* a, const float* g, const float* hw, float* out, int B, int H, int N, int ld,
+                          int mode, cudaStream_t st);
+int te_launch_head_region_mean(const float* g, float* out, int BH, int N, int ld, int r0, int r1, int c0, int c1,
+                               cudaStream_t st);
 int te_launch_prep_mats(const float* in, float* out, long long rows, int N, int ld_in, int ld_out, int normalize,
                         cudaStream_t st);
 int te_launch_extract_row(const float* joint, float* out, int B, int N, int ld, int first, int bert_fix,

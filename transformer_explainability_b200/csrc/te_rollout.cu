@@ -3,6 +3,7 @@
 #include "te_rollout.h"
 #include "te_kernels.h"
 #include "te_rollout_fused.h"
+#include "te_gemm_tc.h"
 #include <string.h>
 
 int te_rollout_chain(const float* mats, int L, int B, int N, int ld, int start_layer, float* joint_a, float* joint_b,
@@ -30,13 +31,30 @@ int te_rollout_chain(const float* mats, int L, int B, int N, int ld, int start_l
 
 int te_rollout_layers(const float* G0, const float* cam0, long long layer_stride, int L, int B, int H, int N,
                       int ld_in, int ld, int start_layer, int normalize, unsigned flags, float* mats, float* joint_a, float* joint_b,
-                      float* joint_out, float* row_out, int first, int bert_fix, cudaStream_t st) {
+                      float* joint_out, float* row_out, int first, int bert_fix, cudaStream_t st, float* diag) {
     if (start_layer < 0 || start_layer >= L) { te_set_last_error("rollout: start_layer out of range"); return TE_ERR_ARG; }
     const float* joint = nullptr;
     if ((flags & 2u) && !joint_out && row_out && te_rollout_fused_supported(N, ld_in, ld)) {
         // row-only consumer (generate_LRP): fused single kernel, G / cam streamed once, nothing else in HBM
         return te_rollout_fused_row(G0, cam0, layer_stride, L, B, H, N, ld_in, start_layer, normalize, row_out, first,
                                     bert_fix, st);
+    } else if ((flags & 2u) && te_tc_bmm_nk_supported(N, ld) && (!normalize || diag)) {
+        // dense joint on the tensor cores, residual form: J <- A_l J + d_l J with A_l = M_l without its identity part
+        // (tcgen05, 3xTF32) and the identity's share d_l (1, or 1/rowsum for BERT) applied in fp32 in the epilogue
+        const long long ms = (long long)B * N * ld;
+        TE_TRY(te_launch_aggregate(G0 + start_layer * layer_stride, cam0 + start_layer * layer_stride,
+                                   mats + start_layer * ms, B, H, N, ld_in, ld, /*add_eye=*/1, normalize, st));
+        joint = mats + start_layer * ms;
+        float* bufs[2] = {joint_a, joint_b};
+        int which = 0;
+        for (int l = start_layer + 1; l < L; ++l) {
+            float* dl = normalize ? diag + (long long)l * B * N : nullptr;
+            TE_TRY(te_launch_aggregate(G0 + l * layer_stride, cam0 + l * layer_stride, mats + l * ms, B, H, N, ld_in, ld,
+                                       /*add_eye=*/0, normalize, st, dl));
+            TE_TRY(te_tc_bmm_nk_resid(mats + l * ms, joint, dl, bufs[which], B, N, ld, st));
+            joint = bufs[which];
+            which ^= 1;
+        }
     } else {
         const long long ms = (long long)B * N * ld;
         for (int l = start_layer; l < L; ++l)

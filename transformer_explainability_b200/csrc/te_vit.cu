@@ -139,6 +139,7 @@ struct Workspace {
     float *x_last, *xf, *logits, *logits2, *seed, *dpool, *rhead0, *rhead1, *shead;
     float *tD[4], *tF[2], *t3D[2], *tA;
     float *mats, *joint[2];
+    float* pix;                       // scratch of the first-layer (pixel) relprop, method="full"
     double* addpart;
     int* index_tmp;
     long long bytes;
@@ -174,6 +175,7 @@ static void carve(const Dims& d, char* base, Workspace& ws) {
     ws.mats = take((long long)d.L * d.B * d.N * d.NP);
     ws.joint[0] = take((long long)d.B * d.N * d.NP);
     ws.joint[1] = take((long long)d.B * d.N * d.NP);
+    ws.pix = take(te_patch_relprop_scratch_floats(d.B, d.Cin, d.img, d.P, d.D));
     ws.addpart = reinterpret_cast<double*>(take((long long)d.B * TE_ADD_SPLIT * 3 * 2));
     ws.index_tmp = reinterpret_cast<int*>(take(d.B));
     ws.bytes = off;
@@ -340,7 +342,7 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
                                 long long workspace_bytes, void* stream) {
     Dims d; Workspace ws;
     TE_TRY(check_ws(cfg, batch, workspace, workspace_bytes, d, ws));
-    if (!weights || !index || !maps) { te_set_last_error("te_vit_attribute: null pointer"); return TE_ERR_ARG; }
+    if (!weights || !index || (!maps && !(flags & TE_FLAG_GRADIENTS_ONLY))) { te_set_last_error("te_vit_attribute: null pointer"); return TE_ERR_ARG; }
     if (start_layer < 0 || start_layer >= d.L) { te_set_last_error("te_vit_attribute: start_layer out of range"); return TE_ERR_ARG; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     Weights w;
@@ -405,6 +407,8 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
         TE_TRY(te_launch_layernorm_bwd(dxn, a.x_in, bw.n1w, a.mean1, a.rstd1, dxb, dxa, d.M, d.D, st));
     }
 
+    if (flags & TE_FLAG_GRADIENTS_ONLY) return TE_OK;      // attention-GradCAM baseline: gradients are all it reads
+
     // ---- relprop  (VisionTransformer.relprop :324-331) --------------------------------------------
     float* R = ws.tD[0]; float* R1 = ws.tD[1]; float* R2 = ws.tD[2]; float* R3 = ws.tD[3];
     float* RF = ws.tF[0]; float* SF = ws.tF[1]; float* S = ws.t3D[0]; float* Rqkv = ws.t3D[1]; float* S1 = ws.tA;
@@ -455,6 +459,36 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
                              start_layer, /*normalize=*/0, flags, ws.mats, ws.joint[0], ws.joint[1], nullptr, maps,
                              d.prefix, /*bert_fix=*/0, st));
     return TE_OK;
+}
+
+// ================================================================================================
+// method="full": relevance of every input pixel   (ViT_LRP.py:337-343)
+//   (cam, _) = self.add.relprop(cam) ; cam = cam[:, 1:] ; cam = self.patch_embed.relprop(cam) ; cam.sum(dim=1)
+// Precondition: te_vit_forward + te_vit_attribute(flags | TE_FLAG_RELPROP_TO_INPUT) on this workspace and these images.
+// ================================================================================================
+extern "C" int te_vit_relprop_pixels(const te_vit_config* cfg, const float* weights, const float* images, int batch,
+                                     float* pixel_maps, float* pixel_relevance, void* workspace, long long workspace_bytes,
+                                     void* stream) {
+    Dims d; Workspace ws;
+    TE_TRY(check_ws(cfg, batch, workspace, workspace_bytes, d, ws));
+    if (!weights || !images || (!pixel_maps && !pixel_relevance)) { te_set_last_error("te_vit_relprop_pixels: null pointer"); return TE_ERR_ARG; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Weights w;
+    bind_weights(cfg, weights, w);
+    float* R = ws.tD[0];                       // relevance at the encoder input (clone1 of block 0)
+    float* tokens = ws.tD[1];                  // cat(cls[,dist], patch_embed(x)): the first operand of self.add (:311)
+    float* Rtok = ws.tD[2];
+    float* patches = ws.tF[0];
+    float* patch_out = ws.tD[3];
+    TE_TRY(te_launch_im2col(images, patches, d.B, d.Cin, d.img, d.img, d.P, st));
+    TE_TRY(linear_fwd(patches, d.KP, w.patchw, w.patchb, patch_out, nullptr, nullptr, (long long)d.B * d.npatch, d.KP,
+                      d.D, TE_EPI_BIAS, st));
+    TE_TRY(te_launch_assemble_tokens(patch_out, w.cls, w.dist, nullptr, tokens, d.B, d.N, d.D, d.prefix, st));
+    // self.add.relprop: x2 = pos_embed, shared by every sample; only the tokens' share is consumed
+    TE_TRY(te_launch_add_relprop_ex(tokens, w.pos, 0, R, Rtok, nullptr, ws.addpart, d.B, (long long)d.N * d.D, st));
+    // cam[:, 1:] -> PatchEmbed.relprop (:238-242) -> Conv2d z^B rule -> sum over channels
+    return te_patch_relprop_run(images, w.patchw, Rtok + (long long)d.prefix * d.D, (long long)d.N * d.D, d.B, d.Cin, d.img,
+                                d.P, d.D, ws.pix, pixel_relevance, pixel_maps, st);
 }
 
 extern "C" int te_vit_explain(const te_vit_config* cfg, const float* weights, const float* derived, const float* images,

@@ -114,7 +114,26 @@ class ViTEngine:
         check(self.lib.te_vit_forward(ctypes.byref(self.cfg), ptr(self.weights), ptr(self._derived(fl)), ptr(images), b,
                                       fl, ptr(logits), ptr(ws), ws.numel() * 4, self._stream()), "te_vit_forward")
         self.last_batch = b
+        self._last_images = images
         return logits
+
+    def relprop_pixels(self, index=None, per_channel=False, flags=None):
+        """``method="full"`` (ViT_LRP.py:337-343) on the activations of the last ``forward``: the relprop is run to
+        the encoder input, through ``self.add`` and the patch convolution's z^B rule.  Returns the relevance of every
+        pixel, [B,H,W] (channels summed, what the reference returns) or [B,C,H,W] with ``per_channel``."""
+        fl = (self.flags if flags is None else flags) | _lib.FLAG_RELPROP_TO_INPUT
+        self.attribute(index=index, start_layer=0, flags=fl)
+        b = self.last_batch
+        images = getattr(self, "_last_images", None)
+        if images is None or images.shape[0] != b:
+            raise RuntimeError("relprop_pixels() needs the images of the preceding forward()")
+        ws = self._workspace(b)
+        c, s = self.cfg.in_chans, self.cfg.img_size
+        out = torch.empty((b, c, s, s) if per_channel else (b, s, s), dtype=torch.float32, device=self.device)
+        check(self.lib.te_vit_relprop_pixels(ctypes.byref(self.cfg), ptr(self.weights), ptr(images), b,
+                                             None if per_channel else ptr(out), ptr(out) if per_channel else None,
+                                             ptr(ws), ws.numel() * 4, self._stream()), "te_vit_relprop_pixels")
+        return out
 
     def attribute(self, index=None, start_layer=0, flags=None):
         """Backward + relprop + rollout on the activations of the last ``forward``.
@@ -149,6 +168,7 @@ class ViTEngine:
                                           ptr(logits[s:e]) if logits is not None else None, ptr(ws), ws.numel() * 4,
                                           self._stream()), "te_vit_explain")
             self.last_batch = e - s
+            self._last_images = images[s:e]
         if return_logits:
             return maps, idx_all, logits
         return maps, idx_all

@@ -126,6 +126,64 @@ def matmul_qk_relprop(q, k, r):
     return rq, rk
 
 
+def _attn_layout(t):
+    """[B,H,N,N] view (row stride ld >= N, as handed out by the engine accessors) -> (tensor, ld)."""
+    if t.dim() != 4 or t.shape[-1] != t.shape[-2] or t.dtype != torch.float32 or not t.is_cuda:
+        raise ValueError("expected an fp32 CUDA tensor [B,H,N,N]")
+    B, H, N, _ = t.shape
+    ld = t.stride(2)
+    if t.stride(3) != 1 or ld < N or t.stride(1) != N * ld or t.stride(0) != H * N * ld:
+        t = t.contiguous()
+        ld = N
+    return t, ld
+
+
+def head_reduce(a, g=None, head_weight=None, mode="mean"):
+    """Reduce an attention-shaped tensor over its heads: a [B,H,N,N] (optionally * g, * head_weight[B,H]) -> [B,N,N].
+    mode: "mean" | "relu_mean" (``clamp(min=0).mean(heads)``) | "mean_relu" (``mean(heads).clamp(min=0)``)."""
+    a, ld = _attn_layout(a)
+    if g is not None:
+        g, ldg = _attn_layout(g)
+        if ldg != ld:
+            a, g, ld = a.contiguous(), g.contiguous(), a.shape[-1]
+    B, H, N, _ = a.shape
+    if head_weight is not None:
+        _req(head_weight)
+    out = torch.empty(B, N, N, device=a.device, dtype=torch.float32)
+    m = {"mean": 0, "relu_mean": 1, "mean_relu": 2}[mode]
+    check(_lib.load().te_head_reduce(ptr(a), ptr(g), ptr(head_weight), B, H, N, ld, m, ptr(out), _stream()),
+          "te_head_reduce")
+    return out
+
+
+def head_region_mean(g, rows=None, cols=None):
+    """``g[b,h, rows, cols].mean()`` per (b,h): [B,H,N,N] -> [B,H] (``grad.mean(dim=[1,2])`` of the GradCAM baselines)."""
+    g, ld = _attn_layout(g)
+    B, H, N, _ = g.shape
+    r0, r1 = rows if rows is not None else (0, N)
+    c0, c1 = cols if cols is not None else (0, N)
+    out = torch.empty(B, H, device=g.device, dtype=torch.float32)
+    check(_lib.load().te_head_region_mean(ptr(g), B, H, N, ld, r0, r1, c0, c1, ptr(out), _stream()), "te_head_region_mean")
+    return out
+
+
+def patch_embed_relprop(images, weight, r, per_channel=True):
+    """``PatchEmbed.relprop`` -> ``Conv2d.relprop`` z^B branch (ViT_LRP.py:238-242, layers_ours.py:242-259).
+    images [B,C,S,S]; weight [D,C,P,P] (or flattened [D,C*P*P]); r [B,(S/P)^2,D] -> [B,C,S,S] (or [B,S,S] channel sum)."""
+    _req(images, weight, r)
+    B, C, S, _ = images.shape
+    D = weight.shape[0]
+    P = int(round((weight.numel() // (D * C)) ** 0.5))
+    lib = _lib.load()
+    nbytes = check(lib.te_patch_embed_relprop_workspace_bytes(B, C, S, P, D), "te_patch_embed_relprop_workspace_bytes")
+    ws = _workspace(nbytes, images.device)
+    out = torch.empty((B, C, S, S) if per_channel else (B, S, S), device=images.device, dtype=torch.float32)
+    check(lib.te_patch_embed_relprop(ptr(images), ptr(weight), ptr(r), B, C, S, P, D, ptr(out) if per_channel else None,
+                                     None if per_channel else ptr(out), ptr(ws), ws.numel() * 4, _stream()),
+          "te_patch_embed_relprop")
+    return out
+
+
 def attribution_rollout(grad, cam, start_layer=0, normalize=False, fused=False, want_joint=True):
     """grad, cam [L,B,H,N,N] -> (joint [B,N,N] or None, row0 [B,N]).
     ``ViT_LRP.py:357-368`` (normalize=False) / ``ExplanationGenerator.py:47-57`` (normalize=True)."""
