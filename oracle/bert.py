@@ -91,8 +91,9 @@ def attention_gradients(cache, seed):
     return list(torch.autograd.grad(loss, [c["probs"] for c in cache["layers"]], retain_graph=True))
 
 
-def relprop(params, cache, seed, lowest=0):
-    """Returns per-layer attn_cam [B,H,S,S] (``BERT.py:380``); layers below ``lowest`` are None."""
+def relprop(params, cache, seed, lowest=0, to_input=False):
+    """Returns per-layer attn_cam [B,H,S,S] (``BERT.py:380``); layers below ``lowest`` are None.
+    ``to_input``: finish the lowest layer too and return ``(cams, r)``, r [B,S,D] = what ``model.relprop`` returns."""
     p = params
     dm = cache["dims"]
     r = rules.linear_relprop(cache["pooled"], p["classifier.weight"], seed)          # classifier ; dropout id
@@ -115,7 +116,7 @@ def relprop(params, cache, seed, lowest=0):
         cam1, cam_v = rules.matmul_av_relprop(c["probs"], c["v"], r_ctx)
         cam1, cam_v = cam1 / 2, cam_v / 2
         cams[i] = cam1
-        if i == lowest:
+        if i == lowest and not to_input:
             break
         cam1, _ = rules.add_relprop(c["scores"], cache["ext_mask"], cam1)                   # mask Add (renormalises)
         cam_q, cam_k = rules.matmul_qk_relprop(c["q"], c["k"], cam1)
@@ -125,7 +126,57 @@ def relprop(params, cache, seed, lowest=0):
         r_v = rules.linear_relprop(c["h"], p[L + "attention.self.value.weight"], _merge(cam_v))
         r_a = rules.clone_relprop(c["h"], (r_q, r_k, r_v))                                  # self.clone (3-way)
         r = rules.clone_relprop(c["h"], (r_a, r_h2))                                        # attention.clone
+    if to_input:
+        return cams, r
     return cams
+
+
+GENERATORS = ("LRP_last_layer", "full_lrp", "attn_last_layer", "rollout", "attn_gradcam")
+
+
+def generate(params, input_ids, attention_mask, num_heads, which, index=None, start_layer=0):
+    """The comparison generators of ``Generator`` (``ExplanationGenerator.py:61-155``), batch = independent
+    sequences: ``which`` in GENERATORS -> [B,S]."""
+    with torch.enable_grad():
+        logits, cache = forward(params, input_ids, attention_mask, num_heads, need_grad=True)
+        if index is None:
+            index = logits.argmax(dim=-1)
+        index = torch.as_tensor(index).reshape(-1).long()
+        seed = torch.zeros_like(logits)
+        seed[torch.arange(logits.shape[0]), index] = 1
+        grads = attention_gradients(cache, seed)
+    with torch.no_grad():
+        cd = {"dims": cache["dims"], "ext_mask": cache["ext_mask"], "h_last": cache["h_last"].detach(),
+              "pooled": cache["pooled"].detach(),
+              "layers": [{k: v.detach() for k, v in c.items()} for c in cache["layers"]]}
+        probs = [c["probs"] for c in cd["layers"]]
+        if which == "LRP_last_layer":                                         # :61-83
+            cams = relprop(params, cd, seed, lowest=cache["dims"].depth - 1)
+            cam = cams[-1].clamp(min=0).mean(dim=1)
+            cam[:, 0, 0] = 0
+            return cam[:, 0]
+        if which == "full_lrp":                                               # :85-105
+            _, r = relprop(params, cd, seed, lowest=0, to_input=True)
+            cam = r.sum(dim=2)
+            cam[:, 0] = 0
+            return cam
+        if which == "attn_last_layer":                                        # :107-113
+            cam = probs[-1].mean(dim=1)
+            cam[:, 0, 0] = 0
+            return cam[:, 0]
+        if which == "rollout":                                                # :115-127
+            joint = rules.rollout([a.mean(dim=1) for a in probs], start_layer=start_layer, normalize=True)
+            joint[:, 0, 0] = 0
+            return joint[:, 0]
+        if which == "attn_gradcam":                                           # :129-155
+            g = grads[-1].mean(dim=(2, 3), keepdim=True)
+            cam = (probs[-1] * g).mean(dim=1).clamp(min=0)
+            lo = cam.amin(dim=(1, 2), keepdim=True)
+            hi = cam.amax(dim=(1, 2), keepdim=True)
+            cam = (cam - lo) / (hi - lo)
+            cam[:, 0, 0] = 0
+            return cam[:, 0]
+    raise ValueError("unknown generator %r" % (which,))
 
 
 def explain(params, input_ids, attention_mask, num_heads, index=None, start_layer=11, return_taps=False):

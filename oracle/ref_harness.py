@@ -133,6 +133,41 @@ def _generate_lrp_any_dtype(model, x, index, start_layer, method, is_ablation=Fa
     return model.relprop(oh.clone(), method=method, is_ablation=is_ablation, start_layer=start_layer, alpha=1)
 
 
+def build_vit_new(name="vit_base_patch16_224", state_dict=None, dtype=torch.float32, **kwargs):
+    """The hook-free reference ViT (``baselines/ViT/ViT_new.py``) that ``Baselines`` explains."""
+    _ensure_path()
+    with _ref_imports():
+        import baselines.ViT.ViT_new as m
+    if name == "custom":
+        model = m.VisionTransformer(**kwargs)
+    else:
+        model = getattr(m, name)(pretrained=False, **kwargs)
+    if state_dict is not None:
+        model.load_state_dict(state_dict)
+    return model.to(dtype).eval()
+
+
+def vit_baselines(model, x, which, **kw):
+    """``Baselines(model).generate_cam_attn / generate_rollout`` (``ViT_explanation_generator.py:45-83``), B=1, CPU."""
+    with _ref_imports():
+        from baselines.ViT.ViT_explanation_generator import Baselines
+    assert x.shape[0] == 1
+    with _cpu_cuda_shim():
+        out = getattr(Baselines(model), "generate_" + which)(x, **kw)
+    return out.detach()
+
+
+def bert_generate(model, input_ids, attention_mask, which, **kw):
+    """The comparison generators of the reference ``Generator`` (``ExplanationGenerator.py:61-155``), B=1, CPU, fp32."""
+    _prepare_bert_imports()
+    assert input_ids.shape[0] == 1
+    with _ref_imports():
+        from BERT_explainability.modules.BERT.ExplanationGenerator import Generator
+        with _cpu_cuda_shim():
+            out = getattr(Generator(model), "generate_" + which)(input_ids, attention_mask, **kw)
+    return out.detach()
+
+
 def vit_logits(model, x):
     with torch.enable_grad():
         return model(x).detach()

@@ -48,9 +48,12 @@ def _merge_heads(t):
     return t.permute(0, 2, 1, 3).reshape(b, n, h * d)           # 'b h n d -> b n (h d)'
 
 
-def forward(params, x, num_heads, need_grad=False):
-    """Returns (logits [B,C], cache).  ``cache`` holds every tensor the relprop needs."""
+def forward(params, x, num_heads, need_grad=False, norm_eps=None):
+    """Returns (logits [B,C], cache).  ``cache`` holds every tensor the relprop needs.
+    ``norm_eps``: one epsilon for every LayerNorm (the ``ViT_new`` factories, ``ViT_new.py:226-254``)."""
     cfg = ViTConfig(params, num_heads)
+    if norm_eps is not None:
+        cfg.eps_block = cfg.eps_final = norm_eps
     p = params
     B = x.shape[0]
     t = F.conv2d(x, p["patch_embed.proj.weight"], p["patch_embed.proj.bias"], stride=cfg.patch)
@@ -304,3 +307,34 @@ def init_params(cfg_name="vit_base_patch16_224", seed=0, dtype=torch.float32, **
             elif k.endswith(".bias") and not k.startswith("patch_embed"):
                 p[k] = 0.05 * torch.randn(p[k].shape, generator=g)
     return {k: v.to(dtype) for k, v in p.items()}, c["heads"]
+
+
+def baseline_rollout(params, x, num_heads, start_layer=0, norm_eps=1e-6):
+    """``Baselines.generate_rollout`` (``ViT_explanation_generator.py:73-83``) on the hook-free ``ViT_new`` model:
+    head-averaged raw attention of every block -> the file's own ROW-NORMALISED rollout (``:7-18``) -> [B,N-1]."""
+    with torch.no_grad():
+        _, cache = forward(params, x, num_heads, norm_eps=norm_eps)
+        mats = [c["attn"].mean(dim=1) for c in cache["blocks"]]
+        return rules.rollout(mats, start_layer=start_layer, normalize=True)[:, 0, 1:]
+
+
+def baseline_cam_attn(params, x, num_heads, index=None, norm_eps=1e-6):
+    """``Baselines.generate_cam_attn`` (``:50-71``): CLS row of the last block's attention weighted per head by the
+    mean (over the patch positions) of its class gradient, relu(mean over heads), min-max normalised -> [B,g,g]."""
+    with torch.enable_grad():
+        logits, cache = forward(params, x, num_heads, need_grad=True, norm_eps=norm_eps)
+        if index is None:
+            index = logits.argmax(dim=-1)
+        index = torch.as_tensor(index).reshape(-1).long()
+        seed = torch.zeros_like(logits)
+        seed[torch.arange(logits.shape[0]), index] = 1
+        grad = attention_gradients(cache, seed)[-1]
+    with torch.no_grad():
+        cam = cache["blocks"][-1]["attn"].detach()[:, :, 0, 1:]               # [B,H,np]
+        g = grad[:, :, 0, 1:].mean(dim=2, keepdim=True)
+        cam = (cam * g).mean(dim=1).clamp(min=0)
+        lo = cam.amin(dim=1, keepdim=True)
+        hi = cam.amax(dim=1, keepdim=True)
+        cam = (cam - lo) / (hi - lo)
+        side = int(round(cam.shape[1] ** 0.5))
+        return cam.reshape(-1, side, side), index

@@ -133,3 +133,33 @@ def test_bert_base_vs_oracle(seq, start):
             seq, start, flags, ["%.1e" % e for e in cam_err], ["%.1e" % e for e in errs], ["%.1e" % e for e in err_ref]))
         assert cam_err[n // 2] < 5e-2
         assert errs[n // 2] <= max(5e-2, 3 * err_ref[n // 2])
+
+
+def test_bert_comparison_generators_vs_golden_reference(golden_dir):
+    """generate_LRP_last_layer / full_lrp / attn_last_layer / rollout / attn_gradcam vs the reference's stored fp32
+    outputs (NaN pattern included) and the fp64 oracle."""
+    from transformer_explainability_b200.BERT_explainability.modules.BERT.ExplanationGenerator import Generator
+    g = np.load(os.path.join(golden_dir, "bert_generators.npz"))
+    params, heads = obert.init_params(seed=int(g["param_seed"]), vocab=100, max_pos=32, dim=64, depth=3, heads=4,
+                                      inter=128, rand_affine=True)
+    model = make_model(params, heads, **TINY)
+    gen = Generator(model)
+    ids, mask = T(g["ids"]), T(g["mask"])
+    p64 = {k: v.double() for k, v in params.items()}
+    tol = {"LRP_last_layer": 2e-2, "full_lrp": 2e-2, "attn_last_layer": 1e-5, "rollout": 1e-5, "attn_gradcam": 2e-3}
+    for key in [k for k in g.files if k.startswith("f32.")]:
+        _, s, which, tag = key.split(".")
+        s = int(s[1:])
+        kw = {"start_layer": int(tag[2:])} if tag.startswith("sl") else ({} if tag == "argmax" else {"index": int(tag[5:])})
+        out = getattr(gen, "generate_" + which)(ids[s:s + 1].cuda(), mask[s:s + 1].cuda(), **kw)
+        ref = T(g[key])
+        assert out.shape == ref.shape == (1, 24), key
+        assert torch.equal(torch.isnan(out.cpu()), torch.isnan(ref)), key
+        if torch.isnan(ref).any():
+            continue
+        ref64 = obert.generate(p64, ids[s:s + 1], mask[s:s + 1], heads, which, **kw)
+        assert rel(out, ref64) < tol[which], "%s rel=%g" % (key, rel(out, ref64))
+    # a batch is a set of independent sequences
+    both = gen.generate_full_lrp(ids.cuda(), mask.cuda())
+    one = gen.generate_full_lrp(ids[1:2].cuda(), mask[1:2].cuda())
+    assert torch.allclose(both[1:2], one, rtol=1e-4, atol=1e-10)

@@ -97,6 +97,41 @@ def test_tiny_other_methods_vs_golden_reference(golden_dir):
     assert torch.allclose(per_channel.sum(dim=1), full, rtol=1e-4, atol=1e-8)
 
 
+def test_baselines_vs_golden_reference(golden_dir):
+    """Baselines.generate_rollout / generate_cam_attn on the ViT_new facade vs the reference's stored outputs and the
+    fp64 oracle (NaN maps — an all-zero GradCAM — must be NaN here too)."""
+    import functools
+    from transformer_explainability_b200.baselines.ViT.ViT_new import VisionTransformer
+    from transformer_explainability_b200.baselines.ViT.ViT_explanation_generator import Baselines
+    g = np.load(os.path.join(golden_dir, "vit_baselines.npz"))
+    params, heads = ovit.init_params("vit_tiny_test", seed=int(g["param_seed"]), rand_affine=True, img=112)
+    model = VisionTransformer(img_size=112, patch_size=8, embed_dim=64, depth=3, num_heads=heads, mlp_ratio=4.,
+                              qkv_bias=True, num_classes=10,
+                              norm_layer=functools.partial(torch.nn.LayerNorm, eps=float(g["norm_eps"])))
+    model.load_state_dict(params)
+    model = model.cuda().eval()
+    base = Baselines(model)
+    x = T(g["x"]).cuda()
+    p64 = {k: v.double() for k, v in params.items()}
+    for s in range(x.shape[0]):
+        for sl in (0, 1):
+            out = base.generate_rollout(x[s:s + 1], start_layer=sl)
+            assert out.shape == (1, 196)
+            assert rel(out, T(g["f32.s%d.rollout.sl%d" % (s, sl)])) < 1e-5
+            assert rel(out, ovit.baseline_rollout(p64, x[s:s + 1].cpu().double(), heads, start_layer=sl)) < 1e-5
+        for tag, idx in (("argmax", None), ("index3", 3), ("index7", 7)):
+            out = base.generate_cam_attn(x[s:s + 1], index=idx)
+            ref = T(g["f32.s%d.cam_attn.%s" % (s, tag)])
+            assert out.shape == ref.shape == (14, 14)
+            assert torch.equal(torch.isnan(out.cpu()), torch.isnan(ref)), (s, tag)
+            if not torch.isnan(ref).any():
+                ref64, _ = ovit.baseline_cam_attn(p64, x[s:s + 1].cpu().double(), heads, index=idx)
+                assert (out.cpu().double() - ref64[0]).abs().max() < 1e-3          # min-max normalised to [0, 1]
+    # batched = per-sample
+    both = base.generate_rollout(x)
+    assert torch.allclose(both[1:2], base.generate_rollout(x[1:2]), rtol=1e-5, atol=1e-9)
+
+
 def test_tiny_batched_equals_single(golden_dir):
     """Batch = independent B=1 explanations: the batched call reproduces the per-sample calls."""
     from transformer_explainability_b200.baselines.ViT.ViT_explanation_generator import LRP

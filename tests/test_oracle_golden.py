@@ -146,3 +146,41 @@ def test_bert_tiny_matches_reference(golden_dir, tag, dtype):
     # padded tokens receive exactly zero relevance (SURVEY.md §8c invariant)
     out, _ = obert.explain(params, ids[1:2], mask[1:2], heads, start_layer=0)
     assert float(out[0, 18:].abs().max()) == 0.0
+
+
+def _same(a, b):
+    """bit-equal including the NaN pattern (an all-zero GradCAM map min-max-normalises to NaN in the reference too)."""
+    return torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(a.nan_to_num(nan=0.), b.nan_to_num(nan=0.))
+
+
+def test_vit_baselines_match_reference(golden_dir):
+    """Baselines.generate_rollout / generate_cam_attn (ViT_explanation_generator.py:45-83) on the ViT_new model."""
+    g = np.load(os.path.join(golden_dir, "vit_baselines.npz"))
+    params, heads = ovit.init_params("vit_tiny_test", seed=int(g["param_seed"]), rand_affine=True, img=112)
+    x = T(g["x"])
+    eps = float(g["norm_eps"])
+    for s in range(x.shape[0]):
+        for sl in (0, 1):
+            out = ovit.baseline_rollout(params, x[s:s + 1], heads, start_layer=sl, norm_eps=eps)
+            assert torch.equal(out, T(g["f32.s%d.rollout.sl%d" % (s, sl)]))
+        for tag, idx in (("argmax", None), ("index3", 3), ("index7", 7)):
+            out, _ = ovit.baseline_cam_attn(params, x[s:s + 1], heads, index=idx, norm_eps=eps)
+            assert _same(out[0], T(g["f32.s%d.cam_attn.%s" % (s, tag)])), (s, tag)
+
+
+def test_bert_generators_match_reference(golden_dir):
+    """generate_LRP_last_layer / full_lrp / attn_last_layer / rollout / attn_gradcam (ExplanationGenerator.py:61-155)."""
+    from oracle import bert as obert
+    g = np.load(os.path.join(golden_dir, "bert_generators.npz"))
+    params, heads = obert.init_params(seed=int(g["param_seed"]), vocab=100, max_pos=32, dim=64, depth=3, heads=4,
+                                      inter=128, rand_affine=True)
+    ids, mask = T(g["ids"]), T(g["mask"])
+    seen = 0
+    for key in [k for k in g.files if k.startswith("f32.")]:
+        _, s, which, tag = key.split(".")
+        s = int(s[1:])
+        kw = {"start_layer": int(tag[2:])} if tag.startswith("sl") else ({} if tag == "argmax" else {"index": int(tag[5:])})
+        out = obert.generate(params, ids[s:s + 1], mask[s:s + 1], heads, which, **kw)
+        assert _same(out, T(g[key])), key
+        seen += 1
+    assert seen == 28

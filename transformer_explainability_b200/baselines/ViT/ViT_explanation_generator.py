@@ -8,7 +8,12 @@ the forward pass (+ the class-gradient of the last block's attention) only.
 import torch
 
 from transformer_explainability_b200 import _lib, ops
-from transformer_explainability_b200.baselines.ViT.ViT_LRP import compute_rollout_attention
+
+
+def compute_rollout_attention(all_layer_matrices, start_layer=0):
+    """``ViT_explanation_generator.py:7-18`` — this file's own rollout ROW-NORMALISES (M + I) / rowsum before chaining
+    (unlike ``ViT_LRP.compute_rollout_attention``); list of [B,N,N] -> [B,N,N]."""
+    return ops.compute_rollout_attention(all_layer_matrices, start_layer=start_layer, normalize=True)
 
 
 class LRP:

@@ -389,6 +389,47 @@ __global__ void aggregate_kernel(const float* __restrict__ G, const float* __res
     }
 }
 
+// same, 128-bit streaming loads (ld_in % 4 == 0, ld % 4 == 0): every lane keeps H independent float4 pairs in flight
+__global__ void aggregate_vec_kernel(const float* __restrict__ G, const float* __restrict__ cam, float* __restrict__ M,
+                                     int B, int H, int N, int ld_in, int ld, int add_eye, int normalize,
+                                     float* __restrict__ diag) {
+    const int lane = threadIdx.x & 31;
+    const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);   // b*N + i
+    if (row >= (long long)B * N) return;
+    const int b = (int)(row / N), i = (int)(row % N);
+    float* out = M + row * ld;
+    float rs = 0.f;
+    for (int j4 = lane; j4 * 4 < ld; j4 += 32) {
+        const int j = j4 * 4;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < N && j < ld_in) {
+#pragma unroll 4
+            for (int h = 0; h < H; ++h) {
+                const long long o = (((long long)b * H + h) * N + i) * ld_in + j;
+                const float4 g = __ldcs(reinterpret_cast<const float4*>(G + o));
+                const float4 c = __ldcs(reinterpret_cast<const float4*>(cam + o));
+                s.x += fmaxf(g.x * c.x, 0.f); s.y += fmaxf(g.y * c.y, 0.f);
+                s.z += fmaxf(g.z * c.z, 0.f); s.w += fmaxf(g.w * c.w, 0.f);
+            }
+        }
+        float v[4] = {s.x / (float)H, s.y / (float)H, s.z / (float)H, s.w / (float)H};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (j + u >= N) v[u] = 0.f;                         // the row padding of G / cam is never trusted
+            else if (add_eye && j + u == i) v[u] += 1.0f;
+            rs += v[u];
+        }
+        *reinterpret_cast<float4*>(out + j) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    if (normalize) {
+        rs = te_warp_sum(rs);
+        if (diag != nullptr) rs += 1.0f;
+        __syncwarp();
+        for (int j = lane; j < N; j += 32) out[j] = out[j] / rs;
+        if (diag != nullptr && lane == 0) diag[row] = 1.0f / rs;
+    }
+}
+
 // head reductions for the secondary methods: one warp per output row
 __global__ void head_reduce_kernel(const float* __restrict__ A, const float* __restrict__ G,
                                    const float* __restrict__ hw, float* __restrict__ out, int B, int H, int N, int ld,
@@ -697,8 +738,14 @@ int te_launch_index_select_relprop(const float* x, const float* r_tok0, const fl
 }
 int te_launch_aggregate(const float* G, const float* cam, float* M, int B, int H, int N, int ld_in, int ld_out,
                         int add_eye, int normalize, cudaStream_t st, float* diag) {
-    aggregate_kernel<<<warp_rows_grid((long long)B * N), kThreads, 0, st>>>(G, cam, M, B, H, N, ld_in, ld_out, add_eye,
-                                                                          normalize, diag);
+    const bool vec = ld_in % 4 == 0 && ld_out % 4 == 0 && ld_in >= ((N + 3) & ~3) &&
+                     ((reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(cam) | reinterpret_cast<uintptr_t>(M)) & 15u) == 0;
+    if (vec)
+        aggregate_vec_kernel<<<warp_rows_grid((long long)B * N), kThreads, 0, st>>>(G, cam, M, B, H, N, ld_in, ld_out,
+                                                                                  add_eye, normalize, diag);
+    else
+        aggregate_kernel<<<warp_rows_grid((long long)B * N), kThreads, 0, st>>>(G, cam, M, B, H, N, ld_in, ld_out, add_eye,
+                                                                              normalize, diag);
     TE_CUDA_CHECK_LAUNCH();
     return TE_OK;
 }
