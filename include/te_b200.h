@@ -48,6 +48,10 @@ extern "C" {
                                          model.relprop() returns in the reference) is left in tensor "relevance_in" */
 
 TE_API const char* te_last_error(void);
+/* Process-wide tuning switches (not part of the reference surface).  name = "zplus_pair_kernels": run the z+ Linear rule
+ * with the CTA-pair (tcgen05 cta_group::2, 256 x 256 MMA) kernels instead of the single-CTA ones; default 0.
+ * Returns TE_OK, or a negative status for an unknown name. */
+TE_API int te_set_option(const char* name, int value);
 TE_API int te_version(void);
 /* number of kernels this library has launched in this process (bench.py reports the delta as gpu_launches) */
 TE_API long long te_kernel_launch_count(void);

@@ -39,6 +39,32 @@ def test_tc_linear_relprop_matches_simt_and_oracle(rows, inf, outf):
     assert rel(tc1, ref) < 3e-3, "single-pass tcgen05 path: rel err %g" % rel(tc1, ref)
 
 
+@pytest.mark.parametrize("rows,inf,outf", [(128, 256, 256), (394, 768, 3072), (1000, 3072, 768), (77, 768, 2304)])
+def test_tc_pair_kernels_cta_group2(rows, inf, outf):
+    """The opt-in CTA-pair (tcgen05 cta_group::2) z+ kernels against the fp64 oracle and the single-CTA kernels
+    (odd tile counts get an all-padding partner CTA)."""
+    from transformer_explainability_b200 import _lib, ops
+    g = torch.Generator().manual_seed(rows + 1)
+    x = torch.randn(rows, inf, generator=g)
+    w = torch.randn(outf, inf, generator=g) * 0.05
+    r = torch.rand(rows, outf, generator=g)
+    b = torch.randn(outf, generator=g)
+    xd, wd, rd, bd = x.cuda(), w.cuda(), r.cuda(), b.cuda()
+    y = ops.linear_forward(xd, wd, bd)
+    one = ops.linear_relprop(xd, wd, rd, tensor_cores=True, y=y, bias=bd)
+    lib = _lib.load()
+    _lib.check(lib.te_set_option(b"zplus_pair_kernels", 1), "te_set_option")
+    try:
+        pair = ops.linear_relprop(xd, wd, rd, tensor_cores=True, y=y, bias=bd)
+        pair_two_pass = ops.linear_relprop(xd, wd, rd, tensor_cores=True)          # two-pass S kernel + pair R kernel
+        torch.cuda.synchronize()
+    finally:
+        _lib.check(lib.te_set_option(b"zplus_pair_kernels", 0), "te_set_option")
+    ref = rules.linear_relprop(x.double(), w.double(), r.double())
+    assert rel(pair, ref) < 3e-3 and rel(pair_two_pass, ref) < 3e-3
+    assert rel(pair, one.double()) < 1e-5          # same operands, same accumulation order per output tile
+
+
 def test_tc_engine_vit_base_vs_simt_and_oracle():
     """ViT-B/16: engine with the tensor-core z+ path vs the fp32 SIMT engine and the fp64 oracle; medians over
     1e-7-perturbed copies (see tests/test_gpu_vit.py::_noise_trials for why)."""

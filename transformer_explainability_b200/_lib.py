@@ -60,6 +60,7 @@ PROTOTYPES = {
     "te_vit_explain": (c_int, [_CFG, _P, _P, _P, c_int, _P, c_int, c_uint, _P, _P, _P, c_ll, _P]),
     "te_vit_tensor": (c_int, [_CFG, c_int, _P, c_char_p, c_int, ctypes.POINTER(_P), ctypes.POINTER(c_ll),
                               ctypes.POINTER(c_ll)]),
+    "te_set_option": (c_int, [c_char_p, c_int]),
     "te_vit_relprop_pixels": (c_int, [_CFG, _P, _P, c_int, _P, _P, _P, c_ll, _P]),
     "te_bert_num_weights": (c_int, [_BCFG]),
     "te_bert_weight_name": (c_char_p, [_BCFG, c_int]),

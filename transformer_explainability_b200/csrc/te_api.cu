@@ -156,6 +156,13 @@ extern "C" int te_matmul_qk_relprop(const float* q, const float* k, const float*
     return TE_OK;
 }
 
+extern "C" int te_set_option(const char* name, int value) {
+    REQ(name != nullptr, "te_set_option: null name");
+    if (strcmp(name, "zplus_pair_kernels") == 0) { te_tc_set_pair_kernels(value); return TE_OK; }
+    te_set_last_error("te_set_option: unknown option");
+    return TE_ERR_ARG;
+}
+
 // ---- head reductions of the secondary methods ------------------------------------------------------------
 extern "C" int te_head_reduce(const float* a, const float* g, const float* head_w, int batch, int heads, int n, int ld,
                               int mode, float* out, void* stream) {

@@ -25,6 +25,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "te_gemm_tc.h"
@@ -150,22 +151,32 @@ constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN 
 // same with BF16 operands (a/b format = 1), kind::f16: K = 16 elements (32 bytes) per MMA, 64 elements per 128-byte row
 constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
+// Ring depth / residency per kernel variant.  The single-pass S kernel has a heavy epilogue (reads R and y, safe_divide,
+// writes S) and only needs 256 TMEM columns: with 2 stages of 48 KiB two CTAs share an SM and one CTA's prologue /
+// epilogue overlaps the other's main loop.  The R kernel owns all 512 TMEM columns, so it stays alone with 4 stages.
+template <int MODE> struct ZpCfg {
+    static constexpr int STAGES = (MODE == MODE_S1) ? 2 : 4;
+    static constexpr int MIN_CTAS = (MODE == MODE_S1) ? 2 : 1;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
 // BF (MODE_R only): A (= S, written as bf16 by the S kernel) and B (bf16 weight copies) are 2-byte operands:
 // one 128-byte swizzle row holds 64 elements, tcgen05.mma.kind::f16, half the shared-memory traffic per flop.
 template <int MODE, bool BF = false>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, ZpCfg<MODE>::MIN_CTAS)
 te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                    const __grid_constant__ CUtensorMap tmB1, const TcParams p) {
     constexpr int KELEMS = BF ? 64 : 32;              // elements per k-block (one 128-byte row)
+    constexpr int NST = ZpCfg<MODE>::STAGES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t bars = smem_base + STAGES * STAGE_BYTES;            // 8-byte barriers
+    const uint32_t bars = smem_base + NST * STAGE_BYTES;            // 8-byte barriers
     auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto xf_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-    auto empty_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
-    const uint32_t accum_bar = bars + 8u * (3 * STAGES);
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 1));
+    auto xf_bar = [&](int s) { return bars + 8u * (NST + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (2 * NST + s); };
+    const uint32_t accum_bar = bars + 8u * (3 * NST);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + NST * STAGE_BYTES + 8 * (3 * NST + 1));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -176,9 +187,9 @@ te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB0) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB1) : "memory");
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < NST; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(xf_bar(s), XF_THREADS);
+            mbar_init(xf_bar(s), XF_THREADS / 32);
             mbar_init(empty_bar(s), 1);
         }
         mbar_init(accum_bar, 1);
@@ -199,8 +210,8 @@ te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // ================= TMA producer =================
         if (lane == 0) {
             for (int it = 0; it < iters; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1u;
+                const int s = it % NST;
+                const uint32_t ph = (it / NST) & 1u;
                 mbar_wait(empty_bar(s), ph ^ 1u);
                 mbar_arrive_expect_tx(full_bar(s), STAGE_BYTES);
                 const int pass = (it >= kb) ? 1 : 0;
@@ -214,8 +225,8 @@ te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // ================= MMA issuer =================
         if (lane == 0) {
             for (int it = 0; it < iters; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1u;
+                const int s = it % NST;
+                const uint32_t ph = (it / NST) & 1u;
                 mbar_wait(MODE != MODE_R ? xf_bar(s) : full_bar(s), ph);
                 tcgen05_fence_after();
                 const int pass = (it >= kb) ? 1 : 0;
@@ -240,8 +251,8 @@ te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int et = threadIdx.x - 64;            // 0..127
         if (MODE != MODE_R) {
             for (int it = 0; it < iters; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1u;
+                const int s = it % NST;
+                const uint32_t ph = (it / NST) & 1u;
                 mbar_wait(full_bar(s), ph);
                 const int pass = (it >= kb) ? 1 : 0;
                 float4* a4 = reinterpret_cast<float4*>(smem_al + s * STAGE_BYTES);
@@ -255,7 +266,8 @@ te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     a4[et + i * XF_THREADS] = v;
                 }
                 fence_proxy_async();                // generic-proxy writes -> visible to the tensor-core (async) proxy
-                mbar_arrive(xf_bar(s));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(xf_bar(s));   // one arrive per warp: 128 arrives on one mbarrier serialise
             }
         }
         mbar_wait(accum_bar, 0);
@@ -328,6 +340,253 @@ te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// =====================================================================================================================
+// CTA-pair version of the z+ kernels (tcgen05 cta_group::2): two CTAs of one cluster (adjacent 128-row tiles, same
+// 256-column tile) execute ONE 256 x 256 x 8 MMA per k-step, issued by the leader CTA.  Each CTA stages its own
+// 128 x 32 activation tile and only HALF of the weight tile (128 of the 256 rows), so a stage is 32 KiB instead of
+// 48 KiB: 6 stages fit where 4 did and every byte brought into shared memory feeds 1.5x the flops — the kernels are
+// bound by bytes in flight (L2 -> smem latency x ring size), not by the tensor pipe (ncu: 46 % / 36 % tensor active).
+//   full[s]   local   TMA bytes of this CTA's A tile + B half
+//   ready[s]  leader  S1 only: one arrive per transform warp of both CTAs (8) after |.| / TF32 rounding of its share
+//                     of A — remote arrive through the cluster address of rank 0.  R has no transform: both CTAs'
+//                     TMA bytes are counted directly on the leader's full[s] (cp.async.bulk.tensor .cta_group::2)
+//   empty[s]  local   tcgen05.commit.cta_group::2 multicast from the leader to both CTAs
+//   accum     local   same multicast commit after the last MMA; each CTA's epilogue reads its own 128 TMEM lanes
+// =====================================================================================================================
+constexpr int STAGES2 = 6;
+constexpr int BH_BYTES = B_BYTES / 2;                             // 16 KiB: this CTA's half of the weight tile
+constexpr int STAGE2_BYTES = A_BYTES + BH_BYTES;                  // 32 KiB
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+constexpr uint32_t kIdesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank0(uint32_t addr) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAITC_LOOP:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAITC_DONE;\n\t"
+        "bra WAITC_LOOP;\n\t"
+        "WAITC_DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+// cta_group::2 TMA load: the bytes are counted on the barrier at the same offset in the LEADER CTA (peer bit cleared)
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+te_tc_zplus2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+                    const __grid_constant__ CUtensorMap tmB1, const TcParams p) {
+    static_assert(MODE == MODE_S1 || MODE == MODE_R, "pair kernel: single-pass S and R only");
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bars = smem_base + STAGES2 * STAGE2_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto ready_bar = [&](int s) { return bars + 8u * (STAGES2 + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (2 * STAGES2 + s); };
+    const uint32_t accum_bar = bars + 8u * (3 * STAGES2);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + STAGES2 * STAGE2_BYTES + 8 * (3 * STAGES2 + 1));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    // 1-D grid of CTA pairs: the column tile runs fastest over the pairs, so the pairs that share an activation row
+    // block are co-resident (L2 reuse of x); the two CTAs of a pair take adjacent 128-row tiles
+    const int ntn = p.N / BN;
+    const int pair = blockIdx.x >> 1;
+    const int m0 = ((pair / ntn) * 2 + (int)rank) * BM, n0 = (pair % ntn) * BN;
+    const int kb = p.K / BK, iters = (MODE == MODE_S1) ? kb : 2 * kb;
+    constexpr uint32_t TMEM_COLS = (MODE == MODE_R) ? 512u : 256u;
+    constexpr uint32_t READY_COUNT = 2u * (XF_THREADS / 32);        // S1: one arrive per transform warp of both CTAs
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB0) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB1) : "memory");
+        for (int s = 0; s < STAGES2; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(ready_bar(s), READY_COUNT);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();                                // barriers of both CTAs initialised, TMEM allocated
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs: own A tile + own half of the weight tile) =================
+        if (lane == 0) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % STAGES2;
+                const uint32_t ph = (it / STAGES2) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                const int pass = (it >= kb) ? 1 : 0;
+                const int k0 = (it - pass * kb) * BK;
+                const uint32_t sa = smem_base + s * STAGE2_BYTES;
+                if (MODE == MODE_S1) {
+                    // the tile is clamped by this CTA's own warps first: bytes are counted on the local barrier
+                    mbar_arrive_expect_tx(full_bar(s), STAGE2_BYTES);
+                    tma_load_2d(sa, &tmA, full_bar(s), k0, m0);
+                    tma_load_2d(sa + A_BYTES, pass ? &tmB1 : &tmB0, full_bar(s), k0, n0 + (int)rank * (BN / 2));
+                } else {
+                    // no transform: both CTAs' bytes are counted directly on the LEADER's barrier (cta_group::2 TMA)
+                    if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * STAGE2_BYTES);
+                    tma2_load_2d(sa, &tmA, full_bar(s), k0, m0);
+                    tma2_load_2d(sa + A_BYTES, pass ? &tmB1 : &tmB0, full_bar(s), k0, n0 + (int)rank * (BN / 2));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (leader && lane == 0) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % STAGES2;
+                const uint32_t ph = (it / STAGES2) & 1u;
+                if (MODE == MODE_S1) mbar_wait_cluster(ready_bar(s), ph);
+                else mbar_wait(full_bar(s), ph);
+                tcgen05_fence_after();
+                const int pass = (it >= kb) ? 1 : 0;
+                const uint32_t sa = smem_base + s * STAGE2_BYTES;
+                const uint64_t adesc = make_smem_desc(sa);
+                const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
+                const uint32_t d = tmem_base + ((MODE == MODE_R && pass) ? (uint32_t)BN : 0u);
+                const bool first = (MODE != MODE_R) ? (it == 0) : (it == 0 || it == kb);
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k)
+                    umma2_tf32(d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc2, (first && k == 0) ? 0u : 1u);
+                umma2_commit_both(empty_bar(s));     // frees this stage in BOTH CTAs when the MMAs retire
+            }
+            umma2_commit_both(accum_bar);
+        }
+        __syncwarp();
+    } else {
+        // ================= tile transform / relay + epilogue: warps 2..5 =================
+        const int et = threadIdx.x - 64;            // 0..127
+        if (MODE == MODE_S1) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % STAGES2;
+                const uint32_t ph = (it / STAGES2) & 1u;
+                mbar_wait(full_bar(s), ph);
+                float4* a4 = reinterpret_cast<float4*>(smem_al + s * STAGE2_BYTES);
+#pragma unroll
+                for (int i = 0; i < A_BYTES / 16 / XF_THREADS; ++i) {
+                    float4 v = a4[et + i * XF_THREADS];
+                    v.x = to_tf32(fabsf(v.x)); v.y = to_tf32(fabsf(v.y)); v.z = to_tf32(fabsf(v.z)); v.w = to_tf32(fabsf(v.w));
+                    a4[et + i * XF_THREADS] = v;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(map_to_rank0(ready_bar(s)));
+            }
+        }
+        __syncwarp();
+        mbar_wait(accum_bar, 0);
+        tcgen05_fence_after();
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool live = row < p.M;
+        const float* erow = p.E + (long long)row * p.lde + n0;
+        float* crow = p.C + (long long)row * p.ldc + n0;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t acc[32];
+            tmem_ld32(tlane + (uint32_t)(c * 32), acc);
+            if (MODE == MODE_S1) {
+                tmem_ld_wait();
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 r = *reinterpret_cast<const float4*>(erow + c * 32 + j);
+                        const float4 y = *reinterpret_cast<const float4*>(p.Y + (long long)row * p.ldy + n0 + c * 32 + j);
+                        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c * 32 + j));
+                        // x+ W+^T + x- W-^T == ( x W^T + |x| |W|^T ) / 2 ,  x W^T = y - bias (saved forward output)
+                        const float z0 = 0.5f * ((y.x - bb.x) + __uint_as_float(acc[j + 0]));
+                        const float z1 = 0.5f * ((y.y - bb.y) + __uint_as_float(acc[j + 1]));
+                        const float z2 = 0.5f * ((y.z - bb.z) + __uint_as_float(acc[j + 2]));
+                        const float z3 = 0.5f * ((y.w - bb.w) + __uint_as_float(acc[j + 3]));
+                        float4 o;
+                        o.x = to_tf32(te_sd(r.x, z0)); o.y = to_tf32(te_sd(r.y, z1));
+                        o.z = to_tf32(te_sd(r.z, z2)); o.w = to_tf32(te_sd(r.w, z3));
+                        *reinterpret_cast<float4*>(crow + c * 32 + j) = o;
+                    }
+                }
+            } else {
+                uint32_t accn[32];
+                tmem_ld32(tlane + (uint32_t)(BN + c * 32), accn);
+                tmem_ld_wait();
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 x = *reinterpret_cast<const float4*>(erow + c * 32 + j);
+                        float4 o;
+                        o.x = fmaxf(x.x, 0.f) * __uint_as_float(acc[j + 0]) + fminf(x.x, 0.f) * __uint_as_float(accn[j + 0]);
+                        o.y = fmaxf(x.y, 0.f) * __uint_as_float(acc[j + 1]) + fminf(x.y, 0.f) * __uint_as_float(accn[j + 1]);
+                        o.z = fmaxf(x.z, 0.f) * __uint_as_float(acc[j + 2]) + fminf(x.z, 0.f) * __uint_as_float(accn[j + 2]);
+                        o.w = fmaxf(x.w, 0.f) * __uint_as_float(acc[j + 3]) + fminf(x.w, 0.f) * __uint_as_float(accn[j + 3]);
+                        *reinterpret_cast<float4*>(crow + c * 32 + j) = o;
+                    }
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();                                // nobody leaves while the peer may still touch this CTA
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -426,7 +685,7 @@ te_tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBl) : "memory");
         for (int s = 0; s < STAGES3; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(xf_bar(s), XF_THREADS);
+            mbar_init(xf_bar(s), XF_THREADS / 32);
             mbar_init(empty_bar(s), 1);
             mbar_init(accfull_bar(s), 1);
             mbar_init(accfree_bar(s), DRAIN_THREADS);
@@ -529,7 +788,8 @@ te_tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     l4[et + i * XF_THREADS] = l;
                 }
                 fence_proxy_async();
-                mbar_arrive(xf_bar(s));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(xf_bar(s));          // one arrive per transform warp
                 // the last stage of chunk c has just been handed to the MMA warp: drain chunk c-1 meanwhile
                 if (((it % CHUNK) == CHUNK - 1 || it == kb - 1) && it / CHUNK >= 1) drain(it / CHUNK - 1);
             }
@@ -775,7 +1035,10 @@ template <int NB> struct NkCfg {
     static constexpr int BN = NB * 32;
     static constexpr int B_BYTES_ = BN * BK * 4;                   // 4 KiB per block
     static constexpr int STAGE = 2 * NK_A + 2 * B_BYTES_;
-    static constexpr int STAGES = (NB <= 2) ? 4 : 2;
+    // attention shape (NB = 2): 2 stages of 48 KiB so that TWO CTAs share an SM — a CTA's whole reduction is only 7
+    // k-blocks, and its prologue / epilogue then overlap the other CTA's main loop
+    static constexpr int STAGES = 2;
+    static constexpr int MIN_CTAS = (NB <= 2) ? 2 : 1;
     static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
     static constexpr int XF4 = (NK_A + B_BYTES_) / 16;
     // wide tiles (the dense rollout product) keep the lo*hi + hi*lo correction terms in a second accumulator at column
@@ -814,7 +1077,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t l
 }
 
 template <int AMN, int EPI, int NB>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, NkCfg<NB>::MIN_CTAS)
 te_tc_attn_nk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const NkParams p) {
     using C = NkCfg<NB>;
     constexpr int NK_BN = C::BN, NK_B = C::B_BYTES_, NK_STAGE = C::STAGE, NK_STAGES = C::STAGES, NK_XF4 = C::XF4;
@@ -843,7 +1106,7 @@ te_tc_attn_nk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < NK_STAGES; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(xf_bar(s), XF_THREADS);
+            mbar_init(xf_bar(s), XF_THREADS / 32);
             mbar_init(empty_bar(s), 1);
         }
         mbar_init(accum_bar, 1);
@@ -936,7 +1199,8 @@ te_tc_attn_nk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 *src = hh; *dst = l;
             }
             fence_proxy_async();
-            mbar_arrive(xf_bar(s));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(xf_bar(s));              // one arrive per transform warp
         }
         const int q = warp & 3;
         const int m = m0 + q * 32 + lane;
@@ -1055,7 +1319,7 @@ int launch(const float* A, long long lda, const float* B0, const float* B1, cons
     }
     static bool attr_set[4] = {false, false, false, false};
     if (!attr_set[MODE]) {
-        if (cudaFuncSetAttribute(te_tc_zplus_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+        if (cudaFuncSetAttribute(te_tc_zplus_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZpCfg<MODE>::SMEM) != cudaSuccess) {
             te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
             return TE_ERR_CUDA;
         }
@@ -1065,7 +1329,47 @@ int launch(const float* A, long long lda, const float* B0, const float* B1, cons
     p.M = (int)M; p.N = N; p.K = K; p.E = E; p.lde = lde; p.C = C; p.ldc = ldc; p.Y = Y; p.ldy = ldy; p.bias = bias;
     p.out_bf16 = out_bf16;
     dim3 grid(N / BN, (unsigned)((M + BM - 1) / BM));
-    te_tc_zplus_kernel<MODE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB0, tmB1, p);
+    te_tc_zplus_kernel<MODE><<<grid, NUM_THREADS, ZpCfg<MODE>::SMEM, st>>>(tmA, tmB0, tmB1, p);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+
+// CTA-pair (cta_group::2) launch of the single-pass S kernel / the R kernel.  Opt-in (TE_B200_ZPLUS_2CTA=1, or
+// te_tc_set_pair_kernels): parity-tested, but as NON-persistent kernels they measured slower than the single-CTA
+// kernels (fc2-shaped rule 2.26 ms vs 1.89 ms; whole step 936 vs 968 expl/s) — a pair can only start when both SMs of
+// a TPC are free and pays two cluster barriers per tile.  They are the base for a persistent version.
+int g_pair_kernels = -1;
+bool use_pair_kernels() {
+    if (g_pair_kernels < 0) {
+        const char* e = getenv("TE_B200_ZPLUS_2CTA");
+        g_pair_kernels = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_pair_kernels == 1;
+}
+
+template <int MODE>
+int launch2(const float* A, long long lda, const float* B0, const float* B1, const float* E, long long lde, float* C,
+            long long ldc, long long M, int N, int K, cudaStream_t st, const float* Y = nullptr, long long ldy = 0,
+            const float* bias = nullptr) {
+    CUtensorMap tmA, tmB0, tmB1;
+    if (!make_map(&tmA, A, M, K, lda, BM) || !make_map(&tmB0, B0, N, K, K, BN / 2) || !make_map(&tmB1, B1, N, K, K, BN / 2)) {
+        te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed");
+        return TE_ERR_CUDA;
+    }
+    static bool attr_set[4] = {false, false, false, false};
+    if (!attr_set[MODE]) {
+        if (cudaFuncSetAttribute(te_tc_zplus2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES) != cudaSuccess) {
+            te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
+            return TE_ERR_CUDA;
+        }
+        attr_set[MODE] = true;
+    }
+    TcParams p;
+    p.M = (int)M; p.N = N; p.K = K; p.E = E; p.lde = lde; p.C = C; p.ldc = ldc; p.Y = Y; p.ldy = ldy; p.bias = bias;
+    p.out_bf16 = 0;
+    const unsigned mtiles = (unsigned)((M + BM - 1) / BM);
+    dim3 grid((unsigned)(N / BN) * ((mtiles + 1u) & ~1u));   // whole CTA pairs: an odd last tile gets an all-padding partner
+    te_tc_zplus2_kernel<MODE><<<grid, NUM_THREADS, SMEM2_BYTES, st>>>(tmA, tmB0, tmB1, p);
     TE_CUDA_CHECK_LAUNCH();
     return TE_OK;
 }
@@ -1104,6 +1408,8 @@ bool te_tc_zplus_supported(long long rows, int in_features, int out_features, lo
     return rows > 0 && rows < (1LL << 31) && in_features % BN == 0 && out_features % BN == 0 && ldx % 4 == 0 &&
            get_encode() != nullptr;
 }
+
+void te_tc_set_pair_kernels(int on) { g_pair_kernels = on ? 1 : 0; }
 
 long long te_tc_derived_floats(int in_features, int out_features) { return 10LL * in_features * out_features; }
 
@@ -1310,8 +1616,12 @@ int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* deriv
     if (y && a16(y) && ldy % 4 == 0 && (!bias || a16(bias))) {
         // single pass: Z = ((y - bias) + |x| |W|^T) / 2 with the saved forward output y = x W^T + bias
         const float* wabs = derived + 8 * n;
-        TE_TRY(launch<MODE_S1>(x, ldx, wabs, wabs, r, ldr, s_scratch, out_features, rows, out_features, in_features, st, y, ldy,
-                               bias, rb ? 1 : 0));
+        if (!rb && use_pair_kernels())
+            TE_TRY(launch2<MODE_S1>(x, ldx, wabs, wabs, r, ldr, s_scratch, out_features, rows, out_features, in_features, st, y,
+                                    ldy, bias));
+        else
+            TE_TRY(launch<MODE_S1>(x, ldx, wabs, wabs, r, ldr, s_scratch, out_features, rows, out_features, in_features, st, y,
+                                   ldy, bias, rb ? 1 : 0));
     } else {
         TE_TRY(launch<MODE_S>(x, ldx, wp, wn, r, ldr, s_scratch, out_features, rows, out_features, in_features, st, nullptr, 0,
                               nullptr, rb ? 1 : 0));
@@ -1321,6 +1631,8 @@ int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* deriv
         return launch_r_bf16(s_scratch, wb, wb + n, x, ldx, out, in_features, rows, in_features, out_features, st);
     }
     // R_in = x+ (S W+) + x- (S W-)          A = S [rows, out] ; B = W+/-^T [in, out]
+    if (use_pair_kernels())
+        return launch2<MODE_R>(s_scratch, out_features, wpt, wnt, x, ldx, out, in_features, rows, in_features, out_features, st);
     TE_TRY(launch<MODE_R>(s_scratch, out_features, wpt, wnt, x, ldx, out, in_features, rows, in_features, out_features, st));
     return TE_OK;
 }

@@ -39,6 +39,10 @@ bool te_tc_attn_nk_supported(int N, int dh, int NP, long long ldx, long long ld_
 int te_tc_attn_nk(const float* map, int NP, int amn, const float* X, long long ldx, int batch, int H, int N, float* out,
                   int ld_out, const float* E, float alpha, int epi, cudaStream_t st);
 
+// 1: run the z+ rule with the CTA-pair (tcgen05 cta_group::2) kernels instead of the single-CTA ones (default 0,
+// or the environment variable TE_B200_ZPLUS_2CTA=1)
+void te_tc_set_pair_kernels(int on);
+
 // dense rollout product out[b] = A[b] * Bm[b] ([batch, N, ld], N <= 224) on tcgen05, fp32-grade 3xTF32
 bool te_tc_bmm_nk_supported(int N, int ld);
 int te_tc_bmm_nk_resid(const float* A, const float* J, const float* rowscale, float* out, int batch, int N, int ld,
