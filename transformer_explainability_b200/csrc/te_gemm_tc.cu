@@ -847,11 +847,14 @@ te_tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // A and B are head slices of packed [batch*N, ld] activations, addressed in place by 2-D tensor maps
 // (column = h*dh + kblock*32, row = b*N + tile row).  Rows of a tile that fall into the next sample (N is not a
 // multiple of 128 / 256) only produce output rows / columns that the epilogue masks.  Both operands are activations,
-// so both are split into hi/lo in shared memory.  One CTA per (b, h, 128-row tile): the whole K (<= 64) is resident,
-// 6 MMAs per 8-wide k-step, one 128 x 256 fp32 accumulator in TMEM, fused epilogue (scale / multiply by E / safe_divide).
+// so both are split into hi/lo in shared memory.  One CTA per (b, h, 128-row tile), K (<= 64) streamed one 32-element
+// k-block at a time through a single operand buffer, 3 MMAs per 8-wide k-step, one 128 x 256 fp32 accumulator in TMEM,
+// fused epilogue (scale / multiply by E / safe_divide).
 // =====================================================================================================================
-constexpr int AT_KB = 2;                                          // max k-blocks (head_dim <= 64)
-constexpr int AT_SMEM = 2 * (AT_KB * A_BYTES + AT_KB * B_BYTES) + 1024 + 256;   // hi + lo of A and B
+// One k-block (32 of the <= 64 head-dim elements) is resident at a time: 96 KiB of operands (hi + lo of A and B), so
+// TWO CTAs share an SM and the TMA wait / split / epilogue of one overlaps the MMAs of the other (a CTA's whole
+// reduction is only 1-2 k-blocks; with everything resident — 192 KiB — the SM ran one CTA at a time, start to end).
+constexpr int AT_SMEM = 2 * (A_BYTES + B_BYTES) + 1024 + 256;
 enum { AT_STORE = 0, AT_MUL = 1, AT_SD = 2, AT_RESID = 3 };
 
 struct AtParams {
@@ -860,16 +863,16 @@ struct AtParams {
 };
 
 template <int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 2)
 te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const AtParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-    // layout: A_hi[kb] | B_hi[kb] | A_lo[kb] | B_lo[kb]
-    constexpr uint32_t OFF_AH = 0, OFF_BH = AT_KB * A_BYTES, OFF_AL = OFF_BH + AT_KB * B_BYTES, OFF_BL = OFF_AL + AT_KB * A_BYTES;
-    constexpr uint32_t TOTAL = OFF_BL + AT_KB * B_BYTES;
+    // layout (one k-block): A_hi | B_hi | A_lo | B_lo
+    constexpr uint32_t OFF_AH = 0, OFF_BH = A_BYTES, OFF_AL = OFF_BH + B_BYTES, OFF_BL = OFF_AL + A_BYTES;
+    constexpr uint32_t TOTAL = OFF_BL + B_BYTES;
     const uint32_t bars = smem_base + TOTAL;
-    const uint32_t full_bar = bars, xf_bar = bars + 8, accum_bar = bars + 16;
+    const uint32_t full_bar = bars, xf_bar = bars + 8, accum_bar = bars + 16, empty_bar = bars + 24;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + TOTAL + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -882,8 +885,9 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         mbar_init(full_bar, 1);
-        mbar_init(xf_bar, XF_THREADS);
+        mbar_init(xf_bar, XF_THREADS / 32);
         mbar_init(accum_bar, 1);
+        mbar_init(empty_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -899,19 +903,20 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_arrive_expect_tx(full_bar, (uint32_t)(kb * (A_BYTES + B_BYTES)));
             for (int k = 0; k < kb; ++k) {
-                tma_load_2d(smem_base + OFF_AH + k * A_BYTES, &tmA, full_bar, h * p.dh + k * BK, b * p.N + m0);
-                tma_load_2d(smem_base + OFF_BH + k * B_BYTES, &tmB, full_bar, h * p.dh + k * BK, b * p.N);
+                if (k > 0) mbar_wait(empty_bar, (uint32_t)((k - 1) & 1));        // MMAs of the previous k-block retired
+                mbar_arrive_expect_tx(full_bar, (uint32_t)(A_BYTES + B_BYTES));
+                tma_load_2d(smem_base + OFF_AH, &tmA, full_bar, h * p.dh + k * BK, b * p.N + m0);
+                tma_load_2d(smem_base + OFF_BH, &tmB, full_bar, h * p.dh + k * BK, b * p.N);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            mbar_wait(xf_bar, 0);
-            tcgen05_fence_after();
+            const uint64_t ah = make_smem_desc(smem_base + OFF_AH), al = make_smem_desc(smem_base + OFF_AL);
+            const uint64_t bh_ = make_smem_desc(smem_base + OFF_BH), bl = make_smem_desc(smem_base + OFF_BL);
             for (int kk = 0; kk < kb; ++kk) {
-                const uint64_t ah = make_smem_desc(smem_base + OFF_AH + kk * A_BYTES), al = make_smem_desc(smem_base + OFF_AL + kk * A_BYTES);
-                const uint64_t bh_ = make_smem_desc(smem_base + OFF_BH + kk * B_BYTES), bl = make_smem_desc(smem_base + OFF_BL + kk * B_BYTES);
+                mbar_wait(xf_bar, (uint32_t)(kk & 1));
+                tcgen05_fence_after();
 #pragma unroll
                 for (int k = 0; k < BK / 8; ++k) {
                     const uint64_t o = (uint64_t)(2 * k);
@@ -919,19 +924,20 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     umma_tf32(tmem_base, ah + o, bl + o, kIdesc, 1u);
                     umma_tf32(tmem_base, ah + o, bh_ + o, kIdesc, 1u);
                 }
+                umma_commit(empty_bar);              // the operand buffer may be refilled when these MMAs retire
             }
             umma_commit(accum_bar);
         }
         __syncwarp();
     } else {
         const int et = threadIdx.x - 64;
-        mbar_wait(full_bar, 0);
-        // split A (kb*16 KiB) and B (kb*32 KiB): hi in place, lo to the *_lo regions (same swizzled offsets)
-        {
+        // split A (16 KiB) and B (32 KiB) of every k-block: hi in place, lo to the *_lo regions (same swizzled offsets)
+        for (int kk = 0; kk < kb; ++kk) {
+            mbar_wait(full_bar, (uint32_t)(kk & 1));
             float4* a4 = reinterpret_cast<float4*>(smem_al + OFF_AH);
             float4* l4 = reinterpret_cast<float4*>(smem_al + OFF_AL);
-            const int na = kb * A_BYTES / 16;
-            for (int i = et; i < na; i += XF_THREADS) {
+#pragma unroll
+            for (int i = et; i < A_BYTES / 16; i += XF_THREADS) {
                 const float4 v = a4[i];
                 float4 hh, l;
                 hh.x = to_tf32(v.x); hh.y = to_tf32(v.y); hh.z = to_tf32(v.z); hh.w = to_tf32(v.w);
@@ -940,17 +946,18 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
             float4* b4 = reinterpret_cast<float4*>(smem_al + OFF_BH);
             float4* m4 = reinterpret_cast<float4*>(smem_al + OFF_BL);
-            const int nb = kb * B_BYTES / 16;
-            for (int i = et; i < nb; i += XF_THREADS) {
+#pragma unroll 4
+            for (int i = et; i < B_BYTES / 16; i += XF_THREADS) {
                 const float4 v = b4[i];
                 float4 hh, l;
                 hh.x = to_tf32(v.x); hh.y = to_tf32(v.y); hh.z = to_tf32(v.z); hh.w = to_tf32(v.w);
                 l.x = to_tf32(v.x - hh.x); l.y = to_tf32(v.y - hh.y); l.z = to_tf32(v.z - hh.z); l.w = to_tf32(v.w - hh.w);
                 b4[i] = hh; m4[i] = l;
             }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(xf_bar);
         }
-        fence_proxy_async();
-        mbar_arrive(xf_bar);
 
         const int q = warp & 3;
         const int i = m0 + q * 32 + lane;                       // query row inside the sample
