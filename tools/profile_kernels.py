@@ -16,7 +16,16 @@ from transformer_explainability_b200 import ops      # noqa: E402
 def main():
     what = sys.argv[1]
     g = torch.Generator(device="cuda").manual_seed(1)
-    if what in ("zplus_tc", "zplus_simt"):
+    if what == "zplus_tc_s1":                     # what the engines run: single-pass S kernel (saved forward output) + R kernel
+        rows, inf, outf = 256 * 197, 3072, 768
+        x = torch.randn(rows, inf, device="cuda", generator=g)
+        w = torch.randn(outf, inf, device="cuda", generator=g) * 0.02
+        b = torch.randn(outf, device="cuda", generator=g) * 0.1
+        r = torch.rand(rows, outf, device="cuda", generator=g)
+        y = ops.linear_forward(x, w, b, tensor_cores=True)
+        for _ in range(2):
+            ops.linear_relprop(x, w, r, tensor_cores=True, y=y, bias=b)
+    elif what in ("zplus_tc", "zplus_simt"):
         rows, inf, outf = 256 * 197, 3072, 768
         x = torch.randn(rows, inf, device="cuda", generator=g)
         w = torch.randn(outf, inf, device="cuda", generator=g) * 0.02

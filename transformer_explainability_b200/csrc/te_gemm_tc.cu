@@ -878,6 +878,7 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bh = blockIdx.y, b = bh / p.H, h = bh % p.H;
     const int m0 = blockIdx.x * BM;
+    const int n0 = blockIdx.z * BN;                    // key-column tile (N > 256: BERT-512 has two)
     const int kb = p.dh / BK;
     constexpr uint32_t TMEM_COLS = 256u;
 
@@ -907,7 +908,7 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (k > 0) mbar_wait(empty_bar, (uint32_t)((k - 1) & 1));        // MMAs of the previous k-block retired
                 mbar_arrive_expect_tx(full_bar, (uint32_t)(A_BYTES + B_BYTES));
                 tma_load_2d(smem_base + OFF_AH, &tmA, full_bar, h * p.dh + k * BK, b * p.N + m0);
-                tma_load_2d(smem_base + OFF_BH, &tmB, full_bar, h * p.dh + k * BK, b * p.N);
+                tma_load_2d(smem_base + OFF_BH, &tmB, full_bar, h * p.dh + k * BK, b * p.N + n0);
             }
         }
     } else if (warp == 1) {
@@ -963,8 +964,9 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int i = m0 + q * 32 + lane;                       // query row inside the sample
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
         const bool live = i < p.N;
-        const long long rowoff = ((long long)bh * p.N + i) * p.ld_out;
-        const int nchunks = (p.N + 31) / 32;
+        const long long rowoff = ((long long)bh * p.N + i) * p.ld_out + n0;
+        const int ncols = min(p.N - n0, BN);              // valid key columns of this tile
+        const int nchunks = (ncols + 31) / 32;
         // E (attention probabilities / attn_cam) comes from HBM: its loads are issued one 32-column chunk ahead so
         // that their latency overlaps the TMEM read, the math and the stores of the previous chunk.  Reading a
         // full float4 whose tail lies in the row padding is memory-safe (ld_out % 4 == 0); the tail is masked.
@@ -974,7 +976,7 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int j = 0; j < 8; ++j) {
                 const int col = c * 32 + j * 4;
                 buf[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (EPI != AT_STORE && live && col < p.N) buf[j] = __ldcs(reinterpret_cast<const float4*>(p.E + rowoff + col));
+                if (EPI != AT_STORE && live && col < ncols) buf[j] = __ldcs(reinterpret_cast<const float4*>(p.E + rowoff + col));
             }
         };
         load_e(0, ebuf[0]);
@@ -994,7 +996,7 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int col = cc * 32 + j * 4;
-                            if (col < p.N) {
+                            if (col < ncols) {
                                 const float e[4] = {ebuf[half][j].x, ebuf[half][j].y, ebuf[half][j].z, ebuf[half][j].w};
                                 float o[4];
 #pragma unroll
@@ -1004,10 +1006,10 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                     else if (EPI == AT_MUL) o[u] = p.alpha * a * e[u];
                                     else o[u] = te_sd(e[u], p.alpha * a);
                                 }
-                                if (col + 3 < p.N) *reinterpret_cast<float4*>(p.out + rowoff + col) = make_float4(o[0], o[1], o[2], o[3]);
+                                if (col + 3 < ncols) *reinterpret_cast<float4*>(p.out + rowoff + col) = make_float4(o[0], o[1], o[2], o[3]);
                                 else {
 #pragma unroll
-                                    for (int u = 0; u < 4; ++u) p.out[rowoff + col + u] = (col + u < p.N) ? o[u] : 0.f;   // zero the row padding
+                                    for (int u = 0; u < 4; ++u) p.out[rowoff + col + u] = (col + u < ncols) ? o[u] : 0.f;   // zero the row padding
                                 }
                             }
                         }
@@ -1468,7 +1470,7 @@ int dispatch3(int epi, const float* A, long long lda, const float* Bh, const flo
 }  // namespace
 
 bool te_tc_attn_supported(int N, int dh, long long lda, long long ldb, int ld_out) {
-    return N >= 1 && N <= BN && (dh == 32 || dh == 64) && lda % 4 == 0 && ldb % 4 == 0 && ld_out % 4 == 0 && get_encode() != nullptr;
+    return N >= 1 && (dh == 32 || dh == 64) && lda % 4 == 0 && ldb % 4 == 0 && ld_out % 4 == 0 && get_encode() != nullptr;
 }
 
 namespace {
@@ -1488,7 +1490,7 @@ int launch_attn(const float* A, long long lda, const float* B, long long ldb, lo
         }
         attr_set = true;
     }
-    dim3 grid((p.N + BM - 1) / BM, batch * p.H);
+    dim3 grid((p.N + BM - 1) / BM, batch * p.H, (p.N + BN - 1) / BN);
     if (grid.y > 65535) { te_set_last_error("te_gemm_tc: batch*heads too large for one launch"); return TE_ERR_ARG; }
     te_tc_attn_nn_kernel<EPI><<<grid, NUM_THREADS, AT_SMEM, st>>>(tmA, tmB, p);
     TE_CUDA_CHECK_LAUNCH();
