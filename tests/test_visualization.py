@@ -39,3 +39,18 @@ def test_generate_visualization_end_to_end_gpu():
     img = torch.rand(3, 224, 224, generator=torch.Generator().manual_seed(1))
     vis = generate_visualization(LRP(m), img)
     assert vis.shape == (224, 224, 3) and vis.dtype == np.uint8
+
+
+def test_eraser_rationale_lines_follow_reference_format():
+    """bert_pipeline.py:563-582: top-k token rationales, one JSON line per document and k, cumulative list."""
+    import json
+    import torch
+    from transformer_explainability_b200 import eraser
+    scores = torch.tensor([[0.1, -3.0, 0.9, 0.5, 0.2, 0.0, 0.7, 0.3]])
+    lines = eraser.rationale_lines(["doc_a"], scores, ks=(2, 3))
+    first = json.loads(lines[2][0])
+    assert first["annotation_id"] == "doc_a" and first["rationales"][0]["docid"] == "doc_a"
+    assert first["rationales"][0]["hard_rationale_predictions"] == [{"start_token": 2, "end_token": 3},
+                                                                    {"start_token": 6, "end_token": 7}]
+    second = json.loads(lines[3][0])["rationales"][0]["hard_rationale_predictions"]
+    assert [r["start_token"] for r in second] == [2, 6, 2, 6, 3]          # the reference never resets the list
