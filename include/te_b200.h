@@ -49,7 +49,8 @@ extern "C" {
 
 TE_API const char* te_last_error(void);
 /* Process-wide tuning switches (not part of the reference surface).  name = "zplus_pair_kernels": run the z+ Linear rule
- * with the CTA-pair (tcgen05 cta_group::2, 256 x 256 MMA) kernels instead of the single-CTA ones; default 0.
+ * with the CTA-pair (tcgen05 cta_group::2, 256 x 256 MMA) kernels instead of the single-CTA ones (2: R kernel only);
+ * name = "linear_pair_kernels": the same for the 3xTF32 forward / backward Linear GEMMs.  Both default to 0.
  * Returns TE_OK, or a negative status for an unknown name. */
 TE_API int te_set_option(const char* name, int value);
 TE_API int te_version(void);

@@ -159,6 +159,7 @@ extern "C" int te_matmul_qk_relprop(const float* q, const float* k, const float*
 extern "C" int te_set_option(const char* name, int value) {
     REQ(name != nullptr, "te_set_option: null name");
     if (strcmp(name, "zplus_pair_kernels") == 0) { te_tc_set_pair_kernels(value); return TE_OK; }
+    if (strcmp(name, "linear_pair_kernels") == 0) { te_tc_set_pair_linear(value); return TE_OK; }
     te_set_last_error("te_set_option: unknown option");
     return TE_ERR_ARG;
 }

@@ -653,6 +653,42 @@ struct Tc3Params {
     float* C; long long ldc; float* C2; long long ldc2;
 };
 
+// epilogue of both 3xTF32 Linear kernels: one output row x 128 columns per thread, from the fp32 register sums
+template <int EPI>
+__device__ __forceinline__ void gemm3x_epilogue(const Tc3Params& p, const float (&sum)[128], int row, int cbase) {
+        if (row < p.M) {
+            const float* erow = p.E ? p.E + (long long)row * p.lde + cbase : nullptr;
+            float* crow = p.C + (long long)row * p.ldc + cbase;
+            float* c2row = p.C2 ? p.C2 + (long long)row * p.ldc2 + cbase : nullptr;
+#pragma unroll
+            for (int j = 0; j < 128; j += 4) {
+                float o[4], o2[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
+                if (EPI == EP_BIAS || EPI == EP_BIAS_GELU || EPI == EP_BIAS_ADD) {
+                    if (p.bias) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
+                        bb[0] = t.x; bb[1] = t.y; bb[2] = t.z; bb[3] = t.w;
+                    }
+                }
+                if (EPI == EP_BIAS_ADD || EPI == EP_GELU_BWD) {
+                    const float4 t = *reinterpret_cast<const float4*>(erow + j);
+                    e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float a = sum[j + u];
+                    if (EPI == EP_STORE) o[u] = a;
+                    else if (EPI == EP_BIAS) o[u] = a + bb[u];
+                    else if (EPI == EP_BIAS_GELU) { o[u] = a + bb[u]; o2[u] = te_gelu(o[u]); }
+                    else if (EPI == EP_BIAS_ADD) { o[u] = a + bb[u]; o2[u] = e[u] + o[u]; }
+                    else o[u] = a * te_gelu_grad(e[u]);
+                }
+                *reinterpret_cast<float4*>(crow + j) = make_float4(o[0], o[1], o[2], o[3]);
+                if (EPI == EP_BIAS_GELU || EPI == EP_BIAS_ADD)
+                    *reinterpret_cast<float4*>(c2row + j) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+            }
+        }
+}
+
 // The tensor core accumulates in fp32 with truncation (round-toward-zero) at every MMA, so a long reduction drifts
 // by ~7e-9*K relative (measured: 2e-5 at K = 3072).  To stay at fp32 grade the reduction is cut into chunks of
 // CHUNK*32 = 128 elements: each chunk accumulates in one of two TMEM accumulators (2 x 256 columns), and while the
@@ -799,45 +835,184 @@ te_tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
 
         // ---- epilogue from the register sums ----
-        const int row = m0 + q * 32 + lane;
-        if (row < p.M) {
-            const int cbase = n0 + half * 128;
-            const float* erow = p.E ? p.E + (long long)row * p.lde + cbase : nullptr;
-            float* crow = p.C + (long long)row * p.ldc + cbase;
-            float* c2row = p.C2 ? p.C2 + (long long)row * p.ldc2 + cbase : nullptr;
-#pragma unroll
-            for (int j = 0; j < 128; j += 4) {
-                float o[4], o2[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
-                if (EPI == EP_BIAS || EPI == EP_BIAS_GELU || EPI == EP_BIAS_ADD) {
-                    if (p.bias) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
-                        bb[0] = t.x; bb[1] = t.y; bb[2] = t.z; bb[3] = t.w;
-                    }
-                }
-                if (EPI == EP_BIAS_ADD || EPI == EP_GELU_BWD) {
-                    const float4 t = *reinterpret_cast<const float4*>(erow + j);
-                    e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float a = sum[j + u];
-                    if (EPI == EP_STORE) o[u] = a;
-                    else if (EPI == EP_BIAS) o[u] = a + bb[u];
-                    else if (EPI == EP_BIAS_GELU) { o[u] = a + bb[u]; o2[u] = te_gelu(o[u]); }
-                    else if (EPI == EP_BIAS_ADD) { o[u] = a + bb[u]; o2[u] = e[u] + o[u]; }
-                    else o[u] = a * te_gelu_grad(e[u]);
-                }
-                *reinterpret_cast<float4*>(crow + j) = make_float4(o[0], o[1], o[2], o[3]);
-                if (EPI == EP_BIAS_GELU || EPI == EP_BIAS_ADD)
-                    *reinterpret_cast<float4*>(c2row + j) = make_float4(o2[0], o2[1], o2[2], o2[3]);
-            }
-        }
+        gemm3x_epilogue<EPI>(p, sum, m0 + q * 32 + lane, n0 + half * 128);
     }
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// =====================================================================================================================
+// CTA-pair version of the 3xTF32 Linear GEMM (tcgen05 cta_group::2): the two CTAs of a cluster own adjacent 128-row
+// tiles of the same 256-column tile and execute ONE 256 x 256 x 8 MMA per issue (leader CTA).  Each CTA stages its own
+// activation tile (raw -> hi, lo) and only its HALF of the pre-split weight tile (128 of the 256 rows of W_hi and
+// W_lo): a stage is 64 KiB instead of 96 KiB, so the ring is 3 deep instead of 2, and per k-block an SM moves
+// 48 + 48 + 96 KiB through shared memory (TMA in, split, MMA operand reads) instead of 80 + 48 + 144 KiB.
+//   full[s]     local    TMA bytes of this CTA's A tile and weight halves
+//   ready[s]    leader   one arrive per transform warp of BOTH CTAs (8) after the hi/lo split (remote arrive)
+//   empty[s]    local    tcgen05.commit.cta_group::2 multicast
+//   accfull[b]  local    same multicast commit at the end of a 128-element chunk
+//   accfree[b]  leader   one arrive per drain warp of BOTH CTAs (16) once accumulator b has been read out
+// =====================================================================================================================
+constexpr int STAGES3P = 3;
+constexpr int STAGE3P_BYTES = 2 * A_BYTES + 2 * BH_BYTES;        // 64 KiB
+constexpr int SMEM3P_BYTES = STAGES3P * STAGE3P_BYTES + 1024 + 256;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS3, 1)
+te_tc_gemm3x2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                     const __grid_constant__ CUtensorMap tmBl, const Tc3Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bars = smem_base + STAGES3P * STAGE3P_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto ready_bar = [&](int s) { return bars + 8u * (STAGES3P + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (2 * STAGES3P + s); };
+    auto accfull_bar = [&](int b) { return bars + 8u * (3 * STAGES3P + b); };
+    auto accfree_bar = [&](int b) { return bars + 8u * (3 * STAGES3P + 2 + b); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + STAGES3P * STAGE3P_BYTES + 8 * (3 * STAGES3P + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int ntn = p.N / BN;
+    const int pair = blockIdx.x >> 1;                 // column tile fastest over the pairs (L2 reuse of the activations)
+    const int m0 = ((pair / ntn) * 2 + (int)rank) * BM, n0 = (pair % ntn) * BN;
+    const int kb = p.K / BK;
+    const int nchunks = (kb + CHUNK - 1) / CHUNK;
+    constexpr uint32_t TMEM_COLS = 512u;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBl) : "memory");
+        for (int s = 0; s < STAGES3P; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(ready_bar(s), 2 * (XF_THREADS / 32));
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(accfull_bar(b), 1);
+            mbar_init(accfree_bar(b), 2 * (DRAIN_THREADS / 32));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < kb; ++it) {
+                const int s = it % STAGES3P;
+                const uint32_t ph = (it / STAGES3P) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_arrive_expect_tx(full_bar(s), A_BYTES + 2 * BH_BYTES);
+                const uint32_t sa = smem_base + s * STAGE3P_BYTES;
+                tma_load_2d(sa, &tmA, full_bar(s), it * BK, m0);                                    // raw A -> A_hi slot
+                tma_load_2d(sa + 2 * A_BYTES, &tmBh, full_bar(s), it * BK, n0 + (int)rank * (BN / 2));
+                tma_load_2d(sa + 2 * A_BYTES + BH_BYTES, &tmBl, full_bar(s), it * BK, n0 + (int)rank * (BN / 2));
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            for (int it = 0; it < kb; ++it) {
+                const int c = it / CHUNK, b = c & 1;
+                const bool chunk_start = (it % CHUNK) == 0;
+                if (chunk_start && c >= 2) {                        // accumulator b drained (chunk c-2) in BOTH CTAs
+                    mbar_wait_cluster(accfree_bar(b), (uint32_t)(((c >> 1) & 1) ^ 1));
+                    tcgen05_fence_after();
+                }
+                const int s = it % STAGES3P;
+                const uint32_t ph = (it / STAGES3P) & 1u;
+                mbar_wait_cluster(ready_bar(s), ph);
+                tcgen05_fence_after();
+                const uint32_t sa = smem_base + s * STAGE3P_BYTES;
+                const uint64_t ah = make_smem_desc(sa), al = make_smem_desc(sa + A_BYTES);
+                const uint64_t bh = make_smem_desc(sa + 2 * A_BYTES), bl = make_smem_desc(sa + 2 * A_BYTES + BH_BYTES);
+                const uint32_t d = tmem_base + (uint32_t)(b * BN);
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    const uint64_t o = (uint64_t)(2 * k);
+                    umma2_tf32(d, al + o, bh + o, kIdesc2, (chunk_start && k == 0) ? 0u : 1u);        // small terms first
+                    umma2_tf32(d, ah + o, bl + o, kIdesc2, 1u);
+                    umma2_tf32(d, ah + o, bh + o, kIdesc2, 1u);
+                }
+                umma2_commit_both(empty_bar(s));
+                if ((it % CHUNK) == CHUNK - 1 || it == kb - 1) umma2_commit_both(accfull_bar(b));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- warps 2..9: row = lane quarter (warp & 3), column half = 0 for warps 2-5, 1 for warps 6-9 ----
+        const int q = warp & 3;
+        const int half = (warp >= 6) ? 1 : 0;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
+        float sum[128];
+#pragma unroll
+        for (int j = 0; j < 128; ++j) sum[j] = 0.f;
+
+        auto drain = [&](int c) {
+            const int b = c & 1;
+            mbar_wait(accfull_bar(b), (uint32_t)((c >> 1) & 1));
+            tcgen05_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+                uint32_t v[16];
+                tmem_ld16(tlane + (uint32_t)(b * BN + cc * 16), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sum[cc * 16 + j] += __uint_as_float(v[j]);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(map_to_rank0(accfree_bar(b)));
+        };
+
+        if (warp < 6) {
+            const int et = threadIdx.x - 64;                        // 0..127: the four transform warps
+            for (int it = 0; it < kb; ++it) {
+                const int s = it % STAGES3P;
+                const uint32_t ph = (it / STAGES3P) & 1u;
+                mbar_wait(full_bar(s), ph);
+                float4* a4 = reinterpret_cast<float4*>(smem_al + s * STAGE3P_BYTES);
+                float4* l4 = reinterpret_cast<float4*>(smem_al + s * STAGE3P_BYTES + A_BYTES);
+#pragma unroll
+                for (int i = 0; i < A_BYTES / 16 / XF_THREADS; ++i) {
+                    const float4 v = a4[et + i * XF_THREADS];
+                    float4 h, l;
+                    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+                    l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+                    a4[et + i * XF_THREADS] = h;
+                    l4[et + i * XF_THREADS] = l;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(map_to_rank0(ready_bar(s)));
+                if (((it % CHUNK) == CHUNK - 1 || it == kb - 1) && it / CHUNK >= 1) drain(it / CHUNK - 1);
+            }
+            drain(nchunks - 1);
+        } else {
+            for (int c = 0; c < nchunks; ++c) drain(c);
+        }
+        gemm3x_epilogue<EPI>(p, sum, m0 + q * 32 + lane, n0 + half * 128);
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -1351,10 +1526,19 @@ int g_pair_kernels = -1;
 bool use_pair_kernels() {
     if (g_pair_kernels < 0) {
         const char* e = getenv("TE_B200_ZPLUS_2CTA");
-        g_pair_kernels = (e && e[0] == '1') ? 1 : 0;
+        g_pair_kernels = (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 0;
     }
-    return g_pair_kernels == 1;
+    return g_pair_kernels >= 1;
 }
+int g_pair_linear = -1;                 // 3xTF32 Linear GEMMs as CTA pairs (TE_B200_LINEAR_2CTA=1 / te_set_option)
+bool use_pair_linear() {
+    if (g_pair_linear < 0) {
+        const char* e = getenv("TE_B200_LINEAR_2CTA");
+        g_pair_linear = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_pair_linear == 1;
+}
+bool use_pair_s_kernel() { return use_pair_kernels() && g_pair_kernels == 1; }   // 2: pair form for the R kernel only
 
 template <int MODE>
 int launch2(const float* A, long long lda, const float* B0, const float* B1, const float* E, long long lde, float* C,
@@ -1418,7 +1602,8 @@ bool te_tc_zplus_supported(long long rows, int in_features, int out_features, lo
            get_encode() != nullptr;
 }
 
-void te_tc_set_pair_kernels(int on) { g_pair_kernels = on ? 1 : 0; }
+void te_tc_set_pair_linear(int on) { g_pair_linear = on ? 1 : 0; }
+void te_tc_set_pair_kernels(int on) { g_pair_kernels = (on == 2) ? 2 : (on ? 1 : 0); }
 
 long long te_tc_derived_floats(int in_features, int out_features) { return 10LL * in_features * out_features; }
 
@@ -1456,7 +1641,39 @@ int launch3(const float* A, long long lda, const float* Bh, const float* Bl, con
     return TE_OK;
 }
 
+template <int EPI>
+int launch3_pair(const float* A, long long lda, const float* Bh, const float* Bl, const Tc3Params& p, cudaStream_t st) {
+    CUtensorMap tmA, tmBh, tmBl;
+    if (!make_map(&tmA, A, p.M, p.K, lda, BM) || !make_map(&tmBh, Bh, p.N, p.K, p.K, BN / 2) ||
+        !make_map(&tmBl, Bl, p.N, p.K, p.K, BN / 2)) {
+        te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed");
+        return TE_ERR_CUDA;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(te_tc_gemm3x2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3P_BYTES) != cudaSuccess) {
+            te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
+            return TE_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    const unsigned mtiles = (unsigned)((p.M + BM - 1) / BM);
+    dim3 grid((unsigned)(p.N / BN) * ((mtiles + 1u) & ~1u));
+    te_tc_gemm3x2_kernel<EPI><<<grid, NUM_THREADS3, SMEM3P_BYTES, st>>>(tmA, tmBh, tmBl, p);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+
 int dispatch3(int epi, const float* A, long long lda, const float* Bh, const float* Bl, const Tc3Params& p, cudaStream_t st) {
+    if (use_pair_linear()) {
+        switch (epi) {
+            case TE_TC_EPI_STORE: return launch3_pair<EP_STORE>(A, lda, Bh, Bl, p, st);
+            case TE_TC_EPI_BIAS: return launch3_pair<EP_BIAS>(A, lda, Bh, Bl, p, st);
+            case TE_TC_EPI_BIAS_GELU: return launch3_pair<EP_BIAS_GELU>(A, lda, Bh, Bl, p, st);
+            case TE_TC_EPI_BIAS_ADD: return launch3_pair<EP_BIAS_ADD>(A, lda, Bh, Bl, p, st);
+            case TE_TC_EPI_GELU_BWD: return launch3_pair<EP_GELU_BWD>(A, lda, Bh, Bl, p, st);
+        }
+    }
     switch (epi) {
         case TE_TC_EPI_STORE: return launch3<EP_STORE>(A, lda, Bh, Bl, p, st);
         case TE_TC_EPI_BIAS: return launch3<EP_BIAS>(A, lda, Bh, Bl, p, st);
@@ -1625,7 +1842,7 @@ int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* deriv
     if (y && a16(y) && ldy % 4 == 0 && (!bias || a16(bias))) {
         // single pass: Z = ((y - bias) + |x| |W|^T) / 2 with the saved forward output y = x W^T + bias
         const float* wabs = derived + 8 * n;
-        if (!rb && use_pair_kernels())
+        if (!rb && use_pair_s_kernel())
             TE_TRY(launch2<MODE_S1>(x, ldx, wabs, wabs, r, ldr, s_scratch, out_features, rows, out_features, in_features, st, y,
                                     ldy, bias));
         else

@@ -42,6 +42,8 @@ int te_tc_attn_nk(const float* map, int NP, int amn, const float* X, long long l
 // 1: run the z+ rule with the CTA-pair (tcgen05 cta_group::2) kernels instead of the single-CTA ones (default 0,
 // or the environment variable TE_B200_ZPLUS_2CTA=1)
 void te_tc_set_pair_kernels(int on);
+// 1: run the 3xTF32 Linear GEMMs with the CTA-pair kernel (default 0, or TE_B200_LINEAR_2CTA=1)
+void te_tc_set_pair_linear(int on);
 
 // dense rollout product out[b] = A[b] * Bm[b] ([batch, N, ld], N <= 224) on tcgen05, fp32-grade 3xTF32
 bool te_tc_bmm_nk_supported(int N, int ld);
