@@ -4,6 +4,7 @@
 
 #include "te_gemm.cuh"
 #include "te_gemm_tc.h"
+#include "te_kernels.h"
 
 namespace te_util {
 
@@ -75,6 +76,16 @@ static inline int attn_nn(bool tc, int B, int H, int N, int NP, int dh, const fl
     const HeadOp none = {nullptr, 0, 0, 0};
     return head_gemm(B, H, head_rows(A, lda, N, dh), TE_L_K, head_rows(Bm, ldb, N, dh), TE_L_K, attn_map(out, H, N, NP),
                      E ? attn_map(E, H, N, NP) : none, N, N, dh, alpha, epi, st);
+}
+
+// P[b,h] = softmax(alpha * Q_h K_h^T): fused into the tensor-core kernel's epilogue when the key axis fits one tile
+// (N <= 256), otherwise scores + row softmax
+static inline int attn_probs(bool tc, int B, int H, int N, int NP, int dh, const float* Q, int ldq, const float* K, int ldk,
+                             float* P, float alpha, cudaStream_t st) {
+    if (tc && N <= 256 && te_tc_attn_supported(N, dh, ldq, ldk, NP))
+        return te_tc_attn_nn(Q, ldq, K, ldk, B, H, N, dh, P, NP, nullptr, alpha, TE_TC_ATTN_SOFTMAX, st);
+    TE_TRY(attn_nn(tc, B, H, N, NP, dh, Q, ldq, K, ldk, P, nullptr, alpha, TE_EPI_STORE, st));
+    return te_launch_softmax(P, (long long)B * H * N, N, NP, st);
 }
 
 // out[b,m,h,:] = epi(alpha * sum_k A_h[m,k] X[b,k,h,:]) with A_h = map[b,h] (amn = 0) or map[b,h]^T (amn = 1)

@@ -1030,7 +1030,7 @@ te_tc_gemm3x2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 // TWO CTAs share an SM and the TMA wait / split / epilogue of one overlaps the MMAs of the other (a CTA's whole
 // reduction is only 1-2 k-blocks; with everything resident — 192 KiB — the SM ran one CTA at a time, start to end).
 constexpr int AT_SMEM = 2 * (A_BYTES + B_BYTES) + 1024 + 256;
-enum { AT_STORE = 0, AT_MUL = 1, AT_SD = 2, AT_RESID = 3 };
+enum { AT_STORE = 0, AT_MUL = 1, AT_SD = 2, AT_RESID = 3, AT_SOFTMAX = 4 };
 
 struct AtParams {
     int N, H, dh, ld_out;            // tokens, heads, head_dim, row stride of out / E
@@ -1145,6 +1145,52 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // E (attention probabilities / attn_cam) comes from HBM: its loads are issued one 32-column chunk ahead so
         // that their latency overlaps the TMEM read, the math and the stores of the previous chunk.  Reading a
         // full float4 whose tail lies in the row padding is memory-safe (ld_out % 4 == 0); the tail is masked.
+        if (EPI == AT_SOFTMAX) {
+            // softmax(alpha * A B^T) over the key axis, fused: every thread owns one query row whose N <= 256 scores sit
+            // in its TMEM lane, so the row maximum, the sum of exponentials and the normalised probabilities come from
+            // three passes over TMEM — the scores never travel to HBM (attn = dots.softmax(dim=-1), ViT_LRP.py:139-141)
+            mbar_wait(accum_bar, 0);
+            tcgen05_fence_after();
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int cc = 0; cc < nchunks; ++cc) {
+                uint32_t acc[32];
+                tmem_ld32(tlane + (uint32_t)(cc * 32), acc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (cc * 32 + j < ncols) mx = fmaxf(mx, p.alpha * __uint_as_float(acc[j]));
+            }
+            float sum = 0.f;
+#pragma unroll 1
+            for (int cc = 0; cc < nchunks; ++cc) {
+                uint32_t acc[32];
+                tmem_ld32(tlane + (uint32_t)(cc * 32), acc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (cc * 32 + j < ncols) sum += expf(p.alpha * __uint_as_float(acc[j]) - mx);
+            }
+#pragma unroll 1
+            for (int cc = 0; cc < nchunks; ++cc) {
+                uint32_t acc[32];
+                tmem_ld32(tlane + (uint32_t)(cc * 32), acc);
+                tmem_ld_wait();
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int col = cc * 32 + j * 4;
+                        if (col < ncols) {
+                            float o[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                o[u] = (col + u < ncols) ? expf(p.alpha * __uint_as_float(acc[j * 4 + u]) - mx) / sum : 0.f;
+                            *reinterpret_cast<float4*>(p.out + rowoff + col) = make_float4(o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                }
+            }
+        } else {
         float4 ebuf[2][8];
         auto load_e = [&](int c, float4 (&buf)[8]) {
 #pragma unroll
@@ -1192,6 +1238,7 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 }
             }
         }
+        }   // EPI != AT_SOFTMAX
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -1725,6 +1772,9 @@ int te_tc_attn_nn(const float* A, long long lda, const float* B, long long ldb, 
         case TE_TC_ATTN_STORE: return launch_attn<AT_STORE>(A, lda, B, ldb, rows, p, batch, st);
         case TE_TC_ATTN_MUL: return launch_attn<AT_MUL>(A, lda, B, ldb, rows, p, batch, st);
         case TE_TC_ATTN_SD: return launch_attn<AT_SD>(A, lda, B, ldb, rows, p, batch, st);
+        case TE_TC_ATTN_SOFTMAX:
+            if (N > BN) break;                        // the whole key axis must sit in one accumulator
+            return launch_attn<AT_SOFTMAX>(A, lda, B, ldb, rows, p, batch, st);
     }
     te_set_last_error("te_gemm_tc: unsupported attention epilogue");
     return TE_ERR_UNSUPPORTED;

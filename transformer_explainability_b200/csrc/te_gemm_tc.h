@@ -29,7 +29,7 @@ int te_tc_linear_bwd(const float* dy, const float* derived, int in_features, int
                      long long rows, int epi, cudaStream_t st);
 
 // attention-shaped N x N contractions (Q K^T, dctx V^T, S2 V^T) on tcgen05, fp32-grade 3xTF32, head slices in place
-enum { TE_TC_ATTN_STORE = 0, TE_TC_ATTN_MUL = 1, TE_TC_ATTN_SD = 2 };
+enum { TE_TC_ATTN_STORE = 0, TE_TC_ATTN_MUL = 1, TE_TC_ATTN_SD = 2, TE_TC_ATTN_SOFTMAX = 3 };   // SOFTMAX: N <= 256
 bool te_tc_attn_supported(int N, int dh, long long lda, long long ldb, int ld_out);
 int te_tc_attn_nn(const float* A, long long lda, const float* B, long long ldb, int batch, int H, int N, int dh,
                   float* out, int ld_out, const float* E, float alpha, int epi, cudaStream_t st);

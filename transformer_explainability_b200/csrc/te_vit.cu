@@ -279,9 +279,8 @@ extern "C" int te_vit_forward(const te_vit_config* cfg, const float* weights, co
         const HeadOp v = head_rows(a.qkv + 2 * d.D, 3 * d.D, d.N, d.dh);
         const HeadOp none = {nullptr, 0, 0, 0};
         // dots = q k^T * scale ; attn = softmax(dots)        (:139-141)
-        TE_TRY(te_util::attn_nn((flags & TE_FLAG_ATTN_TENSOR_CORES) != 0, d.B, d.H, d.N, d.NP, d.dh, a.qkv, 3 * d.D,
-                                a.qkv + d.D, 3 * d.D, a.P, nullptr, scale, TE_EPI_STORE, st));
-        TE_TRY(te_launch_softmax(a.P, (long long)d.B * d.H * d.N, d.N, d.NP, st));
+        TE_TRY(te_util::attn_probs((flags & TE_FLAG_ATTN_TENSOR_CORES) != 0, d.B, d.H, d.N, d.NP, d.dh, a.qkv, 3 * d.D,
+                                   a.qkv + d.D, 3 * d.D, a.P, scale, st));
         // out = attn v -> 'b h n d -> b n (h d)'              (:147-148)
         TE_TRY(te_util::attn_nk((flags & TE_FLAG_ATTN_TENSOR_CORES) != 0, d.B, d.H, d.N, d.NP, d.dh, a.P, 0, a.qkv + 2 * d.D,
                                 3 * d.D, a.ctx, d.D, nullptr, 1.f, TE_EPI_STORE, st));
