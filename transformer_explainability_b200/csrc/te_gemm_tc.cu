@@ -126,6 +126,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float to_tf32(float x) {
@@ -1148,7 +1160,7 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (EPI == AT_SOFTMAX) {
             // softmax(alpha * A B^T) over the key axis, fused: every thread owns one query row whose N <= 256 scores sit
             // in its TMEM lane, so the row maximum, the sum of exponentials and the normalised probabilities come from
-            // three passes over TMEM — the scores never travel to HBM (attn = dots.softmax(dim=-1), ViT_LRP.py:139-141)
+            // three passes over TMEM (the exponentials are written back with tcgen05.st) — the scores never travel to HBM (attn = dots.softmax(dim=-1), ViT_LRP.py:139-141)
             mbar_wait(accum_bar, 0);
             tcgen05_fence_after();
             float mx = -INFINITY;
@@ -1161,6 +1173,7 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 for (int j = 0; j < 32; ++j)
                     if (cc * 32 + j < ncols) mx = fmaxf(mx, p.alpha * __uint_as_float(acc[j]));
             }
+            // pass 2: e = exp(score - max), summed, and written back over the scores in TMEM (one expf per element)
             float sum = 0.f;
 #pragma unroll 1
             for (int cc = 0; cc < nchunks; ++cc) {
@@ -1168,9 +1181,14 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 tmem_ld32(tlane + (uint32_t)(cc * 32), acc);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (cc * 32 + j < ncols) sum += expf(p.alpha * __uint_as_float(acc[j]) - mx);
+                for (int j = 0; j < 32; ++j) {
+                    const float e = (cc * 32 + j < ncols) ? expf(p.alpha * __uint_as_float(acc[j]) - mx) : 0.f;
+                    sum += e;
+                    acc[j] = __float_as_uint(e);
+                }
+                tmem_st32(tlane + (uint32_t)(cc * 32), acc);
             }
+            tmem_st_wait();
 #pragma unroll 1
             for (int cc = 0; cc < nchunks; ++cc) {
                 uint32_t acc[32];
@@ -1183,8 +1201,7 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         if (col < ncols) {
                             float o[4];
 #pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                o[u] = (col + u < ncols) ? expf(p.alpha * __uint_as_float(acc[j * 4 + u]) - mx) / sum : 0.f;
+                            for (int u = 0; u < 4; ++u) o[u] = __uint_as_float(acc[j * 4 + u]) / sum;   // padding holds e = 0
                             *reinterpret_cast<float4*>(p.out + rowoff + col) = make_float4(o[0], o[1], o[2], o[3]);
                         }
                     }
