@@ -119,6 +119,14 @@ def test_patch_embed_zb_rule(ops, B, C, S, P, D):
     assert rel_err(out, ref) < 2e-5
     out_sum = ops.patch_embed_relprop(dev(img), dev(w), dev(r), per_channel=False)
     assert rel_err(out_sum, ref.sum(dim=1)) < 2e-5
+    # the reference-shaped layer class (modules.layers_ours.Conv2d: forward hook stashes X, relprop(R, alpha))
+    from transformer_explainability_b200.modules import layers_ours as L
+    conv = L.Conv2d(C, D, kernel_size=P, stride=P).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(w)
+    conv(dev(img))
+    r_conv = dev(r).transpose(1, 2).reshape(B, D, S // P, S // P).contiguous()
+    assert rel_err(conv.relprop(r_conv, alpha=1), ref) < 2e-5
     # conservation: sum of the pixel relevance == sum of R * (Za - 1e-9) / Za ~= sum R
     assert abs(out.double().sum().item() - r.double().sum().item()) < 1e-3 * r.abs().double().sum().item()
 

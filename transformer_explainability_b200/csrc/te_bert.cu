@@ -268,7 +268,6 @@ extern "C" int te_bert_forward(const te_bert_config* cfg, const float* weights, 
     Weights w;
     bind_weights(cfg, weights, w);
     const float scale = 1.0f / sqrtf((float)d.dh);
-    const HeadOp none = {nullptr, 0, 0, 0};
 
     TE_TRY(te_launch_bert_embed(input_ids, w.word, w.pos, w.type, ws.tD[0], d.B, d.N, d.D, st));
     TE_TRY(te_launch_layernorm(ws.tD[0], w.elnw, w.elnb, ws.layer[0].h, nullptr, nullptr, d.M, d.D, d.eps, st));
@@ -330,10 +329,8 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
     bind_weights(cfg, weights, w);
     const float* dbase = (flags & TE_FLAG_ZPLUS_TENSOR_CORES) ? derived : nullptr;
     const float scale = 1.0f / sqrtf((float)d.dh);
-    const HeadOp none = {nullptr, 0, 0, 0};
     const long long MD = d.M * d.D, DD = (long long)d.D * d.D;
     const int low = (flags & (TE_FLAG_KEEP_ALL_CAMS | TE_FLAG_RELPROP_TO_INPUT)) ? 0 : start_layer;
-    auto amap = [&](const float* p) { return attn_map(p, d.H, d.N, d.NP); };
 
     TE_TRY(te_launch_argmax(ws.logits, index, d.B, d.C, 1, st));
     TE_TRY(te_launch_onehot(index, ws.seed, d.B, d.C, 1.0f, st));

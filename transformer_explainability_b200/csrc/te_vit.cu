@@ -186,11 +186,6 @@ using te_util::HeadOp;
 using te_util::head_rows;
 using te_util::linear_bwd;
 using te_util::linear_fwd;
-static HeadOp attn_map(const float* base, const Dims& d) { return te_util::attn_map(base, d.H, d.N, d.NP); }
-static int head_gemm(const Dims& d, HeadOp A, int alay, HeadOp B, int blay, HeadOp C, HeadOp E, int M, int N, int K,
-                     float alpha, int epi, cudaStream_t st) {
-    return te_util::head_gemm(d.B, d.H, A, alay, B, blay, C, E, M, N, K, alpha, epi, st);
-}
 
 static int check_ws(const te_vit_config* cfg, int batch, void* workspace, long long bytes, Dims& d, Workspace& ws) {
     if (batch <= 0 || !workspace) { te_set_last_error("te_vit: batch <= 0 or null workspace"); return TE_ERR_ARG; }
@@ -277,7 +272,6 @@ extern "C" int te_vit_forward(const te_vit_config* cfg, const float* weights, co
         const HeadOp q = head_rows(a.qkv, 3 * d.D, d.N, d.dh);
         const HeadOp k = head_rows(a.qkv + d.D, 3 * d.D, d.N, d.dh);
         const HeadOp v = head_rows(a.qkv + 2 * d.D, 3 * d.D, d.N, d.dh);
-        const HeadOp none = {nullptr, 0, 0, 0};
         // dots = q k^T * scale ; attn = softmax(dots)        (:139-141)
         TE_TRY(te_util::attn_probs((flags & TE_FLAG_ATTN_TENSOR_CORES) != 0, d.B, d.H, d.N, d.NP, d.dh, a.qkv, 3 * d.D,
                                    a.qkv + d.D, 3 * d.D, a.P, scale, st));
@@ -347,7 +341,6 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
     Weights w;
     bind_weights(cfg, weights, w);
     const float scale = 1.0f / sqrtf((float)d.dh);
-    const HeadOp none = {nullptr, 0, 0, 0};
     const long long MD = d.M * d.D;
     const int low = (flags & (TE_FLAG_KEEP_ALL_CAMS | TE_FLAG_RELPROP_TO_INPUT)) ? 0 : start_layer;   // lowest block the relprop must reach
     const float* dbase = (flags & TE_FLAG_ZPLUS_TENSOR_CORES) ? derived : nullptr;

@@ -162,4 +162,13 @@ class Linear(nn.Linear, RelProp):
 
 class Conv2d(nn.Conv2d, RelProp):
     def relprop(self, R, alpha):
-        raise NotImplementedError("Conv2d.relprop (method='full') is out of scope for the attribution hot path")
+        """``layers_ours.py:242-259``, 3-channel (z^B) branch, for the patch-embedding geometry the reference uses it
+        with (kernel == stride, no padding, ``ViT_LRP.py:228``): R [B,D,H/P,W/P] -> [B,3,H,W]."""
+        _check_alpha(alpha)
+        x = self.X
+        k, st = self.kernel_size, self.stride
+        if x.shape[1] != 3 or k != st or k[0] != k[1] or tuple(self.padding) != (0, 0) or x.shape[2] != x.shape[3]:
+            raise NotImplementedError("Conv2d.relprop: only the 3-channel z^B rule of a square kernel == stride, "
+                                      "unpadded (patch-embedding) convolution is on the attribution path")
+        r = R.flatten(2).transpose(1, 2)                       # [B, np, D], the layout PatchEmbed.relprop receives
+        return ops.patch_embed_relprop(_c(x), _c(self.weight), _c(r), per_channel=True)
