@@ -214,6 +214,9 @@ TE_API int te_patch_embed_relprop(const float* images, const float* weight, cons
                            int img_size, int patch_size, int dim, float* r_pixels, float* r_sum, void* workspace,
                            long long workspace_bytes, void* stream);
 
+/* generate_visualization's tensor part (example.ipynb:57-60): maps [batch, grid*grid] -> reshape grid x grid -> bilinear
+ * x scale (align_corners=False) -> per-sample min-max normalisation -> out [batch, grid*scale, grid*scale]. */
+TE_API int te_relevance_heatmap(const float* maps, int batch, int grid, int scale, float* out, void* stream);
 /* Head reductions of attention-shaped tensors [batch, heads, n, ld] -> out [batch, n, n] (contiguous), the building
  * block of the secondary methods (ViT_LRP.py:345-398; ViT_explanation_generator.py:51-83; BERT
  * ExplanationGenerator.py:61-155):   v_h = a_h (* g_h if g) (* head_w[b,h] if head_w);

@@ -26,6 +26,17 @@ def test_heatmap_matches_notebook_sequence_per_sample():
 
 
 @pytest.mark.gpu
+def test_heatmap_kernel_matches_notebook_sequence():
+    g = torch.Generator().manual_seed(3)
+    maps = torch.rand(7, 196, generator=g) * 3e-4
+    heat = relevance_to_heatmap(maps.cuda())
+    assert heat.shape == (7, 224, 224) and heat.is_cuda
+    for s in range(7):
+        assert (heat[s].cpu() - _notebook_reference(maps[s])).abs().max() < 2e-6
+    assert float(heat.min()) == 0.0 and float(heat.max()) == 1.0
+
+
+@pytest.mark.gpu
 def test_generate_visualization_end_to_end_gpu():
     cv2 = pytest.importorskip("cv2")
     from oracle import vit as ovit

@@ -164,6 +164,11 @@ extern "C" int te_set_option(const char* name, int value) {
     return TE_ERR_ARG;
 }
 
+extern "C" int te_relevance_heatmap(const float* maps, int batch, int grid, int scale, float* out, void* stream) {
+    REQ(maps && out && batch > 0 && grid > 0 && scale > 0, "te_relevance_heatmap: bad argument");
+    return te_launch_relevance_heatmap(maps, out, batch, grid, scale, ST(stream));
+}
+
 // ---- head reductions of the secondary methods ------------------------------------------------------------
 extern "C" int te_head_reduce(const float* a, const float* g, const float* head_w, int batch, int heads, int n, int ld,
                               int mode, float* out, void* stream) {

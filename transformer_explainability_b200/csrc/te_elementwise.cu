@@ -430,6 +430,40 @@ __global__ void aggregate_vec_kernel(const float* __restrict__ G, const float* _
     }
 }
 
+// generate_visualization (example.ipynb:57-60): [g,g] relevance -> bilinear x scale (align_corners=False, the arithmetic of
+// torch.nn.functional.interpolate(mode='bilinear', scale_factor=scale)) -> per-sample min-max.  One block per sample.
+__global__ void relevance_heatmap_kernel(const float* __restrict__ maps, float* __restrict__ out, int g, int scale) {
+    const int G = g * scale, total = G * G;
+    const float* m = maps + (long long)blockIdx.x * g * g;
+    float* o = out + (long long)blockIdx.x * total;
+    const float rs = 1.0f / (float)scale;
+    float mn = INFINITY, mx = -INFINITY;
+    for (int p = threadIdx.x; p < total; p += blockDim.x) {
+        const int y = p / G, x = p % G;
+        const float sy = fmaxf(rs * ((float)y + 0.5f) - 0.5f, 0.f), sx = fmaxf(rs * ((float)x + 0.5f) - 0.5f, 0.f);
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int y1 = y0 + (y0 < g - 1 ? 1 : 0), x1 = x0 + (x0 < g - 1 ? 1 : 0);
+        const float ly1 = sy - (float)y0, ly0 = 1.f - ly1, lx1 = sx - (float)x0, lx0 = 1.f - lx1;
+        const float v = ly0 * (lx0 * m[y0 * g + x0] + lx1 * m[y0 * g + x1]) + ly1 * (lx0 * m[y1 * g + x0] + lx1 * m[y1 * g + x1]);
+        o[p] = v;
+        mn = fminf(mn, v); mx = fmaxf(mx, v);
+    }
+    __shared__ float smn[kThreads / 32], smx[kThreads / 32], bmn, bmx;
+    for (int s = 16; s > 0; s >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, s));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+    }
+    if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < kThreads / 32; ++i) { mn = fminf(mn, smn[i]); mx = fmaxf(mx, smx[i]); }
+        bmn = mn; bmx = mx;
+    }
+    __syncthreads();
+    const float lo = bmn, range = bmx - bmn;
+    for (int p = threadIdx.x; p < total; p += blockDim.x) o[p] = (o[p] - lo) / range;      // each thread re-reads its own writes
+}
+
 // head reductions for the secondary methods: one warp per output row
 __global__ void head_reduce_kernel(const float* __restrict__ A, const float* __restrict__ G,
                                    const float* __restrict__ hw, float* __restrict__ out, int B, int H, int N, int ld,
@@ -746,6 +780,12 @@ int te_launch_aggregate(const float* G, const float* cam, float* M, int B, int H
     else
         aggregate_kernel<<<warp_rows_grid((long long)B * N), kThreads, 0, st>>>(G, cam, M, B, H, N, ld_in, ld_out, add_eye,
                                                                               normalize, diag);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_relevance_heatmap(const float* maps, float* out, int B, int g, int scale, cudaStream_t st) {
+    TE_REQ(B > 0 && g > 0 && scale > 0, "relevance_heatmap: bad shape");
+    relevance_heatmap_kernel<<<B, kThreads, 0, st>>>(maps, out, g, scale);
     TE_CUDA_CHECK_LAUNCH();
     return TE_OK;
 }

@@ -50,6 +50,8 @@ int te_launch_index_select_relprop(const float* x, const float* r_tok0, const fl
 // diag (with add_eye = 0, normalize = 1): identity kept out of M, its normalised weight 1/rowsum written to diag [B*N]
 int te_launch_aggregate(const float* G, const float* cam, float* M, int B, int H, int N, int ld_in, int ld_out,
                         int add_eye, int normalize, cudaStream_t st, float* diag = nullptr);
+// generate_visualization: [B, g*g] -> bilinear x scale -> per-sample min-max -> [B, g*scale, g*scale]
+int te_launch_relevance_heatmap(const float* maps, float* out, int B, int g, int scale, cudaStream_t st);
 // secondary methods: out[b,i,j] = reduce_h( a (* g) (* hw[b,h]) ); mode 0 mean, 1 mean of relu, 2 relu of mean
 int te_launch_head_reduce(const float* a, const float* g, const float* hw, float* out, int B, int H, int N, int ld,
                           int mode, cudaStream_t st);

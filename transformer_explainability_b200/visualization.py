@@ -9,8 +9,17 @@ import torch.nn.functional as F
 
 
 def relevance_to_heatmap(maps, grid=14, scale=16):
-    """[B, grid*grid] -> min-max normalised [B, grid*scale, grid*scale] (device tensor)."""
+    """[B, grid*grid] -> min-max normalised [B, grid*scale, grid*scale] (device tensor).  CUDA tensors go through the
+    engine's kernel (``te_relevance_heatmap``, one block per sample); host tensors follow the notebook's torch sequence."""
     b = maps.shape[0]
+    if maps.is_cuda:
+        from . import _lib
+        m = maps.detach().to(torch.float32).contiguous()
+        out = torch.empty(b, grid * scale, grid * scale, device=m.device, dtype=torch.float32)
+        _lib.check(_lib.load().te_relevance_heatmap(_lib.ptr(m), b, grid, scale, _lib.ptr(out),
+                                                    _lib.ctypes.c_void_p(torch.cuda.current_stream(m.device).cuda_stream)),
+                   "te_relevance_heatmap")
+        return out
     t = maps.reshape(b, 1, grid, grid)
     t = F.interpolate(t, scale_factor=scale, mode='bilinear')
     t = t.reshape(b, -1)
