@@ -1,0 +1,491 @@
+// fp32-grade (3xTF32) Linear GEMMs of the forward pass and of the activation-gradient backward on tcgen05:
+// single-CTA kernel (default) and CTA-pair kernel (opt-in).  Shared PTX wrappers: te_tc_common.cuh.
+#include "te_tc_common.cuh"
+
+namespace {
+
+// =====================================================================================================================
+// fp32-grade Linear GEMM on tensor cores: 3xTF32 error-compensated split
+//   C = A B^T  ~=  A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T ,  x_hi = tf32(x), x_lo = tf32(x - x_hi)
+// A (activations) is split in shared memory by the transform warps; B (frozen weights) is pre-split.
+// Tile 128 x 256 x 32, 2 stages of [A_hi 16K | A_lo 16K | B_hi 32K | B_lo 32K], 12 MMAs per k-block.
+// =====================================================================================================================
+constexpr int STAGES3 = 2;
+constexpr int STAGE3_BYTES = 2 * A_BYTES + 2 * B_BYTES;          // 96 KiB
+constexpr int SMEM3_BYTES = STAGES3 * STAGE3_BYTES + 1024 + 256;
+constexpr int NUM_THREADS3 = 320;                                // TMA, MMA, 4 transform+drain warps, 4 drain warps
+constexpr int DRAIN_THREADS = 256;
+constexpr int CHUNK = 4;                                         // k-blocks (of 32) accumulated inside the tensor core
+enum { EP_STORE = 0, EP_BIAS = 1, EP_BIAS_GELU = 2, EP_BIAS_ADD = 3, EP_GELU_BWD = 4 };
+
+struct Tc3Params {
+    int M, N, K;
+    const float* bias; const float* E; long long lde;
+    float* C; long long ldc; float* C2; long long ldc2;
+};
+
+// epilogue of both 3xTF32 Linear kernels: one output row x 128 columns per thread, from the fp32 register sums
+template <int EPI>
+__device__ __forceinline__ void gemm3x_epilogue(const Tc3Params& p, const float (&sum)[128], int row, int cbase) {
+        if (row < p.M) {
+            const float* erow = p.E ? p.E + (long long)row * p.lde + cbase : nullptr;
+            float* crow = p.C + (long long)row * p.ldc + cbase;
+            float* c2row = p.C2 ? p.C2 + (long long)row * p.ldc2 + cbase : nullptr;
+#pragma unroll
+            for (int j = 0; j < 128; j += 4) {
+                float o[4], o2[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
+                if (EPI == EP_BIAS || EPI == EP_BIAS_GELU || EPI == EP_BIAS_ADD) {
+                    if (p.bias) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
+                        bb[0] = t.x; bb[1] = t.y; bb[2] = t.z; bb[3] = t.w;
+                    }
+                }
+                if (EPI == EP_BIAS_ADD || EPI == EP_GELU_BWD) {
+                    const float4 t = *reinterpret_cast<const float4*>(erow + j);
+                    e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float a = sum[j + u];
+                    if (EPI == EP_STORE) o[u] = a;
+                    else if (EPI == EP_BIAS) o[u] = a + bb[u];
+                    else if (EPI == EP_BIAS_GELU) { o[u] = a + bb[u]; o2[u] = te_gelu(o[u]); }
+                    else if (EPI == EP_BIAS_ADD) { o[u] = a + bb[u]; o2[u] = e[u] + o[u]; }
+                    else o[u] = a * te_gelu_grad(e[u]);
+                }
+                *reinterpret_cast<float4*>(crow + j) = make_float4(o[0], o[1], o[2], o[3]);
+                if (EPI == EP_BIAS_GELU || EPI == EP_BIAS_ADD)
+                    *reinterpret_cast<float4*>(c2row + j) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+            }
+        }
+}
+
+// The tensor core accumulates in fp32 with truncation (round-toward-zero) at every MMA, so a long reduction drifts
+// by ~7e-9*K relative (measured: 2e-5 at K = 3072).  To stay at fp32 grade the reduction is cut into chunks of
+// CHUNK*32 = 128 elements: each chunk accumulates in one of two TMEM accumulators (2 x 256 columns), and while the
+// MMAs of the next chunk run, 8 warps drain the finished accumulator with tcgen05.ld and add it into fp32 register
+// sums with round-to-nearest CUDA-core adds (128 sums per thread: one row x half of the 256 columns).
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS3, 1)      // 10 warps are register-allocated as 12: 168 regs / thread
+te_tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                    const __grid_constant__ CUtensorMap tmBl, const Tc3Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bars = smem_base + STAGES3 * STAGE3_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto xf_bar = [&](int s) { return bars + 8u * (2 + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (4 + s); };
+    auto accfull_bar = [&](int b) { return bars + 8u * (6 + b); };
+    auto accfree_bar = [&](int b) { return bars + 8u * (8 + b); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + STAGES3 * STAGE3_BYTES + 8 * 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kb = p.K / BK;
+    const int nchunks = (kb + CHUNK - 1) / CHUNK;
+    constexpr uint32_t TMEM_COLS = 512u;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBl) : "memory");
+        for (int s = 0; s < STAGES3; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(xf_bar(s), XF_THREADS / 32);
+            mbar_init(empty_bar(s), 1);
+            mbar_init(accfull_bar(s), 1);
+            mbar_init(accfree_bar(s), DRAIN_THREADS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < kb; ++it) {
+                const int s = it % STAGES3;
+                const uint32_t ph = (it / STAGES3) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_arrive_expect_tx(full_bar(s), A_BYTES + 2 * B_BYTES);
+                const uint32_t sa = smem_base + s * STAGE3_BYTES;
+                tma_load_2d(sa, &tmA, full_bar(s), it * BK, m0);                         // raw A -> A_hi slot
+                tma_load_2d(sa + 2 * A_BYTES, &tmBh, full_bar(s), it * BK, n0);
+                tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &tmBl, full_bar(s), it * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int it = 0; it < kb; ++it) {
+                const int c = it / CHUNK, b = c & 1;
+                const bool chunk_start = (it % CHUNK) == 0;
+                if (chunk_start && c >= 2) {                        // accumulator b must have been drained (chunk c-2)
+                    mbar_wait(accfree_bar(b), (uint32_t)(((c >> 1) & 1) ^ 1));
+                    tcgen05_fence_after();
+                }
+                const int s = it % STAGES3;
+                const uint32_t ph = (it / STAGES3) & 1u;
+                mbar_wait(xf_bar(s), ph);
+                tcgen05_fence_after();
+                const uint32_t sa = smem_base + s * STAGE3_BYTES;
+                const uint64_t ah = make_smem_desc(sa), al = make_smem_desc(sa + A_BYTES);
+                const uint64_t bh = make_smem_desc(sa + 2 * A_BYTES), bl = make_smem_desc(sa + 2 * A_BYTES + B_BYTES);
+                const uint32_t d = tmem_base + (uint32_t)(b * BN);
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    const uint64_t o = (uint64_t)(2 * k);
+                    umma_tf32(d, al + o, bh + o, kIdesc, (chunk_start && k == 0) ? 0u : 1u);        // small terms first
+                    umma_tf32(d, ah + o, bl + o, kIdesc, 1u);
+                    umma_tf32(d, ah + o, bh + o, kIdesc, 1u);
+                }
+                umma_commit(empty_bar(s));
+                if ((it % CHUNK) == CHUNK - 1 || it == kb - 1) umma_commit(accfull_bar(b));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- warps 2..9: row = lane quarter (warp & 3), column half = 0 for warps 2-5, 1 for warps 6-9 ----
+        const int q = warp & 3;
+        const int half = (warp >= 6) ? 1 : 0;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
+        float sum[128];
+#pragma unroll
+        for (int j = 0; j < 128; ++j) sum[j] = 0.f;
+
+        auto drain = [&](int c) {
+            const int b = c & 1;
+            mbar_wait(accfull_bar(b), (uint32_t)((c >> 1) & 1));
+            tcgen05_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+                uint32_t v[16];
+                tmem_ld16(tlane + (uint32_t)(b * BN + cc * 16), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sum[cc * 16 + j] += __uint_as_float(v[j]);
+            }
+            tcgen05_fence_before();
+            mbar_arrive(accfree_bar(b));
+        };
+
+        if (warp < 6) {
+            const int et = threadIdx.x - 64;                        // 0..127: the four transform warps
+            for (int it = 0; it < kb; ++it) {
+                const int s = it % STAGES3;
+                const uint32_t ph = (it / STAGES3) & 1u;
+                mbar_wait(full_bar(s), ph);
+                float4* a4 = reinterpret_cast<float4*>(smem_al + s * STAGE3_BYTES);
+                float4* l4 = reinterpret_cast<float4*>(smem_al + s * STAGE3_BYTES + A_BYTES);
+#pragma unroll
+                for (int i = 0; i < A_BYTES / 16 / XF_THREADS; ++i) {
+                    const float4 v = a4[et + i * XF_THREADS];
+                    float4 h, l;
+                    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+                    l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+                    a4[et + i * XF_THREADS] = h;
+                    l4[et + i * XF_THREADS] = l;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(xf_bar(s));          // one arrive per transform warp
+                // the last stage of chunk c has just been handed to the MMA warp: drain chunk c-1 meanwhile
+                if (((it % CHUNK) == CHUNK - 1 || it == kb - 1) && it / CHUNK >= 1) drain(it / CHUNK - 1);
+            }
+            drain(nchunks - 1);
+        } else {
+            for (int c = 0; c < nchunks; ++c) drain(c);
+        }
+
+        // ---- epilogue from the register sums ----
+        gemm3x_epilogue<EPI>(p, sum, m0 + q * 32 + lane, n0 + half * 128);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// =====================================================================================================================
+// CTA-pair version of the 3xTF32 Linear GEMM (tcgen05 cta_group::2): the two CTAs of a cluster own adjacent 128-row
+// tiles of the same 256-column tile and execute ONE 256 x 256 x 8 MMA per issue (leader CTA).  Each CTA stages its own
+// activation tile (raw -> hi, lo) and only its HALF of the pre-split weight tile (128 of the 256 rows of W_hi and
+// W_lo): a stage is 64 KiB instead of 96 KiB, so the ring is 3 deep instead of 2, and per k-block an SM moves
+// 48 + 48 + 96 KiB through shared memory (TMA in, split, MMA operand reads) instead of 80 + 48 + 144 KiB.
+//   full[s]     local    TMA bytes of this CTA's A tile and weight halves
+//   ready[s]    leader   one arrive per transform warp of BOTH CTAs (8) after the hi/lo split (remote arrive)
+//   empty[s]    local    tcgen05.commit.cta_group::2 multicast
+//   accfull[b]  local    same multicast commit at the end of a 128-element chunk
+//   accfree[b]  leader   one arrive per drain warp of BOTH CTAs (16) once accumulator b has been read out
+// =====================================================================================================================
+constexpr int STAGES3P = 3;
+constexpr int STAGE3P_BYTES = 2 * A_BYTES + 2 * BH_BYTES;        // 64 KiB
+constexpr int SMEM3P_BYTES = STAGES3P * STAGE3P_BYTES + 1024 + 256;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS3, 1)
+te_tc_gemm3x2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                     const __grid_constant__ CUtensorMap tmBl, const Tc3Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bars = smem_base + STAGES3P * STAGE3P_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto ready_bar = [&](int s) { return bars + 8u * (STAGES3P + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (2 * STAGES3P + s); };
+    auto accfull_bar = [&](int b) { return bars + 8u * (3 * STAGES3P + b); };
+    auto accfree_bar = [&](int b) { return bars + 8u * (3 * STAGES3P + 2 + b); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + STAGES3P * STAGE3P_BYTES + 8 * (3 * STAGES3P + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int ntn = p.N / BN;
+    const int pair = blockIdx.x >> 1;                 // column tile fastest over the pairs (L2 reuse of the activations)
+    const int m0 = ((pair / ntn) * 2 + (int)rank) * BM, n0 = (pair % ntn) * BN;
+    const int kb = p.K / BK;
+    const int nchunks = (kb + CHUNK - 1) / CHUNK;
+    constexpr uint32_t TMEM_COLS = 512u;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBl) : "memory");
+        for (int s = 0; s < STAGES3P; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(ready_bar(s), 2 * (XF_THREADS / 32));
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(accfull_bar(b), 1);
+            mbar_init(accfree_bar(b), 2 * (DRAIN_THREADS / 32));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < kb; ++it) {
+                const int s = it % STAGES3P;
+                const uint32_t ph = (it / STAGES3P) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_arrive_expect_tx(full_bar(s), A_BYTES + 2 * BH_BYTES);
+                const uint32_t sa = smem_base + s * STAGE3P_BYTES;
+                tma_load_2d(sa, &tmA, full_bar(s), it * BK, m0);                                    // raw A -> A_hi slot
+                tma_load_2d(sa + 2 * A_BYTES, &tmBh, full_bar(s), it * BK, n0 + (int)rank * (BN / 2));
+                tma_load_2d(sa + 2 * A_BYTES + BH_BYTES, &tmBl, full_bar(s), it * BK, n0 + (int)rank * (BN / 2));
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            for (int it = 0; it < kb; ++it) {
+                const int c = it / CHUNK, b = c & 1;
+                const bool chunk_start = (it % CHUNK) == 0;
+                if (chunk_start && c >= 2) {                        // accumulator b drained (chunk c-2) in BOTH CTAs
+                    mbar_wait_cluster(accfree_bar(b), (uint32_t)(((c >> 1) & 1) ^ 1));
+                    tcgen05_fence_after();
+                }
+                const int s = it % STAGES3P;
+                const uint32_t ph = (it / STAGES3P) & 1u;
+                mbar_wait_cluster(ready_bar(s), ph);
+                tcgen05_fence_after();
+                const uint32_t sa = smem_base + s * STAGE3P_BYTES;
+                const uint64_t ah = make_smem_desc(sa), al = make_smem_desc(sa + A_BYTES);
+                const uint64_t bh = make_smem_desc(sa + 2 * A_BYTES), bl = make_smem_desc(sa + 2 * A_BYTES + BH_BYTES);
+                const uint32_t d = tmem_base + (uint32_t)(b * BN);
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    const uint64_t o = (uint64_t)(2 * k);
+                    umma2_tf32(d, al + o, bh + o, kIdesc2, (chunk_start && k == 0) ? 0u : 1u);        // small terms first
+                    umma2_tf32(d, ah + o, bl + o, kIdesc2, 1u);
+                    umma2_tf32(d, ah + o, bh + o, kIdesc2, 1u);
+                }
+                umma2_commit_both(empty_bar(s));
+                if ((it % CHUNK) == CHUNK - 1 || it == kb - 1) umma2_commit_both(accfull_bar(b));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- warps 2..9: row = lane quarter (warp & 3), column half = 0 for warps 2-5, 1 for warps 6-9 ----
+        const int q = warp & 3;
+        const int half = (warp >= 6) ? 1 : 0;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
+        float sum[128];
+#pragma unroll
+        for (int j = 0; j < 128; ++j) sum[j] = 0.f;
+
+        auto drain = [&](int c) {
+            const int b = c & 1;
+            mbar_wait(accfull_bar(b), (uint32_t)((c >> 1) & 1));
+            tcgen05_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+                uint32_t v[16];
+                tmem_ld16(tlane + (uint32_t)(b * BN + cc * 16), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sum[cc * 16 + j] += __uint_as_float(v[j]);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(map_to_rank0(accfree_bar(b)));
+        };
+
+        if (warp < 6) {
+            const int et = threadIdx.x - 64;                        // 0..127: the four transform warps
+            for (int it = 0; it < kb; ++it) {
+                const int s = it % STAGES3P;
+                const uint32_t ph = (it / STAGES3P) & 1u;
+                mbar_wait(full_bar(s), ph);
+                float4* a4 = reinterpret_cast<float4*>(smem_al + s * STAGE3P_BYTES);
+                float4* l4 = reinterpret_cast<float4*>(smem_al + s * STAGE3P_BYTES + A_BYTES);
+#pragma unroll
+                for (int i = 0; i < A_BYTES / 16 / XF_THREADS; ++i) {
+                    const float4 v = a4[et + i * XF_THREADS];
+                    float4 h, l;
+                    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+                    l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+                    a4[et + i * XF_THREADS] = h;
+                    l4[et + i * XF_THREADS] = l;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(map_to_rank0(ready_bar(s)));
+                if (((it % CHUNK) == CHUNK - 1 || it == kb - 1) && it / CHUNK >= 1) drain(it / CHUNK - 1);
+            }
+            drain(nchunks - 1);
+        } else {
+            for (int c = 0; c < nchunks; ++c) drain(c);
+        }
+        gemm3x_epilogue<EPI>(p, sum, m0 + q * 32 + lane, n0 + half * 128);
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------
+int g_pair_linear = -1;                 // 3xTF32 Linear GEMMs as CTA pairs (TE_B200_LINEAR_2CTA=1 / te_set_option)
+bool use_pair_linear() {
+    if (g_pair_linear < 0) {
+        const char* e = getenv("TE_B200_LINEAR_2CTA");
+        g_pair_linear = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_pair_linear == 1;
+}
+template <int EPI>
+int launch3(const float* A, long long lda, const float* Bh, const float* Bl, const Tc3Params& p, cudaStream_t st) {
+    CUtensorMap tmA, tmBh, tmBl;
+    if (!make_map(&tmA, A, p.M, p.K, lda, BM) || !make_map(&tmBh, Bh, p.N, p.K, p.K, BN) ||
+        !make_map(&tmBl, Bl, p.N, p.K, p.K, BN)) {
+        te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed");
+        return TE_ERR_CUDA;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(te_tc_gemm3x_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) != cudaSuccess) {
+            te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
+            return TE_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    dim3 grid(p.N / BN, (unsigned)((p.M + BM - 1) / BM));
+    te_tc_gemm3x_kernel<EPI><<<grid, NUM_THREADS3, SMEM3_BYTES, st>>>(tmA, tmBh, tmBl, p);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+
+template <int EPI>
+int launch3_pair(const float* A, long long lda, const float* Bh, const float* Bl, const Tc3Params& p, cudaStream_t st) {
+    CUtensorMap tmA, tmBh, tmBl;
+    if (!make_map(&tmA, A, p.M, p.K, lda, BM) || !make_map(&tmBh, Bh, p.N, p.K, p.K, BN / 2) ||
+        !make_map(&tmBl, Bl, p.N, p.K, p.K, BN / 2)) {
+        te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed");
+        return TE_ERR_CUDA;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(te_tc_gemm3x2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3P_BYTES) != cudaSuccess) {
+            te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
+            return TE_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    const unsigned mtiles = (unsigned)((p.M + BM - 1) / BM);
+    dim3 grid((unsigned)(p.N / BN) * ((mtiles + 1u) & ~1u));
+    te_tc_gemm3x2_kernel<EPI><<<grid, NUM_THREADS3, SMEM3P_BYTES, st>>>(tmA, tmBh, tmBl, p);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+
+int dispatch3(int epi, const float* A, long long lda, const float* Bh, const float* Bl, const Tc3Params& p, cudaStream_t st) {
+    if (use_pair_linear()) {
+        switch (epi) {
+            case TE_TC_EPI_STORE: return launch3_pair<EP_STORE>(A, lda, Bh, Bl, p, st);
+            case TE_TC_EPI_BIAS: return launch3_pair<EP_BIAS>(A, lda, Bh, Bl, p, st);
+            case TE_TC_EPI_BIAS_GELU: return launch3_pair<EP_BIAS_GELU>(A, lda, Bh, Bl, p, st);
+            case TE_TC_EPI_BIAS_ADD: return launch3_pair<EP_BIAS_ADD>(A, lda, Bh, Bl, p, st);
+            case TE_TC_EPI_GELU_BWD: return launch3_pair<EP_GELU_BWD>(A, lda, Bh, Bl, p, st);
+        }
+    }
+    switch (epi) {
+        case TE_TC_EPI_STORE: return launch3<EP_STORE>(A, lda, Bh, Bl, p, st);
+        case TE_TC_EPI_BIAS: return launch3<EP_BIAS>(A, lda, Bh, Bl, p, st);
+        case TE_TC_EPI_BIAS_GELU: return launch3<EP_BIAS_GELU>(A, lda, Bh, Bl, p, st);
+        case TE_TC_EPI_BIAS_ADD: return launch3<EP_BIAS_ADD>(A, lda, Bh, Bl, p, st);
+        case TE_TC_EPI_GELU_BWD: return launch3<EP_GELU_BWD>(A, lda, Bh, Bl, p, st);
+    }
+    te_set_last_error("te_gemm_tc: unsupported epilogue");
+    return TE_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+void te_tc_set_pair_linear(int on) { g_pair_linear = on ? 1 : 0; }
+
+bool te_tc_gemm3x_supported(long long rows, int K, int N, long long lda) {
+    return rows > 0 && rows < (1LL << 31) && K % BK == 0 && N % BN == 0 && lda % 4 == 0 && get_encode() != nullptr;
+}
+
+// y[rows,out] = x[rows,in] W^T (+ epilogue)   — fp32-grade (3xTF32) on tcgen05
+int te_tc_linear_fwd(const float* x, long long ldx, const float* derived, int in_features, int out_features,
+                     const float* bias, float* y, float* y2, const float* e0, long long rows, int epi, cudaStream_t st) {
+    const long long n = (long long)in_features * out_features;
+    Tc3Params p;
+    p.M = (int)rows; p.N = out_features; p.K = in_features; p.bias = bias; p.E = e0; p.lde = out_features;
+    p.C = y; p.ldc = out_features; p.C2 = y2; p.ldc2 = out_features;
+    return dispatch3(epi, x, ldx, derived + 4 * n, derived + 5 * n, p, st);
+}
+// dx[rows,in] = dy[rows,out] W (+ epilogue)
+int te_tc_linear_bwd(const float* dy, const float* derived, int in_features, int out_features, float* dx, const float* e0,
+                     long long rows, int epi, cudaStream_t st) {
+    const long long n = (long long)in_features * out_features;
+    Tc3Params p;
+    p.M = (int)rows; p.N = in_features; p.K = out_features; p.bias = nullptr; p.E = e0; p.lde = in_features;
+    p.C = dx; p.ldc = in_features; p.C2 = nullptr; p.ldc2 = 0;
+    return dispatch3(epi, dy, out_features, derived + 6 * n, derived + 7 * n, p, st);
+}
+
