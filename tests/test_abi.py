@@ -83,3 +83,61 @@ def test_reference_import_paths_resolve():
     import inspect
     sig = inspect.signature(LRP.generate_LRP)
     assert list(sig.parameters) == ["self", "input", "index", "method", "is_ablation", "start_layer"]
+
+
+def test_bert_weight_table_matches_facade_state_dict():
+    transformers = pytest.importorskip("transformers")
+    from transformer_explainability_b200 import _lib
+    from transformer_explainability_b200.BERT_explainability.modules.BERT.BertForSequenceClassification import \
+        BertForSequenceClassification
+    lib = _lib.load()
+    m = BertForSequenceClassification(transformers.BertConfig(hidden_size=64, num_hidden_layers=2, num_attention_heads=4,
+                                                              intermediate_size=128, vocab_size=100,
+                                                              max_position_embeddings=32, num_labels=2))
+    cfg = m._cfg
+    sd = m.state_dict()
+    n = lib.te_bert_num_weights(ctypes.byref(cfg))
+    seen, end = set(), 0
+    for i in range(n):
+        name = lib.te_bert_weight_name(ctypes.byref(cfg), i).decode()
+        numel = lib.te_bert_weight_numel(ctypes.byref(cfg), i)
+        off = lib.te_bert_weight_offset(ctypes.byref(cfg), i)
+        assert sd[name].numel() == numel, name
+        assert off % 32 == 0 and off >= end
+        end = off + numel
+        seen.add(name)
+    assert seen == {k for k in sd if "position_ids" not in k}
+    assert lib.te_bert_weight_total(ctypes.byref(cfg)) >= end
+
+
+def test_host_only_queries_and_option_errors():
+    """Entry points that need no device: workspace sizes grow with the batch, bad arguments and unknown options are
+    reported through the status code + te_last_error (never an exception, never a crash)."""
+    from transformer_explainability_b200 import _lib
+    lib = _lib.load()
+    assert lib.te_rollout_workspace_bytes(12, 2, 197) < lib.te_rollout_workspace_bytes(12, 4, 197)
+    assert lib.te_rollout_workspace_bytes(0, 2, 197) < 0
+    a = lib.te_patch_embed_relprop_workspace_bytes(1, 3, 224, 16, 768)
+    b = lib.te_patch_embed_relprop_workspace_bytes(2, 3, 224, 16, 768)
+    assert 0 < a < b
+    assert lib.te_patch_embed_relprop_workspace_bytes(1, 3, 225, 16, 768) < 0          # patch does not divide the image
+    assert lib.te_set_option(b"no_such_option", 1) < 0
+    assert b"unknown option" in lib.te_last_error()
+    assert lib.te_set_option(b"zplus_pair_kernels", 0) == 0 and lib.te_set_option(b"linear_pair_kernels", 0) == 0
+
+
+def test_baseline_and_generator_surfaces_resolve():
+    """The comparison classes keep the reference's names and signatures (ViT_explanation_generator.py:45-83,
+    ExplanationGenerator.py:61-155)."""
+    import inspect
+    import transformer_explainability_b200 as te
+    te.install_aliases()
+    from baselines.ViT.ViT_new import vit_base_patch16_224                              # noqa: F401
+    from baselines.ViT.ViT_explanation_generator import Baselines
+    from BERT_explainability.modules.BERT.ExplanationGenerator import Generator
+    assert list(inspect.signature(Baselines.generate_cam_attn).parameters) == ["self", "input", "index"]
+    assert list(inspect.signature(Baselines.generate_rollout).parameters) == ["self", "input", "start_layer"]
+    for name in ("generate_LRP", "generate_LRP_last_layer", "generate_full_lrp", "generate_attn_last_layer",
+                 "generate_rollout", "generate_attn_gradcam"):
+        params = list(inspect.signature(getattr(Generator, name)).parameters)
+        assert params[:3] == ["self", "input_ids", "attention_mask"], name
