@@ -6,7 +6,7 @@ from hypothesis import given, settings, strategies as st
 
 from oracle import rules
 
-SET = dict(max_examples=20, deadline=None)
+SET = dict(max_examples=25, deadline=None, derandomize=True)      # fixed example set: the suite must be reproducible
 
 
 def _t(seed, *shape, scale=1.0):
@@ -20,8 +20,9 @@ def test_linear_rule_conserves_relevance(seed, b, n, fin, fout):
     r = _t(seed + 2, b, n, fout).abs()
     out = rules.linear_relprop(x, w, r)
     z = x.clamp(min=0) @ w.clamp(min=0).t() + x.clamp(max=0) @ w.clamp(max=0).t()
-    kept = (r * z.ne(0)).sum()                       # relevance routed through a zero denominator is dropped by safe_divide
-    assert torch.allclose(out.sum(), kept, rtol=1e-6, atol=1e-9)
+    # safe_divide: R * Z / (Z + 1e-9), and relevance routed through an exactly-zero denominator is dropped
+    kept = (r * z / (z + 1e-9) * z.ne(0)).sum()
+    assert torch.allclose(out.sum(), kept, rtol=1e-9, atol=1e-12)
 
 
 @settings(**SET)
@@ -33,7 +34,7 @@ def test_add_rule_conserves_relevance_per_sample_and_is_batch_independent(seed, 
     assert torch.allclose(total, r.reshape(b, -1).sum(1), rtol=1e-7, atol=1e-9)
     for s in range(b):                                # a batch is a set of independent B=1 explanations
         a1, c1 = rules.add_relprop(x1[s:s + 1], x2[s:s + 1], r[s:s + 1])
-        assert torch.equal(a1[0], a[s]) and torch.equal(c1[0], c[s])
+        assert torch.allclose(a1[0], a[s], rtol=1e-12, atol=0) and torch.allclose(c1[0], c[s], rtol=1e-12, atol=0)
 
 
 @settings(**SET)
@@ -41,8 +42,9 @@ def test_add_rule_conserves_relevance_per_sample_and_is_batch_independent(seed, 
 def test_clone_rule_inverts_a_proportional_split(seed, b, n):
     x = _t(seed, b, n)
     s1, s2 = _t(seed + 1, b, n), _t(seed + 2, b, n)
-    out = rules.clone_relprop(x, (x * s1, x * s2))   # R_i = X * s_i  ->  X * sum_i sd(R_i, X) = X * (s1 + s2)
-    assert torch.allclose(out, x * (s1 + s2), rtol=1e-6, atol=1e-9)
+    out = rules.clone_relprop(x, (x * s1, x * s2))   # R_i = X * s_i  ->  X * sum_i sd(R_i, X) ~= X * (s1 + s2)
+    damp = x / (x + 1e-9)                              # safe_divide's epsilon
+    assert torch.allclose(out, x * (s1 + s2) * damp, rtol=1e-9, atol=1e-12)
 
 
 @settings(**SET)
@@ -76,4 +78,5 @@ def test_matmul_rules_conserve_relevance(seed, b, h, n, d):
     r = _t(seed + 2, b, h, n, d)
     rp, rv = rules.matmul_av_relprop(p, v, r)
     z = p @ v
-    assert torch.allclose(rp.sum() + rv.sum(), 2 * (r * z.ne(0)).sum(), rtol=1e-6, atol=1e-8)   # each operand gets all of R
+    kept = (r * z / (z + 1e-9) * z.ne(0)).sum()       # safe_divide's epsilon; each operand receives all of R
+    assert torch.allclose(rp.sum(), kept, rtol=1e-9, atol=1e-12) and torch.allclose(rv.sum(), kept, rtol=1e-9, atol=1e-12)
