@@ -427,7 +427,10 @@ def main():
 
 def default_flags():
     """Best validated kernel selection: updated as faster paths pass parity."""
-    return 51  # tcgen05 z+ rule (1) + fused row-only rollout (2) + 3xTF32 tcgen05 Linears (16) + N x N attention contractions (32)
+    from transformer_explainability_b200 import _lib
+    # 51 = tcgen05 z+ rule (1) + fused row-only rollout (2) + 3xTF32 tcgen05 Linears (16) + attention contractions (32);
+    # + 256 = single-pass TF32 activation-gradient backward Linears
+    return _lib.FLAG_BENCH_DEFAULT
 
 
 if __name__ == "__main__":

@@ -44,6 +44,10 @@ extern "C" {
                                          (R_in = x+ (S W+) + x- (S W-)) on tcgen05 kind::f16 with bf16 operands */
 #define TE_FLAG_GRADIENTS_ONLY 128u    /* te_*_attribute stops after the class-gradient backward: only "attn_grad" of the layers
                                          >= start_layer is produced (maps may be NULL) — the attention-GradCAM baselines */
+#define TE_FLAG_BACKWARD_TF32 256u     /* with TE_FLAG_LINEAR_TENSOR_CORES: the activation-gradient backward Linears run as
+                                         single-pass TF32 GEMMs (persistent CTA-pair kernel) instead of the 3xTF32 split.
+                                         The gradients only enter the result linearly (relu(G * cam)), never a
+                                         safe_divide denominator: measured effect in profiles/ (r02 parity table) */
 #define TE_FLAG_RELPROP_TO_INPUT 8u   /* finish the lowest block as well: relevance at the encoder input (what
                                          model.relprop() returns in the reference) is left in tensor "relevance_in" */
 
@@ -51,6 +55,8 @@ TE_API const char* te_last_error(void);
 /* Process-wide tuning switches (not part of the reference surface).  name = "zplus_pair_kernels": run the z+ Linear rule
  * with the CTA-pair (tcgen05 cta_group::2, 256 x 256 MMA) kernels instead of the single-CTA ones (2: R kernel only);
  * name = "linear_pair_kernels": the same for the 3xTF32 forward / backward Linear GEMMs.  Both default to 0.
+ * name = "zplus_persistent": 1 (default) runs the z+ rule with the persistent CTA-pair kernels (te_tc_pair.cu), 0 with
+ * the round-1 kernels selected by "zplus_pair_kernels".
  * Returns TE_OK, or a negative status for an unknown name. */
 TE_API int te_set_option(const char* name, int value);
 TE_API int te_version(void);

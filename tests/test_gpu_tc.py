@@ -211,3 +211,41 @@ def test_tc_bf16_second_contraction(rows, inf, outf):
     print("bf16 R kernel rows %d in %d out %d: rel %.2e" % (rows, inf, outf, e))
     assert e < 1.5e-2
     assert abs(out.double().sum().item() - r.double().sum().item()) < 1e-2 * r.sum().item()
+
+
+@pytest.mark.parametrize("rows,inf,outf", [(128, 256, 256), (394, 768, 3072), (1000, 3072, 768), (77, 768, 2304),
+                                           (50432, 768, 768)])
+def test_tc_persistent_pair_kernels(rows, inf, outf):
+    """The persistent CTA-pair (cta_group::2) kernels of te_tc_pair.cu — what the engines run by default: single-pass S
+    kernel with the |x| transform + R kernel whose two products share one A tile, against the round-1 single-CTA kernels
+    (same TF32 operands) and the fp64 oracle; the single-pass TF32 backward Linear against fp64 (TF32 operand error,
+    stated 2e-3 of the tensor maximum).  Shapes include odd tile counts (all-padding partner CTA) and more tiles than
+    clusters (several tiles per persistent cluster, both TMEM accumulator buffers reused)."""
+    from transformer_explainability_b200 import _lib, ops
+    g = torch.Generator().manual_seed(rows + 3)
+    x = torch.randn(rows, inf, generator=g)
+    w = torch.randn(outf, inf, generator=g) * 0.05
+    r = torch.rand(rows, outf, generator=g)
+    b = torch.randn(outf, generator=g)
+    dy = torch.randn(rows, outf, generator=g)
+    xd, wd, rd, bd = x.cuda(), w.cuda(), r.cuda(), b.cuda()
+    y = ops.linear_forward(xd, wd, bd)
+    new = ops.linear_relprop(xd, wd, rd, tensor_cores=True, y=y, bias=bd)
+    lib = _lib.load()
+    _lib.check(lib.te_set_option(b"zplus_persistent", 0), "te_set_option")
+    try:
+        old = ops.linear_relprop(xd, wd, rd, tensor_cores=True, y=y, bias=bd)
+        torch.cuda.synchronize()
+    finally:
+        _lib.check(lib.te_set_option(b"zplus_persistent", 1), "te_set_option")
+    if rows <= 4096:
+        ref = rules.linear_relprop(x.double(), w.double(), r.double())
+        assert rel(new, ref) < 3e-3, "persistent pair z+ kernels: rel err %g" % rel(new, ref)
+    assert rel(new, old.double()) < 2e-5          # same TF32 operands; only the accumulation order inside a tile differs
+    assert abs(new.double().sum().item() - r.double().sum().item()) < 2e-3 * r.sum().item()
+    dx = ops.linear_backward_tf32(dy.cuda(), wd)
+    torch.cuda.synchronize()
+    ref_dx = (dy.double().cuda() @ w.double().cuda()).cpu()
+    e = rel(dx, ref_dx)
+    print("tf32 pair backward rows %d in %d out %d: rel %.2e" % (rows, inf, outf, e))
+    assert e < 2e-3

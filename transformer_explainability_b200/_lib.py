@@ -35,8 +35,11 @@ FLAG_GRADIENTS_ONLY = 128
 FLAG_LINEAR_TENSOR_CORES = 16
 FLAG_ATTN_TENSOR_CORES = 32
 FLAG_ZPLUS_BF16 = 64
+FLAG_BACKWARD_TF32 = 256
 FLAG_TENSOR_CORES = FLAG_ZPLUS_TENSOR_CORES | FLAG_LINEAR_TENSOR_CORES      # the ones that need derived weights
 FLAG_ALL_FAST = FLAG_TENSOR_CORES | FLAG_ATTN_TENSOR_CORES | FLAG_ROLLOUT_FUSED
+# what bench.py runs by default: updated as faster selections pass the parity tests (tests/test_gpu_parity_full.py)
+FLAG_BENCH_DEFAULT = FLAG_ALL_FAST | FLAG_BACKWARD_TF32
 
 _P = c_void_p
 _CFG = ctypes.POINTER(TeVitConfig)
@@ -100,13 +103,19 @@ _lib = None
 
 
 def load():
-    """Load (building first if the .so is absent and nvcc is available).  Raises on failure."""
+    """Load the library, (re)building it first when its source stamp does not match (nvcc available); a stale or
+    missing library without nvcc raises.  Raises on any failure — there is no CPU fallback."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
-        _build.build()
+    from . import build as _build
+    if _build.have_nvcc():
+        _build.build()                   # no-op when the source/header stamp matches the built library
+    elif not os.path.exists(LIB_PATH):
+        raise OSError("%s is missing and nvcc is not available to build it (no CPU fallback)" % LIB_PATH)
+    elif not _build.stamp_matches():
+        raise OSError("%s is stale: csrc/ or include/te_b200.h changed since it was built and nvcc is not available"
+                      % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)          # AttributeError here == header/library mismatch: fail loudly

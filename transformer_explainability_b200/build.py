@@ -29,6 +29,17 @@ def _nvcc():
     return "nvcc"
 
 
+def have_nvcc():
+    import shutil
+    c = _nvcc()
+    return bool(os.path.isabs(c) and os.path.exists(c) or shutil.which(c))
+
+
+def stamp_matches():
+    stamp_file = os.path.join(LIBDIR, "libte_b200.stamp")
+    return os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == _stamp()
+
+
 def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 

@@ -54,6 +54,9 @@ extern "C" int te_linear_backward_ex(const float* dy, const float* w, float* dx,
     REQ(dy && w && dx && rows > 0 && in_features > 0 && out_features > 0, "te_linear_backward_ex: bad argument");
     if ((flags & TE_FLAG_LINEAR_TENSOR_CORES) && scratch && te_tc_gemm3x_supported(rows, out_features, in_features, out_features)) {
         TE_TRY(te_tc_prepare_weights(w, scratch, in_features, out_features, ST(stream)));
+        if ((flags & TE_FLAG_BACKWARD_TF32) && te_tc_pair_supported(rows, out_features, in_features, out_features))
+            return te_tc_pair_linear_bwd(dy, out_features, scratch, in_features, out_features, dx, nullptr, rows, TE_TC_EPI_STORE,
+                                         ST(stream));
         return te_tc_linear_bwd(dy, scratch, in_features, out_features, dx, nullptr, rows, TE_TC_EPI_STORE, ST(stream));
     }
     TeGemm p = g0(1);
@@ -160,6 +163,7 @@ extern "C" int te_set_option(const char* name, int value) {
     REQ(name != nullptr, "te_set_option: null name");
     if (strcmp(name, "zplus_pair_kernels") == 0) { te_tc_set_pair_kernels(value); return TE_OK; }
     if (strcmp(name, "linear_pair_kernels") == 0) { te_tc_set_pair_linear(value); return TE_OK; }
+    if (strcmp(name, "zplus_persistent") == 0) { te_tc_set_zplus_persistent(value); return TE_OK; }
     te_set_last_error("te_set_option: unknown option");
     return TE_ERR_ARG;
 }

@@ -39,8 +39,11 @@ static inline int linear_fwd_tc(const float* dw, const float* x, int lda, const 
         return te_tc_linear_fwd(x, lda, dw, in, out, bias, y, y2, e0, M, epi, st);      // epilogue ids coincide
     return linear_fwd(x, lda, w, bias, y, y2, e0, M, in, out, epi, st);
 }
+// tf32: single-pass TF32 on the persistent CTA-pair kernel (TE_FLAG_BACKWARD_TF32) instead of the 3xTF32 split
 static inline int linear_bwd_tc(const float* dw, const float* dy, const float* w, float* dx, const float* e0, long long M,
-                                int in, int out, int epi, cudaStream_t st) {
+                                int in, int out, int epi, cudaStream_t st, bool tf32 = false) {
+    if (dw && tf32 && (epi == TE_EPI_STORE || epi == TE_EPI_GELU_BWD) && te_tc_pair_supported(M, out, in, out))
+        return te_tc_pair_linear_bwd(dy, out, dw, in, out, dx, e0, M, epi, st);
     if (dw && te_tc_gemm3x_supported(M, out, in, out))
         return te_tc_linear_bwd(dy, dw, in, out, dx, e0, M, epi, st);
     return linear_bwd(dy, w, dx, e0, M, in, out, epi, st);

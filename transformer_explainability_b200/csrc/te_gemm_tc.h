@@ -49,3 +49,15 @@ void te_tc_set_pair_linear(int on);
 bool te_tc_bmm_nk_supported(int N, int ld);
 int te_tc_bmm_nk_resid(const float* A, const float* J, const float* rowscale, float* out, int batch, int N, int ld,
                        cudaStream_t st);
+
+// persistent CTA-pair (cta_group::2) kernels (te_tc_pair.cu): z+ rule contractions and the single-pass TF32 backward Linear
+bool te_tc_pair_supported(long long rows, int K, int N, long long lda);
+int te_tc_pair_zplus_s1(const float* x, long long ldx, const float* derived, const float* r, long long ldr, const float* y,
+                        long long ldy, const float* bias, float* s_out, long long rows, int in_features, int out_features,
+                        cudaStream_t st);
+int te_tc_pair_zplus_r(const float* s, const float* derived, const float* x, long long ldx, float* out, long long ld_out,
+                       long long rows, int in_features, int out_features, cudaStream_t st);
+int te_tc_pair_linear_bwd(const float* dy, long long lddy, const float* derived, int in_features, int out_features, float* dx,
+                          const float* e0, long long rows, int epi, cudaStream_t st);
+// 1 (default): z+ rule on the persistent pair kernels
+void te_tc_set_zplus_persistent(int on);

@@ -65,8 +65,9 @@ int te_launch_fill(float* p, float v, long long n, cudaStream_t st);
 // ---- BERT extras -------------------------------------------------------------------------------
 int te_launch_softmax_masked(float* s, long long rows, int N, int ld, const float* keymask, long long rows_per_batch,
                              cudaStream_t st);
+// ids outside [0, vocab) never index the table: their rows are written as NaN
 int te_launch_bert_embed(const long long* ids, const float* word, const float* pos, const float* type0, float* out,
-                         int B, int S, int D, cudaStream_t st);
+                         int B, int S, int D, int vocab, cudaStream_t st);
 int te_launch_bert_mask(const long long* mask, float* out, long long n, cudaStream_t st);
 int te_launch_tanh(const float* x, float* y, long long n, cudaStream_t st);
 int te_launch_tanh_bwd(const float* dy, const float* y, float* dx, long long n, cudaStream_t st);

@@ -492,13 +492,10 @@ int launch_attn(const float* A, long long lda, const float* B, long long ldb, lo
         te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed (attention)");
         return TE_ERR_CUDA;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(te_tc_attn_nn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) {
-            te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
-            return TE_ERR_CUDA;
-        }
-        attr_set = true;
+    static unsigned long long optin = 0;          // per-device attribute: one bit per device
+    if (!smem_optin(te_tc_attn_nn_kernel<EPI>, AT_SMEM, optin)) {
+        te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
+        return TE_ERR_CUDA;
     }
     dim3 grid((p.N + BM - 1) / BM, batch * p.H, (p.N + BN - 1) / BN);
     if (grid.y > 65535) { te_set_last_error("te_gemm_tc: batch*heads too large for one launch"); return TE_ERR_ARG; }
@@ -557,13 +554,10 @@ int launch_nk(const float* map, int NP, const float* X, long long ldx, const NkP
         te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed (attention nk)");
         return TE_ERR_CUDA;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(te_tc_attn_nk_kernel<AMN, EPI, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, NK_SMEM) != cudaSuccess) {
-            te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
-            return TE_ERR_CUDA;
-        }
-        attr_set = true;
+    static unsigned long long optin = 0;          // per-device attribute: one bit per device
+    if (!smem_optin(te_tc_attn_nk_kernel<AMN, EPI, NB>, NK_SMEM, optin)) {
+        te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
+        return TE_ERR_CUDA;
     }
     dim3 grid((p.N + BM - 1) / BM, batch * p.H);
     if (grid.y > 65535) { te_set_last_error("te_gemm_tc: batch*heads too large for one launch"); return TE_ERR_ARG; }

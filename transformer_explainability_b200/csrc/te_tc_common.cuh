@@ -245,4 +245,17 @@ bool make_map(CUtensorMap* m, const float* base, long long rows, long long cols,
 
 inline bool a16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: remember, per call site, on which
+// devices the opt-in has been made (one bit per device ordinal) instead of a process-wide flag.
+template <typename F>
+inline bool smem_optin(F kernel, int bytes, unsigned long long& done_mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done_mask & bit) return true;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return false;
+    done_mask |= bit;
+    return true;
+}
+
 }  // namespace

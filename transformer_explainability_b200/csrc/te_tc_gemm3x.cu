@@ -404,13 +404,10 @@ int launch3(const float* A, long long lda, const float* Bh, const float* Bl, con
         te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed");
         return TE_ERR_CUDA;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(te_tc_gemm3x_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) != cudaSuccess) {
-            te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
-            return TE_ERR_CUDA;
-        }
-        attr_set = true;
+    static unsigned long long optin = 0;          // per-device attribute: one bit per device
+    if (!smem_optin(te_tc_gemm3x_kernel<EPI>, SMEM3_BYTES, optin)) {
+        te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
+        return TE_ERR_CUDA;
     }
     dim3 grid(p.N / BN, (unsigned)((p.M + BM - 1) / BM));
     te_tc_gemm3x_kernel<EPI><<<grid, NUM_THREADS3, SMEM3_BYTES, st>>>(tmA, tmBh, tmBl, p);
@@ -426,13 +423,10 @@ int launch3_pair(const float* A, long long lda, const float* Bh, const float* Bl
         te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed");
         return TE_ERR_CUDA;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(te_tc_gemm3x2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3P_BYTES) != cudaSuccess) {
-            te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
-            return TE_ERR_CUDA;
-        }
-        attr_set = true;
+    static unsigned long long optin = 0;          // per-device attribute: one bit per device
+    if (!smem_optin(te_tc_gemm3x2_kernel<EPI>, SMEM3P_BYTES, optin)) {
+        te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
+        return TE_ERR_CUDA;
     }
     const unsigned mtiles = (unsigned)((p.M + BM - 1) / BM);
     dim3 grid((unsigned)(p.N / BN) * ((mtiles + 1u) & ~1u));

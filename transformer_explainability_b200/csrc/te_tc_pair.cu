@@ -1,0 +1,414 @@
+// Persistent CTA-pair (tcgen05 cta_group::2) GEMM family: the z+ rule's two contractions and the single-pass TF32
+// activation-gradient Linear, all as ONE kernel template.
+//
+// Why pairs: ncu of the round-1 single-CTA kernels (profiles/r01_ncu_summary.md, prof_zplus_s1.ncu-rep) shows them at the
+// L2 -> SM bandwidth cap, not at the tensor pipe: lts__t_sectors = 11.1 TB/s (R kernel) / 12.8 TB/s (S1 kernel) =
+// 5700 / 6580 bytes per clock against a measured chip cap of ~6300 B/clk, with the tensor pipe 36 % active.  A 128x256
+// tile stages 48 KiB per 4 MMAs (512 tensor cycles) = 96 B/clk/SM = 14 200 B/clk chip-wide at full tensor rate: the
+// cap allows 44 %.  The fix is flops per staged byte:
+//   * a CTA pair executes one 256 x 256 x 8 MMA per issue and each CTA stages only HALF of the weight tile;
+//   * the R kernel's two products (S W+ and S W-) share their A operand (S): one A tile + two weight halves per stage,
+//     8 MMAs per 48 KiB instead of 4  ->  47 B/clk/SM = 6 940 B/clk chip-wide: the cap allows 91 %.
+// Why persistent: the non-persistent pair kernels of round 1 lost to the single-CTA ones (a pair only starts when both
+// SMs of a TPC are free, TMEM alloc + two cluster barriers + an exposed prologue per tile).  Here each cluster loops
+// over tiles (static round-robin, column tile fastest so concurrently running clusters share activation rows in L2);
+// barriers / TMEM are set up once, the TMA producer runs ahead into the next tile during the epilogue, and the modes
+// with one 256-column accumulator double-buffer it in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the
+// MMAs of tile i+1.  The R mode owns all 512 columns (two accumulators): its epilogue is shortened instead (8 warps,
+// x rows prefetched into L2 at tile start, register-double-buffered loads).
+//
+//   mode PM_R    R_in = x+ * (S W+) + x- * (S W-)          A = S [M,K]      B0/B1 = W+^T / W-^T [N,K]   (layers_ours.py:207-230)
+//   mode PM_S1   S = sd(R, ((y - b) + |x| |W|^T) / 2)       A = x -> |x|     B0 = |W| [N,K]
+//   mode PM_LIN  C = epi(A B^T)  single-pass TF32            A = dy           B0 = tf32(W)^T  (activation-gradient backward)
+//
+// Warp roles (both CTAs of the pair): warp 0 TMA producer, warp 1 TMEM allocator + (leader CTA only) MMA issuer,
+// warps 2-9 epilogue (lane quarter = warp % 4, column half = (warp - 2) / 4), warps 10-13 (PM_S1 only) |x| transform.
+// Barriers per CTA:
+//   full[s]     TMA bytes: local (PM_S1: this CTA's own tile is transformed first) or the LEADER's (other modes: both
+//               CTAs' cp.async.bulk.tensor .cta_group::2 count on the leader's barrier, expect_tx = both CTAs' bytes)
+//   ready[s]    leader, PM_S1: one remote arrive per transform warp of both CTAs (8)
+//   empty[s]    local, tcgen05.commit.cta_group::2 multicast from the leader when the MMAs of the stage retire
+//   accfull[b]  local, multicast commit after the last k-block of a tile into accumulator buffer b
+//   accfree[b]  leader, one remote arrive per epilogue warp of both CTAs (16) once buffer b has been read out
+#include "te_tc_common.cuh"
+
+namespace {
+
+enum { PM_R = 0, PM_S1 = 1, PM_LIN = 2 };
+enum { PE_STORE = 0, PE_GELU_BWD = 4 };
+
+struct PairParams {
+    int M, N, K;
+    int tiles_m, tiles_n;                 // tiles_m: 256-row pair tiles
+    const float* E; long long lde;        // PM_R: x [M,N] ; PM_S1: R [M,N] ; PM_LIN/GELU_BWD: h [M,N]
+    float* C; long long ldc;
+    const float* Y; long long ldy; const float* bias;                   // PM_S1: saved forward output y = x W^T + b
+    const float* X; long long ldx; const float* Wp; const float* Wn;    // PM_S1: exact fallback of a cancelled denominator
+};
+
+template <int MODE> struct PairCfg {
+    static constexpr int NB = (MODE == PM_R) ? 2 : 1;                         // weight operands per stage
+    static constexpr bool XF = (MODE == PM_S1);                               // in-smem |x| transform of A
+    static constexpr int STAGE = A_BYTES + NB * BH_BYTES;                     // 48 KiB / 32 KiB
+    static constexpr int NST = (MODE == PM_R) ? 4 : 6;                        // 192 KiB ring
+    static constexpr int ACC_BUFS = (MODE == PM_R) ? 1 : 2;                   // TMEM accumulator buffers of NB x 256 columns
+    static constexpr int THREADS = XF ? 448 : 320;
+    static constexpr int NBARS = 3 * NST + 4;
+    static constexpr int SMEM = NST * STAGE + 1024 + 8 * NBARS + 16;
+};
+
+constexpr int EPI_WARPS = 8;
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// exact z+ denominator of one element from the TF32-rounded W+ / W- copies (rare path, see pair_epilogue_s1)
+__device__ __noinline__ float zplus_exact(const float* __restrict__ xrow, const float* __restrict__ wp,
+                                          const float* __restrict__ wn, int K) {
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) {
+        const float x = xrow[k];
+        acc += fmaxf(x, 0.f) * wp[k] + fminf(x, 0.f) * wn[k];
+    }
+    return acc;
+}
+
+template <int MODE, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<MODE>::THREADS, 1)
+te_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+                  const __grid_constant__ CUtensorMap tmB1, const PairParams p) {
+    using Cfg = PairCfg<MODE>;
+    constexpr int NST = Cfg::NST, NB = Cfg::NB, STAGE = Cfg::STAGE, ACC_BUFS = Cfg::ACC_BUFS;
+    constexpr bool XF = Cfg::XF;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bars = smem_base + NST * STAGE;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto ready_bar = [&](int s) { return bars + 8u * (NST + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (2 * NST + s); };
+    auto accfull_bar = [&](int b) { return bars + 8u * (3 * NST + b); };
+    auto accfree_bar = [&](int b) { return bars + 8u * (3 * NST + 2 + b); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + NST * STAGE + 8 * Cfg::NBARS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+    const int ntiles = p.tiles_m * p.tiles_n;
+    const int kb = p.K / BK;
+    constexpr uint32_t TMEM_COLS = 512u;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB0) : "memory");
+        if (NB == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB1) : "memory");
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(ready_bar(s), 2u * 4u);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(accfull_bar(b), 1);
+            mbar_init(accfree_bar(b), 2u * EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();                                // barriers of both CTAs initialised, TMEM allocated
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs: own A tile + own half of every weight tile) =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = cluster_id; t < ntiles; t += nclusters) {
+                const int m0 = ((t / p.tiles_n) * 2 + (int)rank) * BM, n0 = (t % p.tiles_n) * BN + (int)rank * (BN / 2);
+                for (int kk = 0; kk < kb; ++kk, ++it) {
+                    const int s = (int)(it % NST);
+                    const uint32_t ph = (it / NST) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const uint32_t sa = smem_base + s * STAGE;
+                    if (XF) {
+                        mbar_arrive_expect_tx(full_bar(s), STAGE);
+                        tma_load_2d(sa, &tmA, full_bar(s), kk * BK, m0);
+                        tma_load_2d(sa + A_BYTES, &tmB0, full_bar(s), kk * BK, n0);
+                    } else {
+                        if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * STAGE);
+                        tma2_load_2d(sa, &tmA, full_bar(s), kk * BK, m0);
+                        tma2_load_2d(sa + A_BYTES, &tmB0, full_bar(s), kk * BK, n0);
+                        if (NB == 2) tma2_load_2d(sa + A_BYTES + BH_BYTES, &tmB1, full_bar(s), kk * BK, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (leader && lane == 0) {
+            uint32_t it = 0, ti = 0;
+            for (int t = cluster_id; t < ntiles; t += nclusters, ++ti) {
+                const uint32_t b = ti % ACC_BUFS;
+                if (ti >= (uint32_t)ACC_BUFS) {                 // buffer b read out by the epilogues of BOTH CTAs
+                    mbar_wait_cluster(accfree_bar(b), ((ti / ACC_BUFS) & 1u) ^ 1u);
+                    tcgen05_fence_after();
+                }
+                const uint32_t d0 = tmem_base + b * (uint32_t)(NB * BN);
+                for (int kk = 0; kk < kb; ++kk, ++it) {
+                    const int s = (int)(it % NST);
+                    const uint32_t ph = (it / NST) & 1u;
+                    mbar_wait_cluster(XF ? ready_bar(s) : full_bar(s), ph);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_base + s * STAGE;
+                    const uint64_t adesc = make_smem_desc(sa);
+                    const uint64_t b0desc = make_smem_desc(sa + A_BYTES);
+                    const uint64_t b1desc = make_smem_desc(sa + A_BYTES + BH_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint32_t acc = (kk == 0 && k == 0) ? 0u : 1u;
+                        umma2_tf32(d0, adesc + (uint64_t)(2 * k), b0desc + (uint64_t)(2 * k), kIdesc2, acc);
+                        if (NB == 2) umma2_tf32(d0 + (uint32_t)BN, adesc + (uint64_t)(2 * k), b1desc + (uint64_t)(2 * k), kIdesc2, acc);
+                    }
+                    umma2_commit_both(empty_bar(s));        // frees this stage in BOTH CTAs when the MMAs retire
+                }
+                umma2_commit_both(accfull_bar(b));
+            }
+        }
+        __syncwarp();
+    } else if (warp < 2 + EPI_WARPS) {
+        // ================= epilogue: warps 2..9 =================
+        const int q = warp & 3;                      // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;            // column half of the 256-column tile
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t ti = 0;
+        for (int t = cluster_id; t < ntiles; t += nclusters, ++ti) {
+            const int m0 = ((t / p.tiles_n) * 2 + (int)rank) * BM, n0 = (t % p.tiles_n) * BN + half * (BN / 2);
+            const int row = m0 + q * 32 + lane;
+            const bool live = row < p.M;
+            const uint32_t b = ti % ACC_BUFS;
+            const float* erow = p.E ? p.E + (long long)row * p.lde + n0 : nullptr;
+            const float* yrow = (MODE == PM_S1) ? p.Y + (long long)row * p.ldy + n0 : nullptr;
+            float* crow = p.C + (long long)row * p.ldc + n0;
+            // the epilogue operands of this tile are streamed from HBM exactly once: pull them into L2 while the MMAs run
+            if (live) {
+                if (erow) {
+#pragma unroll
+                    for (int j = 0; j < BN / 2; j += 32) prefetch_l2(erow + j);
+                }
+                if (MODE == PM_S1) {
+#pragma unroll
+                    for (int j = 0; j < BN / 2; j += 32) prefetch_l2(yrow + j);
+                }
+            }
+            mbar_wait(accfull_bar(b), (ti / ACC_BUFS) & 1u);
+            tcgen05_fence_after();
+            const uint32_t tcol = tlane + b * (uint32_t)(NB * BN) + (uint32_t)(half * (BN / 2));
+            if (MODE == PM_S1) {
+                // 16-column chunks: R, y and the accumulator chunk stay in registers beside the rare exact-recompute call
+#pragma unroll 1
+                for (int c = 0; c < BN / 2 / 16; ++c) {
+                    uint32_t acc[16];
+                    tmem_ld16(tcol + (uint32_t)(c * 16), acc);
+                    float4 r[4], y[4];
+                    if (live) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            r[j] = *reinterpret_cast<const float4*>(erow + c * 16 + j * 4);
+                            y[j] = *reinterpret_cast<const float4*>(yrow + c * 16 + j * 4);
+                        }
+                    }
+                    tmem_ld_wait();
+                    if (live) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c * 16 + j * 4));
+                            const float yy[4] = {y[j].x - bb.x, y[j].y - bb.y, y[j].z - bb.z, y[j].w - bb.w};
+                            const float rr[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
+                            float o[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                // x+ W+^T + x- W-^T == ( x W^T + |x| |W|^T ) / 2 ,  x W^T = y - bias (saved forward output).
+                                // The true value is a sum of non-negative products; the identity cancels when almost every
+                                // product is negative (x W^T ~ -|x||W|^T): then Z carries an absolute error of ~2^-11 * a and
+                                // is recomputed exactly (rare; all-zero rows / columns give an exact 0 on both sides).
+                                const float a = __uint_as_float(acc[4 * j + u]);
+                                float z = 0.5f * (yy[u] + a);
+                                if (z < a * 0.0078125f && a > 0.f)
+                                    z = zplus_exact(p.X + (long long)row * p.ldx, p.Wp + (long long)(n0 + c * 16 + j * 4 + u) * p.K,
+                                                    p.Wn + (long long)(n0 + c * 16 + j * 4 + u) * p.K, p.K);
+                                o[u] = to_tf32(te_sd(rr[u], fmaxf(z, 0.f)));
+                            }
+                            *reinterpret_cast<float4*>(crow + c * 16 + j * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll 1
+            for (int c = 0; c < BN / 2 / 32; ++c) {
+                uint32_t acc[32];
+                tmem_ld32(tcol + (uint32_t)(c * 32), acc);
+                if (MODE == PM_R) {
+                    uint32_t accn[32];
+                    tmem_ld32(tcol + (uint32_t)(BN + c * 32), accn);
+                    float4 x[8];
+                    if (live) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) x[j] = *reinterpret_cast<const float4*>(erow + c * 32 + j * 4);
+                    }
+                    tmem_ld_wait();
+                    if (live) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 o;
+                            o.x = fmaxf(x[j].x, 0.f) * __uint_as_float(acc[4 * j + 0]) + fminf(x[j].x, 0.f) * __uint_as_float(accn[4 * j + 0]);
+                            o.y = fmaxf(x[j].y, 0.f) * __uint_as_float(acc[4 * j + 1]) + fminf(x[j].y, 0.f) * __uint_as_float(accn[4 * j + 1]);
+                            o.z = fmaxf(x[j].z, 0.f) * __uint_as_float(acc[4 * j + 2]) + fminf(x[j].z, 0.f) * __uint_as_float(accn[4 * j + 2]);
+                            o.w = fmaxf(x[j].w, 0.f) * __uint_as_float(acc[4 * j + 3]) + fminf(x[j].w, 0.f) * __uint_as_float(accn[4 * j + 3]);
+                            *reinterpret_cast<float4*>(crow + c * 32 + j * 4) = o;
+                        }
+                    }
+                } else {
+                    float4 e[8];
+                    if (EPI == PE_GELU_BWD && live) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) e[j] = *reinterpret_cast<const float4*>(erow + c * 32 + j * 4);
+                    }
+                    tmem_ld_wait();
+                    if (live) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 o = make_float4(__uint_as_float(acc[4 * j + 0]), __uint_as_float(acc[4 * j + 1]),
+                                                   __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+                            if (EPI == PE_GELU_BWD) {
+                                o.x *= te_gelu_grad(e[j].x); o.y *= te_gelu_grad(e[j].y);
+                                o.z *= te_gelu_grad(e[j].z); o.w *= te_gelu_grad(e[j].w);
+                            }
+                            *reinterpret_cast<float4*>(crow + c * 32 + j * 4) = o;
+                        }
+                    }
+                }
+            }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(map_to_rank0(accfree_bar(b)));
+        }
+    } else if (XF) {
+        // ================= |x| transform: warps 10..13 (PM_S1) =================
+        const int et = threadIdx.x - 32 * (2 + EPI_WARPS);            // 0..127
+        uint32_t it = 0;
+        for (int t = cluster_id; t < ntiles; t += nclusters) {
+            for (int kk = 0; kk < kb; ++kk, ++it) {
+                const int s = (int)(it % NST);
+                const uint32_t ph = (it / NST) & 1u;
+                mbar_wait(full_bar(s), ph);
+                float4* a4 = reinterpret_cast<float4*>(smem_al + s * STAGE);
+#pragma unroll
+                for (int i = 0; i < A_BYTES / 16 / XF_THREADS; ++i) {
+                    float4 v = a4[et + i * XF_THREADS];
+                    v.x = to_tf32(fabsf(v.x)); v.y = to_tf32(fabsf(v.y)); v.z = to_tf32(fabsf(v.z)); v.w = to_tf32(fabsf(v.w));
+                    a4[et + i * XF_THREADS] = v;
+                }
+                fence_proxy_async();                // generic-proxy writes -> visible to the tensor-core (async) proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(map_to_rank0(ready_bar(s)));
+            }
+        }
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();                                // nobody leaves while the peer may still touch this CTA
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------
+int sm_pairs() {
+    static int cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    int& c = cache[dev & 63];
+    if (c == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        c = n / 2;
+    }
+    return c;
+}
+
+template <int MODE, int EPI>
+int launch_pair(const float* A, long long lda, const float* B0, const float* B1, PairParams p, cudaStream_t st) {
+    using Cfg = PairCfg<MODE>;
+    CUtensorMap tmA, tmB0, tmB1;
+    if (!make_map(&tmA, A, p.M, p.K, lda, BM) || !make_map(&tmB0, B0, p.N, p.K, p.K, BN / 2) ||
+        !make_map(&tmB1, B1 ? B1 : B0, p.N, p.K, p.K, BN / 2)) {
+        te_set_last_error("te_tc_pair: cuTensorMapEncodeTiled failed");
+        return TE_ERR_CUDA;
+    }
+    static unsigned long long optin = 0;
+    if (!smem_optin(te_tc_pair_kernel<MODE, EPI>, Cfg::SMEM, optin)) {
+        te_set_last_error("te_tc_pair: cannot raise dynamic shared memory");
+        return TE_ERR_CUDA;
+    }
+    const int mt = (p.M + BM - 1) / BM;
+    p.tiles_m = (mt + 1) / 2;
+    p.tiles_n = p.N / BN;
+    const int ntiles = p.tiles_m * p.tiles_n;
+    int pairs = sm_pairs();
+    if (pairs <= 0) { te_set_last_error("te_tc_pair: cannot query the SM count"); return TE_ERR_CUDA; }
+    if (pairs > ntiles) pairs = ntiles;
+    te_tc_pair_kernel<MODE, EPI><<<dim3(2u * (unsigned)pairs), Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB0, tmB1, p);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+
+}  // namespace
+
+bool te_tc_pair_supported(long long rows, int K, int N, long long lda) {
+    return rows > 0 && rows < (1LL << 31) && K % BK == 0 && N % BN == 0 && lda % 4 == 0 && get_encode() != nullptr;
+}
+
+// S = sd(R, ((y - bias) + |x||W|^T)/2)  [rows, out]   (single-pass denominator, see te_tc_zplus.cu)
+int te_tc_pair_zplus_s1(const float* x, long long ldx, const float* derived, const float* r, long long ldr, const float* y,
+                        long long ldy, const float* bias, float* s_out, long long rows, int in_features, int out_features,
+                        cudaStream_t st) {
+    const long long n = (long long)in_features * out_features;
+    PairParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = (int)rows; p.N = out_features; p.K = in_features;
+    p.E = r; p.lde = ldr; p.C = s_out; p.ldc = out_features; p.Y = y; p.ldy = ldy; p.bias = bias;
+    p.X = x; p.ldx = ldx; p.Wp = derived; p.Wn = derived + n;
+    return launch_pair<PM_S1, PE_STORE>(x, ldx, derived + 8 * n, nullptr, p, st);
+}
+
+// R_in = x+ * (S W+) + x- * (S W-)  [rows, in]
+int te_tc_pair_zplus_r(const float* s, const float* derived, const float* x, long long ldx, float* out, long long ld_out,
+                       long long rows, int in_features, int out_features, cudaStream_t st) {
+    const long long n = (long long)in_features * out_features;
+    PairParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = (int)rows; p.N = in_features; p.K = out_features;
+    p.E = x; p.lde = ldx; p.C = out; p.ldc = ld_out;
+    return launch_pair<PM_R, PE_STORE>(s, out_features, derived + 2 * n, derived + 3 * n, p, st);
+}
+
+// dx[rows, in] = epi(dy[rows, out] W)   single-pass TF32 (dy truncated to TF32 by the tensor core, W rounded once)
+int te_tc_pair_linear_bwd(const float* dy, long long lddy, const float* derived, int in_features, int out_features, float* dx,
+                          const float* e0, long long rows, int epi, cudaStream_t st) {
+    const long long n = (long long)in_features * out_features;
+    PairParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = (int)rows; p.N = in_features; p.K = out_features;
+    p.E = e0; p.lde = in_features; p.C = dx; p.ldc = in_features;
+    if (epi == TE_TC_EPI_GELU_BWD) return launch_pair<PM_LIN, PE_GELU_BWD>(dy, lddy, derived + 6 * n, nullptr, p, st);
+    if (epi == TE_TC_EPI_STORE) { p.E = nullptr; return launch_pair<PM_LIN, PE_STORE>(dy, lddy, derived + 6 * n, nullptr, p, st); }
+    te_set_last_error("te_tc_pair_linear_bwd: unsupported epilogue");
+    return TE_ERR_UNSUPPORTED;
+}

@@ -477,13 +477,10 @@ int launch(const float* A, long long lda, const float* B0, const float* B1, cons
         te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed");
         return TE_ERR_CUDA;
     }
-    static bool attr_set[4] = {false, false, false, false};
-    if (!attr_set[MODE]) {
-        if (cudaFuncSetAttribute(te_tc_zplus_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, ZpCfg<MODE>::SMEM) != cudaSuccess) {
-            te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
-            return TE_ERR_CUDA;
-        }
-        attr_set[MODE] = true;
+    static unsigned long long optin = 0;          // per-device attribute: one bit per device
+    if (!smem_optin(te_tc_zplus_kernel<MODE>, ZpCfg<MODE>::SMEM, optin)) {
+        te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
+        return TE_ERR_CUDA;
     }
     TcParams p;
     p.M = (int)M; p.N = N; p.K = K; p.E = E; p.lde = lde; p.C = C; p.ldc = ldc; p.Y = Y; p.ldy = ldy; p.bias = bias;
@@ -517,13 +514,10 @@ int launch2(const float* A, long long lda, const float* B0, const float* B1, con
         te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed");
         return TE_ERR_CUDA;
     }
-    static bool attr_set[4] = {false, false, false, false};
-    if (!attr_set[MODE]) {
-        if (cudaFuncSetAttribute(te_tc_zplus2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES) != cudaSuccess) {
-            te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
-            return TE_ERR_CUDA;
-        }
-        attr_set[MODE] = true;
+    static unsigned long long optin = 0;          // per-device attribute: one bit per device
+    if (!smem_optin(te_tc_zplus2_kernel<MODE>, SMEM2_BYTES, optin)) {
+        te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
+        return TE_ERR_CUDA;
     }
     TcParams p;
     p.M = (int)M; p.N = N; p.K = K; p.E = E; p.lde = lde; p.C = C; p.ldc = ldc; p.Y = Y; p.ldy = ldy; p.bias = bias;
@@ -544,13 +538,10 @@ int launch_r_bf16(const void* A, const void* B0, const void* B1, const float* E,
         te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed (bf16)");
         return TE_ERR_CUDA;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(te_tc_zplus_kernel<MODE_R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
-            te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
-            return TE_ERR_CUDA;
-        }
-        attr_set = true;
+    static unsigned long long optin = 0;          // per-device attribute: one bit per device
+    if (!smem_optin(te_tc_zplus_kernel<MODE_R, true>, SMEM_BYTES, optin)) {
+        te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
+        return TE_ERR_CUDA;
     }
     TcParams p;
     memset(&p, 0, sizeof(p));
@@ -569,6 +560,16 @@ bool te_tc_zplus_supported(long long rows, int in_features, int out_features, lo
 }
 
 void te_tc_set_pair_kernels(int on) { g_pair_kernels = (on == 2) ? 2 : (on ? 1 : 0); }
+
+static int g_zplus_persistent = -1;            // persistent CTA-pair kernels of te_tc_pair.cu (default on; TE_B200_ZPLUS_PERSISTENT=0)
+static bool use_persistent() {
+    if (g_zplus_persistent < 0) {
+        const char* e = getenv("TE_B200_ZPLUS_PERSISTENT");
+        g_zplus_persistent = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_zplus_persistent == 1;
+}
+void te_tc_set_zplus_persistent(int on) { g_zplus_persistent = on ? 1 : 0; }
 
 long long te_tc_derived_floats(int in_features, int out_features) { return 10LL * in_features * out_features; }
 
@@ -590,6 +591,12 @@ int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* deriv
     const float *wp = derived, *wn = derived + n, *wpt = derived + 2 * n, *wnt = derived + 3 * n;
     // S = sd(R, x+ W+^T + x- W-^T)          A = x [rows, in] ; B = W+/- [out, in]
     const bool rb = bf16 && (out_features % 64 == 0);          // S as bf16, R kernel with bf16 operands (kind::f16)
+    if (!rb && use_persistent() && y && a16(y) && ldy % 4 == 0 && (!bias || a16(bias)) &&
+        te_tc_pair_supported(rows, in_features, out_features, ldx) && te_tc_pair_supported(rows, out_features, in_features, out_features)) {
+        // persistent CTA-pair kernels (te_tc_pair.cu): single-pass S, then R with the A operand shared by both products
+        TE_TRY(te_tc_pair_zplus_s1(x, ldx, derived, r, ldr, y, ldy, bias, s_scratch, rows, in_features, out_features, st));
+        return te_tc_pair_zplus_r(s_scratch, derived, x, ldx, out, in_features, rows, in_features, out_features, st);
+    }
     if (y && a16(y) && ldy % 4 == 0 && (!bias || a16(bias))) {
         // single pass: Z = ((y - bias) + |x| |W|^T) / 2 with the saved forward output y = x W^T + bias
         const float* wabs = derived + 8 * n;

@@ -350,6 +350,7 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
     }
     const float* lbase = (flags & TE_FLAG_LINEAR_TENSOR_CORES) ? derived : nullptr;
     const bool atc = (flags & TE_FLAG_ATTN_TENSOR_CORES) != 0;
+    const bool btf = (flags & TE_FLAG_BACKWARD_TF32) != 0;       // single-pass TF32 backward Linears
     const bool zb = (flags & TE_FLAG_ZPLUS_BF16) != 0;
 
     // ---- class index and seeds  (ViT_explanation_generator.py:28-35) ---------------------------
@@ -380,11 +381,11 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
         const HeadOp v = head_rows(a.qkv + 2 * d.D, 3 * d.D, d.N, d.dh);
         const DerivedW lw = bind_derived(d, lbase, l);
         // mlp branch
-        TE_TRY(te_util::linear_bwd_tc(lw.fc2, dxa, bw.fc2w, dF, a.h, d.M, d.F, d.D, TE_EPI_GELU_BWD, st));
-        TE_TRY(te_util::linear_bwd_tc(lw.fc1, dF, bw.fc1w, dxn, nullptr, d.M, d.D, d.F, TE_EPI_STORE, st));
+        TE_TRY(te_util::linear_bwd_tc(lw.fc2, dxa, bw.fc2w, dF, a.h, d.M, d.F, d.D, TE_EPI_GELU_BWD, st, btf));
+        TE_TRY(te_util::linear_bwd_tc(lw.fc1, dF, bw.fc1w, dxn, nullptr, d.M, d.D, d.F, TE_EPI_STORE, st, btf));
         TE_TRY(te_launch_layernorm_bwd(dxn, a.x_mid, bw.n2w, a.mean2, a.rstd2, dxa, dxb, d.M, d.D, st));
         // attention branch
-        TE_TRY(te_util::linear_bwd_tc(lw.proj, dxb, bw.projw, dctx, nullptr, d.M, d.D, d.D, TE_EPI_STORE, st));
+        TE_TRY(te_util::linear_bwd_tc(lw.proj, dxb, bw.projw, dctx, nullptr, d.M, d.D, d.D, TE_EPI_STORE, st, btf));
         TE_TRY(te_util::attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, dctx, d.D, a.qkv + 2 * d.D, 3 * d.D, a.G, nullptr, 1.f,
                                 TE_EPI_STORE, st));                                 // G = dctx v^T
         if (l == start_layer) break;                                                // lower gradients are never read
@@ -395,7 +396,7 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
                                 TE_EPI_STORE, st));                                 // dQ = dS k
         TE_TRY(te_util::attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, dS, 1, a.qkv, 3 * d.D, dqkv + d.D, 3 * d.D, nullptr, 1.f,
                                 TE_EPI_STORE, st));                                 // dK = dS^T q
-        TE_TRY(te_util::linear_bwd_tc(lw.qkv, dqkv, bw.qkvw, dxn, nullptr, d.M, d.D, 3 * d.D, TE_EPI_STORE, st));
+        TE_TRY(te_util::linear_bwd_tc(lw.qkv, dqkv, bw.qkvw, dxn, nullptr, d.M, d.D, 3 * d.D, TE_EPI_STORE, st, btf));
         TE_TRY(te_launch_layernorm_bwd(dxn, a.x_in, bw.n1w, a.mean1, a.rstd1, dxb, dxa, d.M, d.D, st));
     }
 

@@ -6,11 +6,23 @@ flat fp32 weight buffer (the unit of the single NCCL broadcast) and one activati
 stream, and issues O(1) launches per block per BATCH through the C ABI.
 """
 import ctypes
+import functools
 
 import torch
 
 from . import _lib
 from ._lib import TeVitConfig, check, ptr
+
+
+def _on_engine_device(fn):
+    """Make the engine's device current for the duration of the call: the C library launches on the current device
+    and neither it nor ``torch.cuda.current_stream(dev)`` switches devices (a model moved to ``cuda:1`` without
+    ``torch.cuda.set_device(1)`` would otherwise fail with an invalid resource handle)."""
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+    return wrapped
 
 
 def vit_config(img_size=224, patch_size=16, in_chans=3, num_classes=1000, embed_dim=768, depth=12, num_heads=12,
@@ -48,6 +60,7 @@ class ViTEngine:
             self.load_state_dict(state_dict)
 
     # ---- weights ------------------------------------------------------------------------------
+    @_on_engine_device
     def load_state_dict(self, sd):
         """Pack a reference-keyed ``state_dict`` (timm ViT names) into the flat device buffer."""
         host = torch.zeros(self.weights.numel(), dtype=torch.float32)
@@ -63,6 +76,7 @@ class ViTEngine:
         self.weights.copy_(host, non_blocking=False)
         self.derived = None
 
+    @_on_engine_device
     def _derived(self, flags):
         """W+/W-/W+^T/W-^T TF32 copies for the tcgen05 z+ path (built once per weight load)."""
         if not (flags & _lib.FLAG_TENSOR_CORES):
@@ -104,6 +118,7 @@ class ViTEngine:
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ---- the three calls ------------------------------------------------------------------------
+    @_on_engine_device
     def forward(self, images, flags=None):
         """``model(x)``: logits [B,C]; leaves the activations in the workspace."""
         images = images.to(self.device, torch.float32).contiguous()
@@ -117,6 +132,7 @@ class ViTEngine:
         self._last_images = images
         return logits
 
+    @_on_engine_device
     def relprop_pixels(self, index=None, per_channel=False, flags=None):
         """``method="full"`` (ViT_LRP.py:337-343) on the activations of the last ``forward``: the relprop is run to
         the encoder input, through ``self.add`` and the patch convolution's z^B rule.  Returns the relevance of every
@@ -135,6 +151,7 @@ class ViTEngine:
                                              ptr(ws), ws.numel() * 4, self._stream()), "te_vit_relprop_pixels")
         return out
 
+    @_on_engine_device
     def attribute(self, index=None, start_layer=0, flags=None):
         """Backward + relprop + rollout on the activations of the last ``forward``.
         Returns (maps [B,N-prefix], index [B] int32)."""
@@ -150,6 +167,7 @@ class ViTEngine:
               "te_vit_attribute")
         return maps, idx
 
+    @_on_engine_device
     def explain(self, images, index=None, start_layer=0, flags=None, chunk=None, return_logits=False):
         """``LRP.generate_LRP`` for a batch of independent inputs (device-resident in, device-resident out)."""
         images = images.to(self.device, torch.float32).contiguous()
@@ -232,6 +250,7 @@ class BertEngine:
         if state_dict is not None:
             self.load_state_dict(state_dict)
 
+    @_on_engine_device
     def load_state_dict(self, sd):
         host = torch.zeros(self.weights.numel(), dtype=torch.float32)
         for name, numel, off in self.weight_table:
@@ -248,6 +267,7 @@ class BertEngine:
         import torch.distributed as dist
         dist.broadcast(self.weights, src=src, group=group)
 
+    @_on_engine_device
     def _derived(self, flags):
         if not (flags & _lib.FLAG_TENSOR_CORES):
             return None
@@ -280,11 +300,15 @@ class BertEngine:
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _ids(self, input_ids, attention_mask):
+        if not input_ids.is_cuda and input_ids.numel() and (int(input_ids.min()) < 0 or
+                                                            int(input_ids.max()) >= self.cfg.vocab_size):
+            raise ValueError("input_ids outside [0, vocab_size)")     # device-resident ids: the kernel writes NaN rows
         ids = input_ids.to(self.device, torch.int64).contiguous()
         if attention_mask is None:
             attention_mask = torch.ones_like(ids)
         return ids, attention_mask.to(self.device, torch.int64).contiguous()
 
+    @_on_engine_device
     def forward(self, input_ids, attention_mask=None, flags=None):
         ids, mask = self._ids(input_ids, attention_mask)
         b, s = ids.shape
@@ -297,6 +321,7 @@ class BertEngine:
         self.last = (b, s)
         return logits
 
+    @_on_engine_device
     def attribute(self, index=None, start_layer=11, flags=None):
         b, s = self.last
         if b <= 0:
@@ -310,6 +335,7 @@ class BertEngine:
               "te_bert_attribute")
         return maps, idx
 
+    @_on_engine_device
     def explain(self, input_ids, attention_mask=None, index=None, start_layer=11, flags=None, chunk=None,
                 return_logits=False):
         ids, mask = self._ids(input_ids, attention_mask)

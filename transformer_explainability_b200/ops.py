@@ -10,25 +10,62 @@ from . import _lib
 from ._lib import check, ptr
 
 
+import functools
+
+
 def _stream():
     return _lib.ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _on_device(fn):
+    """Run the op with the device of its first CUDA tensor argument current: the C library launches on the current
+    device and the stream handed to it must belong to that device (a model on a non-current GPU otherwise fails with
+    an invalid resource handle)."""
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, (list, tuple)) and a and torch.is_tensor(a[0]):
+                a = a[0]
+            if torch.is_tensor(a) and a.is_cuda:
+                dev = a.device
+                break
+        if dev is None:
+            raise ValueError("te_b200 ops need CUDA tensors (no CPU fallback)")
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
 def _req(*ts):
+    dev = None
     for t in ts:
         if t is None:
             continue
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
             raise ValueError("te_b200 ops need contiguous fp32 CUDA tensors (no CPU fallback)")
+        if dev is not None and t.device != dev:
+            raise ValueError("te_b200 ops: all tensors of one call must live on the same device")
+        dev = t.device
+
+
+def _same_shape(what, *ts):
+    ts = [t for t in ts if t is not None]
+    for t in ts[1:]:
+        if t.shape != ts[0].shape:
+            raise ValueError("%s: shape mismatch %s vs %s" % (what, tuple(ts[0].shape), tuple(t.shape)))
 
 
 def _workspace(nbytes, device):
     return torch.empty((nbytes + 255) // 256 * 64, dtype=torch.float32, device=device)   # 256-byte multiple
 
 
+@_on_device
 def linear_forward(x, w, bias=None, tensor_cores=False):
     """y = x W^T + b.  tensor_cores: fp32-grade 3xTF32 split on tcgen05 (shapes that do not qualify fall back)."""
     _req(x, w, bias)
+    if w.dim() != 2 or x.shape[-1] != w.shape[1] or (bias is not None and bias.numel() != w.shape[0]):
+        raise ValueError("linear_forward: x [...,in], w [out,in], bias [out] expected")
     rows = x.numel() // x.shape[-1]
     y = torch.empty(*x.shape[:-1], w.shape[0], device=x.device, dtype=torch.float32)
     scratch = torch.empty(10 * w.numel(), device=x.device, dtype=torch.float32) if tensor_cores else None
@@ -38,9 +75,12 @@ def linear_forward(x, w, bias=None, tensor_cores=False):
     return y
 
 
+@_on_device
 def linear_backward(dy, w, tensor_cores=False):
     """dx = dy W  (activation gradient of a Linear; no dW on this path)."""
     _req(dy, w)
+    if w.dim() != 2 or dy.shape[-1] != w.shape[0]:
+        raise ValueError("linear_backward: dy [...,out], w [out,in] expected")
     rows = dy.numel() // dy.shape[-1]
     dx = torch.empty(*dy.shape[:-1], w.shape[1], device=dy.device, dtype=torch.float32)
     scratch = torch.empty(10 * w.numel(), device=dy.device, dtype=torch.float32) if tensor_cores else None
@@ -50,10 +90,29 @@ def linear_backward(dy, w, tensor_cores=False):
     return dx
 
 
+@_on_device
+def linear_backward_tf32(dy, w):
+    """dx = dy W as a single-pass TF32 GEMM on the persistent CTA-pair kernel (what TE_FLAG_BACKWARD_TF32 selects)."""
+    _req(dy, w)
+    if w.dim() != 2 or dy.shape[-1] != w.shape[0]:
+        raise ValueError("linear_backward_tf32: dy [...,out], w [out,in] expected")
+    rows = dy.numel() // dy.shape[-1]
+    dx = torch.empty(*dy.shape[:-1], w.shape[1], device=dy.device, dtype=torch.float32)
+    scratch = torch.empty(10 * w.numel(), device=dy.device, dtype=torch.float32)
+    check(_lib.load().te_linear_backward_ex(ptr(dy), ptr(w), ptr(dx), ptr(scratch), rows, w.shape[1], w.shape[0],
+                                            _lib.FLAG_LINEAR_TENSOR_CORES | _lib.FLAG_BACKWARD_TF32, _stream()),
+          "te_linear_backward_ex")
+    return dx
+
+
+@_on_device
 def linear_relprop(x, w, r, tensor_cores=False, y=None, bias=None, bf16=False):
     """``Linear.relprop`` (layers_ours.py:207-230): x [...,in], w [out,in], r [...,out] -> [...,in].
     y / bias: the layer's saved forward output (and bias) — lets the tensor-core path form the denominator in one pass."""
     _req(x, w, r, y, bias)
+    if (w.dim() != 2 or x.shape[-1] != w.shape[1] or r.shape[-1] != w.shape[0] or r.shape[:-1] != x.shape[:-1]
+            or (y is not None and y.shape != r.shape) or (bias is not None and bias.numel() != w.shape[0])):
+        raise ValueError("linear_relprop: x [...,in], w [out,in], r / y [...,out], bias [out] expected")
     rows = x.numel() // x.shape[-1]
     out = torch.empty_like(x)
     nscratch = rows * w.shape[0]
@@ -72,9 +131,13 @@ def linear_relprop(x, w, r, tensor_cores=False, y=None, bias=None, bf16=False):
     return out
 
 
+@_on_device
 def add_relprop(x1, x2, r):
     """``Add.relprop`` (layers_ours.py:97-120), sums per sample (dim 0)."""
     _req(x1, x2, r)
+    _same_shape("add_relprop", x1, x2, r)           # a broadcast operand (pos_embed [1,N,D]) must be expanded by the caller
+    if (x1.numel() // max(x1.shape[0], 1)) % 4 != 0:
+        raise ValueError("add_relprop: elements per sample must be a multiple of 4")
     b = x1.shape[0]
     r1, r2 = torch.empty_like(x1), torch.empty_like(x1)
     scratch = torch.empty(b * 48, device=x1.device, dtype=torch.float64)
@@ -83,10 +146,14 @@ def add_relprop(x1, x2, r):
     return r1, r2
 
 
+@_on_device
 def clone_relprop(x, rs):
     """``Clone.relprop`` (layers_ours.py:151-169) for 2 or 3 branches."""
     rs = list(rs)
     _req(x, *rs)
+    if len(rs) not in (2, 3):
+        raise ValueError("clone_relprop: 2 or 3 branches")
+    _same_shape("clone_relprop", x, *rs)
     out = torch.empty_like(x)
     r3 = rs[2] if len(rs) > 2 else None
     check(_lib.load().te_clone_relprop(ptr(x), ptr(rs[0]), ptr(rs[1]), ptr(r3), ptr(out), x.numel(), _stream()),
@@ -94,8 +161,11 @@ def clone_relprop(x, rs):
     return out
 
 
+@_on_device
 def index_select_relprop(x, r):
     """``IndexSelect.relprop`` (layers_ours.py:129-147), dim=1, index 0: x [B,N,D], r [B,1,D]|[B,D]."""
+    if x.dim() != 3 or r.numel() != x.shape[0] * x.shape[2]:
+        raise ValueError("index_select_relprop: x [B,N,D], r [B,1,D] expected")
     r = r.reshape(x.shape[0], x.shape[2]).contiguous()
     _req(x, r)
     out = torch.empty_like(x)
@@ -104,9 +174,13 @@ def index_select_relprop(x, r):
     return out
 
 
+@_on_device
 def matmul_av_relprop(p, v, r):
     """``einsum('bhij,bhjd->bhid').relprop``: returns UN-halved (R_attn, R_v)."""
     _req(p, v, r)
+    if v.dim() != 4 or p.shape != v.shape[:2] + (v.shape[2], v.shape[2]):
+        raise ValueError("matmul_av_relprop: p [B,H,N,N], v [B,H,N,d], r [B,H,N,d] expected")
+    _same_shape("matmul_av_relprop", v, r)
     b, h, n, d = v.shape
     rp, rv = torch.empty_like(p), torch.empty_like(v)
     scratch = torch.empty(b * h * n * d, device=p.device, dtype=torch.float32)
@@ -115,9 +189,13 @@ def matmul_av_relprop(p, v, r):
     return rp, rv
 
 
+@_on_device
 def matmul_qk_relprop(q, k, r):
     """``einsum('bhid,bhjd->bhij').relprop``: returns UN-halved (R_q, R_k)."""
     _req(q, k, r)
+    if q.dim() != 4 or r.shape != q.shape[:2] + (q.shape[2], q.shape[2]):
+        raise ValueError("matmul_qk_relprop: q, k [B,H,N,d], r [B,H,N,N] expected")
+    _same_shape("matmul_qk_relprop", q, k)
     b, h, n, d = q.shape
     rq, rk = torch.empty_like(q), torch.empty_like(k)
     scratch = torch.empty(b * h * n * n, device=q.device, dtype=torch.float32)
@@ -138,6 +216,7 @@ def _attn_layout(t):
     return t, ld
 
 
+@_on_device
 def head_reduce(a, g=None, head_weight=None, mode="mean"):
     """Reduce an attention-shaped tensor over its heads: a [B,H,N,N] (optionally * g, * head_weight[B,H]) -> [B,N,N].
     mode: "mean" | "relu_mean" (``clamp(min=0).mean(heads)``) | "mean_relu" (``mean(heads).clamp(min=0)``)."""
@@ -156,6 +235,7 @@ def head_reduce(a, g=None, head_weight=None, mode="mean"):
     return out
 
 
+@_on_device
 def head_region_mean(g, rows=None, cols=None):
     """``g[b,h, rows, cols].mean()`` per (b,h): [B,H,N,N] -> [B,H] (``grad.mean(dim=[1,2])`` of the GradCAM baselines)."""
     g, ld = _attn_layout(g)
@@ -167,6 +247,7 @@ def head_region_mean(g, rows=None, cols=None):
     return out
 
 
+@_on_device
 def patch_embed_relprop(images, weight, r, per_channel=True):
     """``PatchEmbed.relprop`` -> ``Conv2d.relprop`` z^B branch (ViT_LRP.py:238-242, layers_ours.py:242-259).
     images [B,C,S,S]; weight [D,C,P,P] (or flattened [D,C*P*P]); r [B,(S/P)^2,D] -> [B,C,S,S] (or [B,S,S] channel sum)."""
@@ -184,10 +265,14 @@ def patch_embed_relprop(images, weight, r, per_channel=True):
     return out
 
 
+@_on_device
 def attribution_rollout(grad, cam, start_layer=0, normalize=False, fused=False, want_joint=True):
     """grad, cam [L,B,H,N,N] -> (joint [B,N,N] or None, row0 [B,N]).
     ``ViT_LRP.py:357-368`` (normalize=False) / ``ExplanationGenerator.py:47-57`` (normalize=True)."""
     _req(grad, cam)
+    _same_shape("attribution_rollout", grad, cam)
+    if grad.dim() != 5 or grad.shape[4] < grad.shape[3] or grad.shape[4] % 4 != 0:
+        raise ValueError("attribution_rollout: grad, cam [L,B,H,N,ld] with ld >= N, ld % 4 == 0 expected")
     L, B, H, N, ld = grad.shape
     lib = _lib.load()
     nbytes = check(lib.te_rollout_workspace_bytes(L, B, N), "te_rollout_workspace_bytes")
@@ -200,6 +285,7 @@ def attribution_rollout(grad, cam, start_layer=0, normalize=False, fused=False, 
     return joint, row0
 
 
+@_on_device
 def compute_rollout_attention(all_layer_matrices, start_layer=0, normalize=False):
     """``compute_rollout_attention`` (ViT_LRP.py:38-49; BERT variant with normalize=True,
     ExplanationGenerator.py:7-18): list of [B,N,N] -> [B,N,N]."""
