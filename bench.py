@@ -62,6 +62,11 @@ def parse():
     ap.add_argument("--cpu-samples", type=int, default=12, help="explanations timed for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the BASELINE batch PER GPU (default, what the driver's scaling run uses); strong: the "
+                         "BASELINE batch as the GLOBAL batch, sharded over the GPUs (SURVEY 8e: 256 -> 32 per GPU at 8). "
+                         "With N > 1 the weak run also reports the strong-scaling numbers under the key 'strong'.")
+    ap.add_argument("--no-graph", action="store_true", help="strong-scaling line without CUDA-graph replay")
     return ap.parse_args()
 
 
@@ -277,9 +282,14 @@ def cpu_baseline(w, state_dict, n_samples):
     if w["kind"] == "bert":
         from oracle import bert as obert
         sd = {k: v for k, v in sd.items() if "position_ids" not in k}
-        kind = "port"
         ones = torch.ones(1, w["tokens"], dtype=torch.long)
-        run = lambda x: obert.explain(sd, x, ones, w["heads"], start_layer=0)[0]      # noqa: E731
+        if ref_harness.available():
+            kind = "reference"
+            model = ref_harness.build_bert(state_dict=sd)
+            run = lambda x: ref_harness.bert_generate_lrp(model, x, ones, start_layer=0)["map"]      # noqa: E731
+        else:
+            kind = "port"
+            run = lambda x: obert.explain(sd, x, ones, w["heads"], start_layer=0)[0]      # noqa: E731
     elif ref_harness.available():
         kind = "reference"
         model = ref_harness.build_vit(w["oracle"], state_dict=sd)
@@ -294,6 +304,8 @@ def cpu_baseline(w, state_dict, n_samples):
         run(xs[i:i + 1])
     dt = time.perf_counter() - t0
     return {"value": round(n_samples / dt, 4), "unit": "expl/s", "cores": torch.get_num_threads(), "kind": kind,
+            "source": ("the reference's own files (%s)" % ("oracle/_ref mirror" if ref_harness.is_mirror() else ref_harness.REF))
+            if kind == "reference" else "oracle port (bit-equal to the reference, tests/test_oracle_golden.py)",
             "sample": "%d B=1 explanations of the same workload (2 warm-up), %.1f s" % (n_samples, dt)}
 
 
@@ -302,23 +314,31 @@ def run_reference_arm(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from transformer_explainability_b200.baselines.ViT import ViT_LRP
-    torch.manual_seed(0)
-    model = getattr(ViT_LRP, w["factory"])(pretrained=False)
+    model = make_model(w, "cpu")
     per_step = 2
     from oracle import ref_harness
     from oracle import vit as ovit
     from oracle import cpu as ocpu
     ocpu.set_torch_threads(cap=256)
-    sd = {k: v.detach().float() for k, v in model.state_dict().items()}
-    if ref_harness.available():
+    sd = {k: v.detach().float() for k, v in model.state_dict().items() if "position_ids" not in k}
+    if w["kind"] == "bert":
+        from oracle import bert as obert
+        ones = torch.ones(1, w["tokens"], dtype=torch.long)
+        if ref_harness.available():
+            kind = "reference"
+            ref = ref_harness.build_bert(state_dict=sd)
+            run = lambda x: ref_harness.bert_generate_lrp(ref, x, ones, start_layer=0)["map"]      # noqa: E731
+        else:
+            kind = "port"
+            run = lambda x: obert.explain(sd, x, ones, w["heads"], start_layer=0)[0]               # noqa: E731
+    elif ref_harness.available():
         kind = "reference"
         ref = ref_harness.build_vit(w["oracle"], state_dict=sd)
         run = lambda x: ref_harness.vit_generate_lrp(ref, x)["map"]        # noqa: E731
     else:
         kind = "port"
         run = lambda x: ovit.explain(sd, x, w["heads"])[0]                 # noqa: E731
-    xs = synthetic_images(per_step * (args.steps + args.warmup), seed=1234)
+    xs = synthetic_inputs(w, per_step * (args.steps + args.warmup), seed=1234)
     i = 0
     for _ in range(args.warmup):
         for _ in range(per_step):
@@ -336,7 +356,8 @@ def run_reference_arm(args, w):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["label"], "per_step": sample},
             "cpu_baseline": {"value": round(val, 4), "unit": "expl/s", "cores": torch.get_num_threads(), "kind": kind,
-                             "sample": sample},
+                             "source": ("oracle/_ref mirror of the reference's own files" if ref_harness.is_mirror() else
+                                        ref_harness.REF) if kind == "reference" else "oracle port", "sample": sample},
             "e2e": {"value": round(val, 4), "unit": "expl/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -398,10 +419,29 @@ def main():
     e2e = world * batch * args.steps / (ms_e2e * 1e-3)
     finite = bool(torch.isfinite(sink["maps"]).all())
 
+    # ---- strong scaling: the BASELINE batch as the GLOBAL batch, contiguous shards (parallel.shard_range), no collective
+    strong = None
+    if world > 1 or args.scaling == "strong":
+        gb = args.batch or w["batch"]
+        lo, hi = parallel.shard_range(gb, rank, world)
+        xs = x_dev[:hi - lo]
+        strong = {"global_batch": gb, "per_gpu_batch": hi - lo, "unit": "expl/s"}
+        variants = [("launches", lambda: explain_call(w, eng, xs, hi - lo))]
+        if w["kind"] == "vit" and not args.no_graph:
+            variants.append(("cuda_graph", lambda: eng.explain_graphed(xs)))
+        for name, fn in variants:
+            ms_s = timed_steps(fn, args.steps, args.warmup, world)
+            strong[name] = {"value": round(gb * args.steps / (ms_s * 1e-3), 2), "ms_per_step": round(ms_s / args.steps, 3)}
+        best = max(v["value"] for k, v in strong.items() if isinstance(v, dict))
+        strong["value"] = best
+        if args.scaling == "strong":
+            value, ms = best, gb * args.steps / best * 1e3
+
     line = {"metric": "explanations_per_sec", "value": round(value, 2), "unit": "expl/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["label"], "per_gpu_batch": batch, "global_batch": batch * world,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["label"], "per_gpu_batch": batch if args.scaling == "weak" else strong["per_gpu_batch"],
+                       "global_batch": batch * world if args.scaling == "weak" else strong["global_batch"],
                        "weights": "random-init (reference constructor distributions)", "engine_flags": flags,
                        "l2": "working set exceeds L2 by orders of magnitude: >50 GB of saved activations are written and "
                              "re-read every step (126 MB L2)",
@@ -410,6 +450,8 @@ def main():
             "e2e": {"value": round(e2e, 2), "unit": "expl/s", "h2d_bytes_per_step": host.numel() * host.element_size(),
                     "d2h_bytes_per_step": sink["maps"].numel() * 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
             "gpu_launches": int(launches)}
+    if strong is not None:
+        line["strong"] = strong
     if rank == 0:
         pk = peaks()
         if not args.no_roofline:

@@ -1,9 +1,10 @@
 """Import and run the UNMODIFIED reference on CPU (TEST INFRASTRUCTURE, authoring container only).
 
-``/root/reference`` does not exist on the GPU box: nothing that runs there may
-import this module.  It is used by ``oracle/make_golden.py`` (fixture generation),
-by the ``-m "not gpu"`` tests that pin the oracle when the reference is present
-(they skip otherwise), and by ``bench.py --impl reference`` when present.
+``/root/reference`` does not exist on the GPU box; there the harness imports the
+byte-for-byte mirror of the hot-path files that ``oracle/fetch_ref.py`` leaves in
+``oracle/_ref`` (git-ignored).  It is used by ``oracle/make_golden.py`` (fixture
+generation), by the ``-m "not gpu"`` tests that pin the oracle when the reference is
+present, and by ``bench.py``'s ``cpu_baseline`` leg / ``--impl reference`` arm.
 
 Shims — each one works around an incompatibility of the
 reference with this container, none changes the arithmetic:
@@ -24,11 +25,25 @@ import types
 
 import torch
 
-REF = os.environ.get("TE_REFERENCE_PATH", "/root/reference")
+def _find_ref():
+    """``/root/reference`` in the authoring container; on the GPU box the byte-for-byte mirror of the hot-path files
+    that ``oracle/fetch_ref.py`` leaves in ``oracle/_ref`` (git-ignored, shipped with the snapshot)."""
+    for c in (os.environ.get("TE_REFERENCE_PATH"), "/root/reference",
+              os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")):
+        if c and os.path.isdir(os.path.join(c, "baselines", "ViT")):
+            return c
+    return os.environ.get("TE_REFERENCE_PATH", "/root/reference")
+
+
+REF = _find_ref()
 
 
 def available():
     return os.path.isdir(os.path.join(REF, "baselines", "ViT"))
+
+
+def is_mirror():
+    return os.path.basename(REF.rstrip("/")) == "_ref"
 
 
 @contextlib.contextmanager

@@ -124,6 +124,7 @@ def test_host_only_queries_and_option_errors():
     assert lib.te_set_option(b"no_such_option", 1) < 0
     assert b"unknown option" in lib.te_last_error()
     assert lib.te_set_option(b"zplus_pair_kernels", 0) == 0 and lib.te_set_option(b"linear_pair_kernels", 0) == 0
+    assert lib.te_set_option(b"zplus_persistent", 1) == 0
 
 
 def test_baseline_and_generator_surfaces_resolve():
@@ -135,6 +136,8 @@ def test_baseline_and_generator_surfaces_resolve():
     from baselines.ViT.ViT_new import vit_base_patch16_224                              # noqa: F401
     from baselines.ViT.ViT_explanation_generator import Baselines
     from BERT_explainability.modules.BERT.ExplanationGenerator import Generator
+    from BERT_explainability.modules.BERT.BERT import BertModel, BertSelfAttention, BertLayer, compute_rollout_attention  # noqa: F401
+    assert all(hasattr(BertSelfAttention, a) for a in ("get_attn", "get_attn_cam", "get_attn_gradients"))      # BERT.py:281-297
     assert list(inspect.signature(Baselines.generate_cam_attn).parameters) == ["self", "input", "index"]
     assert list(inspect.signature(Baselines.generate_rollout).parameters) == ["self", "input", "start_layer"]
     for name in ("generate_LRP", "generate_LRP_last_layer", "generate_full_lrp", "generate_attn_last_layer",

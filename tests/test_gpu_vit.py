@@ -271,3 +271,26 @@ def test_full_batch_properties():
     maps_p, idx_p = eng.explain(xb[perm])
     assert torch.equal(idx_p, idx[perm])
     assert torch.allclose(maps_p, maps[perm], rtol=1e-5, atol=1e-10)
+
+
+def test_cuda_graph_replay_matches_launches():
+    """``ViTEngine.explain_graphed`` (the fixed-shape step captured once in a CUDA graph — what the strong-scaling bench
+    line replays) returns exactly what the launch-by-launch path returns, for new inputs, given class indices, another
+    batch size and the tensor-core kernel selection."""
+    from transformer_explainability_b200 import _lib
+    params, heads = ovit.init_params("vit_tiny_test", seed=2, rand_affine=True, dim=256, heads=4, mlp=256, depth=2, classes=12)
+    model = make_model(params, heads, img_size=32, patch_size=8, embed_dim=256, depth=2, mlp_ratio=1., num_classes=12)
+    eng = model.engine()
+    g = torch.Generator().manual_seed(11)
+    for flags in (0, _lib.FLAG_BENCH_DEFAULT):
+        for b in (5, 3, 5):
+            x = torch.randn(b, 3, 32, 32, generator=g).cuda()
+            want, widx = eng.explain(x, flags=flags)
+            got, gidx = eng.explain_graphed(x, flags=flags)
+            assert torch.equal(gidx, widx)
+            assert torch.equal(got, want)
+        idx = torch.tensor([3, 1, 7, 0, 11], dtype=torch.int32)
+        x = torch.randn(5, 3, 32, 32, generator=g).cuda()
+        want, _ = eng.explain(x, index=idx, flags=flags)
+        got, gidx = eng.explain_graphed(x, index=idx, flags=flags)
+        assert torch.equal(gidx.cpu(), idx) and torch.equal(got, want)

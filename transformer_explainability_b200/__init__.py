@@ -38,6 +38,7 @@ def install_aliases(extra=True):
                 "BERT_explainability.modules.layers_ours":
                     "transformer_explainability_b200.BERT_explainability.modules.layers_ours",
                 "BERT_explainability.modules.BERT": "transformer_explainability_b200.BERT_explainability.modules.BERT",
+                "BERT_explainability.modules.BERT.BERT": "transformer_explainability_b200.BERT_explainability.modules.BERT.BERT",
                 "BERT_explainability.modules.BERT.ExplanationGenerator":
                     "transformer_explainability_b200.BERT_explainability.modules.BERT.ExplanationGenerator",
                 "BERT_explainability.modules.BERT.BertForSequenceClassification":

@@ -191,6 +191,63 @@ class ViTEngine:
             return maps, idx_all, logits
         return maps, idx_all
 
+    # ---- CUDA-graph replay of the fixed-shape step ------------------------------------------------
+    @_on_engine_device
+    def explain_graphed(self, images, index=None, start_layer=0, flags=None, return_logits=False):
+        """``explain`` with the whole step (~40 launches per block) captured once in a CUDA graph and replayed: the
+        shapes, the workspace and every kernel argument are fixed for a given (batch, start_layer, flags), so small
+        per-GPU batches (a fixed global batch sharded over 8 GPUs) are not bound by launch gaps.
+        Inputs are copied into static buffers; outputs are views of static buffers (overwritten by the next call)."""
+        images = images.to(self.device, torch.float32)
+        B = images.shape[0]
+        fl = self.flags if flags is None else flags
+        key = (B, int(start_layer), int(fl), tuple(images.shape[1:]))
+        g = getattr(self, "_graphs", None)
+        if g is None:
+            g = self._graphs = {}
+        if key not in g:
+            if len(g) >= 4:
+                g.clear()                                   # bounded cache: graphs pin their static buffers
+            ws = self._workspace(B)
+            derived = self._derived(fl)
+            st = dict(images=torch.empty_like(images, memory_format=torch.contiguous_format),
+                      idx_in=torch.full((B,), -1, dtype=torch.int32, device=self.device),
+                      idx=torch.full((B,), -1, dtype=torch.int32, device=self.device),
+                      maps=torch.empty(B, self.tokens - self.prefix, dtype=torch.float32, device=self.device),
+                      logits=torch.empty(B, self.cfg.num_classes, dtype=torch.float32, device=self.device), ws=ws)
+            st["images"].copy_(images)
+
+            def run():
+                st["idx"].copy_(st["idx_in"])
+                check(self.lib.te_vit_explain(ctypes.byref(self.cfg), ptr(self.weights), ptr(derived), ptr(st["images"]), B,
+                                              ptr(st["idx"]), int(start_layer), fl, ptr(st["maps"]), ptr(st["logits"]),
+                                              ptr(ws), ws.numel() * 4, self._stream()), "te_vit_explain")
+
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                run()                                       # warm-up outside capture: per-device kernel attributes, allocator
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                run()
+            st["graph"] = graph
+            g[key] = st
+        st = g[key]
+        if st["ws"] is not self._ws:                         # the workspace was re-allocated for another batch size
+            del g[key]
+            return self.explain_graphed(images, index=index, start_layer=start_layer, flags=flags,
+                                        return_logits=return_logits)
+        st["images"].copy_(images, non_blocking=True)
+        st["idx_in"].copy_(self._index_tensor(index, B))
+        st["graph"].replay()
+        self.last_batch = B
+        self._last_images = st["images"]
+        if return_logits:
+            return st["maps"], st["idx"], st["logits"]
+        return st["maps"], st["idx"]
+
     def _index_tensor(self, index, b):
         if index is None:
             return torch.full((b,), -1, dtype=torch.int32, device=self.device)

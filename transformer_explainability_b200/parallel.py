@@ -60,15 +60,20 @@ def gather_maps(local_maps, total, group=None):
     return torch.cat(parts, dim=0)
 
 
-def explain_sharded(engine, images, index=None, start_layer=0, gather=False, chunk=None):
+def explain_sharded(engine, images, index=None, start_layer=0, gather=False, chunk=None, graph=False):
     """Run this rank's contiguous shard of ``images`` through ``engine.explain``.
-    ``images`` may be the full batch (sliced here) — per-rank result, or the gathered [B,N] if ``gather``."""
+    ``images`` may be the full batch (sliced here) — per-rank result, or the gathered [B,N] if ``gather``.
+    graph: replay the shard's step from a CUDA graph (``ViTEngine.explain_graphed``) — small shards of a fixed global
+    batch are otherwise bound by launch gaps."""
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     total = images.shape[0]
     lo, hi = shard_range(total, rank, world)
     idx = None if index is None else torch.as_tensor(index)[lo:hi]
-    maps, cls = engine.explain(images[lo:hi], index=idx, start_layer=start_layer, chunk=chunk)
+    if graph and hasattr(engine, "explain_graphed"):
+        maps, cls = engine.explain_graphed(images[lo:hi], index=idx, start_layer=start_layer)
+    else:
+        maps, cls = engine.explain(images[lo:hi], index=idx, start_layer=start_layer, chunk=chunk)
     if gather:
         return gather_maps(maps, total), cls
     return maps, cls
