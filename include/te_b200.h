@@ -57,6 +57,8 @@ TE_API const char* te_last_error(void);
  * name = "linear_pair_kernels": the same for the 3xTF32 forward / backward Linear GEMMs.  Both default to 0.
  * name = "zplus_persistent": 1 (default) runs the z+ rule with the persistent CTA-pair kernels (te_tc_pair.cu), 0 with
  * the round-1 kernels selected by "zplus_pair_kernels".
+ * name = "cls_row_top_block": 1 (default) runs the three z+ rules of the top block on the pooled-token rows only (exact:
+ * the relevance entering the top block is zero in every other row), 0 on all rows.
  * Returns TE_OK, or a negative status for an unknown name. */
 TE_API int te_set_option(const char* name, int value);
 TE_API int te_version(void);
@@ -190,7 +192,9 @@ TE_API int te_linear_relprop(const float* x, const float* w, const float* r, flo
                       int in_features, int out_features, unsigned flags, void* stream);
 /* Same rule with the Linear's saved forward output y = x W^T + bias [rows,out] supplied (what the engines do): with
  * TE_FLAG_ZPLUS_TENSOR_CORES the denominator is then formed in ONE tensor-core pass through the exact identity
- * x+ W+^T + x- W-^T == ((y - bias) + |x| |W|^T) / 2.  bias may be NULL (no bias).  scratch as above. */
+ * x+ W+^T + x- W-^T == ((y - bias) + |x| |W|^T) / 2.  bias may be NULL (no bias).
+ * scratch: rows*out floats; with TE_FLAG_ZPLUS_TENSOR_CORES: round_up(rows*out,64) + 10*in*out + rows*in floats
+ * (S, the derived weight copies, the tf32(|x|) operand of the single-pass kernel). */
 TE_API int te_linear_relprop_ex(const float* x, const float* w, const float* bias, const float* y, const float* r,
                          float* out, float* scratch, int rows, int in_features, int out_features, unsigned flags,
                          void* stream);

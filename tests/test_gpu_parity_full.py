@@ -146,7 +146,10 @@ def test_conditioned_bert_s512_start_layer0():
         assert e_logit < 2e-5
         assert max(e_g.values()) < tol and max(e_c.values()) < tol
         assert e_map < tol
-        assert e_rng < max(20 * tol, 3 * err_ref)
+        # the conditioned BERT map is nearly flat (range ~ 1/300 of its maximum), so the range-relative number magnifies
+        # every error ~300x: fp32 engine within 3x of the fp32 CPU oracle, TF32 z+ operands 5e-2, TF32 backward 0.3
+        rng_tol = 3 * err_ref if flags == 0 else (0.3 if flags & _lib.FLAG_BACKWARD_TF32 else 5e-2)
+        assert e_rng < rng_tol
         assert float(maps[n - 1, seq * 3 // 4:].abs().max()) == 0.0       # padded tokens: exactly zero relevance
 
 

@@ -294,3 +294,25 @@ def test_cuda_graph_replay_matches_launches():
         want, _ = eng.explain(x, index=idx, flags=flags)
         got, gidx = eng.explain_graphed(x, index=idx, flags=flags)
         assert torch.equal(gidx.cpu(), idx) and torch.equal(got, want)
+
+
+def test_top_block_cls_rows_only_is_exact():
+    """The z+ rules of the top block run on the pooled-token rows only (te_vit.cu; exact structural saving):
+    maps and the top block's attn_cam are bit-identical to the all-rows form, SIMT and tensor-core selections."""
+    from transformer_explainability_b200 import _lib
+    lib = _lib.load()
+    params, heads = ovit.init_params("vit_tiny_test", seed=2, rand_affine=True, dim=256, heads=4, mlp=256, depth=2, classes=12)
+    model = make_model(params, heads, img_size=32, patch_size=8, embed_dim=256, depth=2, mlp_ratio=1., num_classes=12)
+    eng = model.engine()
+    x = torch.randn(6, 3, 32, 32, generator=torch.Generator().manual_seed(4)).cuda()
+    for flags in (0, _lib.FLAG_BENCH_DEFAULT):
+        a, _ = eng.explain(x, flags=flags)
+        cam_a = model.blocks[1].attn.get_attn_cam().clone()
+        _lib.check(lib.te_set_option(b"cls_row_top_block", 0), "te_set_option")
+        try:
+            b, _ = eng.explain(x, flags=flags)
+            cam_b = model.blocks[1].attn.get_attn_cam().clone()
+        finally:
+            _lib.check(lib.te_set_option(b"cls_row_top_block", 1), "te_set_option")
+        assert torch.equal(a, b) and torch.equal(cam_a, cam_b), "flags %d" % flags
+        assert float(cam_a[:, :, 1:, :].abs().max()) == 0.0          # only row 0 of the top block's attn_cam is non-zero

@@ -84,13 +84,16 @@ extern "C" int te_linear_relprop_ex(const float* x, const float* w, const float*
                                     unsigned flags, void* stream) {
     REQ(x && w && r && out && scratch && rows > 0 && in_features > 0 && out_features > 0, "te_linear_relprop_ex: bad argument");
     const float* derived = nullptr;
+    float* xabs = nullptr;
     if ((flags & TE_FLAG_ZPLUS_TENSOR_CORES) && te_tc_zplus_supported(rows, in_features, out_features, in_features)) {
+        // scratch layout with the flag: [rows*out S (64-float aligned) | 10*in*out derived weight copies | rows*in tf32(|x|)]
         float* d = scratch + (((long long)rows * out_features + 63) & ~63LL);
         TE_TRY(te_tc_prepare_weights(w, d, in_features, out_features, ST(stream)));
         derived = d;
+        xabs = d + 10LL * in_features * out_features;
     }
     return te_zplus_linear_relprop_ldr(x, in_features, w, derived, r, out_features, out, scratch, rows, in_features,
-                                       out_features, ST(stream), y, out_features, bias, (flags & TE_FLAG_ZPLUS_BF16) != 0);
+                                       out_features, ST(stream), y, out_features, bias, (flags & TE_FLAG_ZPLUS_BF16) != 0, 0, xabs);
 }
 
 extern "C" int te_add_relprop(const float* x1, const float* x2, const float* r, float* r1, float* r2, void* scratch,
@@ -159,11 +162,16 @@ extern "C" int te_matmul_qk_relprop(const float* q, const float* k, const float*
     return TE_OK;
 }
 
+static int g_cls_rows = 1;
+bool te_engine_cls_rows() { return g_cls_rows != 0; }
+void te_engine_set_cls_rows(int on) { g_cls_rows = on ? 1 : 0; }
+
 extern "C" int te_set_option(const char* name, int value) {
     REQ(name != nullptr, "te_set_option: null name");
     if (strcmp(name, "zplus_pair_kernels") == 0) { te_tc_set_pair_kernels(value); return TE_OK; }
     if (strcmp(name, "linear_pair_kernels") == 0) { te_tc_set_pair_linear(value); return TE_OK; }
     if (strcmp(name, "zplus_persistent") == 0) { te_tc_set_zplus_persistent(value); return TE_OK; }
+    if (strcmp(name, "cls_row_top_block") == 0) { te_engine_set_cls_rows(value); return TE_OK; }
     te_set_last_error("te_set_option: unknown option");
     return TE_ERR_ARG;
 }

@@ -392,13 +392,19 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
         const HeadOp k = head_rows(a.qkv + d.D, 3 * d.D, d.N, d.dh);
         const HeadOp v = head_rows(a.qkv + 2 * d.D, 3 * d.D, d.N, d.dh);
         // BertOutput.relprop :474-487 ; BertIntermediate.relprop :451-456 ; BertLayer.clone
+        // top layer: relevance is non-zero only in the first token's row (pooler, BERT.py:181-190) and every rule down
+        // to the attention-output dense rule is row-wise -> its three z+ rules run on the B first-token rows only (exact)
+        const bool top = (l == d.L - 1) && te_engine_cls_rows();
+        const long long zr = top ? d.B : d.M;
+        const long long sD = top ? (long long)d.N * d.D : d.D, sF = top ? (long long)d.N * d.F : d.F;
         TE_TRY(te_launch_add_relprop(a.d2, a.ao, R, R1, R2, ws.addpart, d.B, (long long)d.N * d.D, st));
-        TE_TRY(te_zplus_linear_relprop_ldr(a.g, d.F, lw.w2, dw.w2, R1, d.D, RF, S, d.M, d.F, d.D, st, a.d2, d.D, lw.b2, zb));
-        TE_TRY(te_zplus_linear_relprop_ldr(a.ao, d.D, lw.w1, dw.w1, RF, d.F, R1, SF, d.M, d.D, d.F, st, a.hpre, d.F, lw.b1, zb));
+        TE_TRY(te_zplus_linear_relprop_ldr(a.g, sF, lw.w2, dw.w2, R1, sD, RF, S, zr, d.F, d.D, st, a.d2, sD, lw.b2, zb, sF, SF));
+        TE_TRY(te_zplus_linear_relprop_ldr(a.ao, sD, lw.w1, dw.w1, RF, sF, R1, SF, zr, d.D, d.F, st, a.hpre, sF, lw.b1, zb, sD, S));
         TE_TRY(te_launch_clone_relprop(a.ao, R1, R2, nullptr, R, MD, st));
         // BertSelfOutput.relprop :427-434
         TE_TRY(te_launch_add_relprop(a.d1, a.h, R, R1, R2, ws.addpart, d.B, (long long)d.N * d.D, st));
-        TE_TRY(te_zplus_linear_relprop_ldr(a.ctx, d.D, lw.ow, dw.o, R1, d.D, R3, S, d.M, d.D, d.D, st, a.d1, d.D, lw.ob, zb));
+        if (top) TE_TRY(te_launch_fill(R3, 0.f, MD, st));
+        TE_TRY(te_zplus_linear_relprop_ldr(a.ctx, sD, lw.ow, dw.o, R1, sD, R3, S, zr, d.D, d.D, st, a.d1, sD, lw.ob, zb, sD, S + MD));
         // BertSelfAttention.relprop :367-409
         TE_TRY(te_launch_sd(R3, a.ctx, S, MD, st));                                       // matmul2: Z == saved ctx
         TE_TRY(attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, S, d.D, a.qkv + 2 * d.D, 3 * d.D, a.cam, a.P, 0.5f, TE_EPI_MUL,
@@ -417,11 +423,11 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
         TE_TRY(attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, ws.tA[0], 1, a.qkv, 3 * d.D, Rqkv + d.D, 3 * d.D, a.qkv + d.D, 0.5f,
                        TE_EPI_MUL, st));
         // query / key / value z+ rules (separate Linears), Clone(3), Clone(2)
-        TE_TRY(te_zplus_linear_relprop_ldr(a.h, d.D, lw.qkvw, dw.q, Rqkv, 3 * d.D, R, S, d.M, d.D, d.D, st, a.qkv, 3 * d.D, lw.qkvb, zb));
+        TE_TRY(te_zplus_linear_relprop_ldr(a.h, d.D, lw.qkvw, dw.q, Rqkv, 3 * d.D, R, S, d.M, d.D, d.D, st, a.qkv, 3 * d.D, lw.qkvb, zb, 0, S + MD));
         TE_TRY(te_zplus_linear_relprop_ldr(a.h, d.D, lw.qkvw + DD, dw.k, Rqkv + d.D, 3 * d.D, R1, S, d.M, d.D, d.D, st, a.qkv + d.D, 3 * d.D,
-                                           lw.qkvb + d.D, zb));
+                                           lw.qkvb + d.D, zb, 0, S + MD));
         TE_TRY(te_zplus_linear_relprop_ldr(a.h, d.D, lw.qkvw + 2 * DD, dw.v, Rqkv + 2 * d.D, 3 * d.D, R3, S, d.M, d.D, d.D, st,
-                                           a.qkv + 2 * d.D, 3 * d.D, lw.qkvb + 2 * d.D, zb));
+                                           a.qkv + 2 * d.D, 3 * d.D, lw.qkvb + 2 * d.D, zb, 0, S + MD));
         TE_TRY(te_launch_clone_relprop(a.h, R, R1, R3, SF, MD, st));                      // self.clone (3-way)
         TE_TRY(te_launch_clone_relprop(a.h, SF, R2, nullptr, R, MD, st));                 // attention.clone
     }

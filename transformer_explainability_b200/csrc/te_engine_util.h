@@ -6,6 +6,11 @@
 #include "te_gemm_tc.h"
 #include "te_kernels.h"
 
+// 1 (default): the z+ rules of the top block run on the pooled-token rows only (exact); te_set_option("cls_row_top_block", 0)
+// restores the all-rows form for A/B comparison
+bool te_engine_cls_rows();
+void te_engine_set_cls_rows(int on);
+
 namespace te_util {
 
 static inline TeGemm gemm0() {

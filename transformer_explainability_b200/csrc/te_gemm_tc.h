@@ -18,7 +18,9 @@ int te_tc_prepare_weights(const float* w, float* derived, int in_features, int o
 int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* derived, const float* r, long long ldr,
                                float* out,
                                float* s_scratch, long long rows, int in_features, int out_features, cudaStream_t st,
-                               const float* y = nullptr, long long ldy = 0, const float* bias = nullptr, bool bf16 = false);
+                               const float* y = nullptr, long long ldy = 0, const float* bias = nullptr, bool bf16 = false,
+                               long long ld_out = 0 /* row stride of out; 0 = in_features */,
+                               float* xabs = nullptr /* scratch [rows, in]: enables the persistent pair kernels */);
 
 // fp32-grade (3xTF32 split) Linear GEMMs on tcgen05; epilogues mirror the SIMT ones
 enum { TE_TC_EPI_STORE = 0, TE_TC_EPI_BIAS = 1, TE_TC_EPI_BIAS_GELU = 2, TE_TC_EPI_BIAS_ADD = 3, TE_TC_EPI_GELU_BWD = 4 };
@@ -52,9 +54,11 @@ int te_tc_bmm_nk_resid(const float* A, const float* J, const float* rowscale, fl
 
 // persistent CTA-pair (cta_group::2) kernels (te_tc_pair.cu): z+ rule contractions and the single-pass TF32 backward Linear
 bool te_tc_pair_supported(long long rows, int K, int N, long long lda);
-int te_tc_pair_zplus_s1(const float* x, long long ldx, const float* derived, const float* r, long long ldr, const float* y,
-                        long long ldy, const float* bias, float* s_out, long long rows, int in_features, int out_features,
-                        cudaStream_t st);
+int te_tc_abs_tf32(const float* x, long long ldx, float* out, long long rows, int cols, cudaStream_t st);
+// xabs: scratch [rows, in] for tf32(|x|), the A operand of the single-pass S kernel
+int te_tc_pair_zplus_s1(const float* x, long long ldx, float* xabs, const float* derived, const float* r, long long ldr,
+                        const float* y, long long ldy, const float* bias, float* s_out, long long rows, int in_features,
+                        int out_features, cudaStream_t st);
 int te_tc_pair_zplus_r(const float* s, const float* derived, const float* x, long long ldx, float* out, long long ld_out,
                        long long rows, int in_features, int out_features, cudaStream_t st);
 int te_tc_pair_linear_bwd(const float* dy, long long lddy, const float* derived, int in_features, int out_features, float* dx,

@@ -207,6 +207,27 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t l
     return d;
 }
 
+// ---- coalesced epilogue: warp-level transpose through shared memory ---------------------------------------------
+// tcgen05.ld hands every thread one accumulator ROW (lane = TMEM lane = tile row).  Reading / writing global memory in that
+// layout touches 32 different 128-byte lines per warp instruction (32 L1 wavefronts for 512 useful bytes): the epilogues
+// were LSU-bound (r02 ncu: ~30k non-MMA cycles per 128x256 tile).  Instead each warp stages 32 rows x 32 columns in a
+// private padded buffer and re-reads it transposed: iteration i (0..7) gives lane the float4 of row 4i + lane/8, columns
+// 4*(lane%8)..+3, so one warp instruction covers 4 rows x 128 contiguous bytes (4 wavefronts).  Row stride 36 floats keeps
+// 128-bit accesses 16-byte aligned and conflict-free in both directions.
+constexpr int EPI_LD = 36;
+constexpr int EPI_STAGE_BYTES = 32 * EPI_LD * 4;      // 4608 B per warp
+
+__device__ __forceinline__ void epi_stage_rows(float* stage, int lane, const uint32_t (&v)[32]) {
+    __syncwarp();                                       // the previous transposed reads of this buffer are done
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(stage + lane * EPI_LD + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+}
+__device__ __forceinline__ float4 epi_read_t(const float* stage, int lane, int i) {
+    return *reinterpret_cast<const float4*>(stage + (4 * i + (lane >> 3)) * EPI_LD + 4 * (lane & 7));
+}
+
 // ---- host: tensor maps ------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -18,15 +18,19 @@
 // x rows prefetched into L2 at tile start, register-double-buffered loads).
 //
 //   mode PM_R    R_in = x+ * (S W+) + x- * (S W-)          A = S [M,K]      B0/B1 = W+^T / W-^T [N,K]   (layers_ours.py:207-230)
-//   mode PM_S1   S = sd(R, ((y - b) + |x| |W|^T) / 2)       A = x -> |x|     B0 = |W| [N,K]
+//   mode PM_S1   S = sd(R, ((y - b) + |x| |W|^T) / 2)       A = tf32(|x|)    B0 = |W| [N,K]
 //   mode PM_LIN  C = epi(A B^T)  single-pass TF32            A = dy           B0 = tf32(W)^T  (activation-gradient backward)
 //
+// The |x| operand of PM_S1 is produced by a separate elementwise pre-pass (te_tc_abs_tf32, one read + one write of x):
+// a first version transformed the tile in shared memory (4 warps between the TMA arrival and the MMA, remote arrives onto
+// the leader's barrier) and ran at 26 % tensor-memory-pipe activity against 78-82 % for the transform-free modes at the
+// same shape (profiles/r02_ncu_pair.md) — the cvt/fence/arrive chain per 512-cycle k-block was the critical path.
+//
 // Warp roles (both CTAs of the pair): warp 0 TMA producer, warp 1 TMEM allocator + (leader CTA only) MMA issuer,
-// warps 2-9 epilogue (lane quarter = warp % 4, column half = (warp - 2) / 4), warps 10-13 (PM_S1 only) |x| transform.
+// warps 2-9 epilogue (lane quarter = warp % 4, column half = (warp - 2) / 4).
 // Barriers per CTA:
-//   full[s]     TMA bytes: local (PM_S1: this CTA's own tile is transformed first) or the LEADER's (other modes: both
-//               CTAs' cp.async.bulk.tensor .cta_group::2 count on the leader's barrier, expect_tx = both CTAs' bytes)
-//   ready[s]    leader, PM_S1: one remote arrive per transform warp of both CTAs (8)
+//   full[s]     LEADER's: both CTAs' cp.async.bulk.tensor .cta_group::2 count on the leader's barrier (expect_tx = both
+//               CTAs' bytes)
 //   empty[s]    local, tcgen05.commit.cta_group::2 multicast from the leader when the MMAs of the stage retire
 //   accfull[b]  local, multicast commit after the last k-block of a tile into accumulator buffer b
 //   accfree[b]  leader, one remote arrive per epilogue warp of both CTAs (16) once buffer b has been read out
@@ -48,13 +52,12 @@ struct PairParams {
 
 template <int MODE> struct PairCfg {
     static constexpr int NB = (MODE == PM_R) ? 2 : 1;                         // weight operands per stage
-    static constexpr bool XF = (MODE == PM_S1);                               // in-smem |x| transform of A
     static constexpr int STAGE = A_BYTES + NB * BH_BYTES;                     // 48 KiB / 32 KiB
-    static constexpr int NST = (MODE == PM_R) ? 4 : 6;                        // 192 KiB ring
+    static constexpr int NST = (MODE == PM_R) ? 3 : 5;                        // 144 / 160 KiB ring (+ 36 KiB epilogue staging)
     static constexpr int ACC_BUFS = (MODE == PM_R) ? 1 : 2;                   // TMEM accumulator buffers of NB x 256 columns
-    static constexpr int THREADS = XF ? 448 : 320;
-    static constexpr int NBARS = 3 * NST + 4;
-    static constexpr int SMEM = NST * STAGE + 1024 + 8 * NBARS + 16;
+    static constexpr int THREADS = 320;
+    static constexpr int NBARS = 2 * NST + 4;
+    static constexpr int SMEM = NST * STAGE + 8 * EPI_STAGE_BYTES + 1024 + 8 * NBARS + 16;
 };
 
 constexpr int EPI_WARPS = 8;
@@ -78,17 +81,15 @@ te_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const __grid_constant__ CUtensorMap tmB1, const PairParams p) {
     using Cfg = PairCfg<MODE>;
     constexpr int NST = Cfg::NST, NB = Cfg::NB, STAGE = Cfg::STAGE, ACC_BUFS = Cfg::ACC_BUFS;
-    constexpr bool XF = Cfg::XF;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t bars = smem_base + NST * STAGE;
+    const uint32_t bars = smem_base + NST * STAGE + 8 * EPI_STAGE_BYTES;
     auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto ready_bar = [&](int s) { return bars + 8u * (NST + s); };
-    auto empty_bar = [&](int s) { return bars + 8u * (2 * NST + s); };
-    auto accfull_bar = [&](int b) { return bars + 8u * (3 * NST + b); };
-    auto accfree_bar = [&](int b) { return bars + 8u * (3 * NST + 2 + b); };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + NST * STAGE + 8 * Cfg::NBARS);
+    auto empty_bar = [&](int s) { return bars + 8u * (NST + s); };
+    auto accfull_bar = [&](int b) { return bars + 8u * (2 * NST + b); };
+    auto accfree_bar = [&](int b) { return bars + 8u * (2 * NST + 2 + b); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + NST * STAGE + 8 * EPI_STAGE_BYTES + 8 * Cfg::NBARS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -104,7 +105,6 @@ te_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (NB == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB1) : "memory");
         for (int s = 0; s < NST; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(ready_bar(s), 2u * 4u);
             mbar_init(empty_bar(s), 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -135,16 +135,10 @@ te_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const uint32_t ph = (it / NST) & 1u;
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t sa = smem_base + s * STAGE;
-                    if (XF) {
-                        mbar_arrive_expect_tx(full_bar(s), STAGE);
-                        tma_load_2d(sa, &tmA, full_bar(s), kk * BK, m0);
-                        tma_load_2d(sa + A_BYTES, &tmB0, full_bar(s), kk * BK, n0);
-                    } else {
-                        if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * STAGE);
-                        tma2_load_2d(sa, &tmA, full_bar(s), kk * BK, m0);
-                        tma2_load_2d(sa + A_BYTES, &tmB0, full_bar(s), kk * BK, n0);
-                        if (NB == 2) tma2_load_2d(sa + A_BYTES + BH_BYTES, &tmB1, full_bar(s), kk * BK, n0);
-                    }
+                    if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * STAGE);
+                    tma2_load_2d(sa, &tmA, full_bar(s), kk * BK, m0);
+                    tma2_load_2d(sa + A_BYTES, &tmB0, full_bar(s), kk * BK, n0);
+                    if (NB == 2) tma2_load_2d(sa + A_BYTES + BH_BYTES, &tmB1, full_bar(s), kk * BK, n0);
                 }
             }
         }
@@ -162,7 +156,7 @@ te_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int kk = 0; kk < kb; ++kk, ++it) {
                     const int s = (int)(it % NST);
                     const uint32_t ph = (it / NST) & 1u;
-                    mbar_wait_cluster(XF ? ready_bar(s) : full_bar(s), ph);
+                    mbar_wait_cluster(full_bar(s), ph);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_base + s * STAGE;
                     const uint64_t adesc = make_smem_desc(sa);
@@ -180,145 +174,123 @@ te_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
         }
         __syncwarp();
-    } else if (warp < 2 + EPI_WARPS) {
+    } else {
         // ================= epilogue: warps 2..9 =================
+        // All global traffic of the epilogue is issued in the TRANSPOSED layout of epi_read_t (4 rows x 128 B per warp
+        // instruction): the accumulator chunk goes TMEM -> registers (lane = row) -> per-warp staging buffer -> registers
+        // (lane = 4 columns of row 4i + lane/8), the operands (x / R, y / h) are loaded and the result stored in that layout.
         const int q = warp & 3;                      // TMEM lane quarter this warp may read
         const int half = (warp - 2) >> 2;            // column half of the 256-column tile
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        float* stage = reinterpret_cast<float*>(smem_al + NST * STAGE + (warp - 2) * EPI_STAGE_BYTES);
+        const int tr = lane >> 3, tc = 4 * (lane & 7);         // transposed coordinates inside a 32 x 32 chunk (row 4i + tr)
         uint32_t ti = 0;
         for (int t = cluster_id; t < ntiles; t += nclusters, ++ti) {
-            const int m0 = ((t / p.tiles_n) * 2 + (int)rank) * BM, n0 = (t % p.tiles_n) * BN + half * (BN / 2);
-            const int row = m0 + q * 32 + lane;
-            const bool live = row < p.M;
+            const int m0 = ((t / p.tiles_n) * 2 + (int)rank) * BM + q * 32, n0 = (t % p.tiles_n) * BN + half * (BN / 2);
             const uint32_t b = ti % ACC_BUFS;
-            const float* erow = p.E ? p.E + (long long)row * p.lde + n0 : nullptr;
-            const float* yrow = (MODE == PM_S1) ? p.Y + (long long)row * p.ldy + n0 : nullptr;
-            float* crow = p.C + (long long)row * p.ldc + n0;
             // the epilogue operands of this tile are streamed from HBM exactly once: pull them into L2 while the MMAs run
-            if (live) {
-                if (erow) {
+            if (m0 + lane < p.M) {
+                if (p.E) {
+                    const float* e = p.E + (long long)(m0 + lane) * p.lde + n0;
 #pragma unroll
-                    for (int j = 0; j < BN / 2; j += 32) prefetch_l2(erow + j);
+                    for (int j = 0; j < BN / 2; j += 32) prefetch_l2(e + j);
                 }
                 if (MODE == PM_S1) {
+                    const float* y = p.Y + (long long)(m0 + lane) * p.ldy + n0;
 #pragma unroll
-                    for (int j = 0; j < BN / 2; j += 32) prefetch_l2(yrow + j);
+                    for (int j = 0; j < BN / 2; j += 32) prefetch_l2(y + j);
                 }
             }
             mbar_wait(accfull_bar(b), (ti / ACC_BUFS) & 1u);
             tcgen05_fence_after();
             const uint32_t tcol = tlane + b * (uint32_t)(NB * BN) + (uint32_t)(half * (BN / 2));
-            if (MODE == PM_S1) {
-                // 16-column chunks: R, y and the accumulator chunk stay in registers beside the rare exact-recompute call
-#pragma unroll 1
-                for (int c = 0; c < BN / 2 / 16; ++c) {
-                    uint32_t acc[16];
-                    tmem_ld16(tcol + (uint32_t)(c * 16), acc);
-                    float4 r[4], y[4];
-                    if (live) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            r[j] = *reinterpret_cast<const float4*>(erow + c * 16 + j * 4);
-                            y[j] = *reinterpret_cast<const float4*>(yrow + c * 16 + j * 4);
-                        }
-                    }
-                    tmem_ld_wait();
-                    if (live) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c * 16 + j * 4));
-                            const float yy[4] = {y[j].x - bb.x, y[j].y - bb.y, y[j].z - bb.z, y[j].w - bb.w};
-                            const float rr[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
-                            float o[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                // x+ W+^T + x- W-^T == ( x W^T + |x| |W|^T ) / 2 ,  x W^T = y - bias (saved forward output).
-                                // The true value is a sum of non-negative products; the identity cancels when almost every
-                                // product is negative (x W^T ~ -|x||W|^T): then Z carries an absolute error of ~2^-11 * a and
-                                // is recomputed exactly (rare; all-zero rows / columns give an exact 0 on both sides).
-                                const float a = __uint_as_float(acc[4 * j + u]);
-                                float z = 0.5f * (yy[u] + a);
-                                if (z < a * 0.0078125f && a > 0.f)
-                                    z = zplus_exact(p.X + (long long)row * p.ldx, p.Wp + (long long)(n0 + c * 16 + j * 4 + u) * p.K,
-                                                    p.Wn + (long long)(n0 + c * 16 + j * 4 + u) * p.K, p.K);
-                                o[u] = to_tf32(te_sd(rr[u], fmaxf(z, 0.f)));
-                            }
-                            *reinterpret_cast<float4*>(crow + c * 16 + j * 4) = make_float4(o[0], o[1], o[2], o[3]);
-                        }
-                    }
-                }
-            } else {
 #pragma unroll 1
             for (int c = 0; c < BN / 2 / 32; ++c) {
+                const int col = n0 + c * 32 + tc;
                 uint32_t acc[32];
                 tmem_ld32(tcol + (uint32_t)(c * 32), acc);
                 if (MODE == PM_R) {
                     uint32_t accn[32];
                     tmem_ld32(tcol + (uint32_t)(BN + c * 32), accn);
                     float4 x[8];
-                    if (live) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) x[j] = *reinterpret_cast<const float4*>(erow + c * 32 + j * 4);
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = m0 + 4 * i + tr;
+                        x[i] = (row < p.M) ? *reinterpret_cast<const float4*>(p.E + (long long)row * p.lde + col) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     tmem_ld_wait();
-                    if (live) {
+                    epi_stage_rows(stage, lane, acc);
+                    float4 ap[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float4 o;
-                            o.x = fmaxf(x[j].x, 0.f) * __uint_as_float(acc[4 * j + 0]) + fminf(x[j].x, 0.f) * __uint_as_float(accn[4 * j + 0]);
-                            o.y = fmaxf(x[j].y, 0.f) * __uint_as_float(acc[4 * j + 1]) + fminf(x[j].y, 0.f) * __uint_as_float(accn[4 * j + 1]);
-                            o.z = fmaxf(x[j].z, 0.f) * __uint_as_float(acc[4 * j + 2]) + fminf(x[j].z, 0.f) * __uint_as_float(accn[4 * j + 2]);
-                            o.w = fmaxf(x[j].w, 0.f) * __uint_as_float(acc[4 * j + 3]) + fminf(x[j].w, 0.f) * __uint_as_float(accn[4 * j + 3]);
-                            *reinterpret_cast<float4*>(crow + c * 32 + j * 4) = o;
+                    for (int i = 0; i < 8; ++i) ap[i] = epi_read_t(stage, lane, i);
+                    epi_stage_rows(stage, lane, accn);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 an = epi_read_t(stage, lane, i);
+                        const int row = m0 + 4 * i + tr;
+                        float4 o;
+                        o.x = fmaxf(x[i].x, 0.f) * ap[i].x + fminf(x[i].x, 0.f) * an.x;
+                        o.y = fmaxf(x[i].y, 0.f) * ap[i].y + fminf(x[i].y, 0.f) * an.y;
+                        o.z = fmaxf(x[i].z, 0.f) * ap[i].z + fminf(x[i].z, 0.f) * an.z;
+                        o.w = fmaxf(x[i].w, 0.f) * ap[i].w + fminf(x[i].w, 0.f) * an.w;
+                        if (row < p.M) *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) = o;
+                    }
+                } else if (MODE == PM_S1) {
+                    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                    tmem_ld_wait();
+                    epi_stage_rows(stage, lane, acc);
+#pragma unroll 2
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = m0 + 4 * i + tr;
+                        if (row >= p.M) continue;
+                        const float4 r = *reinterpret_cast<const float4*>(p.E + (long long)row * p.lde + col);
+                        const float4 y = *reinterpret_cast<const float4*>(p.Y + (long long)row * p.ldy + col);
+                        const float4 a4 = epi_read_t(stage, lane, i);
+                        const float yy[4] = {y.x - bb.x, y.y - bb.y, y.z - bb.z, y.w - bb.w};
+                        const float rr[4] = {r.x, r.y, r.z, r.w};
+                        const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
+                        float o[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            // x+ W+^T + x- W-^T == ( x W^T + |x| |W|^T ) / 2 ,  x W^T = y - bias (saved forward output).
+                            // The true value is a sum of non-negative products; the identity cancels when almost every
+                            // product is negative (x W^T ~ -|x||W|^T): then Z carries an absolute error of ~2^-11 * a and
+                            // is recomputed exactly (rare; all-zero rows / columns give an exact 0 on both sides).
+                            float z = 0.5f * (yy[u] + aa[u]);
+                            if (z < aa[u] * 0.0078125f && aa[u] > 0.f)
+                                z = zplus_exact(p.X + (long long)row * p.ldx, p.Wp + (long long)(col + u) * p.K,
+                                                p.Wn + (long long)(col + u) * p.K, p.K);
+                            o[u] = to_tf32(te_sd(rr[u], fmaxf(z, 0.f)));
                         }
+                        *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) = make_float4(o[0], o[1], o[2], o[3]);
                     }
                 } else {
                     float4 e[8];
-                    if (EPI == PE_GELU_BWD && live) {
+                    if (EPI == PE_GELU_BWD) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) e[j] = *reinterpret_cast<const float4*>(erow + c * 32 + j * 4);
-                    }
-                    tmem_ld_wait();
-                    if (live) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float4 o = make_float4(__uint_as_float(acc[4 * j + 0]), __uint_as_float(acc[4 * j + 1]),
-                                                   __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
-                            if (EPI == PE_GELU_BWD) {
-                                o.x *= te_gelu_grad(e[j].x); o.y *= te_gelu_grad(e[j].y);
-                                o.z *= te_gelu_grad(e[j].z); o.w *= te_gelu_grad(e[j].w);
-                            }
-                            *reinterpret_cast<float4*>(crow + c * 32 + j * 4) = o;
+                        for (int i = 0; i < 8; ++i) {
+                            const int row = m0 + 4 * i + tr;
+                            e[i] = (row < p.M) ? *reinterpret_cast<const float4*>(p.E + (long long)row * p.lde + col) : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
                     }
+                    tmem_ld_wait();
+                    epi_stage_rows(stage, lane, acc);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = m0 + 4 * i + tr;
+                        float4 o = epi_read_t(stage, lane, i);
+                        if (EPI == PE_GELU_BWD) {
+                            o.x *= te_gelu_grad(e[i].x); o.y *= te_gelu_grad(e[i].y);
+                            o.z *= te_gelu_grad(e[i].z); o.w *= te_gelu_grad(e[i].w);
+                        }
+                        if (row < p.M) *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) = o;
+                    }
                 }
-            }
             }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(map_to_rank0(accfree_bar(b)));
-        }
-    } else if (XF) {
-        // ================= |x| transform: warps 10..13 (PM_S1) =================
-        const int et = threadIdx.x - 32 * (2 + EPI_WARPS);            // 0..127
-        uint32_t it = 0;
-        for (int t = cluster_id; t < ntiles; t += nclusters) {
-            for (int kk = 0; kk < kb; ++kk, ++it) {
-                const int s = (int)(it % NST);
-                const uint32_t ph = (it / NST) & 1u;
-                mbar_wait(full_bar(s), ph);
-                float4* a4 = reinterpret_cast<float4*>(smem_al + s * STAGE);
-#pragma unroll
-                for (int i = 0; i < A_BYTES / 16 / XF_THREADS; ++i) {
-                    float4 v = a4[et + i * XF_THREADS];
-                    v.x = to_tf32(fabsf(v.x)); v.y = to_tf32(fabsf(v.y)); v.z = to_tf32(fabsf(v.z)); v.w = to_tf32(fabsf(v.w));
-                    a4[et + i * XF_THREADS] = v;
-                }
-                fence_proxy_async();                // generic-proxy writes -> visible to the tensor-core (async) proxy
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(map_to_rank0(ready_bar(s)));
-            }
         }
     }
     tcgen05_fence_before();
@@ -326,6 +298,18 @@ te_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// |x| rounded to TF32 (rna): the A operand of the single-pass S kernel.  x rows at stride ldx -> compact [rows, cols].
+__global__ void abs_tf32_kernel(const float* __restrict__ x, long long ldx, float* __restrict__ out, long long rows, int cols4) {
+    const long long total = rows * cols4;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long r = t / cols4;
+        const int c = (int)(t - r * cols4);
+        float4 v = *reinterpret_cast<const float4*>(x + r * ldx + 4 * c);
+        v.x = to_tf32(fabsf(v.x)); v.y = to_tf32(fabsf(v.y)); v.z = to_tf32(fabsf(v.z)); v.w = to_tf32(fabsf(v.w));
+        *reinterpret_cast<float4*>(out + t * 4) = v;
     }
 }
 
@@ -375,17 +359,29 @@ bool te_tc_pair_supported(long long rows, int K, int N, long long lda) {
     return rows > 0 && rows < (1LL << 31) && K % BK == 0 && N % BN == 0 && lda % 4 == 0 && get_encode() != nullptr;
 }
 
+int te_tc_abs_tf32(const float* x, long long ldx, float* out, long long rows, int cols, cudaStream_t st) {
+    if (cols % 4 != 0 || ldx % 4 != 0 || !a16(x) || !a16(out)) { te_set_last_error("te_tc_abs_tf32: alignment"); return TE_ERR_ARG; }
+    const long long total = rows * (cols / 4);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    abs_tf32_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, ldx, out, rows, cols / 4);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+
 // S = sd(R, ((y - bias) + |x||W|^T)/2)  [rows, out]   (single-pass denominator, see te_tc_zplus.cu)
-int te_tc_pair_zplus_s1(const float* x, long long ldx, const float* derived, const float* r, long long ldr, const float* y,
-                        long long ldy, const float* bias, float* s_out, long long rows, int in_features, int out_features,
-                        cudaStream_t st) {
+// xabs: scratch [rows, in] that receives tf32(|x|)
+int te_tc_pair_zplus_s1(const float* x, long long ldx, float* xabs, const float* derived, const float* r, long long ldr,
+                        const float* y, long long ldy, const float* bias, float* s_out, long long rows, int in_features,
+                        int out_features, cudaStream_t st) {
     const long long n = (long long)in_features * out_features;
+    TE_TRY(te_tc_abs_tf32(x, ldx, xabs, rows, in_features, st));
     PairParams p;
     memset(&p, 0, sizeof(p));
     p.M = (int)rows; p.N = out_features; p.K = in_features;
     p.E = r; p.lde = ldr; p.C = s_out; p.ldc = out_features; p.Y = y; p.ldy = ldy; p.bias = bias;
     p.X = x; p.ldx = ldx; p.Wp = derived; p.Wn = derived + n;
-    return launch_pair<PM_S1, PE_STORE>(x, ldx, derived + 8 * n, nullptr, p, st);
+    return launch_pair<PM_S1, PE_STORE>(xabs, in_features, derived + 8 * n, nullptr, p, st);
 }
 
 // R_in = x+ * (S W+) + x- * (S W-)  [rows, in]

@@ -582,7 +582,8 @@ int te_tc_prepare_weights(const float* w, float* derived, int in_features, int o
 
 int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* derived, const float* r, long long ldr,
                                float* out, float* s_scratch, long long rows, int in_features, int out_features, cudaStream_t st,
-                               const float* y, long long ldy, const float* bias, bool bf16) {
+                               const float* y, long long ldy, const float* bias, bool bf16, long long ld_out, float* xabs) {
+    if (ld_out == 0) ld_out = in_features;
     if (!a16(x) || !a16(derived) || !a16(r) || !a16(out) || !a16(s_scratch)) {
         te_set_last_error("te_gemm_tc: operands must be 16-byte aligned");
         return TE_ERR_ARG;
@@ -591,11 +592,15 @@ int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* deriv
     const float *wp = derived, *wn = derived + n, *wpt = derived + 2 * n, *wnt = derived + 3 * n;
     // S = sd(R, x+ W+^T + x- W-^T)          A = x [rows, in] ; B = W+/- [out, in]
     const bool rb = bf16 && (out_features % 64 == 0);          // S as bf16, R kernel with bf16 operands (kind::f16)
-    if (!rb && use_persistent() && y && a16(y) && ldy % 4 == 0 && (!bias || a16(bias)) &&
+    if (!rb && use_persistent() && xabs && a16(xabs) && y && a16(y) && ldy % 4 == 0 && (!bias || a16(bias)) &&
         te_tc_pair_supported(rows, in_features, out_features, ldx) && te_tc_pair_supported(rows, out_features, in_features, out_features)) {
         // persistent CTA-pair kernels (te_tc_pair.cu): single-pass S, then R with the A operand shared by both products
-        TE_TRY(te_tc_pair_zplus_s1(x, ldx, derived, r, ldr, y, ldy, bias, s_scratch, rows, in_features, out_features, st));
-        return te_tc_pair_zplus_r(s_scratch, derived, x, ldx, out, in_features, rows, in_features, out_features, st);
+        TE_TRY(te_tc_pair_zplus_s1(x, ldx, xabs, derived, r, ldr, y, ldy, bias, s_scratch, rows, in_features, out_features, st));
+        return te_tc_pair_zplus_r(s_scratch, derived, x, ldx, out, ld_out, rows, in_features, out_features, st);
+    }
+    if (ld_out != in_features) {
+        te_set_last_error("te_gemm_tc: a strided output needs the persistent pair kernels");
+        return TE_ERR_UNSUPPORTED;
     }
     if (y && a16(y) && ldy % 4 == 0 && (!bias || a16(bias))) {
         // single pass: Z = ((y - bias) + |x| |W|^T) / 2 with the saved forward output y = x W^T + bias

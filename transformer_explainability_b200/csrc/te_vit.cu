@@ -421,13 +421,21 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
         const HeadOp k = head_rows(a.qkv + d.D, 3 * d.D, d.N, d.dh);
         const HeadOp v = head_rows(a.qkv + 2 * d.D, 3 * d.D, d.N, d.dh);
         // Block.relprop :203-213
+        // In the TOP block the relevance that enters is non-zero only in the pooled token's row (IndexSelect.relprop, a7),
+        // and every rule down to the proj rule is row-wise: Add / Clone map a zero row to a zero row, the z+ rule computes
+        // each output row from the same input row.  So the three z+ rules of the top block run on the B pooled rows only
+        // (row stride N*D / N*F) — exact (SURVEY.md 8a "structural savings"), bit-identical rows, 1/N of the work.
+        const bool top = (l == d.L - 1) && !cfg->distilled && te_engine_cls_rows();
+        const long long zr = top ? d.B : d.M;                          // rows the z+ rules of this block touch
+        const long long sD = top ? (long long)d.N * d.D : d.D, sF = top ? (long long)d.N * d.F : d.F;
         TE_TRY(te_launch_add_relprop(a.x_mid, a.mlp_out, R, R1, R2, ws.addpart, d.B, (long long)d.N * d.D, st));   // add2
-        TE_TRY(te_zplus_linear_relprop_ldr(a.g, d.F, bw.fc2w, dw.fc2, R2, d.D, RF, S, d.M, d.F, d.D, st, a.mlp_out, d.D, bw.fc2b, zb));                       // fc2 ; GELU id
-        TE_TRY(te_zplus_linear_relprop_ldr(a.xn2, d.D, bw.fc1w, dw.fc1, RF, d.F, R2, SF, d.M, d.D, d.F, st, a.h, d.F, bw.fc1b, zb));                    // fc1 ; norm2 id
+        TE_TRY(te_zplus_linear_relprop_ldr(a.g, sF, bw.fc2w, dw.fc2, R2, sD, RF, S, zr, d.F, d.D, st, a.mlp_out, sD, bw.fc2b, zb, sF, SF));                       // fc2 ; GELU id
+        TE_TRY(te_zplus_linear_relprop_ldr(a.xn2, sD, bw.fc1w, dw.fc1, RF, sF, R2, SF, zr, d.D, d.F, st, a.h, sF, bw.fc1b, zb, sD, S));                    // fc1 ; norm2 id
         TE_TRY(te_launch_clone_relprop(a.x_mid, R1, R2, nullptr, R, MD, st));                                      // clone2
         TE_TRY(te_launch_add_relprop(a.x_in, a.attn_out, R, R1, R2, ws.addpart, d.B, (long long)d.N * d.D, st));    // add1
         // Attention.relprop :154-177
-        TE_TRY(te_zplus_linear_relprop_ldr(a.ctx, d.D, bw.projw, dw.proj, R2, d.D, R3, S, d.M, d.D, d.D, st, a.attn_out, d.D, bw.projb, zb));                    // proj
+        if (top) TE_TRY(te_launch_fill(R3, 0.f, MD, st));                                   // rows the strided rule does not write
+        TE_TRY(te_zplus_linear_relprop_ldr(a.ctx, sD, bw.projw, dw.proj, R2, sD, R3, S, zr, d.D, d.D, st, a.attn_out, sD, bw.projb, zb, sD, S + MD));                    // proj
         // matmul2 rule: Z = attn v is the saved ctx itself (bit-identical recomputation in the reference)
         TE_TRY(te_launch_sd(R3, a.ctx, S, MD, st));
         TE_TRY(te_util::attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, S, d.D, a.qkv + 2 * d.D, 3 * d.D, a.cam, a.P, 0.5f,
@@ -442,7 +450,7 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
                                 TE_EPI_MUL, st));                                   // cam_q
         TE_TRY(te_util::attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, S1, 1, a.qkv, 3 * d.D, Rqkv + d.D, 3 * d.D, a.qkv + d.D, 0.5f,
                                 TE_EPI_MUL, st));                                   // cam_k
-        TE_TRY(te_zplus_linear_relprop_ldr(a.xn1, d.D, bw.qkvw, dw.qkv, Rqkv, 3 * d.D, R2, S, d.M, d.D, 3 * d.D, st, a.qkv, 3 * d.D, bw.qkvb, zb));               // qkv ; norm1 id
+        TE_TRY(te_zplus_linear_relprop_ldr(a.xn1, d.D, bw.qkvw, dw.qkv, Rqkv, 3 * d.D, R2, S, d.M, d.D, 3 * d.D, st, a.qkv, 3 * d.D, bw.qkvb, zb, 0, RF));               // qkv ; norm1 id
         TE_TRY(te_launch_clone_relprop(a.x_in, R1, R2, nullptr, R, MD, st));                                       // clone1
     }
 

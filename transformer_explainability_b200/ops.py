@@ -117,7 +117,7 @@ def linear_relprop(x, w, r, tensor_cores=False, y=None, bias=None, bf16=False):
     out = torch.empty_like(x)
     nscratch = rows * w.shape[0]
     if tensor_cores:
-        nscratch = (nscratch + 63) // 64 * 64 + 10 * w.numel()
+        nscratch = (nscratch + 63) // 64 * 64 + 10 * w.numel() + x.numel()
     scratch = torch.empty(nscratch, device=x.device, dtype=torch.float32)
     flags = _lib.FLAG_ZPLUS_TENSOR_CORES if tensor_cores else 0
     if bf16:
@@ -271,8 +271,8 @@ def attribution_rollout(grad, cam, start_layer=0, normalize=False, fused=False, 
     ``ViT_LRP.py:357-368`` (normalize=False) / ``ExplanationGenerator.py:47-57`` (normalize=True)."""
     _req(grad, cam)
     _same_shape("attribution_rollout", grad, cam)
-    if grad.dim() != 5 or grad.shape[4] < grad.shape[3] or grad.shape[4] % 4 != 0:
-        raise ValueError("attribution_rollout: grad, cam [L,B,H,N,ld] with ld >= N, ld % 4 == 0 expected")
+    if grad.dim() != 5 or grad.shape[4] < grad.shape[3]:
+        raise ValueError("attribution_rollout: grad, cam [L,B,H,N,ld] with ld >= N expected")
     L, B, H, N, ld = grad.shape
     lib = _lib.load()
     nbytes = check(lib.te_rollout_workspace_bytes(L, B, N), "te_rollout_workspace_bytes")
