@@ -126,13 +126,11 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int q = warp & 3;
         const int i = m0 + q * 32 + lane;                       // query row inside the sample
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-        const bool live = i < p.N;
-        const long long rowoff = ((long long)bh * p.N + i) * p.ld_out + n0;
         const int ncols = min(p.N - n0, BN);              // valid key columns of this tile
         const int nchunks = (ncols + 31) / 32;
-        // E (attention probabilities / attn_cam) comes from HBM: its loads are issued one 32-column chunk ahead so
-        // that their latency overlaps the TMEM read, the math and the stores of the previous chunk.  Reading a
-        // full float4 whose tail lies in the row padding is memory-safe (ld_out % 4 == 0); the tail is masked.
+        // per-warp staging buffer of the coalesced epilogue: the operand buffer is idle once the accumulator is complete
+        float* stage = reinterpret_cast<float*>(smem_al + (warp - 2) * EPI_STAGE_BYTES);
+        const int tr = lane >> 3, tc = 4 * (lane & 7);
         if (EPI == AT_SOFTMAX) {
             // softmax(alpha * A B^T) over the key axis, fused: every thread owns one query row whose N <= 256 scores sit
             // in its TMEM lane, so the row maximum, the sum of exponentials and the normalised probabilities come from
@@ -165,70 +163,61 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 tmem_st32(tlane + (uint32_t)(cc * 32), acc);
             }
             tmem_st_wait();
+            // pass 3: normalise in the row layout, store in the transposed (coalesced) layout of epi_read_t
 #pragma unroll 1
             for (int cc = 0; cc < nchunks; ++cc) {
                 uint32_t acc[32];
                 tmem_ld32(tlane + (uint32_t)(cc * 32), acc);
                 tmem_ld_wait();
-                if (live) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int col = cc * 32 + j * 4;
-                        if (col < ncols) {
-                            float o[4];
+                for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) / sum);   // padding holds e = 0
+                epi_stage_rows(stage, lane, acc);
+                const int col = cc * 32 + tc;
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) o[u] = __uint_as_float(acc[j * 4 + u]) / sum;   // padding holds e = 0
-                            *reinterpret_cast<float4*>(p.out + rowoff + col) = make_float4(o[0], o[1], o[2], o[3]);
-                        }
-                    }
+                for (int i2 = 0; i2 < 8; ++i2) {
+                    const int r = m0 + q * 32 + 4 * i2 + tr;
+                    if (r < p.N && col < ncols)
+                        *reinterpret_cast<float4*>(p.out + ((long long)bh * p.N + r) * p.ld_out + n0 + col) = epi_read_t(stage, lane, i2);
                 }
             }
         } else {
-        float4 ebuf[2][8];
-        auto load_e = [&](int c, float4 (&buf)[8]) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int col = c * 32 + j * 4;
-                buf[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (EPI != AT_STORE && live && col < ncols) buf[j] = __ldcs(reinterpret_cast<const float4*>(p.E + rowoff + col));
-            }
-        };
-        load_e(0, ebuf[0]);
+        // E and out are accessed in the transposed layout of epi_read_t (4 rows x 128 B per warp instruction); the loads of
+        // E are issued before the TMEM read completes.  A float4 whose tail lies in the row padding is memory-safe
+        // (ld_out % 4 == 0); the padding columns [ncols, ...) of the last float4 are written as zeros.
         mbar_wait(accum_bar, 0);
         tcgen05_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < nchunks; c += 2) {
+        for (int cc = 0; cc < nchunks; ++cc) {
+            uint32_t acc[32];
+            tmem_ld32(tlane + (uint32_t)(cc * 32), acc);
+            const int col = cc * 32 + tc;
+            float4 e4[8];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int cc = c + half;
-                if (cc < nchunks) {
-                    if (cc + 1 < nchunks) load_e(cc + 1, ebuf[half ^ 1]);
-                    uint32_t acc[32];
-                    tmem_ld32(tlane + (uint32_t)(cc * 32), acc);
-                    tmem_ld_wait();
-                    if (live) {
+            for (int i2 = 0; i2 < 8; ++i2) {
+                const int r = m0 + q * 32 + 4 * i2 + tr;
+                e4[i2] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (EPI != AT_STORE && r < p.N && col < ncols)
+                    e4[i2] = __ldcs(reinterpret_cast<const float4*>(p.E + ((long long)bh * p.N + r) * p.ld_out + n0 + col));
+            }
+            tmem_ld_wait();
+            epi_stage_rows(stage, lane, acc);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int col = cc * 32 + j * 4;
-                            if (col < ncols) {
-                                const float e[4] = {ebuf[half][j].x, ebuf[half][j].y, ebuf[half][j].z, ebuf[half][j].w};
-                                float o[4];
+            for (int i2 = 0; i2 < 8; ++i2) {
+                const int r = m0 + q * 32 + 4 * i2 + tr;
+                if (r >= p.N || col >= ncols) continue;
+                const float4 a4 = epi_read_t(stage, lane, i2);
+                const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+                const float e[4] = {e4[i2].x, e4[i2].y, e4[i2].z, e4[i2].w};
+                float o[4];
 #pragma unroll
-                                for (int u = 0; u < 4; ++u) {
-                                    const float a = __uint_as_float(acc[j * 4 + u]);
-                                    if (EPI == AT_STORE) o[u] = p.alpha * a;
-                                    else if (EPI == AT_MUL) o[u] = p.alpha * a * e[u];
-                                    else o[u] = te_sd(e[u], p.alpha * a);
-                                }
-                                if (col + 3 < ncols) *reinterpret_cast<float4*>(p.out + rowoff + col) = make_float4(o[0], o[1], o[2], o[3]);
-                                else {
-#pragma unroll
-                                    for (int u = 0; u < 4; ++u) p.out[rowoff + col + u] = (col + u < ncols) ? o[u] : 0.f;   // zero the row padding
-                                }
-                            }
-                        }
-                    }
+                for (int u = 0; u < 4; ++u) {
+                    float v;
+                    if (EPI == AT_STORE) v = p.alpha * a[u];
+                    else if (EPI == AT_MUL) v = p.alpha * a[u] * e[u];
+                    else v = te_sd(e[u], p.alpha * a[u]);
+                    o[u] = (col + u < ncols) ? v : 0.f;                                  // zero the row padding
                 }
+                *reinterpret_cast<float4*>(p.out + ((long long)bh * p.N + r) * p.ld_out + n0 + col) = make_float4(o[0], o[1], o[2], o[3]);
             }
         }
         }   // EPI != AT_SOFTMAX

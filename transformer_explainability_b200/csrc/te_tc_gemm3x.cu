@@ -24,40 +24,46 @@ struct Tc3Params {
     float* C; long long ldc; float* C2; long long ldc2;
 };
 
-// epilogue of both 3xTF32 Linear kernels: one output row x 128 columns per thread, from the fp32 register sums
+// epilogue of both 3xTF32 Linear kernels from the fp32 register sums (one tile row x 128 columns per thread).  Global
+// memory is accessed in the transposed layout of epi_read_t (te_tc_common.cuh: 4 rows x 128 contiguous bytes per warp
+// instruction instead of 32 rows x 16 bytes): each 32-column chunk of the sums goes through the warp's staging buffer.
+// stage: 4608 bytes private to the warp — the idle operand ring (every MMA of the tile has retired when this runs).
 template <int EPI>
-__device__ __forceinline__ void gemm3x_epilogue(const Tc3Params& p, const float (&sum)[128], int row, int cbase) {
-        if (row < p.M) {
-            const float* erow = p.E ? p.E + (long long)row * p.lde + cbase : nullptr;
-            float* crow = p.C + (long long)row * p.ldc + cbase;
-            float* c2row = p.C2 ? p.C2 + (long long)row * p.ldc2 + cbase : nullptr;
+__device__ __forceinline__ void gemm3x_epilogue(const Tc3Params& p, const float (&sum)[128], float* stage, int lane, int row0,
+                                                int cbase) {
+    const int tr = lane >> 3, tc = 4 * (lane & 7);
 #pragma unroll
-            for (int j = 0; j < 128; j += 4) {
-                float o[4], o2[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};
-                if (EPI == EP_BIAS || EPI == EP_BIAS_GELU || EPI == EP_BIAS_ADD) {
-                    if (p.bias) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
-                        bb[0] = t.x; bb[1] = t.y; bb[2] = t.z; bb[3] = t.w;
-                    }
-                }
-                if (EPI == EP_BIAS_ADD || EPI == EP_GELU_BWD) {
-                    const float4 t = *reinterpret_cast<const float4*>(erow + j);
-                    e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
-                }
+    for (int cc = 0; cc < 4; ++cc) {
+        uint32_t v[32];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float a = sum[j + u];
-                    if (EPI == EP_STORE) o[u] = a;
-                    else if (EPI == EP_BIAS) o[u] = a + bb[u];
-                    else if (EPI == EP_BIAS_GELU) { o[u] = a + bb[u]; o2[u] = te_gelu(o[u]); }
-                    else if (EPI == EP_BIAS_ADD) { o[u] = a + bb[u]; o2[u] = e[u] + o[u]; }
-                    else o[u] = a * te_gelu_grad(e[u]);
-                }
-                *reinterpret_cast<float4*>(crow + j) = make_float4(o[0], o[1], o[2], o[3]);
-                if (EPI == EP_BIAS_GELU || EPI == EP_BIAS_ADD)
-                    *reinterpret_cast<float4*>(c2row + j) = make_float4(o2[0], o2[1], o2[2], o2[3]);
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(sum[cc * 32 + j]);
+        epi_stage_rows(stage, lane, v);
+        const int col = cbase + cc * 32 + tc;
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((EPI == EP_BIAS || EPI == EP_BIAS_GELU || EPI == EP_BIAS_ADD) && p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = row0 + 4 * i + tr;
+            if (row >= p.M) continue;
+            const float4 a = epi_read_t(stage, lane, i);
+            float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (EPI == EP_BIAS_ADD || EPI == EP_GELU_BWD) e = *reinterpret_cast<const float4*>(p.E + (long long)row * p.lde + col);
+            float4 o, o2 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (EPI == EP_STORE) o = a;
+            else if (EPI == EP_BIAS) o = make_float4(a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w);
+            else if (EPI == EP_BIAS_GELU) {
+                o = make_float4(a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w);
+                o2 = make_float4(te_gelu(o.x), te_gelu(o.y), te_gelu(o.z), te_gelu(o.w));
+            } else if (EPI == EP_BIAS_ADD) {
+                o = make_float4(a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w);
+                o2 = make_float4(e.x + o.x, e.y + o.y, e.z + o.z, e.w + o.w);
+            } else {
+                o = make_float4(a.x * te_gelu_grad(e.x), a.y * te_gelu_grad(e.y), a.z * te_gelu_grad(e.z), a.w * te_gelu_grad(e.w));
             }
+            *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) = o;
+            if (EPI == EP_BIAS_GELU || EPI == EP_BIAS_ADD) *reinterpret_cast<float4*>(p.C2 + (long long)row * p.ldc2 + col) = o2;
         }
+    }
 }
 
 // The tensor core accumulates in fp32 with truncation (round-toward-zero) at every MMA, so a long reduction drifts
@@ -206,7 +212,8 @@ te_tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
 
         // ---- epilogue from the register sums ----
-        gemm3x_epilogue<EPI>(p, sum, m0 + q * 32 + lane, n0 + half * 128);
+        gemm3x_epilogue<EPI>(p, sum, reinterpret_cast<float*>(smem_al + (warp - 2) * EPI_STAGE_BYTES), lane, m0 + q * 32,
+                             n0 + half * 128);
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -377,7 +384,8 @@ te_tc_gemm3x2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         } else {
             for (int c = 0; c < nchunks; ++c) drain(c);
         }
-        gemm3x_epilogue<EPI>(p, sum, m0 + q * 32 + lane, n0 + half * 128);
+        gemm3x_epilogue<EPI>(p, sum, reinterpret_cast<float*>(smem_al + (warp - 2) * EPI_STAGE_BYTES), lane, m0 + q * 32,
+                             n0 + half * 128);
     }
     tcgen05_fence_before();
     cluster_sync_all();

@@ -238,32 +238,63 @@ te_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 } else if (MODE == PM_S1) {
                     float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                    tmem_ld_wait();
-                    epi_stage_rows(stage, lane, acc);
-#pragma unroll 2
+                    // every global load of the chunk is in flight before the TMEM read completes
+                    float4 r[8], y[8];
+#pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int row = m0 + 4 * i + tr;
-                        if (row >= p.M) continue;
-                        const float4 r = *reinterpret_cast<const float4*>(p.E + (long long)row * p.lde + col);
-                        const float4 y = *reinterpret_cast<const float4*>(p.Y + (long long)row * p.ldy + col);
+                        const bool ok = row < p.M;
+                        r[i] = ok ? *reinterpret_cast<const float4*>(p.E + (long long)row * p.lde + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        y[i] = ok ? *reinterpret_cast<const float4*>(p.Y + (long long)row * p.ldy + col) : bb;
+                    }
+                    tmem_ld_wait();
+                    epi_stage_rows(stage, lane, acc);
+                    // x+ W+^T + x- W-^T == ( x W^T + |x| |W|^T ) / 2 ,  x W^T = y - bias (saved forward output).  The true
+                    // value is a sum of non-negative products; the identity cancels when almost every product is negative
+                    // (x W^T ~ -|x||W|^T): then Z carries an absolute error of ~2^-11 * a and is recomputed exactly in a
+                    // second, warp-voted pass (rare; all-zero rows / columns give an exact 0 on both sides).
+                    unsigned redo = 0u;                                  // bit 4i+u: element u of iteration i is cancelled
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
                         const float4 a4 = epi_read_t(stage, lane, i);
-                        const float yy[4] = {y.x - bb.x, y.y - bb.y, y.z - bb.z, y.w - bb.w};
-                        const float rr[4] = {r.x, r.y, r.z, r.w};
+                        const float yy[4] = {y[i].x - bb.x, y[i].y - bb.y, y[i].z - bb.z, y[i].w - bb.w};
+                        const float rr[4] = {r[i].x, r[i].y, r[i].z, r[i].w};
                         const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
                         float o[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            // x+ W+^T + x- W-^T == ( x W^T + |x| |W|^T ) / 2 ,  x W^T = y - bias (saved forward output).
-                            // The true value is a sum of non-negative products; the identity cancels when almost every
-                            // product is negative (x W^T ~ -|x||W|^T): then Z carries an absolute error of ~2^-11 * a and
-                            // is recomputed exactly (rare; all-zero rows / columns give an exact 0 on both sides).
-                            float z = 0.5f * (yy[u] + aa[u]);
-                            if (z < aa[u] * 0.0078125f && aa[u] > 0.f)
-                                z = zplus_exact(p.X + (long long)row * p.ldx, p.Wp + (long long)(col + u) * p.K,
-                                                p.Wn + (long long)(col + u) * p.K, p.K);
+                            const float z = 0.5f * (yy[u] + aa[u]);
+                            if (z < aa[u] * 0.0078125f && aa[u] > 0.f) redo |= 1u << (4 * i + u);
                             o[u] = to_tf32(te_sd(rr[u], fmaxf(z, 0.f)));
                         }
-                        *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) = make_float4(o[0], o[1], o[2], o[3]);
+                        r[i] = make_float4(o[0], o[1], o[2], o[3]);          // r[] now holds S
+                    }
+                    if (__any_sync(0xffffffffu, redo != 0u)) {
+                        // r[] was overwritten: reload the relevance of the few cancelled elements
+                        for (int e = 0; e < 32; ++e) {
+                            if (!((redo >> e) & 1u)) continue;
+                            const int i = e >> 2, u = e & 3;
+                            const int row = m0 + 4 * i + tr;
+                            if (row >= p.M) continue;
+                            const float z = zplus_exact(p.X + (long long)row * p.ldx, p.Wp + (long long)(col + u) * p.K,
+                                                        p.Wn + (long long)(col + u) * p.K, p.K);
+                            const float sv = to_tf32(te_sd(p.E[(long long)row * p.lde + col + u], fmaxf(z, 0.f)));
+                            p.C[(long long)row * p.ldc + col + u] = sv;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = m0 + 4 * i + tr;
+                        if (row >= p.M) continue;
+                        float4 o = r[i];
+                        if (redo & (0xFu << (4 * i))) {                      // keep the exactly recomputed elements
+                            float* cp = p.C + (long long)row * p.ldc + col;
+                            if (redo & (1u << (4 * i + 0))) o.x = cp[0];
+                            if (redo & (1u << (4 * i + 1))) o.y = cp[1];
+                            if (redo & (1u << (4 * i + 2))) o.z = cp[2];
+                            if (redo & (1u << (4 * i + 3))) o.w = cp[3];
+                        }
+                        *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) = o;
                     }
                 } else {
                     float4 e[8];
