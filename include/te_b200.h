@@ -48,6 +48,9 @@ extern "C" {
                                          single-pass TF32 GEMMs (persistent CTA-pair kernel) instead of the 3xTF32 split.
                                          The gradients only enter the result linearly (relu(G * cam)), never a
                                          safe_divide denominator: measured effect in profiles/ (r02 parity table) */
+#define TE_FLAG_RULES_LRP 512u         /* the rule library of modules/layers_lrp.py (baselines/ViT/ViT_orig_LRP.py) instead of
+                                         modules/layers_ours.py: Linear divides its two halves by their OWN denominators
+                                         (layers_lrp.py:199-200), Add has no ratio normalisation (:98-100).  fp32 SIMT rules. */
 #define TE_FLAG_RELPROP_TO_INPUT 8u   /* finish the lowest block as well: relevance at the encoder input (what
                                          model.relprop() returns in the reference) is left in tensor "relevance_in" */
 
@@ -133,6 +136,11 @@ TE_API int te_vit_tensor(const te_vit_config* cfg, int batch, void* workspace, c
 TE_API int te_vit_relprop_pixels(const te_vit_config* cfg, const float* weights, const float* images, int batch,
                           float* pixel_maps, float* pixel_relevance, void* workspace, long long workspace_bytes,
                           void* stream);
+/* Same with the engine flags of the preceding te_vit_attribute call: TE_FLAG_RULES_LRP selects the layers_lrp Add rule for
+ * self.add.relprop (baselines/ViT/ViT_orig_LRP.py, method="full"). */
+TE_API int te_vit_relprop_pixels_ex(const te_vit_config* cfg, const float* weights, const float* images, int batch,
+                                    unsigned flags, float* pixel_maps, float* pixel_relevance, void* workspace,
+                                    long long workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * BERT sequence classifier  (BERT_explainability/modules/BERT/BertForSequenceClassification.py:12-88,
@@ -187,6 +195,7 @@ TE_API int te_bert_tensor(const te_bert_config* cfg, int batch, int seq, void* w
  * that each rule can be parity-tested against the reference layer class it replaces.
  * ---------------------------------------------------------------------------------------------- */
 /* Linear.relprop, alpha=1 (layers_ours.py:207-230): x [rows,in], w [out,in], r [rows,out] -> out [rows,in].
+ * flags & TE_FLAG_RULES_LRP: the layers_lrp variant (modules/layers_lrp.py:187-210, separate denominators).
  * scratch: rows*out floats; with TE_FLAG_ZPLUS_TENSOR_CORES: round_up(rows*out,64) + 10*in*out floats. */
 TE_API int te_linear_relprop(const float* x, const float* w, const float* r, float* out, float* scratch, int rows,
                       int in_features, int out_features, unsigned flags, void* stream);
@@ -199,7 +208,8 @@ TE_API int te_linear_relprop_ex(const float* x, const float* w, const float* bia
                          float* out, float* scratch, int rows, int in_features, int out_features, unsigned flags,
                          void* stream);
 /* Add.relprop (layers_ours.py:97-120) per sample: x1,x2,r [batch,per_sample] -> r1,r2.
- * scratch: batch*48 doubles. */
+ * scratch: batch*48 doubles; scratch == NULL selects the layers_lrp variant (modules/layers_lrp.py:48-60,98-100:
+ * r1 = x1*sd(r, x1+x2), r2 = x2*sd(r, x1+x2), no ratio normalisation). */
 TE_API int te_add_relprop(const float* x1, const float* x2, const float* r, float* r1, float* r2, void* scratch,
                    int batch, long long per_sample, void* stream);
 /* Clone.relprop (layers_ours.py:151-169): out = x * (sd(r1,x)+sd(r2,x)[+sd(r3,x)]); r3 may be NULL. */

@@ -113,6 +113,18 @@ def build_vit(name="vit_base_patch16_224", seed=0, dtype=torch.float32, state_di
     return model.to(dtype).eval()
 
 
+def build_vit_orig_lrp(state_dict=None, dtype=torch.float32, **kwargs):
+    """The reference's ``layers_lrp`` baseline model (``baselines/ViT/ViT_orig_LRP.py``: same architecture as ``ViT_LRP``
+    on the rule library of ``modules/layers_lrp.py``)."""
+    _ensure_path()
+    with _ref_imports():
+        import baselines.ViT.ViT_orig_LRP as m
+    model = m.VisionTransformer(**kwargs)
+    if state_dict is not None:
+        model.load_state_dict(state_dict)
+    return model.to(dtype).eval()
+
+
 def vit_generate_lrp(model, x, index=None, start_layer=0, method="transformer_attribution", taps=False):
     """``LRP(model).generate_LRP`` of the reference, B=1, on CPU.  Returns a dict."""
     with _ref_imports():

@@ -45,6 +45,26 @@ def linear_relprop(x, w, r):
     return px * (s @ pw) + nx * (s @ nw)
 
 
+def linear_relprop_lrp(x, w, r):
+    """``Linear.relprop`` of the ``layers_lrp`` baseline variant (``modules/layers_lrp.py:187-210``, alpha=1): the two
+    halves are divided by their OWN denominators, S1 = sd(R, x+ W+^T), S2 = sd(R, x- W-^T) (``:199-200``; the
+    ``layers_ours`` rule divides both by the sum), R_in = x+ * (S1 W+) + x- * (S2 W-)."""
+    pw = w.clamp(min=0)
+    nw = w.clamp(max=0)
+    px = x.clamp(min=0)
+    nx = x.clamp(max=0)
+    s1 = safe_divide(r, px @ pw.t())
+    s2 = safe_divide(r, nx @ nw.t())
+    return px * (s1 @ pw) + nx * (s2 @ nw)
+
+
+def add_relprop_simple(x1, x2, r):
+    """``Add.relprop`` of the ``layers_lrp`` variant = ``RelPropSimple.relprop`` (``modules/layers_lrp.py:48-60,98-100``):
+    S = sd(R, x1 + x2) ; outputs x1 * S, x2 * S — no ratio re-normalisation."""
+    s = safe_divide(r, x1 + x2)
+    return x1 * s, x2 * s
+
+
 def _per_sample_sum(t):
     return t.reshape(t.shape[0], -1).sum(dim=1).reshape([-1] + [1] * (t.dim() - 1))
 

@@ -105,8 +105,10 @@ def attention_gradients(cache, seed):
     return list(torch.autograd.grad(loss, attns, retain_graph=True))
 
 
-def relprop(params, cache, seed, start_layer=0, taps=None, to_input=False):
+def relprop(params, cache, seed, start_layer=0, taps=None, to_input=False, variant="ours"):
     """LRP pass; returns list (per block) of attn_cam [B,H,N,N] (``ViT_LRP.py:165``).
+    ``variant="lrp"``: the rule library of ``modules/layers_lrp.py`` (``baselines/ViT/ViT_orig_LRP.py``: Linear with
+    separate denominators, Add without ratio normalisation) instead of ``modules/layers_ours.py``.
 
     Blocks below ``start_layer`` are never consumed by the rollout and are returned as None.
     ``to_input=True`` runs every block to its end (what the reference always does, ``:331-332``) and
@@ -115,15 +117,17 @@ def relprop(params, cache, seed, start_layer=0, taps=None, to_input=False):
     cfg = cache["cfg"]
     p = params
     xf = cache["x_final_norm"]
+    lin = rules.linear_relprop_lrp if variant == "lrp" else rules.linear_relprop
+    add = rules.add_relprop_simple if variant == "lrp" else rules.add_relprop
     # head.relprop -> unsqueeze -> pool.relprop (IndexSelect) -> norm.relprop (identity)  :327-330
     if cfg.distilled:
         # extension: averaged logits = Add of two halves; seed relevance split evenly through both heads
-        r_cls = rules.linear_relprop(xf[:, 0], p["head.weight"], seed / 2)
-        r_dst = rules.linear_relprop(xf[:, 1], p["head_dist.weight"], seed / 2)
+        r_cls = lin(xf[:, 0], p["head.weight"], seed / 2)
+        r_dst = lin(xf[:, 1], p["head_dist.weight"], seed / 2)
         r = rules.index_select_relprop(xf, r_cls.unsqueeze(1), 0) + \
             rules.index_select_relprop(xf, r_dst.unsqueeze(1), 1)
     else:
-        r_cls = rules.linear_relprop(xf[:, 0], p["head.weight"], seed)
+        r_cls = lin(xf[:, 0], p["head.weight"], seed)
         r = rules.index_select_relprop(xf, r_cls.unsqueeze(1), 0)
     cams = [None] * cfg.depth
     for i in reversed(range(max(start_layer, 0), cfg.depth)):
@@ -134,23 +138,23 @@ def relprop(params, cache, seed, start_layer=0, taps=None, to_input=False):
             taps[i] = t
             t["r_in"] = r
         # Block.relprop :203-213
-        r1, r2 = rules.add_relprop(c["x_mid"], c["mlp_out"], r)                 # add2
+        r1, r2 = add(c["x_mid"], c["mlp_out"], r)                 # add2
         if t is not None:
             t["add2_r1"], t["add2_r2"] = r1, r2
-        r2 = rules.linear_relprop(c["g"], p[pre + "mlp.fc2.weight"], r2)        # fc2 ; GELU identity
+        r2 = lin(c["g"], p[pre + "mlp.fc2.weight"], r2)        # fc2 ; GELU identity
         if t is not None:
             t["fc2"] = r2
-        r2 = rules.linear_relprop(c["xn2"], p[pre + "mlp.fc1.weight"], r2)      # fc1 ; norm2 identity
+        r2 = lin(c["xn2"], p[pre + "mlp.fc1.weight"], r2)      # fc1 ; norm2 identity
         if t is not None:
             t["fc1"] = r2
         r = rules.clone_relprop(c["x_mid"], (r1, r2))                           # clone2
         if t is not None:
             t["clone2"] = r
-        r1, r2 = rules.add_relprop(c["x_in"], c["attn_out"], r)                 # add1
+        r1, r2 = add(c["x_in"], c["attn_out"], r)                 # add1
         if t is not None:
             t["add1_r1"], t["add1_r2"] = r1, r2
         # Attention.relprop :154-177
-        r2 = rules.linear_relprop(c["ctx"], p[pre + "attn.proj.weight"], r2)
+        r2 = lin(c["ctx"], p[pre + "attn.proj.weight"], r2)
         if t is not None:
             t["proj"] = r2
         r2 = _split_heads(r2, cfg.heads)
@@ -164,7 +168,7 @@ def relprop(params, cache, seed, start_layer=0, taps=None, to_input=False):
         cam_q = cam_q / 2
         cam_k = cam_k / 2
         r_qkv = torch.cat([_merge_heads(cam_q), _merge_heads(cam_k), _merge_heads(cam_v)], dim=-1)
-        r2 = rules.linear_relprop(c["xn1"], p[pre + "attn.qkv.weight"], r_qkv)  # norm1 identity
+        r2 = lin(c["xn1"], p[pre + "attn.qkv.weight"], r_qkv)  # norm1 identity
         r = rules.clone_relprop(c["x_in"], (r1, r2))                            # clone1
         if t is not None:
             t["r_qkv"], t["qkv"], t["clone1"] = r_qkv, r2, r
@@ -176,12 +180,12 @@ def relprop(params, cache, seed, start_layer=0, taps=None, to_input=False):
 METHODS = ("transformer_attribution", "grad", "rollout", "full", "last_layer", "last_layer_attn", "second_layer")
 
 
-def explain_method(params, x, num_heads, method, index=None, start_layer=0, is_ablation=False):
+def explain_method(params, x, num_heads, method, index=None, start_layer=0, is_ablation=False, variant="ours"):
     """``LRP.generate_LRP(method=...)`` for every branch of ``VisionTransformer.relprop``
     (``ViT_LRP.py:337-398``), batch = independent B=1 explanations.  Returns (map, index):
     [B,N-1] for the token methods, [B,H,W] for ``full`` (relevance of every pixel, channels summed)."""
     if method in ("transformer_attribution", "grad"):
-        return explain(params, x, num_heads, index=index, start_layer=start_layer)
+        return explain(params, x, num_heads, index=index, start_layer=start_layer, variant=variant)
     with torch.enable_grad():
         logits, cache = forward(params, x, num_heads, need_grad=True)
         if index is None:
@@ -195,10 +199,10 @@ def explain_method(params, x, num_heads, method, index=None, start_layer=0, is_a
     with torch.no_grad():
         cache_d = {"cfg": cfg, "x_final_norm": cache["x_final_norm"].detach(),
                    "blocks": [{k: v.detach() for k, v in c.items()} for c in cache["blocks"]]}
-        cams, r = relprop(params, cache_d, seed, 0, to_input=True)
+        cams, r = relprop(params, cache_d, seed, 0, to_input=True, variant=variant)
         if method == "full":                                                    # :337-343
             pos = params["pos_embed"].expand_as(cache["tokens_pre_pos"])
-            r, _ = rules.add_relprop(cache["tokens_pre_pos"], pos, r)
+            r, _ = (rules.add_relprop_simple if variant == "lrp" else rules.add_relprop)(cache["tokens_pre_pos"], pos, r)
             r = r[:, first:]
             g = x.shape[-1] // cfg.patch
             r = r.transpose(1, 2).reshape(r.shape[0], cfg.dim, x.shape[-2] // cfg.patch, g)   # PatchEmbed.relprop :238-242
@@ -218,7 +222,7 @@ def explain_method(params, x, num_heads, method, index=None, start_layer=0, is_a
     raise ValueError("unknown method %r" % (method,))
 
 
-def explain(params, x, num_heads, index=None, start_layer=0, return_taps=False):
+def explain(params, x, num_heads, index=None, start_layer=0, return_taps=False, variant="ours"):
     """``LRP.generate_LRP(method='transformer_attribution')`` for a batch of independent
     samples.  Returns (maps [B,N-1(-1 if distilled)], index [B]) (+ taps)."""
     with torch.enable_grad():
@@ -233,7 +237,7 @@ def explain(params, x, num_heads, index=None, start_layer=0, return_taps=False):
         cache_d = {"cfg": cache["cfg"], "x_final_norm": cache["x_final_norm"].detach(),
                    "blocks": [{k: v.detach() for k, v in c.items()} for c in cache["blocks"]]}
         rtaps = {} if return_taps else None
-        cams = relprop(params, cache_d, seed, start_layer, taps=rtaps)
+        cams = relprop(params, cache_d, seed, start_layer, taps=rtaps, variant=variant)
         mats = [rules.aggregate(g, c) if c is not None else torch.zeros_like(g[:, 0])
                 for g, c in zip(grads, cams)]
         joint = rules.rollout(mats, start_layer=start_layer, normalize=False)

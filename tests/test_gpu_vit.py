@@ -316,3 +316,34 @@ def test_top_block_cls_rows_only_is_exact():
             _lib.check(lib.te_set_option(b"cls_row_top_block", 1), "te_set_option")
         assert torch.equal(a, b) and torch.equal(cam_a, cam_b), "flags %d" % flags
         assert float(cam_a[:, :, 1:, :].abs().max()) == 0.0          # only row 0 of the top block's attn_cam is non-zero
+
+
+def test_orig_lrp_variant_vs_golden_reference(golden_dir):
+    """``baselines/ViT/ViT_orig_LRP.py`` (rule library ``modules/layers_lrp.py``) on the engine (TE_FLAG_RULES_LRP) vs the
+    UNMODIFIED reference's fp64 outputs: method = grad (its default), full, last_layer, rollout; and the two rules through
+    the layer-class facade."""
+    from transformer_explainability_b200 import ops
+    from transformer_explainability_b200.baselines.ViT.ViT_orig_LRP import VisionTransformer
+    from transformer_explainability_b200.baselines.ViT.ViT_explanation_generator import LRP
+    from oracle import rules
+    g = np.load(os.path.join(golden_dir, "vit_orig_lrp.npz"))
+    params, heads = ovit.init_params("vit_tiny_test", seed=int(g["param_seed"]), rand_affine=True)
+    m = VisionTransformer(qkv_bias=True, num_heads=heads, **TINY)
+    m.load_state_dict({k: v.float() for k, v in params.items()})
+    m = m.cuda().eval()
+    lrp = LRP(m)
+    x = T(g["x"]).cuda()
+    for key in [k for k in g.files if k.startswith("f64.")]:
+        s, method, sl = int(key.split(".")[1][1:]), key.split(".")[2], int(key.split(".")[3][2:])
+        out = lrp.generate_LRP(x[s:s + 1], method=method, start_layer=sl)
+        ref = T(g[key]).reshape(out.shape)
+        assert rel(out, ref) < 2e-2, "%s rel=%g" % (key, rel(out, ref))
+    with pytest.raises(ValueError):
+        lrp.generate_LRP(x[:1], method="transformer_attribution")
+    gg = torch.Generator().manual_seed(3)
+    xx, w, r = torch.randn(40, 96, generator=gg), torch.randn(64, 96, generator=gg) * 0.1, torch.rand(40, 64, generator=gg)
+    out = ops.linear_relprop(xx.cuda(), w.cuda(), r.cuda(), variant="lrp")
+    assert rel(out, rules.linear_relprop_lrp(xx.double(), w.double(), r.double())) < 1e-5
+    a, b = ops.add_relprop(xx.cuda(), (2 * xx + 1).cuda(), xx.cuda(), variant="lrp")
+    ra, rb = rules.add_relprop_simple(xx.double(), (2 * xx + 1).double(), xx.double())
+    assert rel(a, ra) < 1e-6 and rel(b, rb) < 1e-6

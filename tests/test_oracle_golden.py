@@ -184,3 +184,27 @@ def test_bert_generators_match_reference(golden_dir):
         assert _same(out, T(g[key])), key
         seen += 1
     assert seen == 28
+
+
+@pytest.mark.parametrize("tag,dtype", [("f32", torch.float32), ("f64", torch.float64)])
+def test_vit_orig_lrp_variant_matches_reference(golden_dir, tag, dtype):
+    """The ``layers_lrp`` rule library (``modules/layers_lrp.py``: Linear with separate denominators, Add without ratio
+    normalisation) behind ``baselines/ViT/ViT_orig_LRP.py``: oracle (``variant="lrp"``) bit-equal to the stored outputs
+    of the UNMODIFIED reference for method = grad / full / last_layer / rollout."""
+    g = np.load(os.path.join(golden_dir, "vit_orig_lrp.npz"))
+    params, heads = ovit.init_params("vit_tiny_test", seed=int(g["param_seed"]), rand_affine=True)
+    p = {k: v.to(dtype) for k, v in params.items()}
+    xs = T(g["x"]).to(dtype)
+    keys = [k for k in g.files if k.startswith(tag + ".")]
+    assert len(keys) == 12
+    for key in keys:
+        s, method, sl = int(key.split(".")[1][1:]), key.split(".")[2], int(key.split(".")[3][2:])
+        out, _ = ovit.explain_method(p, xs[s:s + 1], heads, method, start_layer=sl, variant="lrp")
+        assert torch.equal(out, T(g[key]).reshape(out.shape)), key
+    # the two rules on their own, against closed forms written out independently here
+    x, w, r = torch.randn(5, 7, dtype=dtype), torch.randn(4, 7, dtype=dtype), torch.rand(5, 4, dtype=dtype)
+    z1, z2 = x.clamp(min=0) @ w.clamp(min=0).t(), x.clamp(max=0) @ w.clamp(max=0).t()
+    want = x.clamp(min=0) * (rules.safe_divide(r, z1) @ w.clamp(min=0)) + x.clamp(max=0) * (rules.safe_divide(r, z2) @ w.clamp(max=0))
+    assert torch.equal(rules.linear_relprop_lrp(x, w, r), want)
+    a, b = rules.add_relprop_simple(x, 2 * x + 1, x)
+    assert torch.allclose(a + b, x * ((3 * x + 1) != 0))                  # conservation without any re-normalisation

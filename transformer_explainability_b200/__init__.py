@@ -18,10 +18,12 @@ __version__ = "0.1.0"
 _ALIASES = {
     "modules": "transformer_explainability_b200.modules",
     "modules.layers_ours": "transformer_explainability_b200.modules.layers_ours",
+    "modules.layers_lrp": "transformer_explainability_b200.modules.layers_lrp",
     "baselines": "transformer_explainability_b200.baselines",
     "baselines.ViT": "transformer_explainability_b200.baselines.ViT",
     "baselines.ViT.ViT_LRP": "transformer_explainability_b200.baselines.ViT.ViT_LRP",
     "baselines.ViT.ViT_new": "transformer_explainability_b200.baselines.ViT.ViT_new",
+    "baselines.ViT.ViT_orig_LRP": "transformer_explainability_b200.baselines.ViT.ViT_orig_LRP",
     "baselines.ViT.ViT_explanation_generator": "transformer_explainability_b200.baselines.ViT.ViT_explanation_generator",
 }
 

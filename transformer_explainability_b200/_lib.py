@@ -36,6 +36,7 @@ FLAG_LINEAR_TENSOR_CORES = 16
 FLAG_ATTN_TENSOR_CORES = 32
 FLAG_ZPLUS_BF16 = 64
 FLAG_BACKWARD_TF32 = 256
+FLAG_RULES_LRP = 512
 FLAG_TENSOR_CORES = FLAG_ZPLUS_TENSOR_CORES | FLAG_LINEAR_TENSOR_CORES      # the ones that need derived weights
 FLAG_ALL_FAST = FLAG_TENSOR_CORES | FLAG_ATTN_TENSOR_CORES | FLAG_ROLLOUT_FUSED
 # what bench.py runs by default: updated as faster selections pass the parity tests (tests/test_gpu_parity_full.py)
@@ -65,6 +66,7 @@ PROTOTYPES = {
                               ctypes.POINTER(c_ll)]),
     "te_set_option": (c_int, [c_char_p, c_int]),
     "te_vit_relprop_pixels": (c_int, [_CFG, _P, _P, c_int, _P, _P, _P, c_ll, _P]),
+    "te_vit_relprop_pixels_ex": (c_int, [_CFG, _P, _P, c_int, c_uint, _P, _P, _P, c_ll, _P]),
     "te_bert_num_weights": (c_int, [_BCFG]),
     "te_bert_weight_name": (c_char_p, [_BCFG, c_int]),
     "te_bert_weight_numel": (c_ll, [_BCFG, c_int]),

@@ -120,6 +120,7 @@ class VisionTransformer(nn.Module):
         self._engine = None
         self._weights_version = None
         self.engine_flags = 0
+        self._rule_flags = 0                   # ViT_orig_LRP sets TE_FLAG_RULES_LRP (the modules/layers_lrp.py rule library)
         self._init_weights()
 
     def _init_weights(self):
@@ -152,12 +153,12 @@ class VisionTransformer(nn.Module):
             raise RuntimeError("the B200 engine has no CPU path: move the model to a CUDA device (model.cuda())")
         v = self._version()
         if self._engine is None or self._engine.device != dev:
-            self._engine = ViTEngine(self._cfg, device=dev, flags=self.engine_flags)
+            self._engine = ViTEngine(self._cfg, device=dev, flags=self.engine_flags | self._rule_flags)
             self._weights_version = None
         if self._weights_version != v:
             self._engine.load_state_dict(self.state_dict())
             self._weights_version = v
-        self._engine.flags = self.engine_flags
+        self._engine.flags = self.engine_flags | self._rule_flags
         return self._engine
 
     def _engine_tensor(self, name, layer):

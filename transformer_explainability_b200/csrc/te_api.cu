@@ -68,6 +68,9 @@ extern "C" int te_linear_backward_ex(const float* dy, const float* w, float* dx,
 extern "C" int te_linear_relprop(const float* x, const float* w, const float* r, float* out, float* scratch, int rows,
                                  int in_features, int out_features, unsigned flags, void* stream) {
     REQ(x && w && r && out && scratch && rows > 0 && in_features > 0 && out_features > 0, "te_linear_relprop: bad argument");
+    if (flags & TE_FLAG_RULES_LRP)
+        return te_zplus_linear_relprop_lrp(x, in_features, w, r, out_features, out, scratch, rows, in_features, out_features,
+                                           ST(stream));
     const float* derived = nullptr;
     if ((flags & TE_FLAG_ZPLUS_TENSOR_CORES) && te_tc_zplus_supported(rows, in_features, out_features, in_features)) {
         // scratch layout with the flag: [rows*out S | 10*in*out derived weight copies]
@@ -98,7 +101,7 @@ extern "C" int te_linear_relprop_ex(const float* x, const float* w, const float*
 
 extern "C" int te_add_relprop(const float* x1, const float* x2, const float* r, float* r1, float* r2, void* scratch,
                               int batch, long long per_sample, void* stream) {
-    REQ(x1 && x2 && r && r1 && r2 && scratch && batch > 0 && per_sample > 0, "te_add_relprop: bad argument");
+    REQ(x1 && x2 && r && r1 && r2 && batch > 0 && per_sample > 0, "te_add_relprop: bad argument");
     return te_launch_add_relprop(x1, x2, r, r1, r2, reinterpret_cast<double*>(scratch), batch, per_sample, ST(stream));
 }
 

@@ -307,7 +307,8 @@ __global__ void add_scale_kernel(const float* __restrict__ x1, const float* __re
                                  const double* __restrict__ partial, long long per4, long long x2s4) {
     const int b = blockIdx.y;
     __shared__ float fa_s, fb_s;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && partial == nullptr) { fa_s = 1.f; fb_s = 1.f; }     // layers_lrp variant: no ratio normalisation
+    if (threadIdx.x == 0 && partial != nullptr) {
         double A = 0, Bs = 0, rho = 0;
         const double* q = partial + (long long)b * TE_ADD_SPLIT * 3;
         for (int i = 0; i < TE_ADD_SPLIT; ++i) { A += q[i * 3]; Bs += q[i * 3 + 1]; rho += q[i * 3 + 2]; }
@@ -757,8 +758,10 @@ int te_launch_add_relprop_ex(const float* x1, const float* x2, long long x2_samp
     TE_REQ(per_sample % 4 == 0 && x2_sample_stride % 4 == 0, "add_relprop: per-sample size % 4 != 0");
     TE_REQ(B <= 65535, "add_relprop: batch too large for one launch");
     const long long per4 = per_sample / 4, x2s4 = x2_sample_stride / 4;
-    add_reduce_kernel<<<dim3(TE_ADD_SPLIT, B), kThreads, 0, st>>>(x1, x2, r, partial, per4, x2s4);
-    TE_CUDA_CHECK_LAUNCH();
+    if (partial) {                            // null: Add of modules/layers_lrp.py (RelPropSimple) — a = x1*S, b = x2*S only
+        add_reduce_kernel<<<dim3(TE_ADD_SPLIT, B), kThreads, 0, st>>>(x1, x2, r, partial, per4, x2s4);
+        TE_CUDA_CHECK_LAUNCH();
+    }
     int gx = (int)((per4 + kThreads - 1) / kThreads);
     gx = gx > 64 ? 64 : (gx < 1 ? 1 : gx);
     add_scale_kernel<<<dim3(gx, B), kThreads, 0, st>>>(x1, x2, r, r1, r2, partial, per4, x2s4);

@@ -159,6 +159,8 @@ __global__ void __launch_bounds__(256, (TM == 8) ? 2 : 3) te_gemm_kernel(const T
             amode = bmode = ph + 1;
         } else if (XF == TE_XF_B_POS) bmode = 1;
         else if (XF == TE_XF_B_NEG) bmode = 2;
+        else if (XF == TE_XF_AB_POS) amode = bmode = 1;         // x+ W+^T  (layers_lrp Linear rule: separate denominators)
+        else if (XF == TE_XF_AB_NEG) amode = bmode = 2;         // x- W-^T
 #pragma unroll
         for (int i = 0; i < NLD; ++i) {
             ra[i] = clamp4(load_tile4<TM, ALAY>(A, p.lda, p.M, p.K, m0, k0, tid + i * 256, p.vecA), amode);
@@ -262,6 +264,8 @@ int te_gemm_launch(TeGemm p, int alay, int blay, int xf, int epi, cudaStream_t s
     TE_CASE(TE_L_MN, TE_L_MN, TE_XF_NONE, TE_EPI_STORE)
     // relprop
     TE_CASE(TE_L_K, TE_L_K, TE_XF_AB_POSNEG, TE_EPI_SD)
+    TE_CASE(TE_L_K, TE_L_K, TE_XF_AB_POS, TE_EPI_SD)
+    TE_CASE(TE_L_K, TE_L_K, TE_XF_AB_NEG, TE_EPI_SD)
     TE_CASE(TE_L_K, TE_L_MN, TE_XF_B_POS, TE_EPI_MULPOS)
     TE_CASE(TE_L_K, TE_L_MN, TE_XF_B_NEG, TE_EPI_MULNEG_ACC)
     TE_CASE(TE_L_K, TE_L_K, TE_XF_NONE, TE_EPI_SD)

@@ -16,7 +16,7 @@
 #include "te_common.cuh"
 
 enum { TE_L_K = 0, TE_L_MN = 1 };
-enum { TE_XF_NONE = 0, TE_XF_AB_POSNEG = 1, TE_XF_B_POS = 2, TE_XF_B_NEG = 3 };
+enum { TE_XF_NONE = 0, TE_XF_AB_POSNEG = 1, TE_XF_B_POS = 2, TE_XF_B_NEG = 3, TE_XF_AB_POS = 4, TE_XF_AB_NEG = 5 };
 enum {
     TE_EPI_STORE = 0,      // C = alpha*acc
     TE_EPI_BIAS = 1,       // C = acc + bias[n]

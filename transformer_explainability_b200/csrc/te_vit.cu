@@ -351,6 +351,7 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
     const float* lbase = (flags & TE_FLAG_LINEAR_TENSOR_CORES) ? derived : nullptr;
     const bool atc = (flags & TE_FLAG_ATTN_TENSOR_CORES) != 0;
     const bool btf = (flags & TE_FLAG_BACKWARD_TF32) != 0;       // single-pass TF32 backward Linears
+    const bool lrpv = (flags & TE_FLAG_RULES_LRP) != 0;         // rule library of modules/layers_lrp.py (ViT_orig_LRP.py)
     const bool zb = (flags & TE_FLAG_ZPLUS_BF16) != 0;
 
     // ---- class index and seeds  (ViT_explanation_generator.py:28-35) ---------------------------
@@ -406,11 +407,21 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
     float* R = ws.tD[0]; float* R1 = ws.tD[1]; float* R2 = ws.tD[2]; float* R3 = ws.tD[3];
     float* RF = ws.tF[0]; float* SF = ws.tF[1]; float* S = ws.t3D[0]; float* Rqkv = ws.t3D[1]; float* S1 = ws.tA;
     // head.relprop (z+), pool.relprop (IndexSelect), norm.relprop (identity)
-    TE_TRY(te_zplus_linear_relprop(ws.xf, (long long)d.N * d.D, w.headw, nullptr, ws.seed, ws.rhead0, ws.shead, d.B, d.D,
-                                   d.C, st));
+    // z+ rule / Add rule of the selected rule library (layers_ours, or layers_lrp with TE_FLAG_RULES_LRP)
+    auto zrule = [&](const float* x, long long ldx, const float* wt, const float* dwt, const float* r, long long ldr, float* out,
+                     float* sbuf, long long rows, int in, int outf, const float* y, long long ldy, const float* bias,
+                     long long ld_out, float* xabs) -> int {
+        if (lrpv) return te_zplus_linear_relprop_lrp(x, ldx, wt, r, ldr, out, sbuf, rows, in, outf, st);
+        return te_zplus_linear_relprop_ldr(x, ldx, wt, dwt, r, ldr, out, sbuf, rows, in, outf, st, y, ldy, bias, zb, ld_out, xabs);
+    };
+    auto addrule = [&](const float* x1, const float* x2, const float* r, float* r1, float* r2) -> int {
+        return te_launch_add_relprop(x1, x2, r, r1, r2, lrpv ? nullptr : ws.addpart, d.B, (long long)d.N * d.D, st);
+    };
+    TE_TRY(zrule(ws.xf, (long long)d.N * d.D, w.headw, nullptr, ws.seed, d.C, ws.rhead0, ws.shead, d.B, d.D, d.C, nullptr, 0,
+                 nullptr, 0, nullptr));
     if (cfg->distilled)
-        TE_TRY(te_zplus_linear_relprop(ws.xf + d.D, (long long)d.N * d.D, w.headdw, nullptr, ws.seed, ws.rhead1, ws.shead,
-                                       d.B, d.D, d.C, st));
+        TE_TRY(zrule(ws.xf + d.D, (long long)d.N * d.D, w.headdw, nullptr, ws.seed, d.C, ws.rhead1, ws.shead, d.B, d.D, d.C,
+                     nullptr, 0, nullptr, 0, nullptr));
     TE_TRY(te_launch_index_select_relprop(ws.xf, ws.rhead0, cfg->distilled ? ws.rhead1 : nullptr, R, d.B, d.N, d.D, st));
 
     for (int l = d.L - 1; l >= low; --l) {
@@ -425,17 +436,17 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
         // and every rule down to the proj rule is row-wise: Add / Clone map a zero row to a zero row, the z+ rule computes
         // each output row from the same input row.  So the three z+ rules of the top block run on the B pooled rows only
         // (row stride N*D / N*F) — exact (SURVEY.md 8a "structural savings"), bit-identical rows, 1/N of the work.
-        const bool top = (l == d.L - 1) && !cfg->distilled && te_engine_cls_rows();
+        const bool top = (l == d.L - 1) && !cfg->distilled && !lrpv && te_engine_cls_rows();
         const long long zr = top ? d.B : d.M;                          // rows the z+ rules of this block touch
         const long long sD = top ? (long long)d.N * d.D : d.D, sF = top ? (long long)d.N * d.F : d.F;
-        TE_TRY(te_launch_add_relprop(a.x_mid, a.mlp_out, R, R1, R2, ws.addpart, d.B, (long long)d.N * d.D, st));   // add2
-        TE_TRY(te_zplus_linear_relprop_ldr(a.g, sF, bw.fc2w, dw.fc2, R2, sD, RF, S, zr, d.F, d.D, st, a.mlp_out, sD, bw.fc2b, zb, sF, SF));                       // fc2 ; GELU id
-        TE_TRY(te_zplus_linear_relprop_ldr(a.xn2, sD, bw.fc1w, dw.fc1, RF, sF, R2, SF, zr, d.D, d.F, st, a.h, sF, bw.fc1b, zb, sD, S));                    // fc1 ; norm2 id
+        TE_TRY(addrule(a.x_mid, a.mlp_out, R, R1, R2));                                                            // add2
+        TE_TRY(zrule(a.g, sF, bw.fc2w, dw.fc2, R2, sD, RF, S, zr, d.F, d.D, a.mlp_out, sD, bw.fc2b, sF, SF));      // fc2 ; GELU id
+        TE_TRY(zrule(a.xn2, sD, bw.fc1w, dw.fc1, RF, sF, R2, SF, zr, d.D, d.F, a.h, sF, bw.fc1b, sD, S));          // fc1 ; norm2 id
         TE_TRY(te_launch_clone_relprop(a.x_mid, R1, R2, nullptr, R, MD, st));                                      // clone2
-        TE_TRY(te_launch_add_relprop(a.x_in, a.attn_out, R, R1, R2, ws.addpart, d.B, (long long)d.N * d.D, st));    // add1
+        TE_TRY(addrule(a.x_in, a.attn_out, R, R1, R2));                                                            // add1
         // Attention.relprop :154-177
         if (top) TE_TRY(te_launch_fill(R3, 0.f, MD, st));                                   // rows the strided rule does not write
-        TE_TRY(te_zplus_linear_relprop_ldr(a.ctx, sD, bw.projw, dw.proj, R2, sD, R3, S, zr, d.D, d.D, st, a.attn_out, sD, bw.projb, zb, sD, S + MD));                    // proj
+        TE_TRY(zrule(a.ctx, sD, bw.projw, dw.proj, R2, sD, R3, S, zr, d.D, d.D, a.attn_out, sD, bw.projb, sD, S + MD));   // proj
         // matmul2 rule: Z = attn v is the saved ctx itself (bit-identical recomputation in the reference)
         TE_TRY(te_launch_sd(R3, a.ctx, S, MD, st));
         TE_TRY(te_util::attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, S, d.D, a.qkv + 2 * d.D, 3 * d.D, a.cam, a.P, 0.5f,
@@ -450,7 +461,7 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
                                 TE_EPI_MUL, st));                                   // cam_q
         TE_TRY(te_util::attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, S1, 1, a.qkv, 3 * d.D, Rqkv + d.D, 3 * d.D, a.qkv + d.D, 0.5f,
                                 TE_EPI_MUL, st));                                   // cam_k
-        TE_TRY(te_zplus_linear_relprop_ldr(a.xn1, d.D, bw.qkvw, dw.qkv, Rqkv, 3 * d.D, R2, S, d.M, d.D, 3 * d.D, st, a.qkv, 3 * d.D, bw.qkvb, zb, 0, RF));               // qkv ; norm1 id
+        TE_TRY(zrule(a.xn1, d.D, bw.qkvw, dw.qkv, Rqkv, 3 * d.D, R2, S, d.M, d.D, 3 * d.D, a.qkv, 3 * d.D, bw.qkvb, 0, RF));   // qkv ; norm1 id
         TE_TRY(te_launch_clone_relprop(a.x_in, R1, R2, nullptr, R, MD, st));                                       // clone1
     }
 
@@ -470,6 +481,13 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
 extern "C" int te_vit_relprop_pixels(const te_vit_config* cfg, const float* weights, const float* images, int batch,
                                      float* pixel_maps, float* pixel_relevance, void* workspace, long long workspace_bytes,
                                      void* stream) {
+    return te_vit_relprop_pixels_ex(cfg, weights, images, batch, 0u, pixel_maps, pixel_relevance, workspace, workspace_bytes,
+                                    stream);
+}
+
+extern "C" int te_vit_relprop_pixels_ex(const te_vit_config* cfg, const float* weights, const float* images, int batch,
+                                        unsigned flags, float* pixel_maps, float* pixel_relevance, void* workspace,
+                                        long long workspace_bytes, void* stream) {
     Dims d; Workspace ws;
     TE_TRY(check_ws(cfg, batch, workspace, workspace_bytes, d, ws));
     if (!weights || !images || (!pixel_maps && !pixel_relevance)) { te_set_last_error("te_vit_relprop_pixels: null pointer"); return TE_ERR_ARG; }
@@ -486,7 +504,8 @@ extern "C" int te_vit_relprop_pixels(const te_vit_config* cfg, const float* weig
                       d.D, TE_EPI_BIAS, st));
     TE_TRY(te_launch_assemble_tokens(patch_out, w.cls, w.dist, nullptr, tokens, d.B, d.N, d.D, d.prefix, st));
     // self.add.relprop: x2 = pos_embed, shared by every sample; only the tokens' share is consumed
-    TE_TRY(te_launch_add_relprop_ex(tokens, w.pos, 0, R, Rtok, nullptr, ws.addpart, d.B, (long long)d.N * d.D, st));
+    TE_TRY(te_launch_add_relprop_ex(tokens, w.pos, 0, R, Rtok, nullptr, (flags & TE_FLAG_RULES_LRP) ? nullptr : ws.addpart, d.B,
+                                    (long long)d.N * d.D, st));
     // cam[:, 1:] -> PatchEmbed.relprop (:238-242) -> Conv2d z^B rule -> sum over channels
     return te_patch_relprop_run(images, w.patchw, Rtok + (long long)d.prefix * d.D, (long long)d.N * d.D, d.B, d.Cin, d.img,
                                 d.P, d.D, ws.pix, pixel_relevance, pixel_maps, st);

@@ -21,3 +21,8 @@ int te_zplus_linear_relprop_ldr(const float* x, long long ldx, const float* w, c
 // uses the round-1 kernels.
 // ld_out: row stride of out (0 = in_features).  With row strides on x, r, y and out the rule runs on a strided subset of
 // token rows — the CLS rows of the top block, the only rows whose relevance is non-zero there.
+
+// Linear.relprop of the layers_lrp baseline variant (modules/layers_lrp.py:187-210, alpha=1): S1 = sd(R, x+ W+^T),
+// S2 = sd(R, x- W-^T) (separate denominators), R_in = x+ * (S1 W+) + x- * (S2 W-).  fp32 SIMT; s_scratch [rows, out].
+int te_zplus_linear_relprop_lrp(const float* x, long long ldx, const float* w, const float* r, long long ldr, float* out,
+                                float* s_scratch, long long rows, int in_features, int out_features, cudaStream_t st);

@@ -146,9 +146,9 @@ class ViTEngine:
         ws = self._workspace(b)
         c, s = self.cfg.in_chans, self.cfg.img_size
         out = torch.empty((b, c, s, s) if per_channel else (b, s, s), dtype=torch.float32, device=self.device)
-        check(self.lib.te_vit_relprop_pixels(ctypes.byref(self.cfg), ptr(self.weights), ptr(images), b,
-                                             None if per_channel else ptr(out), ptr(out) if per_channel else None,
-                                             ptr(ws), ws.numel() * 4, self._stream()), "te_vit_relprop_pixels")
+        check(self.lib.te_vit_relprop_pixels_ex(ctypes.byref(self.cfg), ptr(self.weights), ptr(images), b, fl,
+                                                None if per_channel else ptr(out), ptr(out) if per_channel else None,
+                                                ptr(ws), ws.numel() * 4, self._stream()), "te_vit_relprop_pixels_ex")
         return out
 
     @_on_engine_device

@@ -106,9 +106,10 @@ def linear_backward_tf32(dy, w):
 
 
 @_on_device
-def linear_relprop(x, w, r, tensor_cores=False, y=None, bias=None, bf16=False):
+def linear_relprop(x, w, r, tensor_cores=False, y=None, bias=None, bf16=False, variant="ours"):
     """``Linear.relprop`` (layers_ours.py:207-230): x [...,in], w [out,in], r [...,out] -> [...,in].
-    y / bias: the layer's saved forward output (and bias) — lets the tensor-core path form the denominator in one pass."""
+    y / bias: the layer's saved forward output (and bias) — lets the tensor-core path form the denominator in one pass.
+    variant="lrp": the rule of ``modules/layers_lrp.py:187-210`` (separate denominators; fp32 SIMT)."""
     _req(x, w, r, y, bias)
     if (w.dim() != 2 or x.shape[-1] != w.shape[1] or r.shape[-1] != w.shape[0] or r.shape[:-1] != x.shape[:-1]
             or (y is not None and y.shape != r.shape) or (bias is not None and bias.numel() != w.shape[0])):
@@ -122,6 +123,10 @@ def linear_relprop(x, w, r, tensor_cores=False, y=None, bias=None, bf16=False):
     flags = _lib.FLAG_ZPLUS_TENSOR_CORES if tensor_cores else 0
     if bf16:
         flags |= _lib.FLAG_ZPLUS_BF16
+    if variant == "lrp":
+        flags, y = _lib.FLAG_RULES_LRP, None
+    elif variant != "ours":
+        raise ValueError("variant: 'ours' or 'lrp'")
     if y is not None:
         check(_lib.load().te_linear_relprop_ex(ptr(x), ptr(w), ptr(bias), ptr(y), ptr(r), ptr(out), ptr(scratch), rows,
                                                x.shape[-1], w.shape[0], flags, _stream()), "te_linear_relprop_ex")
@@ -132,15 +137,16 @@ def linear_relprop(x, w, r, tensor_cores=False, y=None, bias=None, bf16=False):
 
 
 @_on_device
-def add_relprop(x1, x2, r):
-    """``Add.relprop`` (layers_ours.py:97-120), sums per sample (dim 0)."""
+def add_relprop(x1, x2, r, variant="ours"):
+    """``Add.relprop`` (layers_ours.py:97-120), sums per sample (dim 0).  variant="lrp": ``modules/layers_lrp.py:98-100``
+    (x1*S, x2*S with S = sd(r, x1+x2); no ratio normalisation)."""
     _req(x1, x2, r)
     _same_shape("add_relprop", x1, x2, r)           # a broadcast operand (pos_embed [1,N,D]) must be expanded by the caller
     if (x1.numel() // max(x1.shape[0], 1)) % 4 != 0:
         raise ValueError("add_relprop: elements per sample must be a multiple of 4")
     b = x1.shape[0]
     r1, r2 = torch.empty_like(x1), torch.empty_like(x1)
-    scratch = torch.empty(b * 48, device=x1.device, dtype=torch.float64)
+    scratch = None if variant == "lrp" else torch.empty(b * 48, device=x1.device, dtype=torch.float64)
     check(_lib.load().te_add_relprop(ptr(x1), ptr(x2), ptr(r), ptr(r1), ptr(r2), ptr(scratch), b, x1.numel() // b,
                                      _stream()), "te_add_relprop")
     return r1, r2
