@@ -237,36 +237,88 @@ def roofline_zplus(w, batch, flags, pk):
             "note": ("algorithmic = 8*rows*in*out (SURVEY 8a); the tcgen05 path executes 6*rows*in*out: the denominator is "
                      "formed in one pass from the saved forward output, ((y-b) + |x||W|^T)/2; each launch also derives "
                      "the TF32 weight copies (prepare kernel, <1% of the time)") if tc else "fp32 SIMT reference path",
-            "peak_source": pk["source"] + "; TF32 dense taken as bf16/2"}
+            "peak_source": pk["source"] + "; TF32 dense taken as bf16/2 (tf32_matmul_measured_tflops: cuBLAS TF32 8192^3 on this box)"}
 
 
-def roofline_rollout(w, flags, pk):
+def _time_ms(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def measured_tf32_peak():
+    """cuBLAS TF32 matmul 8192^3 (torch.matmul with TF32 allowed), best of 5 — printed beside the bf16/2 convention."""
+    try:
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn(8192, 8192, device="cuda")
+        b = torch.randn(8192, 8192, device="cuda")
+        best = min(_time_ms(lambda: torch.matmul(a, b), reps=3, warm=1) for _ in range(5))
+        torch.backends.cuda.matmul.allow_tf32 = prev
+        return round(2.0 * 8192 ** 3 / (best * 1e-3) / 1e12, 1)
+    except Exception:
+        return None
+
+
+def roofline_linear(w, batch, flags, pk):
+    """The two Linear GEMM families of the forward / activation-gradient backward at the fc1 shape: 3xTF32 (fp32-grade)
+    forward and — with TE_FLAG_BACKWARD_TF32 — the single-pass TF32 backward on the persistent pair kernel."""
+    from transformer_explainability_b200 import ops, _lib
+    rows, inf, outf = batch * w["tokens"], w["dim"], w["mlp"]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(rows, inf, device="cuda", generator=g)
+    wt = torch.randn(outf, inf, device="cuda", generator=g) * 0.02
+    bias = torch.randn(outf, device="cuda", generator=g) * 0.02
+    dy = torch.randn(rows, outf, device="cuda", generator=g)
+    flops = 2.0 * rows * inf * outf
+    peak = pk["bf16_tflops"] / 2.0
+    out = {}
+    tc = bool(flags & _lib.FLAG_LINEAR_TENSOR_CORES)
+    ms = _time_ms(lambda: ops.linear_forward(x, wt, bias, tensor_cores=tc))
+    out["forward"] = {"kernel": "linear_forward[%s] rows=%d in=%d out=%d" % ("tcgen05-3xTF32" if tc else "simt-fp32", rows, inf, outf),
+                      "bound": "tensor", "achieved": round(flops / ms / 1e9, 2), "peak": round(peak, 1), "unit": "TFLOP/s",
+                      "frac": round(flops / ms / 1e9 / peak, 4), "ms": round(ms, 3),
+                      "note": "fp32-grade: 3 TF32 MMAs per product (issue rate = 3x achieved)"}
+    if tc and (flags & _lib.FLAG_BACKWARD_TF32):
+        ms = _time_ms(lambda: ops.linear_backward_tf32(dy, wt))
+        what = "tcgen05-TF32 persistent pair"
+    else:
+        ms = _time_ms(lambda: ops.linear_backward(dy, wt, tensor_cores=tc))
+        what = "tcgen05-3xTF32" if tc else "simt-fp32"
+    out["backward"] = {"kernel": "linear_backward[%s] rows=%d in=%d out=%d" % (what, rows, inf, outf), "bound": "tensor",
+                       "achieved": round(flops / ms / 1e9, 2), "peak": round(peak, 1), "unit": "TFLOP/s",
+                       "frac": round(flops / ms / 1e9 / peak, 4), "ms": round(ms, 3)}
+    return out
+
+
+def roofline_rollout(w, flags, pk, B=32, dense=False):
     """The fused-rollout target of the north star: aggregation + rollout over resident G/cam, HBM-bound.
-    Algorithmic bytes per explanation = 2*L*H*N^2*4 (+ 4N out)  (SURVEY.md §8d)."""
+    Algorithmic bytes per explanation = 2*L*H*N^2*4 (+ 4N out; + 4N^2 when the dense joint is returned)  (SURVEY.md §8d).
+    dense: the [B,N,N] joint through the aggregation kernel + the N x N x N chain on tcgen05 (compute_rollout_attention's
+    consumers); otherwise row 0 only (all generate_LRP reads) through the single fused kernel."""
     from transformer_explainability_b200 import ops, _lib
     L, H, N = w["depth"], w["heads"], w["tokens"]
-    B = 32
     ld = (N + 3) // 4 * 4
     g = torch.Generator(device="cuda").manual_seed(2)
     grad = torch.randn(L, B, H, N, ld, device="cuda", generator=g) * 0.05
     cam = torch.randn(L, B, H, N, ld, device="cuda", generator=g) * 0.05
     fused = bool(flags & _lib.FLAG_ROLLOUT_FUSED)
-    for _ in range(2):
-        ops.attribution_rollout(grad, cam, fused=fused, want_joint=False)
-    torch.cuda.synchronize()
-    reps = 5
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        ops.attribution_rollout(grad, cam, fused=fused, want_joint=False)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    nbytes = B * (2.0 * L * H * N * N * 4 + 4 * N)
+    norm = w["kind"] == "bert"
+    ms = _time_ms(lambda: ops.attribution_rollout(grad, cam, normalize=norm, fused=fused, want_joint=dense))
+    nbytes = B * (2.0 * L * H * N * N * 4 + 4 * N + (4.0 * N * N if dense else 0.0))
     achieved = nbytes / (ms * 1e-3) / 1e9
-    return {"kernel": "attribution_rollout[%s] L=%d B=%d H=%d N=%d" % ("fused" if fused else "aggregate+bmm", L, B, H, N),
+    return {"kernel": "attribution_rollout[%s] L=%d B=%d H=%d N=%d" % (
+                ("aggregate + tcgen05 N^3 chain, dense joint" if dense else "fused row-only") if fused else "aggregate+bmm", L, B, H, N),
             "bound": "hbm", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
-            "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": measured_traffic("rollout_fused" if fused else "rollout"),
+            "frac": round(achieved / pk["hbm_gbs"], 4),
+            "traffic": None if dense else measured_traffic("rollout_fused" if fused else "rollout"),
             "algorithmic_bytes": nbytes, "ms": round(ms, 3), "peak_source": pk["source"]}
 
 
@@ -455,8 +507,16 @@ def main():
     if rank == 0:
         pk = peaks()
         if not args.no_roofline:
+            del x_dev
+            eng._ws = None
+            eng._graphs = {}
+            torch.cuda.empty_cache()
             line["roofline"] = roofline_zplus(w, batch, flags, pk)
-            line["roofline_rollout"] = roofline_rollout(w, flags, pk)
+            line["roofline"]["tf32_matmul_measured_tflops"] = measured_tf32_peak()
+            line["roofline_linear"] = roofline_linear(w, batch, flags, pk)
+            rb = min(batch, 256 if w["tokens"] <= 256 else 32)
+            line["roofline_rollout"] = roofline_rollout(w, flags, pk, B=rb)
+            line["roofline_rollout_dense"] = roofline_rollout(w, flags, pk, B=min(rb, 64), dense=True)
         if world == 1 and not args.no_cpu_baseline:
             del eng._ws
             eng._ws = None

@@ -48,10 +48,9 @@ def is_mirror():
 
 @contextlib.contextmanager
 def _cpu_cuda_shim():
-    """Make ``Tensor.cuda()`` a no-op while the reference runs on a GPU-less host."""
-    if torch.cuda.is_available():
-        yield
-        return
+    """Make ``Tensor.cuda()`` a no-op while the reference runs: the harness always runs the reference ON THE HOST CORES
+    (it is the CPU arm), also on a GPU box, where the hard-coded ``.cuda()`` on the one-hot
+    (``ViT_explanation_generator.py:35``) would otherwise mix a CUDA tensor into a CPU model."""
     orig = torch.Tensor.cuda
     torch.Tensor.cuda = lambda self, *a, **k: self
     try:
