@@ -365,10 +365,10 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
                        TE_EPI_STORE, st));                                                                      // G = dctx v^T
         if (l == start_layer) break;
         TE_TRY(attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, a.P, 1, dctx, d.D, dqkv + 2 * d.D, 3 * d.D, nullptr, 1.f,
-                       TE_EPI_STORE, st));
+                       TE_EPI_STORE, st, btf));                                                                 // dV = P^T dctx
         TE_TRY(te_launch_softmax_bwd(a.P, a.G, dS, (long long)d.B * d.H * d.N, d.N, d.NP, scale, st));
-        TE_TRY(attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, dS, 0, a.qkv + d.D, 3 * d.D, dqkv, 3 * d.D, nullptr, 1.f, TE_EPI_STORE, st));
-        TE_TRY(attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, dS, 1, a.qkv, 3 * d.D, dqkv + d.D, 3 * d.D, nullptr, 1.f, TE_EPI_STORE, st));
+        TE_TRY(attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, dS, 0, a.qkv + d.D, 3 * d.D, dqkv, 3 * d.D, nullptr, 1.f, TE_EPI_STORE, st, btf));   // dQ
+        TE_TRY(attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, dS, 1, a.qkv, 3 * d.D, dqkv + d.D, 3 * d.D, nullptr, 1.f, TE_EPI_STORE, st, btf));   // dK
         TE_TRY(linear_bwd_tc(tw.qkv, dqkv, lw.qkvw, dxn, nullptr, d.M, d.D, 3 * d.D, TE_EPI_STORE, st, btf));
         TE_TRY(te_launch_add2(dxn, dsx, dxa, MD, st));                                                          // d h
     }

@@ -431,6 +431,60 @@ __global__ void aggregate_vec_kernel(const float* __restrict__ G, const float* _
     }
 }
 
+// All layers of the dense rollout in ONE launch (blockIdx.y = layer - first_layer): the per-layer launches of the composed
+// path left the aggregation latency-bound (one short row per warp, a few thousand warps per launch: 0.39-0.47 of the HBM
+// peak for the whole dense call); with every layer in flight at once and all H head rows of a lane's float4 column issued
+// back to back the stream is deep enough to approach the copy bandwidth.  Layer `first_layer` keeps its identity inside M
+// (it is the chain's start, ViT_LRP.py:46); the others are written WITHOUT it (residual form of te_tc_bmm_nk_resid) and, when
+// normalising, export the identity's weight 1 / rowsum to diag.
+__global__ void aggregate_layers_vec_kernel(const float* __restrict__ G0, const float* __restrict__ cam0, long long in_layer_stride,
+                                            float* __restrict__ M0, long long m_layer_stride, int B, int H, int N, int ld_in,
+                                            int ld, int first_layer, int normalize, float* __restrict__ diag0) {
+    const int lane = threadIdx.x & 31;
+    const int layer = first_layer + blockIdx.y;
+    const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);   // b*N + i
+    if (row >= (long long)B * N) return;
+    const int b = (int)(row / N), i = (int)(row % N);
+    const float* __restrict__ G = G0 + (long long)layer * in_layer_stride;
+    const float* __restrict__ cam = cam0 + (long long)layer * in_layer_stride;
+    float* out = M0 + (long long)layer * m_layer_stride + row * ld;
+    const bool eye = blockIdx.y == 0;
+    float* diag = (!eye && diag0) ? diag0 + (long long)layer * B * N : nullptr;
+    float rs = 0.f;
+    const float inv_h = 1.0f / (float)H;
+    for (int j4 = lane; j4 * 4 < ld; j4 += 32) {
+        const int j = j4 * 4;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < N && j < ld_in) {
+            const long long o0 = (((long long)b * H) * N + i) * ld_in + j;
+            const long long hs = (long long)N * ld_in;
+#pragma unroll 6
+            for (int h = 0; h < H; ++h) {
+                const float4 g = __ldcs(reinterpret_cast<const float4*>(G + o0 + h * hs));
+                const float4 c = __ldcs(reinterpret_cast<const float4*>(cam + o0 + h * hs));
+                s.x += fmaxf(g.x * c.x, 0.f); s.y += fmaxf(g.y * c.y, 0.f);
+                s.z += fmaxf(g.z * c.z, 0.f); s.w += fmaxf(g.w * c.w, 0.f);
+            }
+        }
+        float v[4] = {s.x / (float)H, s.y / (float)H, s.z / (float)H, s.w / (float)H};
+        (void)inv_h;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (j + u >= N) v[u] = 0.f;                         // the row padding of G / cam is never trusted
+            else if (eye && j + u == i) v[u] += 1.0f;
+            rs += v[u];
+        }
+        *reinterpret_cast<float4*>(out + j) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    if (normalize) {
+        rs = te_warp_sum(rs);
+        if (diag != nullptr) rs += 1.0f;
+        __syncwarp();
+        for (int j = lane; j < N; j += 32) out[j] = out[j] / rs;
+        if (diag != nullptr && lane == 0) diag[row] = 1.0f / rs;
+    }
+}
+
 // generate_visualization (example.ipynb:57-60): [g,g] relevance -> bilinear x scale (align_corners=False, the arithmetic of
 // torch.nn.functional.interpolate(mode='bilinear', scale_factor=scale)) -> per-sample min-max.  One block per sample.
 __global__ void relevance_heatmap_kernel(const float* __restrict__ maps, float* __restrict__ out, int g, int scale) {
@@ -788,6 +842,19 @@ int te_launch_aggregate(const float* G, const float* cam, float* M, int B, int H
     else
         aggregate_kernel<<<warp_rows_grid((long long)B * N), kThreads, 0, st>>>(G, cam, M, B, H, N, ld_in, ld_out, add_eye,
                                                                               normalize, diag);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int te_launch_aggregate_layers(const float* G0, const float* cam0, long long in_layer_stride, float* M0, long long m_layer_stride,
+                               int B, int H, int N, int ld_in, int ld_out, int first_layer, int num_layers, int normalize,
+                               cudaStream_t st, float* diag0) {
+    const bool vec = ld_in % 4 == 0 && ld_out % 4 == 0 && ld_in >= ((N + 3) & ~3) && in_layer_stride % 4 == 0 &&
+                     m_layer_stride % 4 == 0 &&
+                     ((reinterpret_cast<uintptr_t>(G0) | reinterpret_cast<uintptr_t>(cam0) | reinterpret_cast<uintptr_t>(M0)) & 15u) == 0;
+    TE_REQ(vec && num_layers >= 1 && num_layers <= 65535, "aggregate_layers: unsupported layout");
+    dim3 grid(warp_rows_grid((long long)B * N), num_layers);
+    aggregate_layers_vec_kernel<<<grid, kThreads, 0, st>>>(G0, cam0, in_layer_stride, M0, m_layer_stride, B, H, N, ld_in, ld_out,
+                                                          first_layer, normalize, diag0);
     TE_CUDA_CHECK_LAUNCH();
     return TE_OK;
 }

@@ -97,12 +97,13 @@ static inline int attn_probs(bool tc, int B, int H, int N, int NP, int dh, const
 }
 
 // out[b,m,h,:] = epi(alpha * sum_k A_h[m,k] X[b,k,h,:]) with A_h = map[b,h] (amn = 0) or map[b,h]^T (amn = 1)
+// tf32: single-pass TF32 (activation-gradient contractions, TE_FLAG_BACKWARD_TF32)
 static inline int attn_nk(bool tc, int B, int H, int N, int NP, int dh, const float* map, int amn, const float* X, int ldx,
-                          float* out, int ld_out, const float* E, float alpha, int epi, cudaStream_t st) {
-    if (tc && te_tc_attn_nk_supported(N, dh, NP, ldx, ld_out) && (!E || true)) {
+                          float* out, int ld_out, const float* E, float alpha, int epi, cudaStream_t st, bool tf32 = false) {
+    if (tc && te_tc_attn_nk_supported(N, dh, NP, ldx, ld_out)) {
         const int e = (epi == TE_EPI_STORE) ? TE_TC_ATTN_STORE : TE_TC_ATTN_MUL;
         if (epi == TE_EPI_STORE || epi == TE_EPI_MUL)
-            return te_tc_attn_nk(map, NP, amn, X, ldx, B, H, N, out, ld_out, E, alpha, e, st);
+            return te_tc_attn_nk(map, NP, amn, X, ldx, B, H, N, out, ld_out, E, alpha, e, st, tf32);
     }
     const HeadOp none = {nullptr, 0, 0, 0};
     return head_gemm(B, H, attn_map(map, H, N, NP), amn ? TE_L_MN : TE_L_K, head_rows(X, ldx, N, dh), TE_L_MN,

@@ -38,8 +38,10 @@ int te_tc_attn_nn(const float* A, long long lda, const float* B, long long ldb, 
 
 // attention-shaped N x d contractions with the reduction over tokens (attn v, attn^T dctx, dS k, dS^T q, S1 k, S1^T q ...)
 bool te_tc_attn_nk_supported(int N, int dh, int NP, long long ldx, long long ld_out);
+// single_pass (STORE epilogue only): one TF32 MMA per k-step on the raw operands instead of the 3xTF32 split — the
+// activation-gradient contractions under TE_FLAG_BACKWARD_TF32
 int te_tc_attn_nk(const float* map, int NP, int amn, const float* X, long long ldx, int batch, int H, int N, float* out,
-                  int ld_out, const float* E, float alpha, int epi, cudaStream_t st);
+                  int ld_out, const float* E, float alpha, int epi, cudaStream_t st, bool single_pass = false);
 
 // 1: run the z+ rule with the CTA-pair (tcgen05 cta_group::2) kernels instead of the single-CTA ones (default 0,
 // or the environment variable TE_B200_ZPLUS_2CTA=1)

@@ -51,6 +51,11 @@ int te_launch_index_select_relprop(const float* x, const float* r_tok0, const fl
 // diag (with add_eye = 0, normalize = 1): identity kept out of M, its normalised weight 1/rowsum written to diag [B*N]
 int te_launch_aggregate(const float* G, const float* cam, float* M, int B, int H, int N, int ld_in, int ld_out,
                         int add_eye, int normalize, cudaStream_t st, float* diag = nullptr);
+// every layer first_layer .. first_layer+num_layers-1 in one launch (vectorised layouts only): layer first_layer keeps its
+// identity inside M, the others are written in the residual form (identity left out, its normalised weight in diag)
+int te_launch_aggregate_layers(const float* G0, const float* cam0, long long in_layer_stride, float* M0, long long m_layer_stride,
+                               int B, int H, int N, int ld_in, int ld_out, int first_layer, int num_layers, int normalize,
+                               cudaStream_t st, float* diag0 = nullptr);
 // generate_visualization: [B, g*g] -> bilinear x scale -> per-sample min-max -> [B, g*scale, g*scale]
 int te_launch_relevance_heatmap(const float* maps, float* out, int B, int g, int scale, cudaStream_t st);
 // secondary methods: out[b,i,j] = reduce_h( a (* g) (* hw[b,h]) ); mode 0 mean, 1 mean of relu, 2 relu of mean

@@ -42,15 +42,23 @@ int te_rollout_layers(const float* G0, const float* cam0, long long layer_stride
         // dense joint on the tensor cores, residual form: J <- A_l J + d_l J with A_l = M_l without its identity part
         // (tcgen05, 3xTF32) and the identity's share d_l (1, or 1/rowsum for BERT) applied in fp32 in the epilogue
         const long long ms = (long long)B * N * ld;
-        TE_TRY(te_launch_aggregate(G0 + start_layer * layer_stride, cam0 + start_layer * layer_stride,
-                                   mats + start_layer * ms, B, H, N, ld_in, ld, /*add_eye=*/1, normalize, st));
+        const bool one_launch = ld_in % 4 == 0 && ld % 4 == 0 && ld_in >= ((N + 3) & ~3) && layer_stride % 4 == 0 &&
+                                ((reinterpret_cast<uintptr_t>(G0) | reinterpret_cast<uintptr_t>(cam0) |
+                                  reinterpret_cast<uintptr_t>(mats)) & 15u) == 0;
+        if (one_launch)          // every layer's aggregation in flight at once: the stream is deep enough for the copy bandwidth
+            TE_TRY(te_launch_aggregate_layers(G0, cam0, layer_stride, mats, ms, B, H, N, ld_in, ld, start_layer, L - start_layer,
+                                              normalize, st, normalize ? diag : nullptr));
+        else
+            TE_TRY(te_launch_aggregate(G0 + start_layer * layer_stride, cam0 + start_layer * layer_stride,
+                                       mats + start_layer * ms, B, H, N, ld_in, ld, /*add_eye=*/1, normalize, st));
         joint = mats + start_layer * ms;
         float* bufs[2] = {joint_a, joint_b};
         int which = 0;
         for (int l = start_layer + 1; l < L; ++l) {
             float* dl = normalize ? diag + (long long)l * B * N : nullptr;
-            TE_TRY(te_launch_aggregate(G0 + l * layer_stride, cam0 + l * layer_stride, mats + l * ms, B, H, N, ld_in, ld,
-                                       /*add_eye=*/0, normalize, st, dl));
+            if (!one_launch)
+                TE_TRY(te_launch_aggregate(G0 + l * layer_stride, cam0 + l * layer_stride, mats + l * ms, B, H, N, ld_in, ld,
+                                           /*add_eye=*/0, normalize, st, dl));
             TE_TRY(te_tc_bmm_nk_resid(mats + l * ms, joint, dl, bufs[which], B, N, ld, st));
             joint = bufs[which];
             which ^= 1;

@@ -244,13 +244,16 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 // NB = number of 32-wide output-column blocks: 2 for the head_dim-64 attention products, 7 (N <= 224) for the dense
 // rollout product J <- (M_l + I) J, which is the same contraction with H = 1 (A = M_l K-major, B = J MN-major).
 constexpr int NK_A = A_BYTES;                                      // 16 KiB
-template <int NB> struct NkCfg {
+// SP (single pass): raw fp32 operands straight from TMA to one TF32 MMA per k-step — no hi/lo split, no transform warps in
+// the chain, half the stage, twice the ring depth.  Used for the activation-gradient contractions (attn^T dctx, dS k,
+// dS^T q) under TE_FLAG_BACKWARD_TF32: the gradients enter the result linearly (relu(G * cam)), never a denominator.
+template <int NB, bool SP = false> struct NkCfg {
     static constexpr int BN = NB * 32;
     static constexpr int B_BYTES_ = BN * BK * 4;                   // 4 KiB per block
-    static constexpr int STAGE = 2 * NK_A + 2 * B_BYTES_;
-    // attention shape (NB = 2): 2 stages of 48 KiB so that TWO CTAs share an SM — a CTA's whole reduction is only 7
-    // k-blocks, and its prologue / epilogue then overlap the other CTA's main loop
-    static constexpr int STAGES = 2;
+    static constexpr int STAGE = SP ? (NK_A + B_BYTES_) : (2 * NK_A + 2 * B_BYTES_);
+    // attention shape (NB = 2): 2 stages of 48 KiB (SP: 4 of 24 KiB) so that TWO CTAs share an SM — a CTA's whole
+    // reduction is only 7 k-blocks, and its prologue / epilogue then overlap the other CTA's main loop
+    static constexpr int STAGES = SP ? 4 : 2;
     static constexpr int MIN_CTAS = (NB <= 2) ? 2 : 1;
     static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
     static constexpr int XF4 = (NK_A + B_BYTES_) / 16;
@@ -270,10 +273,10 @@ struct NkParams {
     const float* E; float* out; float alpha;
 };
 
-template <int AMN, int EPI, int NB>
-__global__ void __launch_bounds__(NUM_THREADS, NkCfg<NB>::MIN_CTAS)
+template <int AMN, int EPI, int NB, bool SP = false>
+__global__ void __launch_bounds__(NUM_THREADS, NkCfg<NB, SP>::MIN_CTAS)
 te_tc_attn_nk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const NkParams p) {
-    using C = NkCfg<NB>;
+    using C = NkCfg<NB, SP>;
     constexpr int NK_BN = C::BN, NK_B = C::B_BYTES_, NK_STAGE = C::STAGE, NK_STAGES = C::STAGES, NK_XF4 = C::XF4;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -284,7 +287,7 @@ te_tc_attn_nk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     auto empty_bar = [&](int s) { return bars + 8u * (2 * NK_STAGES + s); };
     const uint32_t accum_bar = bars + 8u * (3 * NK_STAGES);
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + NK_STAGES * NK_STAGE + 8 * (3 * NK_STAGES + 1));
-    constexpr uint32_t OFF_AL = NK_A, OFF_BH = 2 * NK_A, OFF_BL = 2 * NK_A + NK_B;
+    constexpr uint32_t OFF_AL = NK_A, OFF_BH = SP ? NK_A : 2 * NK_A, OFF_BL = 2 * NK_A + NK_B;
     // instruction descriptor: tf32, M = 128, N = 64, A major = AMN, B major = MN
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)AMN << 15) | (1u << 16) |
                                ((uint32_t)(NK_BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -343,12 +346,17 @@ te_tc_attn_nk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int it = 0; it < kb; ++it) {
                 const int s = it % NK_STAGES;
                 const uint32_t ph = (it / NK_STAGES) & 1u;
-                mbar_wait(xf_bar(s), ph);
+                mbar_wait(SP ? full_bar(s) : xf_bar(s), ph);
                 tcgen05_fence_after();
                 const uint32_t sa = smem_base + s * NK_STAGE;
 #pragma unroll
                 for (int k = 0; k < BK / 8; ++k) {
                     uint64_t ah, al;
+                    if (SP) {                     // one TF32 MMA per k-step on the raw operands
+                        ah = (AMN == 0) ? make_smem_desc(sa) + (uint64_t)(2 * k) : make_smem_desc_mn(sa + k * 1024, 4096);
+                        umma_tf32(tmem_base, ah, make_smem_desc_mn(sa + OFF_BH + k * 1024, 4096), idesc, (it == 0 && k == 0) ? 0u : 1u);
+                        continue;
+                    }
                     if (AMN == 0) {
                         ah = make_smem_desc(sa) + (uint64_t)(2 * k);                      // +32 B along the K-major row
                         al = make_smem_desc(sa + OFF_AL) + (uint64_t)(2 * k);
@@ -376,7 +384,7 @@ te_tc_attn_nk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         __syncwarp();
     } else {
         const int et = threadIdx.x - 64;
-        for (int it = 0; it < kb; ++it) {
+        for (int it = 0; it < (SP ? 0 : kb); ++it) {
             const int s = it % NK_STAGES;
             const uint32_t ph = (it / NK_STAGES) & 1u;
             mbar_wait(full_bar(s), ph);
@@ -439,7 +447,8 @@ te_tc_attn_nk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const float a = __uint_as_float(acc[j * 4 + u]);
-                            float v = p.alpha * a;
+                            // SP: both raw operands were truncated to TF32 by the tensor core (mean shrink 3.4e-4 each)
+                            float v = p.alpha * a * (SP ? 1.00068f : 1.0f);
                             if (EPI == AT_MUL) {
                                 const float4 e4 = ebuf[(EPI == AT_MUL) ? c * 8 + j : 0];
                                 const float e = (u == 0) ? e4.x : (u == 1) ? e4.y : (u == 2) ? e4.z : e4.w;
@@ -532,9 +541,9 @@ bool make_map3(CUtensorMap* m, const float* base, long long cols, long long rows
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int AMN, int EPI, int NB>
+template <int AMN, int EPI, int NB, bool SP = false>
 int launch_nk(const float* map, int NP, const float* X, long long ldx, const NkParams& p, int batch, cudaStream_t st) {
-    constexpr int NK_SMEM = NkCfg<NB>::SMEM;
+    constexpr int NK_SMEM = NkCfg<NB, SP>::SMEM;
     CUtensorMap tmA, tmB;
     // attention-shaped map [batch*H, N, NP] ; activation [batch, N, ldx]
     if (!make_map3(&tmA, map, NP, p.N, p.a_shared ? (long long)batch : (long long)batch * p.H, NP, (long long)p.N * NP, 32,
@@ -544,13 +553,13 @@ int launch_nk(const float* map, int NP, const float* X, long long ldx, const NkP
         return TE_ERR_CUDA;
     }
     static unsigned long long optin = 0;          // per-device attribute: one bit per device
-    if (!smem_optin(te_tc_attn_nk_kernel<AMN, EPI, NB>, NK_SMEM, optin)) {
+    if (!smem_optin(te_tc_attn_nk_kernel<AMN, EPI, NB, SP>, NK_SMEM, optin)) {
         te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
         return TE_ERR_CUDA;
     }
     dim3 grid((p.N + BM - 1) / BM, batch * p.H);
     if (grid.y > 65535) { te_set_last_error("te_gemm_tc: batch*heads too large for one launch"); return TE_ERR_ARG; }
-    te_tc_attn_nk_kernel<AMN, EPI, NB><<<grid, NUM_THREADS, NK_SMEM, st>>>(tmA, tmB, p);
+    te_tc_attn_nk_kernel<AMN, EPI, NB, SP><<<grid, NUM_THREADS, NK_SMEM, st>>>(tmA, tmB, p);
     TE_CUDA_CHECK_LAUNCH();
     return TE_OK;
 }
@@ -559,10 +568,12 @@ int launch_nk(const float* map, int NP, const float* X, long long ldx, const NkP
 // out[b, m, h, :] = epi(alpha * sum_k A_h[m,k] X[b,k,h,:]) ; A_h = map[b,h] (amn = 0) or its transpose (amn = 1);
 // X, out, E: packed activations [batch, N, ld] (head h at columns h*64..); epi: TE_TC_ATTN_STORE / TE_TC_ATTN_MUL
 int te_tc_attn_nk(const float* map, int NP, int amn, const float* X, long long ldx, int batch, int H, int N, float* out,
-                  int ld_out, const float* E, float alpha, int epi, cudaStream_t st) {
+                  int ld_out, const float* E, float alpha, int epi, cudaStream_t st, bool single_pass) {
     NkParams p;
     p.N = N; p.H = H; p.ld_out = ld_out; p.n_out = H * 64; p.n_pad = H * 64; p.a_shared = 0; p.rowscale = nullptr;
     p.E = E; p.out = out; p.alpha = alpha;
+    if (single_pass && epi == TE_TC_ATTN_STORE)
+        return amn ? launch_nk<1, AT_STORE, 2, true>(map, NP, X, ldx, p, batch, st) : launch_nk<0, AT_STORE, 2, true>(map, NP, X, ldx, p, batch, st);
     if (epi == TE_TC_ATTN_STORE) return amn ? launch_nk<1, AT_STORE, 2>(map, NP, X, ldx, p, batch, st) : launch_nk<0, AT_STORE, 2>(map, NP, X, ldx, p, batch, st);
     if (epi == TE_TC_ATTN_MUL) return amn ? launch_nk<1, AT_MUL, 2>(map, NP, X, ldx, p, batch, st) : launch_nk<0, AT_MUL, 2>(map, NP, X, ldx, p, batch, st);
     te_set_last_error("te_gemm_tc: unsupported attention nk epilogue");

@@ -391,12 +391,12 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
                                 TE_EPI_STORE, st));                                 // G = dctx v^T
         if (l == start_layer) break;                                                // lower gradients are never read
         TE_TRY(te_util::attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, a.P, 1, dctx, d.D, dqkv + 2 * d.D, 3 * d.D, nullptr, 1.f,
-                                TE_EPI_STORE, st));                                 // dV = P^T dctx
+                                TE_EPI_STORE, st, btf));                                 // dV = P^T dctx
         TE_TRY(te_launch_softmax_bwd(a.P, a.G, dS, (long long)d.B * d.H * d.N, d.N, d.NP, scale, st));
         TE_TRY(te_util::attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, dS, 0, a.qkv + d.D, 3 * d.D, dqkv, 3 * d.D, nullptr, 1.f,
-                                TE_EPI_STORE, st));                                 // dQ = dS k
+                                TE_EPI_STORE, st, btf));                                 // dQ = dS k
         TE_TRY(te_util::attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, dS, 1, a.qkv, 3 * d.D, dqkv + d.D, 3 * d.D, nullptr, 1.f,
-                                TE_EPI_STORE, st));                                 // dK = dS^T q
+                                TE_EPI_STORE, st, btf));                                 // dK = dS^T q
         TE_TRY(te_util::linear_bwd_tc(lw.qkv, dqkv, bw.qkvw, dxn, nullptr, d.M, d.D, 3 * d.D, TE_EPI_STORE, st, btf));
         TE_TRY(te_launch_layernorm_bwd(dxn, a.x_in, bw.n1w, a.mean1, a.rstd1, dxb, dxa, d.M, d.D, st));
     }
