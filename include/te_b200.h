@@ -48,6 +48,9 @@ extern "C" {
                                          single-pass TF32 GEMMs (persistent CTA-pair kernel) instead of the 3xTF32 split.
                                          The gradients only enter the result linearly (relu(G * cam)), never a
                                          safe_divide denominator: measured effect in profiles/ (r02 parity table) */
+#define TE_FLAG_RELPROP_TF32 1024u     /* with TE_FLAG_ATTN_TENSOR_CORES: the attention-shaped contractions of the relprop whose
+                                         result is relevance (attn_cam = P * (S V^T) / 2, P^T S, S1 K, S1^T Q) run single-pass
+                                         TF32 like the z+ rule does; the denominator Q K^T keeps the 3xTF32 split */
 #define TE_FLAG_RULES_LRP 512u         /* the rule library of modules/layers_lrp.py (baselines/ViT/ViT_orig_LRP.py) instead of
                                          modules/layers_ours.py: Linear divides its two halves by their OWN denominators
                                          (layers_lrp.py:199-200), Add has no ratio normalisation (:98-100).  fp32 SIMT rules. */

@@ -15,14 +15,9 @@ def _notebook_reference(row):
     return (t - t.min()) / (t.max() - t.min())
 
 
-def test_heatmap_matches_notebook_sequence_per_sample():
-    g = torch.Generator().manual_seed(0)
-    maps = torch.rand(5, 196, generator=g) * 1e-4
-    heat = relevance_to_heatmap(maps)
-    assert heat.shape == (5, 224, 224)
-    for s in range(5):
-        assert torch.equal(heat[s], _notebook_reference(maps[s]))
-    assert float(heat.min()) == 0.0 and float(heat.max()) == 1.0
+def test_heatmap_has_no_host_path():
+    with pytest.raises(ValueError):
+        relevance_to_heatmap(torch.rand(2, 196))
 
 
 @pytest.mark.gpu

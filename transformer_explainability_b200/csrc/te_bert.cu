@@ -324,6 +324,7 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
     const float* lbase = (flags & TE_FLAG_LINEAR_TENSOR_CORES) ? derived : nullptr;
     const bool atc = (flags & TE_FLAG_ATTN_TENSOR_CORES) != 0;
     const bool btf = (flags & TE_FLAG_BACKWARD_TF32) != 0;       // single-pass TF32 backward Linears
+    const bool rtf = (flags & TE_FLAG_RELPROP_TF32) != 0;        // single-pass TF32 relevance-side attention contractions
     const bool zb = (flags & TE_FLAG_ZPLUS_BF16) != 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     Weights w;
@@ -362,7 +363,7 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
         TE_TRY(te_launch_layernorm_bwd(dxn, a.s1, lw.ln1w, a.mean1, a.rstd1, nullptr, dsx, d.M, d.D, st));    // d s1
         TE_TRY(linear_bwd_tc(tw.o, dsx, lw.ow, dctx, nullptr, d.M, d.D, d.D, TE_EPI_STORE, st, btf));
         TE_TRY(attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, dctx, d.D, a.qkv + 2 * d.D, 3 * d.D, a.G, nullptr, 1.f,
-                       TE_EPI_STORE, st));                                                                      // G = dctx v^T
+                       TE_EPI_STORE, st, btf));                                                                      // G = dctx v^T
         if (l == start_layer) break;
         TE_TRY(attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, a.P, 1, dctx, d.D, dqkv + 2 * d.D, 3 * d.D, nullptr, 1.f,
                        TE_EPI_STORE, st, btf));                                                                 // dV = P^T dctx
@@ -408,10 +409,10 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
         // BertSelfAttention.relprop :367-409
         TE_TRY(te_launch_sd(R3, a.ctx, S, MD, st));                                       // matmul2: Z == saved ctx
         TE_TRY(attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, S, d.D, a.qkv + 2 * d.D, 3 * d.D, a.cam, a.P, 0.5f, TE_EPI_MUL,
-                       st));                                                              // attn_cam   :380
+                       st, rtf));                                                              // attn_cam   :380
         if (l == low && !(flags & TE_FLAG_RELPROP_TO_INPUT)) break;
         TE_TRY(attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, a.P, 1, S, d.D, Rqkv + 2 * d.D, 3 * d.D, a.qkv + 2 * d.D, 0.5f, TE_EPI_MUL,
-                       st));
+                       st, rtf));
         // add([scores, mask]).relprop : scores = q k^T / sqrt(d) recomputed ; relevance renormalised  :386-388
         TE_TRY(attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, a.qkv, 3 * d.D, a.qkv + d.D, 3 * d.D, ws.tA[0], nullptr, scale,
                        TE_EPI_STORE, st));
@@ -419,9 +420,9 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
         // matmul1 rule on the unscaled product
         TE_TRY(attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, a.qkv, 3 * d.D, a.qkv + d.D, 3 * d.D, ws.tA[0], ws.tA[1], 1.f,
                        TE_EPI_SD, st));
-        TE_TRY(attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, ws.tA[0], 0, a.qkv + d.D, 3 * d.D, Rqkv, 3 * d.D, a.qkv, 0.5f, TE_EPI_MUL, st));
+        TE_TRY(attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, ws.tA[0], 0, a.qkv + d.D, 3 * d.D, Rqkv, 3 * d.D, a.qkv, 0.5f, TE_EPI_MUL, st, rtf));
         TE_TRY(attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, ws.tA[0], 1, a.qkv, 3 * d.D, Rqkv + d.D, 3 * d.D, a.qkv + d.D, 0.5f,
-                       TE_EPI_MUL, st));
+                       TE_EPI_MUL, st, rtf));
         // query / key / value z+ rules (separate Linears), Clone(3), Clone(2)
         TE_TRY(te_zplus_linear_relprop_ldr(a.h, d.D, lw.qkvw, dw.q, Rqkv, 3 * d.D, R, S, d.M, d.D, d.D, st, a.qkv, 3 * d.D, lw.qkvb, zb, 0, S + MD));
         TE_TRY(te_zplus_linear_relprop_ldr(a.h, d.D, lw.qkvw + DD, dw.k, Rqkv + d.D, 3 * d.D, R1, S, d.M, d.D, d.D, st, a.qkv + d.D, 3 * d.D,

@@ -75,11 +75,12 @@ static inline int head_gemm(int B, int H, HeadOp A, int alay, HeadOp Bm, int bla
 
 // out[b,h,:,:] = epi(alpha * A_h B_h^T) for head slices A, B of packed [batch*N, ld] activations
 // (Q K^T, dctx V^T, S2 V^T).  tc: fp32-grade 3xTF32 tensor-core kernel when the shape qualifies.
+// tf32: single-pass TF32 (STORE / MUL epilogues; gradient and relevance products, never a denominator)
 static inline int attn_nn(bool tc, int B, int H, int N, int NP, int dh, const float* A, int lda, const float* Bm, int ldb,
-                          float* out, const float* E, float alpha, int epi, cudaStream_t st) {
+                          float* out, const float* E, float alpha, int epi, cudaStream_t st, bool tf32 = false) {
     if (tc && te_tc_attn_supported(N, dh, lda, ldb, NP)) {
         const int e = (epi == TE_EPI_STORE) ? TE_TC_ATTN_STORE : (epi == TE_EPI_MUL) ? TE_TC_ATTN_MUL : TE_TC_ATTN_SD;
-        return te_tc_attn_nn(A, lda, Bm, ldb, B, H, N, dh, out, NP, E, alpha, e, st);
+        return te_tc_attn_nn(A, lda, Bm, ldb, B, H, N, dh, out, NP, E, alpha, e, st, tf32 && N <= 256 && epi != TE_EPI_SD);
     }
     const HeadOp none = {nullptr, 0, 0, 0};
     return head_gemm(B, H, head_rows(A, lda, N, dh), TE_L_K, head_rows(Bm, ldb, N, dh), TE_L_K, attn_map(out, H, N, NP),

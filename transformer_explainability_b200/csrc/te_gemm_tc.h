@@ -33,13 +33,14 @@ int te_tc_linear_bwd(const float* dy, const float* derived, int in_features, int
 // attention-shaped N x N contractions (Q K^T, dctx V^T, S2 V^T) on tcgen05, fp32-grade 3xTF32, head slices in place
 enum { TE_TC_ATTN_STORE = 0, TE_TC_ATTN_MUL = 1, TE_TC_ATTN_SD = 2, TE_TC_ATTN_SOFTMAX = 3 };   // SOFTMAX: N <= 256
 bool te_tc_attn_supported(int N, int dh, long long lda, long long ldb, int ld_out);
+// single_pass (STORE / MUL epilogues): one TF32 MMA per k-step on the raw operands (gradient / relevance products only)
 int te_tc_attn_nn(const float* A, long long lda, const float* B, long long ldb, int batch, int H, int N, int dh,
-                  float* out, int ld_out, const float* E, float alpha, int epi, cudaStream_t st);
+                  float* out, int ld_out, const float* E, float alpha, int epi, cudaStream_t st, bool single_pass = false);
 
 // attention-shaped N x d contractions with the reduction over tokens (attn v, attn^T dctx, dS k, dS^T q, S1 k, S1^T q ...)
 bool te_tc_attn_nk_supported(int N, int dh, int NP, long long ldx, long long ld_out);
-// single_pass (STORE epilogue only): one TF32 MMA per k-step on the raw operands instead of the 3xTF32 split — the
-// activation-gradient contractions under TE_FLAG_BACKWARD_TF32
+// single_pass (STORE / MUL epilogues): one TF32 MMA per k-step on the raw operands instead of the 3xTF32 split — the
+// activation-gradient contractions under TE_FLAG_BACKWARD_TF32, the relevance contractions under TE_FLAG_RELPROP_TF32
 int te_tc_attn_nk(const float* map, int NP, int amn, const float* X, long long ldx, int batch, int H, int N, float* out,
                   int ld_out, const float* E, float alpha, int epi, cudaStream_t st, bool single_pass = false);
 

@@ -25,7 +25,11 @@ struct AtParams {
     const float* E; float* out; float alpha;
 };
 
-template <int EPI>
+// SP (single pass): the raw fp32 operands go straight from TMA to one TF32 MMA per k-step (no hi/lo split); both k-blocks
+// of the head dimension are resident at once (the lo regions hold the second one).  For the contractions whose result is
+// relevance or a gradient — G = dctx V^T under TE_FLAG_BACKWARD_TF32, attn_cam = P * (S V^T) / 2 under
+// TE_FLAG_RELPROP_TF32 — never for a safe_divide denominator (Q K^T stays 3xTF32).
+template <int EPI, bool SP = false>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const AtParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -49,7 +53,7 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         mbar_init(full_bar, 1);
-        mbar_init(xf_bar, XF_THREADS / 32);
+        mbar_init(xf_bar, SP ? 1 : XF_THREADS / 32);           // SP: TMA barrier of the second k-block
         mbar_init(accum_bar, 1);
         mbar_init(empty_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -67,7 +71,15 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int k = 0; k < kb; ++k) {
+            if (SP) {
+                for (int k = 0; k < kb && k < 2; ++k) {                          // dh <= 64: at most two k-blocks, both resident
+                    const uint32_t bar = k ? xf_bar : full_bar;
+                    mbar_arrive_expect_tx(bar, (uint32_t)(A_BYTES + B_BYTES));
+                    tma_load_2d(smem_base + (k ? OFF_AL : OFF_AH), &tmA, bar, h * p.dh + k * BK, b * p.N + m0);
+                    tma_load_2d(smem_base + (k ? OFF_BL : OFF_BH), &tmB, bar, h * p.dh + k * BK, b * p.N + n0);
+                }
+            }
+            for (int k = 0; k < (SP ? 0 : kb); ++k) {
                 if (k > 0) mbar_wait(empty_bar, (uint32_t)((k - 1) & 1));        // MMAs of the previous k-block retired
                 mbar_arrive_expect_tx(full_bar, (uint32_t)(A_BYTES + B_BYTES));
                 tma_load_2d(smem_base + OFF_AH, &tmA, full_bar, h * p.dh + k * BK, b * p.N + m0);
@@ -79,6 +91,15 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const uint64_t ah = make_smem_desc(smem_base + OFF_AH), al = make_smem_desc(smem_base + OFF_AL);
             const uint64_t bh_ = make_smem_desc(smem_base + OFF_BH), bl = make_smem_desc(smem_base + OFF_BL);
             for (int kk = 0; kk < kb; ++kk) {
+                if (SP) {
+                    mbar_wait(kk ? xf_bar : full_bar, 0u);
+                    tcgen05_fence_after();
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k)
+                        umma_tf32(tmem_base, (kk ? al : ah) + (uint64_t)(2 * k), (kk ? bl : bh_) + (uint64_t)(2 * k), kIdesc,
+                                  (kk == 0 && k == 0) ? 0u : 1u);
+                    continue;
+                }
                 mbar_wait(xf_bar, (uint32_t)(kk & 1));
                 tcgen05_fence_after();
 #pragma unroll
@@ -96,7 +117,7 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     } else {
         const int et = threadIdx.x - 64;
         // split A (16 KiB) and B (32 KiB) of every k-block: hi in place, lo to the *_lo regions (same swizzled offsets)
-        for (int kk = 0; kk < kb; ++kk) {
+        for (int kk = 0; kk < (SP ? 0 : kb); ++kk) {
             mbar_wait(full_bar, (uint32_t)(kk & 1));
             float4* a4 = reinterpret_cast<float4*>(smem_al + OFF_AH);
             float4* l4 = reinterpret_cast<float4*>(smem_al + OFF_AL);
@@ -211,10 +232,12 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 float o[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
+                    // SP: both raw operands were truncated to TF32 by the tensor core (mean shrink 3.4e-4 each): compensated
+                    const float av = p.alpha * a[u] * (SP ? 1.00068f : 1.0f);
                     float v;
-                    if (EPI == AT_STORE) v = p.alpha * a[u];
-                    else if (EPI == AT_MUL) v = p.alpha * a[u] * e[u];
-                    else v = te_sd(e[u], p.alpha * a[u]);
+                    if (EPI == AT_STORE) v = av;
+                    else if (EPI == AT_MUL) v = av * e[u];
+                    else v = te_sd(e[u], av);
                     o[u] = (col + u < ncols) ? v : 0.f;                                  // zero the row padding
                 }
                 *reinterpret_cast<float4*>(p.out + ((long long)bh * p.N + r) * p.ld_out + n0 + col) = make_float4(o[0], o[1], o[2], o[3]);
@@ -482,7 +505,7 @@ bool te_tc_attn_supported(int N, int dh, long long lda, long long ldb, int ld_ou
 }
 
 namespace {
-template <int EPI>
+template <int EPI, bool SP = false>
 int launch_attn(const float* A, long long lda, const float* B, long long ldb, long long total_rows, const AtParams& p,
                 int batch, cudaStream_t st) {
     CUtensorMap tmA, tmB;
@@ -491,13 +514,13 @@ int launch_attn(const float* A, long long lda, const float* B, long long ldb, lo
         return TE_ERR_CUDA;
     }
     static unsigned long long optin = 0;          // per-device attribute: one bit per device
-    if (!smem_optin(te_tc_attn_nn_kernel<EPI>, AT_SMEM, optin)) {
+    if (!smem_optin(te_tc_attn_nn_kernel<EPI, SP>, AT_SMEM, optin)) {
         te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
         return TE_ERR_CUDA;
     }
     dim3 grid((p.N + BM - 1) / BM, batch * p.H, (p.N + BN - 1) / BN);
     if (grid.y > 65535) { te_set_last_error("te_gemm_tc: batch*heads too large for one launch"); return TE_ERR_ARG; }
-    te_tc_attn_nn_kernel<EPI><<<grid, NUM_THREADS, AT_SMEM, st>>>(tmA, tmB, p);
+    te_tc_attn_nn_kernel<EPI, SP><<<grid, NUM_THREADS, AT_SMEM, st>>>(tmA, tmB, p);
     TE_CUDA_CHECK_LAUNCH();
     return TE_OK;
 }
@@ -505,10 +528,12 @@ int launch_attn(const float* A, long long lda, const float* B, long long ldb, lo
 
 // out[b,h,i,j] = epi(alpha * sum_d A[b*N+i, h*dh+d] * B[b*N+j, h*dh+d]);  out / E are [batch,H,N,ld_out]
 int te_tc_attn_nn(const float* A, long long lda, const float* B, long long ldb, int batch, int H, int N, int dh,
-                  float* out, int ld_out, const float* E, float alpha, int epi, cudaStream_t st) {
+                  float* out, int ld_out, const float* E, float alpha, int epi, cudaStream_t st, bool single_pass) {
     AtParams p;
     p.N = N; p.H = H; p.dh = dh; p.ld_out = ld_out; p.E = E; p.out = out; p.alpha = alpha;
     const long long rows = (long long)batch * N;
+    if (single_pass && epi == TE_TC_ATTN_STORE) return launch_attn<AT_STORE, true>(A, lda, B, ldb, rows, p, batch, st);
+    if (single_pass && epi == TE_TC_ATTN_MUL) return launch_attn<AT_MUL, true>(A, lda, B, ldb, rows, p, batch, st);
     switch (epi) {
         case TE_TC_ATTN_STORE: return launch_attn<AT_STORE>(A, lda, B, ldb, rows, p, batch, st);
         case TE_TC_ATTN_MUL: return launch_attn<AT_MUL>(A, lda, B, ldb, rows, p, batch, st);
@@ -574,6 +599,8 @@ int te_tc_attn_nk(const float* map, int NP, int amn, const float* X, long long l
     p.E = E; p.out = out; p.alpha = alpha;
     if (single_pass && epi == TE_TC_ATTN_STORE)
         return amn ? launch_nk<1, AT_STORE, 2, true>(map, NP, X, ldx, p, batch, st) : launch_nk<0, AT_STORE, 2, true>(map, NP, X, ldx, p, batch, st);
+    if (single_pass && epi == TE_TC_ATTN_MUL)
+        return amn ? launch_nk<1, AT_MUL, 2, true>(map, NP, X, ldx, p, batch, st) : launch_nk<0, AT_MUL, 2, true>(map, NP, X, ldx, p, batch, st);
     if (epi == TE_TC_ATTN_STORE) return amn ? launch_nk<1, AT_STORE, 2>(map, NP, X, ldx, p, batch, st) : launch_nk<0, AT_STORE, 2>(map, NP, X, ldx, p, batch, st);
     if (epi == TE_TC_ATTN_MUL) return amn ? launch_nk<1, AT_MUL, 2>(map, NP, X, ldx, p, batch, st) : launch_nk<0, AT_MUL, 2>(map, NP, X, ldx, p, batch, st);
     te_set_last_error("te_gemm_tc: unsupported attention nk epilogue");

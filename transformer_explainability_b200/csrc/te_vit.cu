@@ -351,6 +351,7 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
     const float* lbase = (flags & TE_FLAG_LINEAR_TENSOR_CORES) ? derived : nullptr;
     const bool atc = (flags & TE_FLAG_ATTN_TENSOR_CORES) != 0;
     const bool btf = (flags & TE_FLAG_BACKWARD_TF32) != 0;       // single-pass TF32 backward Linears
+    const bool rtf = (flags & TE_FLAG_RELPROP_TF32) != 0;        // single-pass TF32 relevance-side attention contractions
     const bool lrpv = (flags & TE_FLAG_RULES_LRP) != 0;         // rule library of modules/layers_lrp.py (ViT_orig_LRP.py)
     const bool zb = (flags & TE_FLAG_ZPLUS_BF16) != 0;
 
@@ -388,7 +389,7 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
         // attention branch
         TE_TRY(te_util::linear_bwd_tc(lw.proj, dxb, bw.projw, dctx, nullptr, d.M, d.D, d.D, TE_EPI_STORE, st, btf));
         TE_TRY(te_util::attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, dctx, d.D, a.qkv + 2 * d.D, 3 * d.D, a.G, nullptr, 1.f,
-                                TE_EPI_STORE, st));                                 // G = dctx v^T
+                                TE_EPI_STORE, st, btf));                                 // G = dctx v^T
         if (l == start_layer) break;                                                // lower gradients are never read
         TE_TRY(te_util::attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, a.P, 1, dctx, d.D, dqkv + 2 * d.D, 3 * d.D, nullptr, 1.f,
                                 TE_EPI_STORE, st, btf));                                 // dV = P^T dctx
@@ -450,17 +451,17 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
         // matmul2 rule: Z = attn v is the saved ctx itself (bit-identical recomputation in the reference)
         TE_TRY(te_launch_sd(R3, a.ctx, S, MD, st));
         TE_TRY(te_util::attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, S, d.D, a.qkv + 2 * d.D, 3 * d.D, a.cam, a.P, 0.5f,
-                                TE_EPI_MUL, st));                                   // attn_cam = (P * (S v^T)) / 2   :160-165
+                                TE_EPI_MUL, st, rtf));                                   // attn_cam = (P * (S v^T)) / 2   :160-165
         if (l == low && !(flags & TE_FLAG_RELPROP_TO_INPUT)) break;                                                        // nothing below is consumed
         TE_TRY(te_util::attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, a.P, 1, S, d.D, Rqkv + 2 * d.D, 3 * d.D, a.qkv + 2 * d.D, 0.5f,
-                                TE_EPI_MUL, st));                                   // cam_v
+                                TE_EPI_MUL, st, rtf));                                   // cam_v
         // matmul1 rule (unscaled Z = q k^T)  :170-173
         TE_TRY(te_util::attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, a.qkv, 3 * d.D, a.qkv + d.D, 3 * d.D, S1, a.cam, 1.f,
                                 TE_EPI_SD, st));
         TE_TRY(te_util::attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, S1, 0, a.qkv + d.D, 3 * d.D, Rqkv, 3 * d.D, a.qkv, 0.5f,
-                                TE_EPI_MUL, st));                                   // cam_q
+                                TE_EPI_MUL, st, rtf));                                   // cam_q
         TE_TRY(te_util::attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, S1, 1, a.qkv, 3 * d.D, Rqkv + d.D, 3 * d.D, a.qkv + d.D, 0.5f,
-                                TE_EPI_MUL, st));                                   // cam_k
+                                TE_EPI_MUL, st, rtf));                                   // cam_k
         TE_TRY(zrule(a.xn1, d.D, bw.qkvw, dw.qkv, Rqkv, 3 * d.D, R2, S, d.M, d.D, 3 * d.D, a.qkv, 3 * d.D, bw.qkvb, 0, RF));   // qkv ; norm1 id
         TE_TRY(te_launch_clone_relprop(a.x_in, R1, R2, nullptr, R, MD, st));                                       // clone1
     }

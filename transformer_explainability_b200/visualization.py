@@ -5,27 +5,22 @@ the JET overlay (cv2) stays on the host exactly like the notebook.
 """
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 
 def relevance_to_heatmap(maps, grid=14, scale=16):
-    """[B, grid*grid] -> min-max normalised [B, grid*scale, grid*scale] (device tensor).  CUDA tensors go through the
-    engine's kernel (``te_relevance_heatmap``, one block per sample); host tensors follow the notebook's torch sequence."""
+    """[B, grid*grid] -> min-max normalised [B, grid*scale, grid*scale] (device tensor) through the engine's kernel
+    (``te_relevance_heatmap``, one block per sample).  CUDA tensors only: there is no host path."""
     b = maps.shape[0]
-    if maps.is_cuda:
-        from . import _lib
-        m = maps.detach().to(torch.float32).contiguous()
-        out = torch.empty(b, grid * scale, grid * scale, device=m.device, dtype=torch.float32)
+    if not maps.is_cuda:
+        raise ValueError("relevance_to_heatmap needs a CUDA tensor (no CPU fallback)")
+    from . import _lib
+    m = maps.detach().to(torch.float32).contiguous()
+    out = torch.empty(b, grid * scale, grid * scale, device=m.device, dtype=torch.float32)
+    with torch.cuda.device(m.device):
         _lib.check(_lib.load().te_relevance_heatmap(_lib.ptr(m), b, grid, scale, _lib.ptr(out),
                                                     _lib.ctypes.c_void_p(torch.cuda.current_stream(m.device).cuda_stream)),
                    "te_relevance_heatmap")
-        return out
-    t = maps.reshape(b, 1, grid, grid)
-    t = F.interpolate(t, scale_factor=scale, mode='bilinear')
-    t = t.reshape(b, -1)
-    mn = t.min(dim=1, keepdim=True).values
-    mx = t.max(dim=1, keepdim=True).values
-    return ((t - mn) / (mx - mn)).reshape(b, grid * scale, grid * scale)
+    return out
 
 
 def show_cam_on_image(img, mask):
