@@ -63,6 +63,8 @@ TE_API const char* te_last_error(void);
  * name = "linear_pair_kernels": the same for the 3xTF32 forward / backward Linear GEMMs.  Both default to 0.
  * name = "zplus_persistent": 1 (default) runs the z+ rule with the persistent CTA-pair kernels (te_tc_pair.cu), 0 with
  * the round-1 kernels selected by "zplus_pair_kernels".
+ * name = "linear_mixed": 1 runs the forward Linears with the mixed-kind split (main term TF32, the two correction terms as bf16
+ * MMAs: two thirds of the tensor cycles of the 3xTF32 kernel at the same fp32-grade accuracy), 0 (default) with 3xTF32.
  * name = "cls_row_top_block": 1 (default) runs the three z+ rules of the top block on the pooled-token rows only (exact:
  * the relevance entering the top block is zero in every other row), 0 on all rows.
  * Returns TE_OK, or a negative status for an unknown name. */
@@ -199,13 +201,13 @@ TE_API int te_bert_tensor(const te_bert_config* cfg, int batch, int seq, void* w
  * ---------------------------------------------------------------------------------------------- */
 /* Linear.relprop, alpha=1 (layers_ours.py:207-230): x [rows,in], w [out,in], r [rows,out] -> out [rows,in].
  * flags & TE_FLAG_RULES_LRP: the layers_lrp variant (modules/layers_lrp.py:187-210, separate denominators).
- * scratch: rows*out floats; with TE_FLAG_ZPLUS_TENSOR_CORES: round_up(rows*out,64) + 10*in*out floats. */
+ * scratch: rows*out floats; with TE_FLAG_ZPLUS_TENSOR_CORES: round_up(rows*out,64) + 11*in*out floats. */
 TE_API int te_linear_relprop(const float* x, const float* w, const float* r, float* out, float* scratch, int rows,
                       int in_features, int out_features, unsigned flags, void* stream);
 /* Same rule with the Linear's saved forward output y = x W^T + bias [rows,out] supplied (what the engines do): with
  * TE_FLAG_ZPLUS_TENSOR_CORES the denominator is then formed in ONE tensor-core pass through the exact identity
  * x+ W+^T + x- W-^T == ((y - bias) + |x| |W|^T) / 2.  bias may be NULL (no bias).
- * scratch: rows*out floats; with TE_FLAG_ZPLUS_TENSOR_CORES: round_up(rows*out,64) + 10*in*out + rows*in floats
+ * scratch: rows*out floats; with TE_FLAG_ZPLUS_TENSOR_CORES: round_up(rows*out,64) + 11*in*out + rows*in floats
  * (S, the derived weight copies, the tf32(|x|) operand of the single-pass kernel). */
 TE_API int te_linear_relprop_ex(const float* x, const float* w, const float* bias, const float* y, const float* r,
                          float* out, float* scratch, int rows, int in_features, int out_features, unsigned flags,
@@ -265,7 +267,7 @@ TE_API int te_compute_rollout_attention(const float* mats, int layers, int batch
                                  float* joint, void* workspace, long long workspace_bytes, void* stream);
 
 /* Plain Linear GEMMs — exported for kernel unit tests only.  flags & TE_FLAG_LINEAR_TENSOR_CORES selects the
- * tcgen05 3xTF32 path (scratch: 10*in*out floats for the derived weight copies; may be NULL otherwise). */
+ * tcgen05 3xTF32 path (scratch: 11*in*out floats for the derived weight copies; may be NULL otherwise). */
 TE_API int te_linear_forward(const float* x, const float* w, const float* bias, float* y, int rows, int in_features,
                       int out_features, void* stream);
 TE_API int te_linear_forward_ex(const float* x, const float* w, const float* bias, float* y, float* scratch, int rows,

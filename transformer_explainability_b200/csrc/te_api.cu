@@ -73,7 +73,7 @@ extern "C" int te_linear_relprop(const float* x, const float* w, const float* r,
                                            ST(stream));
     const float* derived = nullptr;
     if ((flags & TE_FLAG_ZPLUS_TENSOR_CORES) && te_tc_zplus_supported(rows, in_features, out_features, in_features)) {
-        // scratch layout with the flag: [rows*out S | 10*in*out derived weight copies]
+        // scratch layout with the flag: [rows*out S | 11*in*out derived weight copies]
         float* d = scratch + (((long long)rows * out_features + 63) & ~63LL);
         TE_TRY(te_tc_prepare_weights(w, d, in_features, out_features, ST(stream)));
         derived = d;
@@ -89,11 +89,11 @@ extern "C" int te_linear_relprop_ex(const float* x, const float* w, const float*
     const float* derived = nullptr;
     float* xabs = nullptr;
     if ((flags & TE_FLAG_ZPLUS_TENSOR_CORES) && te_tc_zplus_supported(rows, in_features, out_features, in_features)) {
-        // scratch layout with the flag: [rows*out S (64-float aligned) | 10*in*out derived weight copies | rows*in tf32(|x|)]
+        // scratch layout with the flag: [rows*out S (64-float aligned) | 11*in*out derived weight copies | rows*in tf32(|x|)]
         float* d = scratch + (((long long)rows * out_features + 63) & ~63LL);
         TE_TRY(te_tc_prepare_weights(w, d, in_features, out_features, ST(stream)));
         derived = d;
-        xabs = d + 10LL * in_features * out_features;
+        xabs = d + te_tc_derived_floats(in_features, out_features);
     }
     return te_zplus_linear_relprop_ldr(x, in_features, w, derived, r, out_features, out, scratch, rows, in_features,
                                        out_features, ST(stream), y, out_features, bias, (flags & TE_FLAG_ZPLUS_BF16) != 0, 0, xabs);
@@ -173,6 +173,7 @@ extern "C" int te_set_option(const char* name, int value) {
     REQ(name != nullptr, "te_set_option: null name");
     if (strcmp(name, "zplus_pair_kernels") == 0) { te_tc_set_pair_kernels(value); return TE_OK; }
     if (strcmp(name, "linear_pair_kernels") == 0) { te_tc_set_pair_linear(value); return TE_OK; }
+    if (strcmp(name, "linear_mixed") == 0) { te_tc_set_mixed_linear(value); return TE_OK; }
     if (strcmp(name, "zplus_persistent") == 0) { te_tc_set_zplus_persistent(value); return TE_OK; }
     if (strcmp(name, "cls_row_top_block") == 0) { te_engine_set_cls_rows(value); return TE_OK; }
     te_set_last_error("te_set_option: unknown option");

@@ -10,7 +10,8 @@ bool te_tc_zplus_supported(long long rows, int in_features, int out_features, lo
 //                                     fp32-grade 3xTF32 forward / backward Linear GEMMs
 //   [ |W| ]                          operand of the single-pass S kernel
 //   [ bf16(W+^T) | bf16(W-^T) ]      2-byte operands of the bf16 R kernel (kind::f16)
-// = 10*in*out floats
+//   [ bf16(W_hi) | bf16(W_lo) ]      2-byte operands of the correction terms of the mixed-kind forward GEMM
+// = 11*in*out floats
 long long te_tc_derived_floats(int in_features, int out_features);
 int te_tc_prepare_weights(const float* w, float* derived, int in_features, int out_features, cudaStream_t st);
 // y / bias (optional): the Linear's saved forward output y = x W^T + bias [rows, out] (row stride ldy).  When given,
@@ -49,6 +50,8 @@ int te_tc_attn_nk(const float* map, int NP, int amn, const float* X, long long l
 void te_tc_set_pair_kernels(int on);
 // 1: run the 3xTF32 Linear GEMMs with the CTA-pair kernel (default 0, or TE_B200_LINEAR_2CTA=1)
 void te_tc_set_pair_linear(int on);
+// 1: forward Linears with the mixed-kind split (main term TF32, correction terms bf16; default 0 or TE_B200_LINEAR_MIXED=1)
+void te_tc_set_mixed_linear(int on);
 
 // dense rollout product out[b] = A[b] * Bm[b] ([batch, N, ld], N <= 224) on tcgen05, fp32-grade 3xTF32
 bool te_tc_bmm_nk_supported(int N, int ld);

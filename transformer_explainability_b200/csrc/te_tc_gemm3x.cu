@@ -224,6 +224,196 @@ te_tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // =====================================================================================================================
+// Mixed-kind fp32-grade Linear GEMM: the two CORRECTION terms of the error-compensated split run as bf16 MMAs.
+//   C = A B^T ~= A_hi B_hi^T (kind::tf32)  +  bf16(A_lo) bf16(B_hi)^T  +  bf16(A_hi) bf16(B_lo)^T (kind::f16, fp32 accumulate)
+// The correction terms are 2^-11 of the main term, so the 2^-8 relative error of a bf16 x bf16 product contributes 2^-19 —
+// below the fp32 rounding of the result (simulated: 7.0e-7 of the result maximum against 6.2e-7 for a plain fp32 GEMM and
+// 7.5e-8 for the exact three-term sum, K = 768 and 3072).  A bf16 MMA covers K = 16 per issue at the cycle cost of a K = 8 TF32
+// MMA, so a 32-element k-block takes 4 + 2 + 2 = 8 MMA slots instead of 12: the 3xTF32 kernel sits at 0.81 of the TF32 issue
+// roof (0.27 algorithmic), this form needs two thirds of its tensor cycles.
+// Stage (96 KiB, 2 stages): A_hi tf32 16K | bf16(A_hi) 8K | bf16(A_lo) 8K | B_hi tf32 32K | bf16(B_hi) 16K | bf16(B_lo) 16K.
+// The bf16 tiles are K-major with 64-byte rows in the SWIZZLE_64B layout (16-byte chunk index XOR (row / 2) % 4): TMA writes
+// the weight tiles that way (CU_TENSOR_MAP_SWIZZLE_64B), the transform warps write the activation tiles.
+// =====================================================================================================================
+constexpr int A16_BYTES = BM * BK * 2;                            // 8 KiB
+constexpr int B16_BYTES = BN * BK * 2;                            // 16 KiB
+constexpr uint32_t M_OFF_AH = 0, M_OFF_A16H = A_BYTES, M_OFF_A16L = A_BYTES + A16_BYTES, M_OFF_BH = A_BYTES + 2 * A16_BYTES,
+                   M_OFF_B16H = M_OFF_BH + B_BYTES, M_OFF_B16L = M_OFF_B16H + B16_BYTES;
+static_assert(M_OFF_B16L + B16_BYTES == STAGE3_BYTES, "mixed stage = 96 KiB");
+
+// K-major SWIZZLE_64B descriptor: 64-byte rows, 8-row (512 B) atoms
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS3, 1)
+te_tc_gemm3m_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                    const __grid_constant__ CUtensorMap tmB16h, const __grid_constant__ CUtensorMap tmB16l, const Tc3Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bars = smem_base + STAGES3 * STAGE3_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto xf_bar = [&](int s) { return bars + 8u * (2 + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (4 + s); };
+    auto accfull_bar = [&](int b) { return bars + 8u * (6 + b); };
+    auto accfree_bar = [&](int b) { return bars + 8u * (8 + b); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + STAGES3 * STAGE3_BYTES + 8 * 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kb = p.K / BK;
+    const int nchunks = (kb + CHUNK - 1) / CHUNK;
+    constexpr uint32_t TMEM_COLS = 512u;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB16h) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB16l) : "memory");
+        for (int s = 0; s < STAGES3; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(xf_bar(s), XF_THREADS / 32);
+            mbar_init(empty_bar(s), 1);
+            mbar_init(accfull_bar(s), 1);
+            mbar_init(accfree_bar(s), DRAIN_THREADS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < kb; ++it) {
+                const int s = it % STAGES3;
+                const uint32_t ph = (it / STAGES3) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_arrive_expect_tx(full_bar(s), A_BYTES + B_BYTES + 2 * B16_BYTES);
+                const uint32_t sa = smem_base + s * STAGE3_BYTES;
+                tma_load_2d(sa + M_OFF_AH, &tmA, full_bar(s), it * BK, m0);                  // raw A -> A_hi slot
+                tma_load_2d(sa + M_OFF_BH, &tmBh, full_bar(s), it * BK, n0);
+                tma_load_2d(sa + M_OFF_B16H, &tmB16h, full_bar(s), it * BK, n0);
+                tma_load_2d(sa + M_OFF_B16L, &tmB16l, full_bar(s), it * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int it = 0; it < kb; ++it) {
+                const int c = it / CHUNK, b = c & 1;
+                const bool chunk_start = (it % CHUNK) == 0;
+                if (chunk_start && c >= 2) {                        // accumulator b must have been drained (chunk c-2)
+                    mbar_wait(accfree_bar(b), (uint32_t)(((c >> 1) & 1) ^ 1));
+                    tcgen05_fence_after();
+                }
+                const int s = it % STAGES3;
+                const uint32_t ph = (it / STAGES3) & 1u;
+                mbar_wait(xf_bar(s), ph);
+                tcgen05_fence_after();
+                const uint32_t sa = smem_base + s * STAGE3_BYTES;
+                const uint64_t ah = make_smem_desc(sa + M_OFF_AH), bh = make_smem_desc(sa + M_OFF_BH);
+                const uint64_t a16h = make_smem_desc_sw64(sa + M_OFF_A16H), a16l = make_smem_desc_sw64(sa + M_OFF_A16L);
+                const uint64_t b16h = make_smem_desc_sw64(sa + M_OFF_B16H), b16l = make_smem_desc_sw64(sa + M_OFF_B16L);
+                const uint32_t d = tmem_base + (uint32_t)(b * BN);
+                // small terms first: two bf16 MMAs (K = 16 each) per correction term, then four TF32 MMAs (K = 8) of the main term
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    const uint64_t o = (uint64_t)(2 * k);
+                    umma_bf16(d, a16l + o, b16h + o, kIdescBf16, (chunk_start && k == 0) ? 0u : 1u);
+                    umma_bf16(d, a16h + o, b16l + o, kIdescBf16, 1u);
+                }
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) umma_tf32(d, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), kIdesc, 1u);
+                umma_commit(empty_bar(s));
+                if ((it % CHUNK) == CHUNK - 1 || it == kb - 1) umma_commit(accfull_bar(b));
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const int half = (warp >= 6) ? 1 : 0;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
+        float sum[128];
+#pragma unroll
+        for (int j = 0; j < 128; ++j) sum[j] = 0.f;
+
+        auto drain = [&](int c) {
+            const int b = c & 1;
+            mbar_wait(accfull_bar(b), (uint32_t)((c >> 1) & 1));
+            tcgen05_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+                uint32_t v[16];
+                tmem_ld16(tlane + (uint32_t)(b * BN + cc * 16), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sum[cc * 16 + j] += __uint_as_float(v[j]);
+            }
+            tcgen05_fence_before();
+            mbar_arrive(accfree_bar(b));
+        };
+
+        if (warp < 6) {
+            const int et = threadIdx.x - 64;                        // 0..127: the four transform warps
+            for (int it = 0; it < kb; ++it) {
+                const int s = it % STAGES3;
+                const uint32_t ph = (it / STAGES3) & 1u;
+                mbar_wait(full_bar(s), ph);
+                uint8_t* st8 = smem_al + s * STAGE3_BYTES;
+                float4* a4 = reinterpret_cast<float4*>(st8 + M_OFF_AH);
+#pragma unroll
+                for (int i = 0; i < A_BYTES / 16 / XF_THREADS; ++i) {
+                    const int idx = et + i * XF_THREADS;            // float4 index inside the SWIZZLE_128B tile
+                    const int r = idx >> 3, lc = (idx & 7) ^ (r & 7);   // row, LOGICAL 16-byte chunk (4 k values)
+                    const float4 v = a4[idx];
+                    float4 h;
+                    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+                    a4[idx] = h;
+                    const __nv_bfloat162 h01 = __floats2bfloat162_rn(h.x, h.y), h23 = __floats2bfloat162_rn(h.z, h.w);
+                    const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - h.x, v.y - h.y), l23 = __floats2bfloat162_rn(v.z - h.z, v.w - h.w);
+                    // bf16 tile: row r (64 bytes), logical 8-byte slot lc -> 16-byte chunk (lc >> 1) ^ ((r >> 1) & 3), half lc & 1
+                    const uint32_t off = (uint32_t)r * 64u + ((uint32_t)((lc >> 1) ^ ((r >> 1) & 3)) << 4) + ((uint32_t)(lc & 1) << 3);
+                    uint2 hb, lb;
+                    hb.x = *reinterpret_cast<const uint32_t*>(&h01); hb.y = *reinterpret_cast<const uint32_t*>(&h23);
+                    lb.x = *reinterpret_cast<const uint32_t*>(&l01); lb.y = *reinterpret_cast<const uint32_t*>(&l23);
+                    *reinterpret_cast<uint2*>(st8 + M_OFF_A16H + off) = hb;
+                    *reinterpret_cast<uint2*>(st8 + M_OFF_A16L + off) = lb;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(xf_bar(s));
+                if (((it % CHUNK) == CHUNK - 1 || it == kb - 1) && it / CHUNK >= 1) drain(it / CHUNK - 1);
+            }
+            drain(nchunks - 1);
+        } else {
+            for (int c = 0; c < nchunks; ++c) drain(c);
+        }
+        gemm3x_epilogue<EPI>(p, sum, reinterpret_cast<float*>(smem_al + (warp - 2) * EPI_STAGE_BYTES), lane, m0 + q * 32,
+                             n0 + half * 128);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// =====================================================================================================================
 // CTA-pair version of the 3xTF32 Linear GEMM (tcgen05 cta_group::2): the two CTAs of a cluster own adjacent 128-row
 // tiles of the same 256-column tile and execute ONE 256 x 256 x 8 MMA per issue (leader CTA).  Each CTA stages its own
 // activation tile (raw -> hi, lo) and only its HALF of the pre-split weight tile (128 of the 256 rows of W_hi and
@@ -464,9 +654,63 @@ int dispatch3(int epi, const float* A, long long lda, const float* Bh, const flo
     return TE_ERR_UNSUPPORTED;
 }
 
+// bf16 [rows, cols] K-major, 64-byte rows, SWIZZLE_64B (box = 32 elements x box_rows)
+bool make_map_bf16_sw64(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int g_mixed_linear = -1;                // forward Linears with bf16 correction terms (TE_B200_LINEAR_MIXED=0/1, te_set_option)
+bool use_mixed_linear() {
+    if (g_mixed_linear < 0) {
+        const char* e = getenv("TE_B200_LINEAR_MIXED");
+        g_mixed_linear = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_mixed_linear == 1;
+}
+
+template <int EPI>
+int launch3m(const float* A, long long lda, const float* Bh, const void* B16h, const void* B16l, const Tc3Params& p, cudaStream_t st) {
+    CUtensorMap tmA, tmBh, tm16h, tm16l;
+    if (!make_map(&tmA, A, p.M, p.K, lda, BM) || !make_map(&tmBh, Bh, p.N, p.K, p.K, BN) ||
+        !make_map_bf16_sw64(&tm16h, B16h, p.N, p.K, p.K, BN) || !make_map_bf16_sw64(&tm16l, B16l, p.N, p.K, p.K, BN)) {
+        te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed (mixed)");
+        return TE_ERR_CUDA;
+    }
+    static unsigned long long optin = 0;
+    if (!smem_optin(te_tc_gemm3m_kernel<EPI>, SMEM3_BYTES, optin)) {
+        te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
+        return TE_ERR_CUDA;
+    }
+    dim3 grid(p.N / BN, (unsigned)((p.M + BM - 1) / BM));
+    te_tc_gemm3m_kernel<EPI><<<grid, NUM_THREADS3, SMEM3_BYTES, st>>>(tmA, tmBh, tm16h, tm16l, p);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int dispatch3m(int epi, const float* A, long long lda, const float* Bh, const void* B16h, const void* B16l, const Tc3Params& p,
+               cudaStream_t st) {
+    switch (epi) {
+        case TE_TC_EPI_STORE: return launch3m<EP_STORE>(A, lda, Bh, B16h, B16l, p, st);
+        case TE_TC_EPI_BIAS: return launch3m<EP_BIAS>(A, lda, Bh, B16h, B16l, p, st);
+        case TE_TC_EPI_BIAS_GELU: return launch3m<EP_BIAS_GELU>(A, lda, Bh, B16h, B16l, p, st);
+        case TE_TC_EPI_BIAS_ADD: return launch3m<EP_BIAS_ADD>(A, lda, Bh, B16h, B16l, p, st);
+        case TE_TC_EPI_GELU_BWD: return launch3m<EP_GELU_BWD>(A, lda, Bh, B16h, B16l, p, st);
+    }
+    te_set_last_error("te_gemm_tc: unsupported epilogue");
+    return TE_ERR_UNSUPPORTED;
+}
+
 }  // namespace
 
 void te_tc_set_pair_linear(int on) { g_pair_linear = on ? 1 : 0; }
+void te_tc_set_mixed_linear(int on) { g_mixed_linear = on ? 1 : 0; }
 
 bool te_tc_gemm3x_supported(long long rows, int K, int N, long long lda) {
     return rows > 0 && rows < (1LL << 31) && K % BK == 0 && N % BN == 0 && lda % 4 == 0 && get_encode() != nullptr;
@@ -479,6 +723,10 @@ int te_tc_linear_fwd(const float* x, long long ldx, const float* derived, int in
     Tc3Params p;
     p.M = (int)rows; p.N = out_features; p.K = in_features; p.bias = bias; p.E = e0; p.lde = out_features;
     p.C = y; p.ldc = out_features; p.C2 = y2; p.ldc2 = out_features;
+    if (use_mixed_linear()) {           // main term TF32, correction terms bf16: [bf16(W_hi) | bf16(W_lo)] live at derived + 10 n
+        const __nv_bfloat16* w16 = reinterpret_cast<const __nv_bfloat16*>(derived + 10 * n);
+        return dispatch3m(epi, x, ldx, derived + 4 * n, w16, w16 + n, p, st);
+    }
     return dispatch3(epi, x, ldx, derived + 4 * n, derived + 5 * n, p, st);
 }
 // dx[rows,in] = dy[rows,out] W (+ epilogue)

@@ -429,6 +429,7 @@ te_tc_zplus2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 __global__ void prepare_weights_kernel(const float* __restrict__ w, float* __restrict__ d, int out_f, int in_f) {
     // d = [ W+ | W- | W+^T | W-^T | W_hi | W_lo | W^T_hi | W^T_lo | |W| ] (fp32, in*out floats each)
     //     [ bf16(W+^T) | bf16(W-^T) ]  (2-byte elements: in*out/2 floats each)
+    //     [ bf16(W_hi) | bf16(W_lo) ]  (K-major [out,in], 2-byte elements): the correction operands of the mixed-kind forward
     const long long n = (long long)out_f * in_f;
     float *wp = d, *wn = d + n, *wpt = d + 2 * n, *wnt = d + 3 * n, *wh = d + 4 * n, *wl = d + 5 * n, *wth = d + 6 * n,
           *wtl = d + 7 * n, *wa = d + 8 * n;
@@ -446,6 +447,9 @@ __global__ void prepare_weights_kernel(const float* __restrict__ w, float* __res
             wh[idx] = hi;
             wl[idx] = to_tf32(v - hi);
             wa[idx] = to_tf32(fabsf(v));
+            __nv_bfloat16* mb = reinterpret_cast<__nv_bfloat16*>(d + 10 * n);        // [ bf16(W_hi) | bf16(W_lo) ]: mixed-kind forward
+            mb[idx] = __float2bfloat16_rn(hi);
+            mb[n + idx] = __float2bfloat16_rn(v - hi);
         }
         tile[i][threadIdx.x] = v;
     }
@@ -571,7 +575,7 @@ static bool use_persistent() {
 }
 void te_tc_set_zplus_persistent(int on) { g_zplus_persistent = on ? 1 : 0; }
 
-long long te_tc_derived_floats(int in_features, int out_features) { return 10LL * in_features * out_features; }
+long long te_tc_derived_floats(int in_features, int out_features) { return 11LL * in_features * out_features; }
 
 int te_tc_prepare_weights(const float* w, float* derived, int in_features, int out_features, cudaStream_t st) {
     dim3 grid((in_features + 31) / 32, (out_features + 31) / 32), block(32, 8);
