@@ -71,3 +71,5 @@ int te_tc_pair_linear_bwd(const float* dy, long long lddy, const float* derived,
                           const float* e0, long long rows, int epi, cudaStream_t st);
 // 1 (default): z+ rule on the persistent pair kernels
 void te_tc_set_zplus_persistent(int on);
+// 1 (default): the 3xTF32 N x N attention kernel runs in its persistent, TMEM-double-buffered form when N <= 224
+void te_tc_set_attn_persistent(int on);

@@ -25,6 +25,103 @@ struct AtParams {
     const float* E; float* out; float alpha;
 };
 
+// Epilogue of the N x N attention kernels (shared by the one-tile-per-CTA and the persistent kernel): the finished 128 x ncols
+// accumulator sits at TMEM address tlane (this warp's lane quarter q); rows m0 + q*32 .. of head bh, key columns n0 .. n0+ncols.
+template <int EPI, bool SP>
+__device__ __forceinline__ void attn_nn_epilogue(const AtParams& p, uint32_t tlane, float* stage, int lane, int q, int bh, int m0,
+                                                 int n0, int ncols) {
+        const int nchunks = (ncols + 31) / 32;
+        const int tr = lane >> 3, tc = 4 * (lane & 7);
+        if (EPI == AT_SOFTMAX) {
+            // softmax(alpha * A B^T) over the key axis, fused: every thread owns one query row whose N <= 256 scores sit
+            // in its TMEM lane, so the row maximum, the sum of exponentials and the normalised probabilities come from
+            // three passes over TMEM (the exponentials are written back with tcgen05.st) — the scores never travel to HBM (attn = dots.softmax(dim=-1), ViT_LRP.py:139-141)
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int cc = 0; cc < nchunks; ++cc) {
+                uint32_t acc[32];
+                tmem_ld32(tlane + (uint32_t)(cc * 32), acc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (cc * 32 + j < ncols) mx = fmaxf(mx, p.alpha * __uint_as_float(acc[j]));
+            }
+            // pass 2: e = exp(score - max), summed, and written back over the scores in TMEM (one expf per element)
+            float sum = 0.f;
+#pragma unroll 1
+            for (int cc = 0; cc < nchunks; ++cc) {
+                uint32_t acc[32];
+                tmem_ld32(tlane + (uint32_t)(cc * 32), acc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float e = (cc * 32 + j < ncols) ? expf(p.alpha * __uint_as_float(acc[j]) - mx) : 0.f;
+                    sum += e;
+                    acc[j] = __float_as_uint(e);
+                }
+                tmem_st32(tlane + (uint32_t)(cc * 32), acc);
+            }
+            tmem_st_wait();
+            // pass 3: normalise in the row layout, store in the transposed (coalesced) layout of epi_read_t
+#pragma unroll 1
+            for (int cc = 0; cc < nchunks; ++cc) {
+                uint32_t acc[32];
+                tmem_ld32(tlane + (uint32_t)(cc * 32), acc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) / sum);   // padding holds e = 0
+                epi_stage_rows(stage, lane, acc);
+                const int col = cc * 32 + tc;
+#pragma unroll
+                for (int i2 = 0; i2 < 8; ++i2) {
+                    const int r = m0 + q * 32 + 4 * i2 + tr;
+                    if (r < p.N && col < ncols)
+                        *reinterpret_cast<float4*>(p.out + ((long long)bh * p.N + r) * p.ld_out + n0 + col) = epi_read_t(stage, lane, i2);
+                }
+            }
+        } else {
+        // E and out are accessed in the transposed layout of epi_read_t (4 rows x 128 B per warp instruction); the loads of
+        // E are issued before the TMEM read completes.  A float4 whose tail lies in the row padding is memory-safe
+        // (ld_out % 4 == 0); the padding columns [ncols, ...) of the last float4 are written as zeros.
+#pragma unroll 1
+        for (int cc = 0; cc < nchunks; ++cc) {
+            uint32_t acc[32];
+            tmem_ld32(tlane + (uint32_t)(cc * 32), acc);
+            const int col = cc * 32 + tc;
+            float4 e4[8];
+#pragma unroll
+            for (int i2 = 0; i2 < 8; ++i2) {
+                const int r = m0 + q * 32 + 4 * i2 + tr;
+                e4[i2] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (EPI != AT_STORE && r < p.N && col < ncols)
+                    e4[i2] = __ldcs(reinterpret_cast<const float4*>(p.E + ((long long)bh * p.N + r) * p.ld_out + n0 + col));
+            }
+            tmem_ld_wait();
+            epi_stage_rows(stage, lane, acc);
+#pragma unroll
+            for (int i2 = 0; i2 < 8; ++i2) {
+                const int r = m0 + q * 32 + 4 * i2 + tr;
+                if (r >= p.N || col >= ncols) continue;
+                const float4 a4 = epi_read_t(stage, lane, i2);
+                const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+                const float e[4] = {e4[i2].x, e4[i2].y, e4[i2].z, e4[i2].w};
+                float o[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    // SP: both raw operands were truncated to TF32 by the tensor core (mean shrink 3.4e-4 each): compensated
+                    const float av = p.alpha * a[u] * (SP ? 1.00068f : 1.0f);
+                    float v;
+                    if (EPI == AT_STORE) v = av;
+                    else if (EPI == AT_MUL) v = av * e[u];
+                    else v = te_sd(e[u], av);
+                    o[u] = (col + u < ncols) ? v : 0.f;                                  // zero the row padding
+                }
+                *reinterpret_cast<float4*>(p.out + ((long long)bh * p.N + r) * p.ld_out + n0 + col) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+        }   // EPI != AT_SOFTMAX
+}
+
 // SP (single pass): the raw fp32 operands go straight from TMA to one TF32 MMA per k-step (no hi/lo split); both k-blocks
 // of the head dimension are resident at once (the lo regions hold the second one).  For the contractions whose result is
 // relevance or a gradient — G = dctx V^T under TE_FLAG_BACKWARD_TF32, attn_cam = P * (S V^T) / 2 under
@@ -145,105 +242,183 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
 
         const int q = warp & 3;
-        const int i = m0 + q * 32 + lane;                       // query row inside the sample
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
         const int ncols = min(p.N - n0, BN);              // valid key columns of this tile
-        const int nchunks = (ncols + 31) / 32;
         // per-warp staging buffer of the coalesced epilogue: the operand buffer is idle once the accumulator is complete
         float* stage = reinterpret_cast<float*>(smem_al + (warp - 2) * EPI_STAGE_BYTES);
-        const int tr = lane >> 3, tc = 4 * (lane & 7);
-        if (EPI == AT_SOFTMAX) {
-            // softmax(alpha * A B^T) over the key axis, fused: every thread owns one query row whose N <= 256 scores sit
-            // in its TMEM lane, so the row maximum, the sum of exponentials and the normalised probabilities come from
-            // three passes over TMEM (the exponentials are written back with tcgen05.st) — the scores never travel to HBM (attn = dots.softmax(dim=-1), ViT_LRP.py:139-141)
-            mbar_wait(accum_bar, 0);
-            tcgen05_fence_after();
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int cc = 0; cc < nchunks; ++cc) {
-                uint32_t acc[32];
-                tmem_ld32(tlane + (uint32_t)(cc * 32), acc);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (cc * 32 + j < ncols) mx = fmaxf(mx, p.alpha * __uint_as_float(acc[j]));
-            }
-            // pass 2: e = exp(score - max), summed, and written back over the scores in TMEM (one expf per element)
-            float sum = 0.f;
-#pragma unroll 1
-            for (int cc = 0; cc < nchunks; ++cc) {
-                uint32_t acc[32];
-                tmem_ld32(tlane + (uint32_t)(cc * 32), acc);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float e = (cc * 32 + j < ncols) ? expf(p.alpha * __uint_as_float(acc[j]) - mx) : 0.f;
-                    sum += e;
-                    acc[j] = __float_as_uint(e);
-                }
-                tmem_st32(tlane + (uint32_t)(cc * 32), acc);
-            }
-            tmem_st_wait();
-            // pass 3: normalise in the row layout, store in the transposed (coalesced) layout of epi_read_t
-#pragma unroll 1
-            for (int cc = 0; cc < nchunks; ++cc) {
-                uint32_t acc[32];
-                tmem_ld32(tlane + (uint32_t)(cc * 32), acc);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) / sum);   // padding holds e = 0
-                epi_stage_rows(stage, lane, acc);
-                const int col = cc * 32 + tc;
-#pragma unroll
-                for (int i2 = 0; i2 < 8; ++i2) {
-                    const int r = m0 + q * 32 + 4 * i2 + tr;
-                    if (r < p.N && col < ncols)
-                        *reinterpret_cast<float4*>(p.out + ((long long)bh * p.N + r) * p.ld_out + n0 + col) = epi_read_t(stage, lane, i2);
-                }
-            }
-        } else {
-        // E and out are accessed in the transposed layout of epi_read_t (4 rows x 128 B per warp instruction); the loads of
-        // E are issued before the TMEM read completes.  A float4 whose tail lies in the row padding is memory-safe
-        // (ld_out % 4 == 0); the padding columns [ncols, ...) of the last float4 are written as zeros.
         mbar_wait(accum_bar, 0);
         tcgen05_fence_after();
-#pragma unroll 1
-        for (int cc = 0; cc < nchunks; ++cc) {
-            uint32_t acc[32];
-            tmem_ld32(tlane + (uint32_t)(cc * 32), acc);
-            const int col = cc * 32 + tc;
-            float4 e4[8];
-#pragma unroll
-            for (int i2 = 0; i2 < 8; ++i2) {
-                const int r = m0 + q * 32 + 4 * i2 + tr;
-                e4[i2] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (EPI != AT_STORE && r < p.N && col < ncols)
-                    e4[i2] = __ldcs(reinterpret_cast<const float4*>(p.E + ((long long)bh * p.N + r) * p.ld_out + n0 + col));
-            }
-            tmem_ld_wait();
-            epi_stage_rows(stage, lane, acc);
-#pragma unroll
-            for (int i2 = 0; i2 < 8; ++i2) {
-                const int r = m0 + q * 32 + 4 * i2 + tr;
-                if (r >= p.N || col >= ncols) continue;
-                const float4 a4 = epi_read_t(stage, lane, i2);
-                const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-                const float e[4] = {e4[i2].x, e4[i2].y, e4[i2].z, e4[i2].w};
-                float o[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    // SP: both raw operands were truncated to TF32 by the tensor core (mean shrink 3.4e-4 each): compensated
-                    const float av = p.alpha * a[u] * (SP ? 1.00068f : 1.0f);
-                    float v;
-                    if (EPI == AT_STORE) v = av;
-                    else if (EPI == AT_MUL) v = av * e[u];
-                    else v = te_sd(e[u], av);
-                    o[u] = (col + u < ncols) ? v : 0.f;                                  // zero the row padding
+        attn_nn_epilogue<EPI, SP>(p, tlane, stage, lane, q, bh, m0, n0, ncols);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// =====================================================================================================================
+// Persistent form of the fp32-grade (3xTF32) N x N attention kernel for N <= 224 (ViT / DeiT): the one-tile-per-CTA kernel
+// above runs the chain TMA -> hi/lo split -> MMA -> epilogue of a tile start to end (two CTAs per SM overlap a little of it) and
+// sits 4-8x above the HBM bound of its outputs.  Here one CTA per SM loops over (batch*head, row tile) work items with dedicated
+// warps per role, a 2-stage operand ring (one 32-element k-block of A and of the 224-row B tile per stage, hi + lo: 88 KiB) that
+// the producer fills ahead across tile boundaries, and the 256-column accumulator DOUBLE-BUFFERED in TMEM, so the epilogue of
+// item i (scale / * E / safe_divide / the three-pass softmax) overlaps the split and the MMAs of item i+1.
+//   warp 0 TMA producer · warp 1 MMA issuer · warps 2-5 hi/lo split · warps 6-9 epilogue (lane quarter = warp & 3)
+//   full[s] TMA bytes · xf[s] split done (4 warps) · empty[s] tcgen05.commit · accfull[b] last commit of an item ·
+//   accfree[b] accumulator read out (4 warps)
+// =====================================================================================================================
+constexpr int PN_BN = 224;                                         // B rows (keys) per tile: N <= 224
+constexpr int PN_B_BYTES = PN_BN * BK * 4;                         // 28 KiB
+constexpr int PN_STAGE = 2 * A_BYTES + 2 * PN_B_BYTES;             // 88 KiB
+constexpr int PN_STAGES = 2;
+constexpr int PN_THREADS = 320;
+constexpr int PN_SMEM = PN_STAGES * PN_STAGE + 4 * EPI_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t kIdescN224 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(PN_BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+template <int EPI>
+__global__ void __launch_bounds__(PN_THREADS, 1)
+te_tc_attn_nn_p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const AtParams p,
+                       int items) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    constexpr uint32_t OFF_AH = 0, OFF_AL = A_BYTES, OFF_BH = 2 * A_BYTES, OFF_BL = 2 * A_BYTES + PN_B_BYTES;
+    const uint32_t bars = smem_base + PN_STAGES * PN_STAGE + 4 * EPI_STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto xf_bar = [&](int s) { return bars + 8u * (2 + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (4 + s); };
+    auto accfull_bar = [&](int b) { return bars + 8u * (6 + b); };
+    auto accfree_bar = [&](int b) { return bars + 8u * (8 + b); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + PN_STAGES * PN_STAGE + 4 * EPI_STAGE_BYTES + 8 * 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kb = p.dh / BK;
+    const int mtiles = (p.N + BM - 1) / BM;
+    constexpr uint32_t TMEM_COLS = 512u;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(xf_bar(s), 4);
+            mbar_init(empty_bar(s), 1);
+            mbar_init(accfull_bar(s), 1);
+            mbar_init(accfree_bar(s), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int w = blockIdx.x; w < items; w += gridDim.x) {
+                const int bh = w / mtiles, m0 = (w % mtiles) * BM, b = bh / p.H, h = bh % p.H;
+                for (int kk = 0; kk < kb; ++kk, ++it) {
+                    const int s = (int)(it & 1u);
+                    const uint32_t ph = (it >> 1) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_arrive_expect_tx(full_bar(s), (uint32_t)(A_BYTES + PN_B_BYTES));
+                    const uint32_t sa = smem_base + s * PN_STAGE;
+                    tma_load_2d(sa + OFF_AH, &tmA, full_bar(s), h * p.dh + kk * BK, b * p.N + m0);
+                    tma_load_2d(sa + OFF_BH, &tmB, full_bar(s), h * p.dh + kk * BK, b * p.N);
                 }
-                *reinterpret_cast<float4*>(p.out + ((long long)bh * p.N + r) * p.ld_out + n0 + col) = make_float4(o[0], o[1], o[2], o[3]);
             }
         }
-        }   // EPI != AT_SOFTMAX
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t it = 0, wi = 0;
+            for (int w = blockIdx.x; w < items; w += gridDim.x, ++wi) {
+                const uint32_t ab = wi & 1u;
+                if (wi >= 2) {                                   // accumulator buffer ab read out by the epilogue of item wi-2
+                    mbar_wait(accfree_bar(ab), ((wi >> 1) & 1u) ^ 1u);
+                    tcgen05_fence_after();
+                }
+                const uint32_t d = tmem_base + ab * 256u;
+                for (int kk = 0; kk < kb; ++kk, ++it) {
+                    const int s = (int)(it & 1u);
+                    const uint32_t ph = (it >> 1) & 1u;
+                    mbar_wait(xf_bar(s), ph);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_base + s * PN_STAGE;
+                    const uint64_t ah = make_smem_desc(sa + OFF_AH), al = make_smem_desc(sa + OFF_AL);
+                    const uint64_t bh_ = make_smem_desc(sa + OFF_BH), bl = make_smem_desc(sa + OFF_BL);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint64_t o = (uint64_t)(2 * k);
+                        umma_tf32(d, al + o, bh_ + o, kIdescN224, (kk == 0 && k == 0) ? 0u : 1u);
+                        umma_tf32(d, ah + o, bl + o, kIdescN224, 1u);
+                        umma_tf32(d, ah + o, bh_ + o, kIdescN224, 1u);
+                    }
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(accfull_bar(ab));
+            }
+        }
+        __syncwarp();
+    } else if (warp < 6) {
+        // ---- hi / lo split of every staged k-block: hi in place, lo into the *_lo regions (same swizzled offsets) ----
+        const int et = threadIdx.x - 64;
+        uint32_t it = 0;
+        for (int w = blockIdx.x; w < items; w += gridDim.x) {
+            for (int kk = 0; kk < kb; ++kk, ++it) {
+                const int s = (int)(it & 1u);
+                const uint32_t ph = (it >> 1) & 1u;
+                mbar_wait(full_bar(s), ph);
+                uint8_t* st8 = smem_al + s * PN_STAGE;
+                float4* a4 = reinterpret_cast<float4*>(st8 + OFF_AH);
+                float4* l4 = reinterpret_cast<float4*>(st8 + OFF_AL);
+#pragma unroll
+                for (int i = et; i < A_BYTES / 16; i += XF_THREADS) {
+                    const float4 v = a4[i];
+                    float4 hh, l;
+                    hh.x = to_tf32(v.x); hh.y = to_tf32(v.y); hh.z = to_tf32(v.z); hh.w = to_tf32(v.w);
+                    l.x = to_tf32(v.x - hh.x); l.y = to_tf32(v.y - hh.y); l.z = to_tf32(v.z - hh.z); l.w = to_tf32(v.w - hh.w);
+                    a4[i] = hh; l4[i] = l;
+                }
+                float4* b4 = reinterpret_cast<float4*>(st8 + OFF_BH);
+                float4* m4 = reinterpret_cast<float4*>(st8 + OFF_BL);
+#pragma unroll 2
+                for (int i = et; i < PN_B_BYTES / 16; i += XF_THREADS) {
+                    const float4 v = b4[i];
+                    float4 hh, l;
+                    hh.x = to_tf32(v.x); hh.y = to_tf32(v.y); hh.z = to_tf32(v.z); hh.w = to_tf32(v.w);
+                    l.x = to_tf32(v.x - hh.x); l.y = to_tf32(v.y - hh.y); l.z = to_tf32(v.z - hh.z); l.w = to_tf32(v.w - hh.w);
+                    b4[i] = hh; m4[i] = l;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(xf_bar(s));
+            }
+        }
+    } else {
+        // ---- epilogue: warps 6..9 ----
+        const int q = warp & 3;
+        float* stage = reinterpret_cast<float*>(smem_al + PN_STAGES * PN_STAGE + (warp - 6) * EPI_STAGE_BYTES);
+        uint32_t wi = 0;
+        for (int w = blockIdx.x; w < items; w += gridDim.x, ++wi) {
+            const int bh = w / mtiles, m0 = (w % mtiles) * BM;
+            const uint32_t ab = wi & 1u;
+            mbar_wait(accfull_bar(ab), (wi >> 1) & 1u);
+            tcgen05_fence_after();
+            const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256u;
+            attn_nn_epilogue<EPI, false>(p, tlane, stage, lane, q, bh, m0, 0, p.N);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(accfree_bar(ab));
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -505,6 +680,45 @@ bool te_tc_attn_supported(int N, int dh, long long lda, long long ldb, int ld_ou
 }
 
 namespace {
+int g_attn_persistent = -1;             // persistent N x N kernel for N <= 224 (default on; TE_B200_ATTN_PERSISTENT=0 / te_set_option)
+bool use_attn_persistent() {
+    if (g_attn_persistent < 0) {
+        const char* e = getenv("TE_B200_ATTN_PERSISTENT");
+        g_attn_persistent = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_attn_persistent == 1;
+}
+int attn_sm_count() {
+    static int cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    int& c = cache[dev & 63];
+    if (c == 0 && cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return c;
+}
+
+template <int EPI>
+int launch_attn_p(const float* A, long long lda, const float* B, long long ldb, long long total_rows, const AtParams& p,
+                  int batch, cudaStream_t st) {
+    CUtensorMap tmA, tmB;
+    if (!make_map(&tmA, A, total_rows, (long long)p.H * p.dh, lda, BM) || !make_map(&tmB, B, total_rows, (long long)p.H * p.dh, ldb, PN_BN)) {
+        te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed (attention, persistent)");
+        return TE_ERR_CUDA;
+    }
+    static unsigned long long optin = 0;
+    if (!smem_optin(te_tc_attn_nn_p_kernel<EPI>, PN_SMEM, optin)) {
+        te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
+        return TE_ERR_CUDA;
+    }
+    const int items = batch * p.H * ((p.N + BM - 1) / BM);
+    int grid = attn_sm_count();
+    if (grid <= 0) { te_set_last_error("te_gemm_tc: cannot query the SM count"); return TE_ERR_CUDA; }
+    if (grid > items) grid = items;
+    te_tc_attn_nn_p_kernel<EPI><<<grid, PN_THREADS, PN_SMEM, st>>>(tmA, tmB, p, items);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+
 template <int EPI, bool SP = false>
 int launch_attn(const float* A, long long lda, const float* B, long long ldb, long long total_rows, const AtParams& p,
                 int batch, cudaStream_t st) {
@@ -534,6 +748,14 @@ int te_tc_attn_nn(const float* A, long long lda, const float* B, long long ldb, 
     const long long rows = (long long)batch * N;
     if (single_pass && epi == TE_TC_ATTN_STORE) return launch_attn<AT_STORE, true>(A, lda, B, ldb, rows, p, batch, st);
     if (single_pass && epi == TE_TC_ATTN_MUL) return launch_attn<AT_MUL, true>(A, lda, B, ldb, rows, p, batch, st);
+    if (N <= PN_BN && use_attn_persistent()) {
+        switch (epi) {
+            case TE_TC_ATTN_STORE: return launch_attn_p<AT_STORE>(A, lda, B, ldb, rows, p, batch, st);
+            case TE_TC_ATTN_MUL: return launch_attn_p<AT_MUL>(A, lda, B, ldb, rows, p, batch, st);
+            case TE_TC_ATTN_SD: return launch_attn_p<AT_SD>(A, lda, B, ldb, rows, p, batch, st);
+            case TE_TC_ATTN_SOFTMAX: return launch_attn_p<AT_SOFTMAX>(A, lda, B, ldb, rows, p, batch, st);
+        }
+    }
     switch (epi) {
         case TE_TC_ATTN_STORE: return launch_attn<AT_STORE>(A, lda, B, ldb, rows, p, batch, st);
         case TE_TC_ATTN_MUL: return launch_attn<AT_MUL>(A, lda, B, ldb, rows, p, batch, st);
@@ -545,6 +767,8 @@ int te_tc_attn_nn(const float* A, long long lda, const float* B, long long ldb, 
     te_set_last_error("te_gemm_tc: unsupported attention epilogue");
     return TE_ERR_UNSUPPORTED;
 }
+
+void te_tc_set_attn_persistent(int on) { g_attn_persistent = on ? 1 : 0; }
 
 bool te_tc_attn_nk_supported(int N, int dh, int NP, long long ldx, long long ld_out) {
     return N >= 1 && dh == 64 && NP % 4 == 0 && ldx % 4 == 0 && ld_out % 4 == 0 && get_encode() != nullptr;
