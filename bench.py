@@ -482,10 +482,17 @@ def main():
         if w["kind"] == "vit" and not args.no_graph:
             variants.append(("cuda_graph", lambda: eng.explain_graphed(xs)))
         for name, fn in variants:
-            ms_s = timed_steps(fn, args.steps, args.warmup, world)
-            strong[name] = {"value": round(gb * args.steps / (ms_s * 1e-3), 2), "ms_per_step": round(ms_s / args.steps, 3)}
-        best = max(v["value"] for k, v in strong.items() if isinstance(v, dict))
+            try:
+                ms_s = timed_steps(fn, args.steps, args.warmup, world)
+                strong[name] = {"value": round(gb * args.steps / (ms_s * 1e-3), 2), "ms_per_step": round(ms_s / args.steps, 3)}
+            except Exception as exc:                                  # the weak line must survive a failure of the extra line
+                if name == "launches" or world == 1:
+                    raise
+                strong[name] = {"error": str(exc)[:200]}
+        best = max(v["value"] for k, v in strong.items() if isinstance(v, dict) and "value" in v)
         strong["value"] = best
+        strong["note"] = ("global batch %d sharded contiguously over %d GPU(s); limited by tile quantisation of %d token rows "
+                          "per GPU, not by launch gaps" % (gb, world, (hi - lo) * w["tokens"]))
         if args.scaling == "strong":
             value, ms = best, gb * args.steps / best * 1e3
 

@@ -272,3 +272,25 @@ def test_tc_mixed_kind_linear_is_fp32_grade(rows, inf, outf):
     e3, em = rel(y3, ref_y), rel(ym, ref_y)
     print("rows %d in %d out %d: 3xTF32 %.2e  mixed %.2e" % (rows, inf, outf, e3, em))
     assert em < 1.5e-8 * inf + 2e-6
+
+
+@pytest.mark.parametrize("rows,inf,outf", [(128, 256, 256), (394, 768, 3072), (1000, 3072, 768), (77, 768, 2304)])
+def test_tc_bf16_single_pass_denominator(rows, inf, outf):
+    """TE_FLAG_ZPLUS_S1_BF16: the |x||W|^T term of the single-pass z+ denominator with bf16 operands (persistent pair kernel,
+    kind::f16).  A sum of K non-negative products: the 2^-9 operand roundings average out; stated tolerance = the TF32 path's."""
+    from transformer_explainability_b200 import ops
+    g = torch.Generator().manual_seed(rows + 5)
+    x = torch.randn(rows, inf, generator=g)
+    w = torch.randn(outf, inf, generator=g) * 0.05
+    b = torch.randn(outf, generator=g)
+    r = torch.rand(rows, outf, generator=g)
+    xd, wd, rd, bd = x.cuda(), w.cuda(), r.cuda(), b.cuda()
+    y = ops.linear_forward(xd, wd, bd)
+    tf = ops.linear_relprop(xd, wd, rd, tensor_cores=True, y=y, bias=bd)
+    bf = ops.linear_relprop(xd, wd, rd, tensor_cores=True, y=y, bias=bd, bf16="s1")
+    torch.cuda.synchronize()
+    ref = rules.linear_relprop(x.double(), w.double(), r.double())
+    e_tf, e_bf = rel(tf, ref), rel(bf, ref)
+    print("bf16 S1 rows %d in %d out %d: TF32 %.2e  bf16 denominator %.2e" % (rows, inf, outf, e_tf, e_bf))
+    assert e_bf < 3e-3
+    assert abs(bf.double().sum().item() - r.double().sum().item()) < 2e-3 * r.sum().item()

@@ -73,7 +73,7 @@ extern "C" int te_linear_relprop(const float* x, const float* w, const float* r,
                                            ST(stream));
     const float* derived = nullptr;
     if ((flags & TE_FLAG_ZPLUS_TENSOR_CORES) && te_tc_zplus_supported(rows, in_features, out_features, in_features)) {
-        // scratch layout with the flag: [rows*out S | 11*in*out derived weight copies]
+        // scratch layout with the flag: [rows*out S | 12*in*out derived weight copies]
         float* d = scratch + (((long long)rows * out_features + 63) & ~63LL);
         TE_TRY(te_tc_prepare_weights(w, d, in_features, out_features, ST(stream)));
         derived = d;
@@ -89,14 +89,15 @@ extern "C" int te_linear_relprop_ex(const float* x, const float* w, const float*
     const float* derived = nullptr;
     float* xabs = nullptr;
     if ((flags & TE_FLAG_ZPLUS_TENSOR_CORES) && te_tc_zplus_supported(rows, in_features, out_features, in_features)) {
-        // scratch layout with the flag: [rows*out S (64-float aligned) | 11*in*out derived weight copies | rows*in tf32(|x|)]
+        // scratch layout with the flag: [rows*out S (64-float aligned) | 12*in*out derived weight copies | rows*in tf32(|x|)]
         float* d = scratch + (((long long)rows * out_features + 63) & ~63LL);
         TE_TRY(te_tc_prepare_weights(w, d, in_features, out_features, ST(stream)));
         derived = d;
         xabs = d + te_tc_derived_floats(in_features, out_features);
     }
     return te_zplus_linear_relprop_ldr(x, in_features, w, derived, r, out_features, out, scratch, rows, in_features,
-                                       out_features, ST(stream), y, out_features, bias, (flags & TE_FLAG_ZPLUS_BF16) != 0, 0, xabs);
+                                       out_features, ST(stream), y, out_features, bias,
+                                       ((flags & TE_FLAG_ZPLUS_BF16) ? 1 : 0) | ((flags & TE_FLAG_ZPLUS_S1_BF16) ? 2 : 0), 0, xabs);
 }
 
 extern "C" int te_add_relprop(const float* x1, const float* x2, const float* r, float* r1, float* r2, void* scratch,

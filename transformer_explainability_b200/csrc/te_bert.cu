@@ -325,7 +325,7 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
     const bool atc = (flags & TE_FLAG_ATTN_TENSOR_CORES) != 0;
     const bool btf = (flags & TE_FLAG_BACKWARD_TF32) != 0;       // single-pass TF32 backward Linears
     const bool rtf = (flags & TE_FLAG_RELPROP_TF32) != 0;        // single-pass TF32 relevance-side attention contractions
-    const bool zb = (flags & TE_FLAG_ZPLUS_BF16) != 0;
+    const int zb = ((flags & TE_FLAG_ZPLUS_BF16) ? 1 : 0) | ((flags & TE_FLAG_ZPLUS_S1_BF16) ? 2 : 0);   // bf16 variants of the z+ rule
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     Weights w;
     bind_weights(cfg, weights, w);

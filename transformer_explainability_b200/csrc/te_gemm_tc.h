@@ -11,7 +11,8 @@ bool te_tc_zplus_supported(long long rows, int in_features, int out_features, lo
 //   [ |W| ]                          operand of the single-pass S kernel
 //   [ bf16(W+^T) | bf16(W-^T) ]      2-byte operands of the bf16 R kernel (kind::f16)
 //   [ bf16(W_hi) | bf16(W_lo) ]      2-byte operands of the correction terms of the mixed-kind forward GEMM
-// = 11*in*out floats
+//   [ bf16(|W|) ]                    2-byte operand of the bf16 S1 kernel (TE_FLAG_ZPLUS_S1_BF16), in*out/2 floats
+// = 12*in*out floats (the last half block is padding)
 long long te_tc_derived_floats(int in_features, int out_features);
 int te_tc_prepare_weights(const float* w, float* derived, int in_features, int out_features, cudaStream_t st);
 // y / bias (optional): the Linear's saved forward output y = x W^T + bias [rows, out] (row stride ldy).  When given,
@@ -19,7 +20,8 @@ int te_tc_prepare_weights(const float* w, float* derived, int in_features, int o
 int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* derived, const float* r, long long ldr,
                                float* out,
                                float* s_scratch, long long rows, int in_features, int out_features, cudaStream_t st,
-                               const float* y = nullptr, long long ldy = 0, const float* bias = nullptr, bool bf16 = false,
+                               const float* y = nullptr, long long ldy = 0, const float* bias = nullptr,
+                               int bf16 = 0 /* 1: round-1 bf16 R kernel (flag 64); 2: bf16 single-pass S kernel (flag 2048) */,
                                long long ld_out = 0 /* row stride of out; 0 = in_features */,
                                float* xabs = nullptr /* scratch [rows, in]: enables the persistent pair kernels */);
 
@@ -64,7 +66,7 @@ int te_tc_abs_tf32(const float* x, long long ldx, float* out, long long rows, in
 // xabs: scratch [rows, in] for tf32(|x|), the A operand of the single-pass S kernel
 int te_tc_pair_zplus_s1(const float* x, long long ldx, float* xabs, const float* derived, const float* r, long long ldr,
                         const float* y, long long ldy, const float* bias, float* s_out, long long rows, int in_features,
-                        int out_features, cudaStream_t st);
+                        int out_features, cudaStream_t st, bool bf16 = false);
 int te_tc_pair_zplus_r(const float* s, const float* derived, const float* x, long long ldx, float* out, long long ld_out,
                        long long rows, int in_features, int out_features, cudaStream_t st);
 int te_tc_pair_linear_bwd(const float* dy, long long lddy, const float* derived, int in_features, int out_features, float* dx,

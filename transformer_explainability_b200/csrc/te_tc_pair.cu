@@ -76,10 +76,15 @@ __device__ __noinline__ float zplus_exact(const float* __restrict__ xrow, const 
     return acc;
 }
 
-template <int MODE, int EPI>
+// BF (PM_S1 only): |x| and |W| are bf16 (kind::f16, 64 elements per 128-byte row): the denominator term |x||W|^T is a sum of K
+// non-negative products whose independent 2^-9 rounding errors average out (relative error ~2^-9 / sqrt(K)), at half the staged
+// bytes and half the tensor cycles per flop of the TF32 form — the S1 kernel sits at its L2 cap (62 B/clk/SM, 68 %).
+template <int MODE, int EPI, bool BF = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<MODE>::THREADS, 1)
 te_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                   const __grid_constant__ CUtensorMap tmB1, const PairParams p) {
+    static_assert(!BF || MODE == PM_S1, "bf16 operands: S1 kernel only");
+    constexpr int KELEMS = BF ? 64 : BK;
     using Cfg = PairCfg<MODE>;
     constexpr int NST = Cfg::NST, NB = Cfg::NB, STAGE = Cfg::STAGE, ACC_BUFS = Cfg::ACC_BUFS;
     extern __shared__ uint8_t smem_raw[];
@@ -97,7 +102,7 @@ te_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
     const int ntiles = p.tiles_m * p.tiles_n;
-    const int kb = p.K / BK;
+    const int kb = p.K / KELEMS;
     constexpr uint32_t TMEM_COLS = 512u;
 
     if (warp == 0 && lane == 0) {
@@ -137,9 +142,9 @@ te_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t sa = smem_base + s * STAGE;
                     if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * STAGE);
-                    tma2_load_2d(sa, &tmA, full_bar(s), kk * BK, m0);
-                    tma2_load_2d(sa + A_BYTES, &tmB0, full_bar(s), kk * BK, n0);
-                    if (NB == 2) tma2_load_2d(sa + A_BYTES + BH_BYTES, &tmB1, full_bar(s), kk * BK, n0);
+                    tma2_load_2d(sa, &tmA, full_bar(s), kk * KELEMS, m0);
+                    tma2_load_2d(sa + A_BYTES, &tmB0, full_bar(s), kk * KELEMS, n0);
+                    if (NB == 2) tma2_load_2d(sa + A_BYTES + BH_BYTES, &tmB1, full_bar(s), kk * KELEMS, n0);
                 }
             }
         }
@@ -166,6 +171,7 @@ te_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k) {
                         const uint32_t acc = (kk == 0 && k == 0) ? 0u : 1u;
+                        if (BF) { umma2_bf16(d0, adesc + (uint64_t)(2 * k), b0desc + (uint64_t)(2 * k), kIdesc2Bf16, acc); continue; }
                         umma2_tf32(d0, adesc + (uint64_t)(2 * k), b0desc + (uint64_t)(2 * k), kIdesc2, acc);
                         if (NB == 2) umma2_tf32(d0 + (uint32_t)BN, adesc + (uint64_t)(2 * k), b1desc + (uint64_t)(2 * k), kIdesc2, acc);
                     }
@@ -349,6 +355,21 @@ __global__ void abs_tf32_kernel(const float* __restrict__ x, long long ldx, floa
     }
 }
 
+// same with a bf16 result: the A operand of the bf16 S1 kernel
+__global__ void abs_bf16_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ out, long long rows, int cols4) {
+    const long long total = rows * cols4;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long r = t / cols4;
+        const int c = (int)(t - r * cols4);
+        const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + 4 * c);
+        const __nv_bfloat162 a = __floats2bfloat162_rn(fabsf(v.x), fabsf(v.y)), b = __floats2bfloat162_rn(fabsf(v.z), fabsf(v.w));
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&a);
+        pk.y = *reinterpret_cast<const uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(out + t * 4) = pk;
+    }
+}
+
 // ---- host ---------------------------------------------------------------------------------------------------
 int sm_pairs() {
     static int cache[64];
@@ -363,17 +384,17 @@ int sm_pairs() {
     return c;
 }
 
-template <int MODE, int EPI>
+template <int MODE, int EPI, bool BF = false>
 int launch_pair(const float* A, long long lda, const float* B0, const float* B1, PairParams p, cudaStream_t st) {
     using Cfg = PairCfg<MODE>;
     CUtensorMap tmA, tmB0, tmB1;
-    if (!make_map(&tmA, A, p.M, p.K, lda, BM) || !make_map(&tmB0, B0, p.N, p.K, p.K, BN / 2) ||
-        !make_map(&tmB1, B1 ? B1 : B0, p.N, p.K, p.K, BN / 2)) {
+    if (!make_map_t(&tmA, A, p.M, p.K, lda, BM, BF) || !make_map_t(&tmB0, B0, p.N, p.K, p.K, BN / 2, BF) ||
+        !make_map_t(&tmB1, B1 ? B1 : B0, p.N, p.K, p.K, BN / 2, BF)) {
         te_set_last_error("te_tc_pair: cuTensorMapEncodeTiled failed");
         return TE_ERR_CUDA;
     }
     static unsigned long long optin = 0;
-    if (!smem_optin(te_tc_pair_kernel<MODE, EPI>, Cfg::SMEM, optin)) {
+    if (!smem_optin(te_tc_pair_kernel<MODE, EPI, BF>, Cfg::SMEM, optin)) {
         te_set_last_error("te_tc_pair: cannot raise dynamic shared memory");
         return TE_ERR_CUDA;
     }
@@ -384,7 +405,7 @@ int launch_pair(const float* A, long long lda, const float* B0, const float* B1,
     int pairs = sm_pairs();
     if (pairs <= 0) { te_set_last_error("te_tc_pair: cannot query the SM count"); return TE_ERR_CUDA; }
     if (pairs > ntiles) pairs = ntiles;
-    te_tc_pair_kernel<MODE, EPI><<<dim3(2u * (unsigned)pairs), Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB0, tmB1, p);
+    te_tc_pair_kernel<MODE, EPI, BF><<<dim3(2u * (unsigned)pairs), Cfg::THREADS, Cfg::SMEM, st>>>(tmA, tmB0, tmB1, p);
     TE_CUDA_CHECK_LAUNCH();
     return TE_OK;
 }
@@ -409,8 +430,23 @@ int te_tc_abs_tf32(const float* x, long long ldx, float* out, long long rows, in
 // xabs: scratch [rows, in] that receives tf32(|x|)
 int te_tc_pair_zplus_s1(const float* x, long long ldx, float* xabs, const float* derived, const float* r, long long ldr,
                         const float* y, long long ldy, const float* bias, float* s_out, long long rows, int in_features,
-                        int out_features, cudaStream_t st) {
+                        int out_features, cudaStream_t st, bool bf16) {
     const long long n = (long long)in_features * out_features;
+    if (bf16 && in_features % 64 == 0) {
+        PairParams p;
+        memset(&p, 0, sizeof(p));
+        p.M = (int)rows; p.N = out_features; p.K = in_features;
+        p.E = r; p.lde = ldr; p.C = s_out; p.ldc = out_features; p.Y = y; p.ldy = ldy; p.bias = bias;
+        p.X = x; p.ldx = ldx; p.Wp = derived; p.Wn = derived + n;
+        if (ldx % 4 != 0 || !a16(x) || !a16(xabs)) { te_set_last_error("te_tc_pair_zplus_s1: alignment"); return TE_ERR_ARG; }
+        const long long total = rows * (in_features / 4);
+        long long blocks = (total + 255) / 256;
+        if (blocks > 148LL * 16) blocks = 148LL * 16;
+        abs_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, ldx, reinterpret_cast<__nv_bfloat16*>(xabs), rows, in_features / 4);
+        TE_CUDA_CHECK_LAUNCH();
+        // bf16(|W|) [out, in] lives at derived + 11 n (te_tc_prepare_weights)
+        return launch_pair<PM_S1, PE_STORE, true>(xabs, in_features, derived + 11 * n, nullptr, p, st);
+    }
     TE_TRY(te_tc_abs_tf32(x, ldx, xabs, rows, in_features, st));
     PairParams p;
     memset(&p, 0, sizeof(p));

@@ -450,6 +450,7 @@ __global__ void prepare_weights_kernel(const float* __restrict__ w, float* __res
             __nv_bfloat16* mb = reinterpret_cast<__nv_bfloat16*>(d + 10 * n);        // [ bf16(W_hi) | bf16(W_lo) ]: mixed-kind forward
             mb[idx] = __float2bfloat16_rn(hi);
             mb[n + idx] = __float2bfloat16_rn(v - hi);
+            reinterpret_cast<__nv_bfloat16*>(d + 11 * n)[idx] = __float2bfloat16_rn(fabsf(v));      // bf16(|W|): bf16 S1 kernel
         }
         tile[i][threadIdx.x] = v;
     }
@@ -575,7 +576,7 @@ static bool use_persistent() {
 }
 void te_tc_set_zplus_persistent(int on) { g_zplus_persistent = on ? 1 : 0; }
 
-long long te_tc_derived_floats(int in_features, int out_features) { return 11LL * in_features * out_features; }
+long long te_tc_derived_floats(int in_features, int out_features) { return 12LL * in_features * out_features; }
 
 int te_tc_prepare_weights(const float* w, float* derived, int in_features, int out_features, cudaStream_t st) {
     dim3 grid((in_features + 31) / 32, (out_features + 31) / 32), block(32, 8);
@@ -586,7 +587,7 @@ int te_tc_prepare_weights(const float* w, float* derived, int in_features, int o
 
 int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* derived, const float* r, long long ldr,
                                float* out, float* s_scratch, long long rows, int in_features, int out_features, cudaStream_t st,
-                               const float* y, long long ldy, const float* bias, bool bf16, long long ld_out, float* xabs) {
+                               const float* y, long long ldy, const float* bias, int bf16, long long ld_out, float* xabs) {
     if (ld_out == 0) ld_out = in_features;
     if (!a16(x) || !a16(derived) || !a16(r) || !a16(out) || !a16(s_scratch)) {
         te_set_last_error("te_gemm_tc: operands must be 16-byte aligned");
@@ -595,11 +596,12 @@ int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* deriv
     const long long n = (long long)in_features * out_features;
     const float *wp = derived, *wn = derived + n, *wpt = derived + 2 * n, *wnt = derived + 3 * n;
     // S = sd(R, x+ W+^T + x- W-^T)          A = x [rows, in] ; B = W+/- [out, in]
-    const bool rb = bf16 && (out_features % 64 == 0);          // S as bf16, R kernel with bf16 operands (kind::f16)
+    const bool rb = (bf16 & 1) && (out_features % 64 == 0);          // S as bf16, R kernel with bf16 operands (kind::f16)
     if (!rb && use_persistent() && xabs && a16(xabs) && y && a16(y) && ldy % 4 == 0 && (!bias || a16(bias)) &&
         te_tc_pair_supported(rows, in_features, out_features, ldx) && te_tc_pair_supported(rows, out_features, in_features, out_features)) {
         // persistent CTA-pair kernels (te_tc_pair.cu): single-pass S, then R with the A operand shared by both products
-        TE_TRY(te_tc_pair_zplus_s1(x, ldx, xabs, derived, r, ldr, y, ldy, bias, s_scratch, rows, in_features, out_features, st));
+        TE_TRY(te_tc_pair_zplus_s1(x, ldx, xabs, derived, r, ldr, y, ldy, bias, s_scratch, rows, in_features, out_features, st,
+                                   (bf16 & 2) != 0));
         return te_tc_pair_zplus_r(s_scratch, derived, x, ldx, out, ld_out, rows, in_features, out_features, st);
     }
     if (ld_out != in_features) {

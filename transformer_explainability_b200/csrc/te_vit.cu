@@ -353,7 +353,7 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
     const bool btf = (flags & TE_FLAG_BACKWARD_TF32) != 0;       // single-pass TF32 backward Linears
     const bool rtf = (flags & TE_FLAG_RELPROP_TF32) != 0;        // single-pass TF32 relevance-side attention contractions
     const bool lrpv = (flags & TE_FLAG_RULES_LRP) != 0;         // rule library of modules/layers_lrp.py (ViT_orig_LRP.py)
-    const bool zb = (flags & TE_FLAG_ZPLUS_BF16) != 0;
+    const int zb = ((flags & TE_FLAG_ZPLUS_BF16) ? 1 : 0) | ((flags & TE_FLAG_ZPLUS_S1_BF16) ? 2 : 0);   // bf16 variants of the z+ rule
 
     // ---- class index and seeds  (ViT_explanation_generator.py:28-35) ---------------------------
     TE_TRY(te_launch_argmax(ws.logits, index, d.B, d.C, /*only_negative=*/1, st));

@@ -13,7 +13,7 @@ int te_zplus_linear_relprop(const float* x, long long ldx, const float* w, const
 
 int te_zplus_linear_relprop_ldr(const float* x, long long ldx, const float* w, const float* w_derived, const float* r,
                                 long long ldr, float* out, float* s_scratch, long long rows, int in_features,
-                                int out_features, cudaStream_t st, const float* y, long long ldy, const float* bias, bool bf16,
+                                int out_features, cudaStream_t st, const float* y, long long ldy, const float* bias, int bf16,
                                 long long ld_out, float* xabs) {
     if (rows <= 0) return TE_OK;
     if (ld_out == 0) ld_out = in_features;

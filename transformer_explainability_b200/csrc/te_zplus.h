@@ -15,7 +15,7 @@ int te_zplus_linear_relprop(const float* x, long long ldx, const float* w, const
 int te_zplus_linear_relprop_ldr(const float* x, long long ldx, const float* w, const float* w_derived, const float* r,
                                 long long ldr, float* out, float* s_scratch, long long rows, int in_features,
                                 int out_features, cudaStream_t st, const float* y = nullptr, long long ldy = 0,
-                                const float* bias = nullptr, bool bf16 = false, long long ld_out = 0,
+                                const float* bias = nullptr, int bf16 = 0, long long ld_out = 0,
                                 float* xabs = nullptr);
 // xabs: scratch [rows, in] (the tf32(|x|) operand of the persistent single-pass S kernel); without it the tensor-core path
 // uses the round-1 kernels.

@@ -68,7 +68,7 @@ def linear_forward(x, w, bias=None, tensor_cores=False):
         raise ValueError("linear_forward: x [...,in], w [out,in], bias [out] expected")
     rows = x.numel() // x.shape[-1]
     y = torch.empty(*x.shape[:-1], w.shape[0], device=x.device, dtype=torch.float32)
-    scratch = torch.empty(11 * w.numel(), device=x.device, dtype=torch.float32) if tensor_cores else None
+    scratch = torch.empty(12 * w.numel(), device=x.device, dtype=torch.float32) if tensor_cores else None
     check(_lib.load().te_linear_forward_ex(ptr(x), ptr(w), ptr(bias), ptr(y), ptr(scratch), rows, x.shape[-1], w.shape[0],
                                            _lib.FLAG_LINEAR_TENSOR_CORES if tensor_cores else 0, _stream()),
           "te_linear_forward_ex")
@@ -83,7 +83,7 @@ def linear_backward(dy, w, tensor_cores=False):
         raise ValueError("linear_backward: dy [...,out], w [out,in] expected")
     rows = dy.numel() // dy.shape[-1]
     dx = torch.empty(*dy.shape[:-1], w.shape[1], device=dy.device, dtype=torch.float32)
-    scratch = torch.empty(11 * w.numel(), device=dy.device, dtype=torch.float32) if tensor_cores else None
+    scratch = torch.empty(12 * w.numel(), device=dy.device, dtype=torch.float32) if tensor_cores else None
     check(_lib.load().te_linear_backward_ex(ptr(dy), ptr(w), ptr(dx), ptr(scratch), rows, w.shape[1], w.shape[0],
                                             _lib.FLAG_LINEAR_TENSOR_CORES if tensor_cores else 0, _stream()),
           "te_linear_backward_ex")
@@ -98,7 +98,7 @@ def linear_backward_tf32(dy, w):
         raise ValueError("linear_backward_tf32: dy [...,out], w [out,in] expected")
     rows = dy.numel() // dy.shape[-1]
     dx = torch.empty(*dy.shape[:-1], w.shape[1], device=dy.device, dtype=torch.float32)
-    scratch = torch.empty(11 * w.numel(), device=dy.device, dtype=torch.float32)
+    scratch = torch.empty(12 * w.numel(), device=dy.device, dtype=torch.float32)
     check(_lib.load().te_linear_backward_ex(ptr(dy), ptr(w), ptr(dx), ptr(scratch), rows, w.shape[1], w.shape[0],
                                             _lib.FLAG_LINEAR_TENSOR_CORES | _lib.FLAG_BACKWARD_TF32, _stream()),
           "te_linear_backward_ex")
@@ -118,10 +118,12 @@ def linear_relprop(x, w, r, tensor_cores=False, y=None, bias=None, bf16=False, v
     out = torch.empty_like(x)
     nscratch = rows * w.shape[0]
     if tensor_cores:
-        nscratch = (nscratch + 63) // 64 * 64 + 11 * w.numel() + x.numel()
+        nscratch = (nscratch + 63) // 64 * 64 + 12 * w.numel() + x.numel()
     scratch = torch.empty(nscratch, device=x.device, dtype=torch.float32)
     flags = _lib.FLAG_ZPLUS_TENSOR_CORES if tensor_cores else 0
-    if bf16:
+    if bf16 == "s1":
+        flags |= _lib.FLAG_ZPLUS_S1_BF16              # bf16 operands for the |x||W|^T term of the single-pass denominator
+    elif bf16:
         flags |= _lib.FLAG_ZPLUS_BF16
     if variant == "lrp":
         flags, y = _lib.FLAG_RULES_LRP, None
