@@ -65,10 +65,11 @@ TE_API const char* te_last_error(void);
  * name = "linear_pair_kernels": the same for the 3xTF32 forward / backward Linear GEMMs.  Both default to 0.
  * name = "zplus_persistent": 1 (default) runs the z+ rule with the persistent CTA-pair kernels (te_tc_pair.cu), 0 with
  * the round-1 kernels selected by "zplus_pair_kernels".
- * name = "attn_persistent": 1 (default) runs the fp32-grade N x N attention kernel in its persistent, TMEM-double-buffered form
- * (N <= 224), 0 one tile per CTA.
+ * name = "attn_persistent": 1 runs the fp32-grade N x N attention kernel in its persistent, TMEM-double-buffered form (N <= 224),
+ * 0 (default) one tile per CTA, two CTAs per SM.
  * name = "linear_mixed": 1 runs the forward Linears with the mixed-kind split (main term TF32, the two correction terms as bf16
- * MMAs: two thirds of the tensor cycles of the 3xTF32 kernel at the same fp32-grade accuracy), 0 (default) with 3xTF32.
+ * MMAs: two thirds of the tensor cycles of the 3xTF32 kernel at the same fp32-grade accuracy), 2 its persistent CTA-pair form
+ * (48 KiB staged per k-block instead of 80), 0 with 3xTF32.
  * name = "cls_row_top_block": 1 (default) runs the three z+ rules of the top block on the pooled-token rows only (exact:
  * the relevance entering the top block is zero in every other row), 0 on all rows.
  * Returns TE_OK, or a negative status for an unknown name. */

@@ -251,7 +251,8 @@ def test_tc_persistent_pair_kernels(rows, inf, outf):
     assert e < 2e-3
 
 
-@pytest.mark.parametrize("rows,inf,outf", [(128, 256, 256), (394, 768, 3072), (1000, 3072, 768), (77, 768, 2304)])
+@pytest.mark.parametrize("rows,inf,outf", [(128, 256, 256), (394, 768, 3072), (1000, 3072, 768), (77, 768, 2304),
+                                           (20000, 768, 768)])
 def test_tc_mixed_kind_linear_is_fp32_grade(rows, inf, outf):
     """Forward Linear with the mixed-kind split (te_set_option("linear_mixed", 1)): main term TF32, the two correction terms
     as bf16 MMAs (SWIZZLE_64B operand tiles).  Same fp32-grade bound as the 3xTF32 kernel, every epilogue."""
@@ -263,15 +264,17 @@ def test_tc_mixed_kind_linear_is_fp32_grade(rows, inf, outf):
     ref_y = torch.nn.functional.linear(x.double(), w.double(), b.double())
     lib = _lib.load()
     y3 = ops.linear_forward(x.cuda(), w.cuda(), b.cuda(), tensor_cores=True)
-    _lib.check(lib.te_set_option(b"linear_mixed", 1), "te_set_option")
     try:
+        _lib.check(lib.te_set_option(b"linear_mixed", 1), "te_set_option")
         ym = ops.linear_forward(x.cuda(), w.cuda(), b.cuda(), tensor_cores=True)
+        _lib.check(lib.te_set_option(b"linear_mixed", 2), "te_set_option")         # persistent CTA-pair form
+        yp = ops.linear_forward(x.cuda(), w.cuda(), b.cuda(), tensor_cores=True)
         torch.cuda.synchronize()
     finally:
         _lib.check(lib.te_set_option(b"linear_mixed", 0), "te_set_option")
-    e3, em = rel(y3, ref_y), rel(ym, ref_y)
-    print("rows %d in %d out %d: 3xTF32 %.2e  mixed %.2e" % (rows, inf, outf, e3, em))
-    assert em < 1.5e-8 * inf + 2e-6
+    e3, em, ep = rel(y3, ref_y), rel(ym, ref_y), rel(yp, ref_y)
+    print("rows %d in %d out %d: 3xTF32 %.2e  mixed %.2e  mixed persistent pair %.2e" % (rows, inf, outf, e3, em, ep))
+    assert em < 1.5e-8 * inf + 2e-6 and ep < 1.5e-8 * inf + 2e-6
 
 
 @pytest.mark.parametrize("rows,inf,outf", [(128, 256, 256), (394, 768, 3072), (1000, 3072, 768), (77, 768, 2304)])

@@ -52,7 +52,8 @@ int te_tc_attn_nk(const float* map, int NP, int amn, const float* X, long long l
 void te_tc_set_pair_kernels(int on);
 // 1: run the 3xTF32 Linear GEMMs with the CTA-pair kernel (default 0, or TE_B200_LINEAR_2CTA=1)
 void te_tc_set_pair_linear(int on);
-// 1: forward Linears with the mixed-kind split (main term TF32, correction terms bf16; default 0 or TE_B200_LINEAR_MIXED=1)
+// 1: forward Linears with the mixed-kind split (main term TF32, correction terms bf16), single CTA; 2: its persistent CTA-pair form
+// (default 0, or TE_B200_LINEAR_MIXED=1|2)
 void te_tc_set_mixed_linear(int on);
 
 // dense rollout product out[b] = A[b] * Bm[b] ([batch, N, ld], N <= 224) on tcgen05, fp32-grade 3xTF32
@@ -73,5 +74,5 @@ int te_tc_pair_linear_bwd(const float* dy, long long lddy, const float* derived,
                           const float* e0, long long rows, int epi, cudaStream_t st);
 // 1 (default): z+ rule on the persistent pair kernels
 void te_tc_set_zplus_persistent(int on);
-// 1 (default): the 3xTF32 N x N attention kernel runs in its persistent, TMEM-double-buffered form when N <= 224
+// 1: the 3xTF32 N x N attention kernel runs in its persistent, TMEM-double-buffered form when N <= 224 (default 0: measured slower)
 void te_tc_set_attn_persistent(int on);

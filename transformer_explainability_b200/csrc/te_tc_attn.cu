@@ -680,11 +680,15 @@ bool te_tc_attn_supported(int N, int dh, long long lda, long long ldb, int ld_ou
 }
 
 namespace {
-int g_attn_persistent = -1;             // persistent N x N kernel for N <= 224 (default on; TE_B200_ATTN_PERSISTENT=0 / te_set_option)
+// persistent N x N kernel for N <= 224: opt-in (TE_B200_ATTN_PERSISTENT=1 / te_set_option).  Measured SLOWER than two resident
+// one-tile CTAs per SM (0.79 / 0.81 ms against 0.54 / 0.57 ms per launch for the softmax / S1 epilogues, step 1484 vs 1524
+// expl/s): with one CTA per SM only 4 epilogue warps work on an epilogue of ~37 k cycles per item (three TMEM passes with
+// expf, or HBM-latency-bound E loads), where the resident pair has 8; kept as the base of a version with 8-12 epilogue warps.
+int g_attn_persistent = -1;
 bool use_attn_persistent() {
     if (g_attn_persistent < 0) {
         const char* e = getenv("TE_B200_ATTN_PERSISTENT");
-        g_attn_persistent = (e && e[0] == '0') ? 0 : 1;
+        g_attn_persistent = (e && e[0] == '1') ? 1 : 0;
     }
     return g_attn_persistent == 1;
 }

@@ -240,6 +240,21 @@ __device__ __forceinline__ float4 epi_read_t(const float* stage, int lane, int i
     return *reinterpret_cast<const float4*>(stage + (4 * i + (lane >> 3)) * EPI_LD + 4 * (lane & 7));
 }
 
+// 16-column form of the same transpose (2560 B per warp, for kernels whose shared memory is full): iteration i (0..3) gives lane the
+// float4 of row 8i + lane/4, columns 4*(lane%4)..+3 — 8 rows x 64 contiguous bytes per warp instruction.
+constexpr int EPI16_LD = 20;
+constexpr int EPI16_STAGE_BYTES = 32 * EPI16_LD * 4;   // 2560 B per warp
+__device__ __forceinline__ void epi16_stage_rows(float* stage, int lane, const float (&v)[16]) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<float4*>(stage + lane * EPI16_LD + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+}
+__device__ __forceinline__ float4 epi16_read_t(const float* stage, int lane, int i) {
+    return *reinterpret_cast<const float4*>(stage + (8 * i + (lane >> 2)) * EPI16_LD + 4 * (lane & 3));
+}
+
 // ---- host: tensor maps ------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -414,6 +414,239 @@ te_tc_gemm3m_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // =====================================================================================================================
+// Persistent CTA-pair form of the mixed-kind fp32-grade Linear GEMM.  The single-CTA kernels above stage 80 KiB per k-block
+// (raw A + the weight tiles) = 53-73 B/clk/SM against the chip-wide L2 -> SM cap of ~42 B/clk/SM: they are L2-bound (the
+// mixed-kind kernel removed a third of the MMA cycles and its time did not change).  Here a CTA pair (tcgen05 cta_group::2,
+// 256 x 256 tile) stages per CTA its own A tile and HALF of every weight tile: 16 K raw A + 16 K W_hi half + 8 K + 8 K bf16
+// halves = 48 KiB per k-block of 8 MMA slots (4 TF32 + 2 + 2 bf16, 256 x 256) = 47 B/clk/SM.
+//   warp 0 TMA (both CTAs) · warp 1 MMA (leader) · warps 2-3 hi / bf16 split of the A tile · warps 4-11 chunk drain + epilogue
+//   full[s] local TMA bytes · ready[s] leader, one remote arrive per split warp of both CTAs (4) · empty[s] local multicast
+//   commit · accfull[b] local multicast commit per 128-element chunk · accfree[b] leader, one remote arrive per drain warp (16)
+// Persistent: static round-robin over 256 x 256 tiles (column tile fastest); barriers / TMEM set up once; chunks alternate
+// between the two 256-column TMEM accumulators ACROSS tile boundaries, so while the drain warps store tile i from their
+// register sums the MMAs of tile i+1's first two chunks already run.
+// =====================================================================================================================
+constexpr int MP_STAGES = 3;
+constexpr int MP_STAGE = A_BYTES + 2 * A16_BYTES + BH_BYTES + B16_BYTES;     // 64 KiB: A_hi | a16h | a16l | Bh half | b16h half | b16l half
+constexpr uint32_t MP_OFF_AH = 0, MP_OFF_A16H = A_BYTES, MP_OFF_A16L = A_BYTES + A16_BYTES, MP_OFF_BH = A_BYTES + 2 * A16_BYTES,
+                   MP_OFF_B16H = MP_OFF_BH + BH_BYTES, MP_OFF_B16L = MP_OFF_B16H + B16_BYTES / 2;
+constexpr int MP_THREADS = 384, MP_XF_THREADS = 64, MP_DRAIN_WARPS = 8;
+constexpr int MP_SMEM = MP_STAGES * MP_STAGE + MP_DRAIN_WARPS * EPI16_STAGE_BYTES + 1024 + 256;
+
+template <int EPI>
+__device__ __forceinline__ void gemm3x_epilogue16(const Tc3Params& p, float (&sum)[128], float* stage, int lane, int row0, int cbase) {
+    const int tr = lane >> 2, tc = 4 * (lane & 3);
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { v[j] = sum[cc * 16 + j]; sum[cc * 16 + j] = 0.f; }
+        epi16_stage_rows(stage, lane, v);
+        const int col = cbase + cc * 16 + tc;
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((EPI == EP_BIAS || EPI == EP_BIAS_GELU || EPI == EP_BIAS_ADD) && p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = row0 + 8 * i + tr;
+            if (row >= p.M) continue;
+            const float4 a = epi16_read_t(stage, lane, i);
+            float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (EPI == EP_BIAS_ADD || EPI == EP_GELU_BWD) e = *reinterpret_cast<const float4*>(p.E + (long long)row * p.lde + col);
+            float4 o, o2 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (EPI == EP_STORE) o = a;
+            else if (EPI == EP_BIAS) o = make_float4(a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w);
+            else if (EPI == EP_BIAS_GELU) {
+                o = make_float4(a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w);
+                o2 = make_float4(te_gelu(o.x), te_gelu(o.y), te_gelu(o.z), te_gelu(o.w));
+            } else if (EPI == EP_BIAS_ADD) {
+                o = make_float4(a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w);
+                o2 = make_float4(e.x + o.x, e.y + o.y, e.z + o.z, e.w + o.w);
+            } else {
+                o = make_float4(a.x * te_gelu_grad(e.x), a.y * te_gelu_grad(e.y), a.z * te_gelu_grad(e.z), a.w * te_gelu_grad(e.w));
+            }
+            *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) = o;
+            if (EPI == EP_BIAS_GELU || EPI == EP_BIAS_ADD) *reinterpret_cast<float4*>(p.C2 + (long long)row * p.ldc2 + col) = o2;
+        }
+    }
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MP_THREADS, 1)
+te_tc_gemm3mp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                     const __grid_constant__ CUtensorMap tmB16h, const __grid_constant__ CUtensorMap tmB16l, const Tc3Params p,
+                     int tiles_m, int tiles_n) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bars = smem_base + MP_STAGES * MP_STAGE + MP_DRAIN_WARPS * EPI16_STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto ready_bar = [&](int s) { return bars + 8u * (MP_STAGES + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (2 * MP_STAGES + s); };
+    auto accfull_bar = [&](int b) { return bars + 8u * (3 * MP_STAGES + b); };
+    auto accfree_bar = [&](int b) { return bars + 8u * (3 * MP_STAGES + 2 + b); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_al + MP_STAGES * MP_STAGE + MP_DRAIN_WARPS * EPI16_STAGE_BYTES + 8 * (3 * MP_STAGES + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+    const int ntiles = tiles_m * tiles_n;
+    const int kb = p.K / BK;
+    const int nchunks = (kb + CHUNK - 1) / CHUNK;
+    constexpr uint32_t TMEM_COLS = 512u;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB16h) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB16l) : "memory");
+        for (int s = 0; s < MP_STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(ready_bar(s), 2u * (MP_XF_THREADS / 32));
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(accfull_bar(b), 1);
+            mbar_init(accfree_bar(b), 2u * MP_DRAIN_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = cluster_id; t < ntiles; t += nclusters) {
+                const int m0 = ((t / tiles_n) * 2 + (int)rank) * BM, n0 = (t % tiles_n) * BN + (int)rank * (BN / 2);
+                for (int kk = 0; kk < kb; ++kk, ++it) {
+                    const int s = (int)(it % MP_STAGES);
+                    const uint32_t ph = (it / MP_STAGES) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_arrive_expect_tx(full_bar(s), A_BYTES + BH_BYTES + B16_BYTES);
+                    const uint32_t sa = smem_base + s * MP_STAGE;
+                    tma_load_2d(sa + MP_OFF_AH, &tmA, full_bar(s), kk * BK, m0);                    // raw A -> A_hi slot
+                    tma_load_2d(sa + MP_OFF_BH, &tmBh, full_bar(s), kk * BK, n0);
+                    tma_load_2d(sa + MP_OFF_B16H, &tmB16h, full_bar(s), kk * BK, n0);
+                    tma_load_2d(sa + MP_OFF_B16L, &tmB16l, full_bar(s), kk * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            uint32_t it = 0, gc = 0;
+            for (int t = cluster_id; t < ntiles; t += nclusters) {
+                for (int kk = 0; kk < kb; ++kk, ++it) {
+                    const bool chunk_start = (kk % CHUNK) == 0;
+                    const uint32_t b = gc & 1u;
+                    if (chunk_start && gc >= 2) {                       // accumulator b drained (chunk gc-2) in BOTH CTAs
+                        mbar_wait_cluster(accfree_bar(b), ((gc >> 1) & 1u) ^ 1u);
+                        tcgen05_fence_after();
+                    }
+                    const int s = (int)(it % MP_STAGES);
+                    const uint32_t ph = (it / MP_STAGES) & 1u;
+                    mbar_wait_cluster(ready_bar(s), ph);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_base + s * MP_STAGE;
+                    const uint64_t ah = make_smem_desc(sa + MP_OFF_AH), bh = make_smem_desc(sa + MP_OFF_BH);
+                    const uint64_t a16h = make_smem_desc_sw64(sa + MP_OFF_A16H), a16l = make_smem_desc_sw64(sa + MP_OFF_A16L);
+                    const uint64_t b16h = make_smem_desc_sw64(sa + MP_OFF_B16H), b16l = make_smem_desc_sw64(sa + MP_OFF_B16L);
+                    const uint32_t d = tmem_base + b * (uint32_t)BN;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t o = (uint64_t)(2 * k);
+                        umma2_bf16(d, a16l + o, b16h + o, kIdesc2Bf16, (chunk_start && k == 0) ? 0u : 1u);
+                        umma2_bf16(d, a16h + o, b16l + o, kIdesc2Bf16, 1u);
+                    }
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) umma2_tf32(d, ah + (uint64_t)(2 * k), bh + (uint64_t)(2 * k), kIdesc2, 1u);
+                    umma2_commit_both(empty_bar(s));
+                    if ((kk % CHUNK) == CHUNK - 1 || kk == kb - 1) { umma2_commit_both(accfull_bar(b)); ++gc; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp < 4) {
+        // ---- A tile: hi (tf32, in place) + bf16(hi) + bf16(lo): warps 2-3 of both CTAs ----
+        const int et = threadIdx.x - 64;                                // 0..63
+        uint32_t it = 0;
+        for (int t = cluster_id; t < ntiles; t += nclusters) {
+            for (int kk = 0; kk < kb; ++kk, ++it) {
+                const int s = (int)(it % MP_STAGES);
+                const uint32_t ph = (it / MP_STAGES) & 1u;
+                mbar_wait(full_bar(s), ph);
+                uint8_t* st8 = smem_al + s * MP_STAGE;
+                float4* a4 = reinterpret_cast<float4*>(st8 + MP_OFF_AH);
+#pragma unroll 4
+                for (int i = 0; i < A_BYTES / 16 / MP_XF_THREADS; ++i) {
+                    const int idx = et + i * MP_XF_THREADS;
+                    const int r = idx >> 3, lc = (idx & 7) ^ (r & 7);
+                    const float4 v = a4[idx];
+                    float4 h;
+                    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+                    a4[idx] = h;
+                    const __nv_bfloat162 h01 = __floats2bfloat162_rn(h.x, h.y), h23 = __floats2bfloat162_rn(h.z, h.w);
+                    const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - h.x, v.y - h.y), l23 = __floats2bfloat162_rn(v.z - h.z, v.w - h.w);
+                    const uint32_t off = (uint32_t)r * 64u + ((uint32_t)((lc >> 1) ^ ((r >> 1) & 3)) << 4) + ((uint32_t)(lc & 1) << 3);
+                    uint2 hb, lb;
+                    hb.x = *reinterpret_cast<const uint32_t*>(&h01); hb.y = *reinterpret_cast<const uint32_t*>(&h23);
+                    lb.x = *reinterpret_cast<const uint32_t*>(&l01); lb.y = *reinterpret_cast<const uint32_t*>(&l23);
+                    *reinterpret_cast<uint2*>(st8 + MP_OFF_A16H + off) = hb;
+                    *reinterpret_cast<uint2*>(st8 + MP_OFF_A16L + off) = lb;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(map_to_rank0(ready_bar(s)));
+            }
+        }
+    } else {
+        // ---- chunk drain + epilogue: warps 4..11 (lane quarter = warp & 3, column half = (warp - 4) / 4) ----
+        const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
+        float* stage = reinterpret_cast<float*>(smem_al + MP_STAGES * MP_STAGE + (warp - 4) * EPI16_STAGE_BYTES);
+        float sum[128];
+#pragma unroll
+        for (int j = 0; j < 128; ++j) sum[j] = 0.f;
+        uint32_t gc = 0;
+        for (int t = cluster_id; t < ntiles; t += nclusters) {
+            const int m0 = ((t / tiles_n) * 2 + (int)rank) * BM, n0 = (t % tiles_n) * BN;
+            for (int c = 0; c < nchunks; ++c, ++gc) {
+                const uint32_t b = gc & 1u;
+                mbar_wait(accfull_bar(b), (gc >> 1) & 1u);
+                tcgen05_fence_after();
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    uint32_t v[16];
+                    tmem_ld16(tlane + b * (uint32_t)BN + (uint32_t)(cc * 16), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sum[cc * 16 + j] += __uint_as_float(v[j]);
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(map_to_rank0(accfree_bar(b)));
+            }
+            gemm3x_epilogue16<EPI>(p, sum, stage, lane, m0 + q * 32, n0 + half * 128);      // also zeroes the sums
+        }
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// =====================================================================================================================
 // CTA-pair version of the 3xTF32 Linear GEMM (tcgen05 cta_group::2): the two CTAs of a cluster own adjacent 128-row
 // tiles of the same 256-column tile and execute ONE 256 x 256 x 8 MMA per issue (leader CTA).  Each CTA stages its own
 // activation tile (raw -> hi, lo) and only its HALF of the pre-split weight tile (128 of the 256 rows of W_hi and
@@ -671,9 +904,9 @@ int g_mixed_linear = -1;                // forward Linears with bf16 correction 
 bool use_mixed_linear() {
     if (g_mixed_linear < 0) {
         const char* e = getenv("TE_B200_LINEAR_MIXED");
-        g_mixed_linear = (e && e[0] == '1') ? 1 : 0;
+        g_mixed_linear = (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 0;
     }
-    return g_mixed_linear == 1;
+    return g_mixed_linear >= 1;
 }
 
 template <int EPI>
@@ -707,10 +940,57 @@ int dispatch3m(int epi, const float* A, long long lda, const float* Bh, const vo
     return TE_ERR_UNSUPPORTED;
 }
 
+int mp_sm_pairs() {
+    static int cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    int& c = cache[dev & 63];
+    if (c == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        c = n / 2;
+    }
+    return c;
+}
+template <int EPI>
+int launch3mp(const float* A, long long lda, const float* Bh, const void* B16h, const void* B16l, const Tc3Params& p, cudaStream_t st) {
+    CUtensorMap tmA, tmBh, tm16h, tm16l;
+    if (!make_map(&tmA, A, p.M, p.K, lda, BM) || !make_map(&tmBh, Bh, p.N, p.K, p.K, BN / 2) ||
+        !make_map_bf16_sw64(&tm16h, B16h, p.N, p.K, p.K, BN / 2) || !make_map_bf16_sw64(&tm16l, B16l, p.N, p.K, p.K, BN / 2)) {
+        te_set_last_error("te_gemm_tc: cuTensorMapEncodeTiled failed (mixed pair)");
+        return TE_ERR_CUDA;
+    }
+    static unsigned long long optin = 0;
+    if (!smem_optin(te_tc_gemm3mp_kernel<EPI>, MP_SMEM, optin)) {
+        te_set_last_error("te_gemm_tc: cannot raise dynamic shared memory");
+        return TE_ERR_CUDA;
+    }
+    const int mt = (p.M + BM - 1) / BM;
+    const int tiles_m = (mt + 1) / 2, tiles_n = p.N / BN;
+    int pairs = mp_sm_pairs();
+    if (pairs <= 0) { te_set_last_error("te_gemm_tc: cannot query the SM count"); return TE_ERR_CUDA; }
+    if (pairs > tiles_m * tiles_n) pairs = tiles_m * tiles_n;
+    te_tc_gemm3mp_kernel<EPI><<<dim3(2u * (unsigned)pairs), MP_THREADS, MP_SMEM, st>>>(tmA, tmBh, tm16h, tm16l, p, tiles_m, tiles_n);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+int dispatch3mp(int epi, const float* A, long long lda, const float* Bh, const void* B16h, const void* B16l, const Tc3Params& p,
+                cudaStream_t st) {
+    switch (epi) {
+        case TE_TC_EPI_STORE: return launch3mp<EP_STORE>(A, lda, Bh, B16h, B16l, p, st);
+        case TE_TC_EPI_BIAS: return launch3mp<EP_BIAS>(A, lda, Bh, B16h, B16l, p, st);
+        case TE_TC_EPI_BIAS_GELU: return launch3mp<EP_BIAS_GELU>(A, lda, Bh, B16h, B16l, p, st);
+        case TE_TC_EPI_BIAS_ADD: return launch3mp<EP_BIAS_ADD>(A, lda, Bh, B16h, B16l, p, st);
+        case TE_TC_EPI_GELU_BWD: return launch3mp<EP_GELU_BWD>(A, lda, Bh, B16h, B16l, p, st);
+    }
+    te_set_last_error("te_gemm_tc: unsupported epilogue");
+    return TE_ERR_UNSUPPORTED;
+}
+
 }  // namespace
 
 void te_tc_set_pair_linear(int on) { g_pair_linear = on ? 1 : 0; }
-void te_tc_set_mixed_linear(int on) { g_mixed_linear = on ? 1 : 0; }
+void te_tc_set_mixed_linear(int on) { g_mixed_linear = (on == 2) ? 2 : (on ? 1 : 0); }
 
 bool te_tc_gemm3x_supported(long long rows, int K, int N, long long lda) {
     return rows > 0 && rows < (1LL << 31) && K % BK == 0 && N % BN == 0 && lda % 4 == 0 && get_encode() != nullptr;
@@ -725,6 +1005,7 @@ int te_tc_linear_fwd(const float* x, long long ldx, const float* derived, int in
     p.C = y; p.ldc = out_features; p.C2 = y2; p.ldc2 = out_features;
     if (use_mixed_linear()) {           // main term TF32, correction terms bf16: [bf16(W_hi) | bf16(W_lo)] live at derived + 10 n
         const __nv_bfloat16* w16 = reinterpret_cast<const __nv_bfloat16*>(derived + 10 * n);
+        if (g_mixed_linear == 2) return dispatch3mp(epi, x, ldx, derived + 4 * n, w16, w16 + n, p, st);     // persistent CTA pair
         return dispatch3m(epi, x, ldx, derived + 4 * n, w16, w16 + n, p, st);
     }
     return dispatch3(epi, x, ldx, derived + 4 * n, derived + 5 * n, p, st);
