@@ -41,6 +41,9 @@ def _flag_sets():
     out = [(0, 2e-4), (_lib.FLAG_ALL_FAST, 5e-3), (_lib.FLAG_ALL_FAST | _lib.FLAG_BACKWARD_TF32, 5e-3)]
     if _lib.FLAG_BENCH_DEFAULT not in [f for f, _ in out]:
         out.append((_lib.FLAG_BENCH_DEFAULT, 5e-3))
+    opt = _lib.FLAG_BENCH_DEFAULT | _lib.FLAG_ZPLUS_S1_BF16            # opt-in: bf16 operands for the z+ denominator term
+    if opt not in [f for f, _ in out]:
+        out.append((opt, 5e-3))
     return out
 
 

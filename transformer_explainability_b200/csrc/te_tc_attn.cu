@@ -213,6 +213,16 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         __syncwarp();
     } else {
         const int et = threadIdx.x - 64;
+        if (EPI == AT_MUL || EPI == AT_SD) {
+            // the epilogue operand E (attention probabilities / attn_cam) is streamed from HBM exactly once: pull this tile's rows
+            // into L2 now, while the operands are loaded and the MMAs run, so that the epilogue's loads are L2 hits
+            const int pr = m0 + et;                                  // one row per thread
+            if (pr < p.N) {
+                const float* e = p.E + ((long long)bh * p.N + pr) * p.ld_out + n0;
+                const int nc = min(p.N - n0, BN);
+                for (int j = 0; j < nc; j += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(e + j));
+            }
+        }
         // split A (16 KiB) and B (32 KiB) of every k-block: hi in place, lo to the *_lo regions (same swizzled offsets)
         for (int kk = 0; kk < (SP ? 0 : kb); ++kk) {
             mbar_wait(full_bar, (uint32_t)(kk & 1));
