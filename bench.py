@@ -80,12 +80,16 @@ def peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
-def measured_traffic(key):
+def measured_traffic(key, units=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch (group) from the committed ncu --set full capture of the
-    same kernel at the same shape (profiles/ncu_traffic.json), or None."""
+    same kernel at the same shape (profiles/ncu_traffic.json), or None.  Entries captured at another batch carry
+    `bytes_per_unit` (bytes per explanation) and are scaled by `units`."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            return json.load(f).get(key, {}).get("bytes")
+            e = json.load(f).get(key, {})
+        if units is not None and e.get("bytes_per_unit") is not None:
+            return int(e["bytes_per_unit"] * units)
+        return e.get("bytes")
     except (OSError, ValueError):
         return None
 
@@ -318,7 +322,7 @@ def roofline_rollout(w, flags, pk, B=32, dense=False):
                 ("aggregate + tcgen05 N^3 chain, dense joint" if dense else "fused row-only") if fused else "aggregate+bmm", L, B, H, N),
             "bound": "hbm", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
             "frac": round(achieved / pk["hbm_gbs"], 4),
-            "traffic": None if dense else measured_traffic("rollout_fused" if fused else "rollout"),
+            "traffic": None if dense else measured_traffic("rollout_fused" if fused else "rollout", units=B),
             "algorithmic_bytes": nbytes, "ms": round(ms, 3), "peak_source": pk["source"]}
 
 

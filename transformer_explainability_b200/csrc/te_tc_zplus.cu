@@ -183,8 +183,10 @@ te_tc_zplus_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             const float4 y = *reinterpret_cast<const float4*>(p.Y + (long long)row * p.ldy + n0 + c * 32 + j);
                             float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c * 32 + j));
-                            z[0] = 0.5f * ((y.x - bb.x) + z[0]); z[1] = 0.5f * ((y.y - bb.y) + z[1]);
-                            z[2] = 0.5f * ((y.z - bb.z) + z[2]); z[3] = 0.5f * ((y.w - bb.w) + z[3]);
+                            // the true value is a sum of non-negative terms: a negative result is cancellation noise (the persistent
+                            // kernel of te_tc_pair.cu additionally recomputes cancelled elements exactly)
+                            z[0] = fmaxf(0.5f * ((y.x - bb.x) + z[0]), 0.f); z[1] = fmaxf(0.5f * ((y.y - bb.y) + z[1]), 0.f);
+                            z[2] = fmaxf(0.5f * ((y.z - bb.z) + z[2]), 0.f); z[3] = fmaxf(0.5f * ((y.w - bb.w) + z[3]), 0.f);
                         }
                         if (p.out_bf16) {
                             __nv_bfloat162 lo = __floats2bfloat162_rn(te_sd(r.x, z[0]), te_sd(r.y, z[1]));
@@ -387,10 +389,10 @@ te_tc_zplus2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c * 32 + j));
                         // x+ W+^T + x- W-^T == ( x W^T + |x| |W|^T ) / 2 ,  x W^T = y - bias (saved forward output)
-                        const float z0 = 0.5f * ((y.x - bb.x) + __uint_as_float(acc[j + 0]));
-                        const float z1 = 0.5f * ((y.y - bb.y) + __uint_as_float(acc[j + 1]));
-                        const float z2 = 0.5f * ((y.z - bb.z) + __uint_as_float(acc[j + 2]));
-                        const float z3 = 0.5f * ((y.w - bb.w) + __uint_as_float(acc[j + 3]));
+                        const float z0 = fmaxf(0.5f * ((y.x - bb.x) + __uint_as_float(acc[j + 0])), 0.f);
+                        const float z1 = fmaxf(0.5f * ((y.y - bb.y) + __uint_as_float(acc[j + 1])), 0.f);
+                        const float z2 = fmaxf(0.5f * ((y.z - bb.z) + __uint_as_float(acc[j + 2])), 0.f);
+                        const float z3 = fmaxf(0.5f * ((y.w - bb.w) + __uint_as_float(acc[j + 3])), 0.f);
                         float4 o;
                         o.x = to_tf32(te_sd(r.x, z0)); o.y = to_tf32(te_sd(r.y, z1));
                         o.z = to_tf32(te_sd(r.z, z2)); o.w = to_tf32(te_sd(r.w, z3));
