@@ -53,6 +53,9 @@ extern "C" {
                                          TF32 like the z+ rule does; the denominator Q K^T keeps the 3xTF32 split */
 #define TE_FLAG_ZPLUS_S1_BF16 2048u    /* with TE_FLAG_ZPLUS_TENSOR_CORES: the |x| |W|^T term of the single-pass z+ denominator with bf16
                                          operands (a sum of K non-negative products: rounding errors average to ~2^-9 / sqrt(K)) */
+#define TE_FLAG_LINEAR_F16_SPLIT 4096u  /* with TE_FLAG_LINEAR_TENSOR_CORES: the forward Linears on tcgen05 kind::f16 with a row-scaled
+                                         * fp16 (hi, lo) split of both operands (3 MMAs per k-step, same 22-bit operand precision
+                                         * as the 3xTF32 split at half the tensor cycles and a third of the staged bytes) */
 #define TE_FLAG_RULES_LRP 512u         /* the rule library of modules/layers_lrp.py (baselines/ViT/ViT_orig_LRP.py) instead of
                                          modules/layers_ours.py: Linear divides its two halves by their OWN denominators
                                          (layers_lrp.py:199-200), Add has no ratio normalisation (:98-100).  fp32 SIMT rules. */
@@ -206,13 +209,13 @@ TE_API int te_bert_tensor(const te_bert_config* cfg, int batch, int seq, void* w
  * ---------------------------------------------------------------------------------------------- */
 /* Linear.relprop, alpha=1 (layers_ours.py:207-230): x [rows,in], w [out,in], r [rows,out] -> out [rows,in].
  * flags & TE_FLAG_RULES_LRP: the layers_lrp variant (modules/layers_lrp.py:187-210, separate denominators).
- * scratch: rows*out floats; with TE_FLAG_ZPLUS_TENSOR_CORES: round_up(rows*out,64) + 12*in*out floats. */
+ * scratch: rows*out floats; with TE_FLAG_ZPLUS_TENSOR_CORES: round_up(rows*out,64) + 13*in*out floats. */
 TE_API int te_linear_relprop(const float* x, const float* w, const float* r, float* out, float* scratch, int rows,
                       int in_features, int out_features, unsigned flags, void* stream);
 /* Same rule with the Linear's saved forward output y = x W^T + bias [rows,out] supplied (what the engines do): with
  * TE_FLAG_ZPLUS_TENSOR_CORES the denominator is then formed in ONE tensor-core pass through the exact identity
  * x+ W+^T + x- W-^T == ((y - bias) + |x| |W|^T) / 2.  bias may be NULL (no bias).
- * scratch: rows*out floats; with TE_FLAG_ZPLUS_TENSOR_CORES: round_up(rows*out,64) + 12*in*out + rows*in floats
+ * scratch: rows*out floats; with TE_FLAG_ZPLUS_TENSOR_CORES: round_up(rows*out,64) + 13*in*out + rows*in floats
  * (S, the derived weight copies, the tf32(|x|) operand of the single-pass kernel). */
 TE_API int te_linear_relprop_ex(const float* x, const float* w, const float* bias, const float* y, const float* r,
                          float* out, float* scratch, int rows, int in_features, int out_features, unsigned flags,
@@ -272,7 +275,9 @@ TE_API int te_compute_rollout_attention(const float* mats, int layers, int batch
                                  float* joint, void* workspace, long long workspace_bytes, void* stream);
 
 /* Plain Linear GEMMs — exported for kernel unit tests only.  flags & TE_FLAG_LINEAR_TENSOR_CORES selects the
- * tcgen05 3xTF32 path (scratch: 12*in*out floats for the derived weight copies; may be NULL otherwise). */
+ * tcgen05 3xTF32 path (scratch: 13*in*out floats for the derived weight copies; may be NULL otherwise); with
+ * TE_FLAG_LINEAR_F16_SPLIT as well, te_linear_forward_ex runs the fp16-split kernel (scratch: 13*in*out +
+ * round_up(rows*in,64) + rows*ceil(in/128) floats). */
 TE_API int te_linear_forward(const float* x, const float* w, const float* bias, float* y, int rows, int in_features,
                       int out_features, void* stream);
 TE_API int te_linear_forward_ex(const float* x, const float* w, const float* bias, float* y, float* scratch, int rows,

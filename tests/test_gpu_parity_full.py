@@ -38,10 +38,13 @@ def rel(a, b):
 
 def _flag_sets():
     from transformer_explainability_b200 import _lib
-    out = [(0, 2e-4), (_lib.FLAG_ALL_FAST, 5e-3), (_lib.FLAG_ALL_FAST | _lib.FLAG_BACKWARD_TF32, 5e-3)]
+    out = [(0, 2e-4), (_lib.FLAG_ALL_FAST, 5e-3),
+           (_lib.FLAG_ALL_FAST | _lib.FLAG_LINEAR_F16_SPLIT, 5e-3),     # 4147: fp32-grade forward Linears as the fp16 split
+           (_lib.FLAG_ALL_FAST | _lib.FLAG_BACKWARD_TF32, 5e-3)]
     out.append((_lib.FLAG_ALL_FAST | _lib.FLAG_BACKWARD_TF32 | _lib.FLAG_RELPROP_TF32, 5e-3))        # 1331
+    out.append((_lib.FLAG_ALL_FAST | _lib.FLAG_BACKWARD_TF32 | _lib.FLAG_RELPROP_TF32 | _lib.FLAG_ZPLUS_S1_BF16, 5e-3))   # 3379
     if _lib.FLAG_BENCH_DEFAULT not in [f for f, _ in out]:
-        out.append((_lib.FLAG_BENCH_DEFAULT, 5e-3))                     # 3379: + bf16 operands for the z+ denominator term
+        out.append((_lib.FLAG_BENCH_DEFAULT, 5e-3))                     # 7475: 3379 + fp16-split forward Linears
     return out
 
 

@@ -297,3 +297,35 @@ def test_tc_bf16_single_pass_denominator(rows, inf, outf):
     print("bf16 S1 rows %d in %d out %d: TF32 %.2e  bf16 denominator %.2e" % (rows, inf, outf, e_tf, e_bf))
     assert e_bf < 3e-3
     assert abs(bf.double().sum().item() - r.double().sum().item()) < 2e-3 * r.sum().item()
+
+
+@pytest.mark.parametrize("rows,inf,outf", [(128, 256, 256), (394, 768, 3072), (1000, 3072, 768), (77, 768, 2304),
+                                           (20000, 768, 768), (300, 64, 256)])
+def test_tc_f16_split_linear_is_fp32_grade(rows, inf, outf):
+    """TE_FLAG_LINEAR_F16_SPLIT: forward Linear on tcgen05 kind::f16 with the row-scaled fp16 (hi, lo) split of both operands
+    (te_tc_fwd16.cu).  fp16 carries the same 11-bit significand as TF32, so the bound is the 3xTF32 one; the per-row power-of-two
+    scaling has to cope with rows and weight rows whose magnitudes span 12 decades, zero rows, and activations spanning four
+    decades inside a row."""
+    from transformer_explainability_b200 import ops
+    g = torch.Generator().manual_seed(rows + 23)
+    x = torch.randn(rows, inf, generator=g) * torch.logspace(-3, 1, inf)
+    x = x * torch.logspace(-6, 6, rows)[:, None]                   # row magnitudes 1e-6 .. 1e6 (fp16 alone would over/underflow)
+    x[rows // 2] = 0.0
+    w = torch.randn(outf, inf, generator=g) * 0.05 * torch.logspace(-4, 2, outf)[:, None]
+    w[3] = 0.0
+    b = torch.randn(outf, generator=g)
+    ref = torch.nn.functional.linear(x.double(), w.double())
+    # without a bias: at row magnitudes of 1e-6 a bias of O(1) would swamp the product and hide the kernel's error
+    y3 = ops.linear_forward(x.cuda(), w.cuda(), None, tensor_cores=True)
+    yh = ops.linear_forward(x.cuda(), w.cuda(), None, tensor_cores=True, f16_split=True)
+    yb = ops.linear_forward(x.cuda(), w.cuda(), b.cuda(), tensor_cores=True, f16_split=True)
+    torch.cuda.synchronize()
+    # error of every element relative to the scale of its own row and column
+    scale = (x.double().abs() @ w.double().abs().T).clamp_min(1e-300) / inf ** 0.5
+    e3 = ((y3.double().cpu() - ref).abs() / scale).max().item()
+    eh = ((yh.double().cpu() - ref).abs() / scale).max().item()
+    print("rows %d in %d out %d: 3xTF32 %.2e  fp16 split %.2e (per-element, relative to |x||W|^T / sqrt(K))" % (rows, inf, outf, e3, eh))
+    assert torch.isfinite(yh).all()
+    assert eh < 2e-5 and eh < 2 * e3 + 1e-6          # fp32 grade, and no worse than the 3xTF32 kernel on the same data
+    assert (yh[rows // 2] == 0).all() and (yh[:, 3] == 0).all()                       # zero row / zero weight row: exactly zero
+    assert torch.equal(yb.cpu(), (yh.cpu() + b))                                      # the bias is added last, in fp32

@@ -54,6 +54,9 @@ def main():
         fl = 2.0 * rows * inf * outf
         print("linear fwd 3xTF32 %-5s: %.3f ms  %.1f TFLOP/s algorithmic = %.3f of TF32 roof (x3 issue)" % (
             name, ms, fl / ms / 1e9, fl / ms / 1e9 / peak), flush=True)
+        ms = timeit(lambda: ops.linear_forward(x, w, b, tensor_cores=True, f16_split=True))
+        print("linear fwd fp16-split %-5s: %.3f ms  %.1f TFLOP/s algorithmic = %.3f of TF32 roof (incl. the row-split pre-pass)" % (
+            name, ms, fl / ms / 1e9, fl / ms / 1e9 / peak), flush=True)
         ms = timeit(lambda: ops.linear_backward(dy, w, tensor_cores=True))
         print("linear bwd 3xTF32 %-5s: %.3f ms  %.1f TFLOP/s algorithmic = %.3f of TF32 roof (x3 issue)" % (
             name, ms, fl / ms / 1e9, fl / ms / 1e9 / peak), flush=True)

@@ -39,10 +39,11 @@ FLAG_BACKWARD_TF32 = 256
 FLAG_RULES_LRP = 512
 FLAG_RELPROP_TF32 = 1024
 FLAG_ZPLUS_S1_BF16 = 2048
+FLAG_LINEAR_F16_SPLIT = 4096
 FLAG_TENSOR_CORES = FLAG_ZPLUS_TENSOR_CORES | FLAG_LINEAR_TENSOR_CORES      # the ones that need derived weights
 FLAG_ALL_FAST = FLAG_TENSOR_CORES | FLAG_ATTN_TENSOR_CORES | FLAG_ROLLOUT_FUSED
 # what bench.py runs by default: updated as faster selections pass the parity tests (tests/test_gpu_parity_full.py)
-FLAG_BENCH_DEFAULT = FLAG_ALL_FAST | FLAG_BACKWARD_TF32 | FLAG_RELPROP_TF32 | FLAG_ZPLUS_S1_BF16
+FLAG_BENCH_DEFAULT = FLAG_ALL_FAST | FLAG_BACKWARD_TF32 | FLAG_RELPROP_TF32 | FLAG_ZPLUS_S1_BF16 | FLAG_LINEAR_F16_SPLIT
 
 _P = c_void_p
 _CFG = ctypes.POINTER(TeVitConfig)

@@ -41,6 +41,15 @@ extern "C" int te_linear_forward(const float* x, const float* w, const float* bi
 extern "C" int te_linear_forward_ex(const float* x, const float* w, const float* bias, float* y, float* scratch, int rows,
                                     int in_features, int out_features, unsigned flags, void* stream) {
     REQ(x && w && y && rows > 0 && in_features > 0 && out_features > 0, "te_linear_forward_ex: bad argument");
+    if ((flags & TE_FLAG_LINEAR_TENSOR_CORES) && (flags & TE_FLAG_LINEAR_F16_SPLIT) && scratch &&
+        te_tc_fwd16_supported(rows, in_features, out_features, in_features)) {
+        // scratch layout with both flags: [13*in*out derived | round_up(rows*in,64) fp16 hi,lo split of x | rows*ceil(in/128) block scales]
+        TE_TRY(te_tc_prepare_weights(w, scratch, in_features, out_features, ST(stream)));
+        float* split = scratch + te_tc_derived_floats(in_features, out_features);
+        float* scale = split + (((long long)rows * in_features + 63) & ~63LL);
+        return te_tc_linear_fwd16(x, in_features, split, scale, scratch, in_features, out_features, bias, y, nullptr, nullptr,
+                                  rows, TE_TC_EPI_BIAS, ST(stream));
+    }
     if ((flags & TE_FLAG_LINEAR_TENSOR_CORES) && scratch && te_tc_gemm3x_supported(rows, in_features, out_features, in_features)) {
         TE_TRY(te_tc_prepare_weights(w, scratch, in_features, out_features, ST(stream)));
         return te_tc_linear_fwd(x, in_features, scratch, in_features, out_features, bias, y, nullptr, nullptr, rows,
@@ -73,7 +82,7 @@ extern "C" int te_linear_relprop(const float* x, const float* w, const float* r,
                                            ST(stream));
     const float* derived = nullptr;
     if ((flags & TE_FLAG_ZPLUS_TENSOR_CORES) && te_tc_zplus_supported(rows, in_features, out_features, in_features)) {
-        // scratch layout with the flag: [rows*out S | 12*in*out derived weight copies]
+        // scratch layout with the flag: [rows*out S | 13*in*out derived weight copies]
         float* d = scratch + (((long long)rows * out_features + 63) & ~63LL);
         TE_TRY(te_tc_prepare_weights(w, d, in_features, out_features, ST(stream)));
         derived = d;
@@ -89,7 +98,7 @@ extern "C" int te_linear_relprop_ex(const float* x, const float* w, const float*
     const float* derived = nullptr;
     float* xabs = nullptr;
     if ((flags & TE_FLAG_ZPLUS_TENSOR_CORES) && te_tc_zplus_supported(rows, in_features, out_features, in_features)) {
-        // scratch layout with the flag: [rows*out S (64-float aligned) | 12*in*out derived weight copies | rows*in tf32(|x|)]
+        // scratch layout with the flag: [rows*out S (64-float aligned) | 13*in*out derived weight copies | rows*in tf32(|x|)]
         float* d = scratch + (((long long)rows * out_features + 63) & ~63LL);
         TE_TRY(te_tc_prepare_weights(w, d, in_features, out_features, ST(stream)));
         derived = d;

@@ -265,12 +265,25 @@ extern "C" int te_bert_forward(const te_bert_config* cfg, const float* weights, 
     }
     const float* lbase = (flags & TE_FLAG_LINEAR_TENSOR_CORES) ? derived : nullptr;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // fp16-split forward Linears (te_tc_fwd16.cu): split of the D-wide inputs in A = tD[1] (+ scales tD[2]), of the GELU output in
+    // B = tF[1] (+ scales tD[3]); all idle until the backward pass.  Every LayerNorm emits the split of its output (the hidden
+    // state feeds the next layer's qkv); the attention context and the GELU output go through the pre-pass.
+    const bool f16 = lbase && (flags & TE_FLAG_LINEAR_F16_SPLIT) && d.F >= d.D && te_tc_fwd16_supported(d.M, d.D, 3 * d.D, d.D) &&
+                     te_tc_fwd16_supported(d.M, d.D, d.D, d.D) && te_tc_fwd16_supported(d.M, d.D, d.F, d.D) &&
+                     te_tc_fwd16_supported(d.M, d.F, d.D, d.F);
+    const te_util::F16Split fsA_ready = {ws.tD[1], ws.tD[2], true};
+    const te_util::F16Split fsA_pre = {ws.tD[1], ws.tD[2], false};
+    const te_util::F16Split fsB_pre = {ws.tF[1], ws.tD[3], false};
+    auto layernorm = [&](const float* x, const float* g, const float* b, float* y, float* mean, float* rstd) {
+        return f16 ? te_launch_layernorm_split(x, g, b, y, mean, rstd, d.M, d.D, d.eps, ws.tD[1], ws.tD[2], st)
+                   : te_launch_layernorm(x, g, b, y, mean, rstd, d.M, d.D, d.eps, st);
+    };
     Weights w;
     bind_weights(cfg, weights, w);
     const float scale = 1.0f / sqrtf((float)d.dh);
 
     TE_TRY(te_launch_bert_embed(input_ids, w.word, w.pos, w.type, ws.tD[0], d.B, d.N, d.D, d.V, st));
-    TE_TRY(te_launch_layernorm(ws.tD[0], w.elnw, w.elnb, ws.layer[0].h, nullptr, nullptr, d.M, d.D, d.eps, st));
+    TE_TRY(layernorm(ws.tD[0], w.elnw, w.elnb, ws.layer[0].h, nullptr, nullptr));
     TE_TRY(te_launch_bert_mask(attention_mask, ws.maskadd, (long long)d.B * d.N, st));
 
     for (int l = 0; l < d.L; ++l) {
@@ -278,7 +291,8 @@ extern "C" int te_bert_forward(const te_bert_config* cfg, const float* weights, 
         const LayerW& lw = w.layer[l];
         float* h_next = (l + 1 < d.L) ? ws.layer[l + 1].h : ws.h_last;
         const DerivedW tw = bind_derived(d, lbase, l);
-        TE_TRY(linear_fwd_tc(tw.qkv, a.h, d.D, lw.qkvw, lw.qkvb, a.qkv, nullptr, nullptr, d.M, d.D, 3 * d.D, TE_EPI_BIAS, st));
+        TE_TRY(linear_fwd_tc(tw.qkv, a.h, d.D, lw.qkvw, lw.qkvb, a.qkv, nullptr, nullptr, d.M, d.D, 3 * d.D, TE_EPI_BIAS, st,
+                             f16 ? &fsA_ready : nullptr));
         const HeadOp q = head_rows(a.qkv, 3 * d.D, d.N, d.dh);
         const HeadOp k = head_rows(a.qkv + d.D, 3 * d.D, d.N, d.dh);
         const HeadOp v = head_rows(a.qkv + 2 * d.D, 3 * d.D, d.N, d.dh);
@@ -289,12 +303,15 @@ extern "C" int te_bert_forward(const te_bert_config* cfg, const float* weights, 
         TE_TRY(attn_nk((flags & TE_FLAG_ATTN_TENSOR_CORES) != 0, d.B, d.H, d.N, d.NP, d.dh, a.P, 0, a.qkv + 2 * d.D, 3 * d.D,
                        a.ctx, d.D, nullptr, 1.f, TE_EPI_STORE, st));
         // BertSelfOutput: dense -> add([dense, input]) -> LayerNorm
-        TE_TRY(linear_fwd_tc(tw.o, a.ctx, d.D, lw.ow, lw.ob, a.d1, a.s1, a.h, d.M, d.D, d.D, TE_EPI_BIAS_ADD, st));
-        TE_TRY(te_launch_layernorm(a.s1, lw.ln1w, lw.ln1b, a.ao, a.mean1, a.rstd1, d.M, d.D, d.eps, st));
+        TE_TRY(linear_fwd_tc(tw.o, a.ctx, d.D, lw.ow, lw.ob, a.d1, a.s1, a.h, d.M, d.D, d.D, TE_EPI_BIAS_ADD, st,
+                             f16 ? &fsA_pre : nullptr));
+        TE_TRY(layernorm(a.s1, lw.ln1w, lw.ln1b, a.ao, a.mean1, a.rstd1));
         // BertIntermediate (dense + GELU), BertOutput (dense -> add -> LayerNorm)
-        TE_TRY(linear_fwd_tc(tw.w1, a.ao, d.D, lw.w1, lw.b1, a.hpre, a.g, nullptr, d.M, d.D, d.F, TE_EPI_BIAS_GELU, st));
-        TE_TRY(linear_fwd_tc(tw.w2, a.g, d.F, lw.w2, lw.b2, a.d2, a.s2, a.ao, d.M, d.F, d.D, TE_EPI_BIAS_ADD, st));
-        TE_TRY(te_launch_layernorm(a.s2, lw.ln2w, lw.ln2b, h_next, a.mean2, a.rstd2, d.M, d.D, d.eps, st));
+        TE_TRY(linear_fwd_tc(tw.w1, a.ao, d.D, lw.w1, lw.b1, a.hpre, a.g, nullptr, d.M, d.D, d.F, TE_EPI_BIAS_GELU, st,
+                             f16 ? &fsA_ready : nullptr));
+        TE_TRY(linear_fwd_tc(tw.w2, a.g, d.F, lw.w2, lw.b2, a.d2, a.s2, a.ao, d.M, d.F, d.D, TE_EPI_BIAS_ADD, st,
+                             f16 ? &fsB_pre : nullptr));
+        TE_TRY(layernorm(a.s2, lw.ln2w, lw.ln2b, h_next, a.mean2, a.rstd2));
     }
     // pooler (first token -> dense -> tanh), classifier
     TE_TRY(linear_fwd(ws.h_last, d.N * d.D, w.poolw, w.poolb, ws.pd, nullptr, nullptr, d.B, d.D, d.D, TE_EPI_BIAS, st));

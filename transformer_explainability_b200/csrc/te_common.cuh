@@ -1,5 +1,6 @@
 // Shared device helpers for the sm_100a transformer-attribution kernels.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -56,6 +57,31 @@ __device__ __forceinline__ float te_warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
+}
+
+// ---- block-scaled fp16 (hi, lo) split: the operand format of the fp16-split Linear GEMM (te_tc_fwd16.cu) -------------------
+// A block of values with largest magnitude m is stored as 2^-e (hi + lo) with 2^e m in [2^14, 2^15): hi = fp16(2^e x),
+// lo = fp16(2^e x - hi).  s = 2^e, si = 2^-e (exact powers of two).  Zero / non-finite blocks keep e = 0.
+__device__ __forceinline__ void te_f16_block_scale(float m, float& s, float& si) {
+    s = 1.f; si = 1.f;
+    if (m > 0.f && m < 3.0e38f) {
+        int e;
+        frexpf(m, &e);                           // m = f 2^e, f in [0.5, 1)
+        e = max(e, -100);
+        s = ldexpf(1.f, 15 - e);
+        si = ldexpf(1.f, e - 15);
+    }
+}
+__device__ __forceinline__ float te_absmax4(const float4 v) {
+    return fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+}
+__device__ __forceinline__ void te_f16_split4(const float4 v, float s, uint2& hi, uint2& lo) {
+    const float a0 = v.x * s, a1 = v.y * s, a2 = v.z * s, a3 = v.w * s;
+    const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(a0 - f01.x, a1 - f01.y), l23 = __floats2half2_rn(a2 - f23.x, a3 - f23.y);
+    hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+    lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
 }
 
 static inline int te_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -78,9 +78,13 @@ __device__ __forceinline__ void row_stats(const float* __restrict__ xr, int D, i
     rstd = 1.0f / sqrtf(var + eps);
 }
 
+// SPLIT: also emit the block-scaled fp16 (hi, lo) split of y (one scale per 128 columns: exactly one warp iteration), the A
+// operand of the fp16-split Linear that consumes y (te_tc_fwd16.cu) — saves that GEMM's pre-pass over y.
+template <bool SPLIT>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                  const float* __restrict__ b, float* __restrict__ y, float* __restrict__ mean_o,
-                                 float* __restrict__ rstd_o, long long rows, int D, float eps) {
+                                 float* __restrict__ rstd_o, long long rows, int D, float eps, __half* __restrict__ hi,
+                                 __half* __restrict__ lo, float* __restrict__ scale) {
     const int lane = threadIdx.x & 31;
     const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -88,16 +92,31 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
     float mean, rstd;
     row_stats(xr, D, lane, eps, mean, rstd);
     float* yr = y + row * D;
-    for (int i = lane * 4; i < D; i += 128) {
-        const float4 v = *reinterpret_cast<const float4*>(xr + i);
-        const float4 ww = *reinterpret_cast<const float4*>(w + i);
-        const float4 bb = *reinterpret_cast<const float4*>(b + i);
-        float4 o;
-        o.x = (v.x - mean) * rstd * ww.x + bb.x;
-        o.y = (v.y - mean) * rstd * ww.y + bb.y;
-        o.z = (v.z - mean) * rstd * ww.z + bb.z;
-        o.w = (v.w - mean) * rstd * ww.w + bb.w;
-        *reinterpret_cast<float4*>(yr + i) = o;
+    const int nblk = (D + 127) / 128;
+    for (int base = 0; base < D; base += 128) {
+        const int i = base + lane * 4;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < D) {
+            const float4 v = *reinterpret_cast<const float4*>(xr + i);
+            const float4 ww = *reinterpret_cast<const float4*>(w + i);
+            const float4 bb = *reinterpret_cast<const float4*>(b + i);
+            o.x = (v.x - mean) * rstd * ww.x + bb.x;
+            o.y = (v.y - mean) * rstd * ww.y + bb.y;
+            o.z = (v.z - mean) * rstd * ww.z + bb.z;
+            o.w = (v.w - mean) * rstd * ww.w + bb.w;
+            *reinterpret_cast<float4*>(yr + i) = o;
+        }
+        if (SPLIT) {
+            float s, si;
+            te_f16_block_scale(te_warp_max(te_absmax4(o)), s, si);
+            if (i < D) {
+                uint2 h, l;
+                te_f16_split4(o, s, h, l);
+                *reinterpret_cast<uint2*>(hi + row * D + i) = h;
+                *reinterpret_cast<uint2*>(lo + row * D + i) = l;
+            }
+            if (lane == 0) scale[row * nblk + base / 128] = si;
+        }
     }
     if (lane == 0) {
         if (mean_o) mean_o[row] = mean;
@@ -745,7 +764,19 @@ int te_launch_layernorm(const float* x, const float* w, const float* b, float* y
                         long long rows, int D, float eps, cudaStream_t st) {
     TE_REQ(D % 4 == 0, "layernorm: D % 4 != 0");
     if (rows <= 0) return TE_OK;
-    layernorm_kernel<<<warp_rows_grid(rows), kThreads, 0, st>>>(x, w, b, y, mean, rstd, rows, D, eps);
+    layernorm_kernel<false><<<warp_rows_grid(rows), kThreads, 0, st>>>(x, w, b, y, mean, rstd, rows, D, eps, nullptr, nullptr,
+                                                                       nullptr);
+    TE_CUDA_CHECK_LAUNCH();
+    return TE_OK;
+}
+// LayerNorm that also emits the block-scaled fp16 split of y: split = [hi | lo] fp16 [rows, D] (rows*D floats), scale [rows, ceil(D/128)]
+int te_launch_layernorm_split(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd,
+                              long long rows, int D, float eps, float* split, float* scale, cudaStream_t st) {
+    TE_REQ(D % 4 == 0, "layernorm: D % 4 != 0");
+    TE_REQ(split && scale, "layernorm_split: null split buffers");
+    if (rows <= 0) return TE_OK;
+    __half* hi = reinterpret_cast<__half*>(split);
+    layernorm_kernel<true><<<warp_rows_grid(rows), kThreads, 0, st>>>(x, w, b, y, mean, rstd, rows, D, eps, hi, hi + rows * D, scale);
     TE_CUDA_CHECK_LAUNCH();
     return TE_OK;
 }

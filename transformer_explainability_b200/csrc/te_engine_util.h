@@ -38,8 +38,14 @@ static inline int linear_bwd(const float* dy, const float* w, float* dx, const f
 }
 
 // tensor-core (3xTF32) variants when the derived weight copies are supplied and the shape qualifies
+// fp16-split forward Linear (TE_FLAG_LINEAR_F16_SPLIT, te_tc_fwd16.cu): where the block-scaled split of the input lives
+// (M*in floats + M*ceil(in/128) floats) and whether its producer already filled it (ready: te_launch_layernorm_split)
+struct F16Split { float* split; float* scale; bool ready; };
 static inline int linear_fwd_tc(const float* dw, const float* x, int lda, const float* w, const float* bias, float* y,
-                                float* y2, const float* e0, long long M, int in, int out, int epi, cudaStream_t st) {
+                                float* y2, const float* e0, long long M, int in, int out, int epi, cudaStream_t st,
+                                const F16Split* fs = nullptr) {
+    if (dw && fs && fs->split && epi != TE_EPI_GELU_BWD && te_tc_fwd16_supported(M, in, out, lda))
+        return te_tc_linear_fwd16(fs->ready ? nullptr : x, lda, fs->split, fs->scale, dw, in, out, bias, y, y2, e0, M, epi, st);
     if (dw && te_tc_gemm3x_supported(M, in, out, lda))
         return te_tc_linear_fwd(x, lda, dw, in, out, bias, y, y2, e0, M, epi, st);      // epilogue ids coincide
     return linear_fwd(x, lda, w, bias, y, y2, e0, M, in, out, epi, st);

@@ -12,7 +12,9 @@ bool te_tc_zplus_supported(long long rows, int in_features, int out_features, lo
 //   [ bf16(W+^T) | bf16(W-^T) ]      2-byte operands of the bf16 R kernel (kind::f16)
 //   [ bf16(W_hi) | bf16(W_lo) ]      2-byte operands of the correction terms of the mixed-kind forward GEMM
 //   [ bf16(|W|) ]                    2-byte operand of the bf16 S1 kernel (TE_FLAG_ZPLUS_S1_BF16), in*out/2 floats
-// = 12*in*out floats (the last half block is padding)
+//   [ fp16 hi | fp16 lo | 2^-f ]     row-scaled fp16 split of W [out,in] for the fp16-split forward GEMM (te_tc_fwd16.cu):
+//                                     in*out/2 + in*out/2 + out floats, starting at 11.5*in*out
+// = 13*in*out floats (the tail is padding)
 long long te_tc_derived_floats(int in_features, int out_features);
 int te_tc_prepare_weights(const float* w, float* derived, int in_features, int out_features, cudaStream_t st);
 // y / bias (optional): the Linear's saved forward output y = x W^T + bias [rows, out] (row stride ldy).  When given,
@@ -32,6 +34,19 @@ int te_tc_linear_fwd(const float* x, long long ldx, const float* derived, int in
                      const float* bias, float* y, float* y2, const float* e0, long long rows, int epi, cudaStream_t st);
 int te_tc_linear_bwd(const float* dy, const float* derived, int in_features, int out_features, float* dx, const float* e0,
                      long long rows, int epi, cudaStream_t st);
+
+// fp32-grade forward Linear on tcgen05 kind::f16 (te_tc_fwd16.cu): block-scaled fp16 (hi, lo) split of both operands, three MMAs
+// per k-step, persistent CTA pairs.  Activations: one scale per (row, 128 k) — split = [hi | lo] fp16 [rows, in] (rows*in floats),
+// scale [rows, ceil(in/128)]; weights: one scale per row of W (derived buffer).
+bool te_tc_fwd16_supported(long long rows, int K, int N, long long lda);
+int te_tc_rowsplit_f16(const float* x, long long ldx, long long rows, int cols, void* hi, void* lo, float* scale_inv,
+                       cudaStream_t st);
+int te_tc_blocksplit_f16(const float* x, long long ldx, long long rows, int cols, float* split, float* scale_inv, cudaStream_t st);
+// x != NULL: split / scale are scratch filled by the pre-pass; x == NULL: they were filled by the producer of x
+// (te_launch_layernorm_split)
+int te_tc_linear_fwd16(const float* x, long long ldx, float* split, float* scale, const float* derived, int in_features,
+                       int out_features, const float* bias, float* y, float* y2, const float* e0, long long rows, int epi,
+                       cudaStream_t st);
 
 // attention-shaped N x N contractions (Q K^T, dctx V^T, S2 V^T) on tcgen05, fp32-grade 3xTF32, head slices in place
 enum { TE_TC_ATTN_STORE = 0, TE_TC_ATTN_MUL = 1, TE_TC_ATTN_SD = 2, TE_TC_ATTN_SOFTMAX = 3 };   // SOFTMAX: N <= 256

@@ -10,6 +10,10 @@ int te_launch_assemble_tokens(const float* patch_out, const float* cls, const fl
 // ---- normalisation ---------------------------------------------------------------------------
 int te_launch_layernorm(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd,
                         long long rows, int D, float eps, cudaStream_t st);
+// same, also emitting the block-scaled fp16 (hi, lo) split of y for the fp16-split Linear that consumes it (te_tc_fwd16.cu):
+// split = [hi | lo] fp16 [rows, D] (rows*D floats), scale [rows, ceil(D/128)]
+int te_launch_layernorm_split(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd,
+                              long long rows, int D, float eps, float* split, float* scale, cudaStream_t st);
 int te_launch_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean, const float* rstd,
                             const float* dres, float* dx, long long rows, int D, cudaStream_t st);
 // rows of dy / x / dx addressed as base + row*row_stride (used for the CLS-only final norm)

@@ -578,12 +578,16 @@ static bool use_persistent() {
 }
 void te_tc_set_zplus_persistent(int on) { g_zplus_persistent = on ? 1 : 0; }
 
-long long te_tc_derived_floats(int in_features, int out_features) { return 12LL * in_features * out_features; }
+long long te_tc_derived_floats(int in_features, int out_features) { return 13LL * in_features * out_features; }
 
 int te_tc_prepare_weights(const float* w, float* derived, int in_features, int out_features, cudaStream_t st) {
     dim3 grid((in_features + 31) / 32, (out_features + 31) / 32), block(32, 8);
     prepare_weights_kernel<<<grid, block, 0, st>>>(w, derived, out_features, in_features);
     TE_CUDA_CHECK_LAUNCH();
+    const long long n = (long long)in_features * out_features;
+    if (in_features % 8 == 0 && in_features >= 8 && a16(w))        // row-scaled fp16 split: [hi | lo | 2^-f] from 11.5 n
+        TE_TRY(te_tc_rowsplit_f16(w, in_features, out_features, in_features, derived + 11 * n + n / 2, derived + 12 * n,
+                                  derived + 12 * n + n / 2, st));
     return TE_OK;
 }
 

@@ -248,6 +248,16 @@ extern "C" int te_vit_forward(const te_vit_config* cfg, const float* weights, co
         return TE_ERR_ARG;
     }
     const float* lbase = (flags & TE_FLAG_LINEAR_TENSOR_CORES) ? derived : nullptr;
+    // fp16-split forward Linears (te_tc_fwd16.cu).  The block-scaled split of every Linear input lives in buffers that are idle
+    // until the backward pass: A = tD[1] (+ scales tD[0]) for the D-wide inputs, B = tF[1] (+ scales tD[2]) for the GELU output.
+    // LayerNorm emits the split of what it produces; the attention output and the GELU output go through the pre-pass (emitting
+    // the split from the fc1 GELU epilogue was measured: 1.01 ms against 0.56 + 0.2 ms, profiles/r02_results.md).
+    const bool f16 = lbase && (flags & TE_FLAG_LINEAR_F16_SPLIT) && d.F >= d.D && te_tc_fwd16_supported(d.M, d.D, 3 * d.D, d.D) &&
+                     te_tc_fwd16_supported(d.M, d.D, d.D, d.D) && te_tc_fwd16_supported(d.M, d.D, d.F, d.D) &&
+                     te_tc_fwd16_supported(d.M, d.F, d.D, d.F);
+    const te_util::F16Split fsA_ready = {ws.tD[1], ws.tD[0], true};
+    const te_util::F16Split fsA_pre = {ws.tD[1], ws.tD[0], false};
+    const te_util::F16Split fsB_pre = {ws.tF[1], ws.tD[2], false};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     Weights w;
     bind_weights(cfg, weights, w);
@@ -266,9 +276,13 @@ extern "C" int te_vit_forward(const te_vit_config* cfg, const float* weights, co
         const BlockW& bw = w.blk[l];
         float* x_next = (l + 1 < d.L) ? ws.layer[l + 1].x_in : ws.x_last;
         const DerivedW lw = bind_derived(d, lbase, l);
-        TE_TRY(te_launch_layernorm(a.x_in, bw.n1w, bw.n1b, a.xn1, a.mean1, a.rstd1, d.M, d.D, cfg->eps_block, st));
+        if (f16)
+            TE_TRY(te_launch_layernorm_split(a.x_in, bw.n1w, bw.n1b, a.xn1, a.mean1, a.rstd1, d.M, d.D, cfg->eps_block, ws.tD[1],
+                                             ws.tD[0], st));
+        else
+            TE_TRY(te_launch_layernorm(a.x_in, bw.n1w, bw.n1b, a.xn1, a.mean1, a.rstd1, d.M, d.D, cfg->eps_block, st));
         TE_TRY(te_util::linear_fwd_tc(lw.qkv, a.xn1, d.D, bw.qkvw, bw.qkvb, a.qkv, nullptr, nullptr, d.M, d.D, 3 * d.D,
-                                      TE_EPI_BIAS, st));
+                                      TE_EPI_BIAS, st, f16 ? &fsA_ready : nullptr));
         const HeadOp q = head_rows(a.qkv, 3 * d.D, d.N, d.dh);
         const HeadOp k = head_rows(a.qkv + d.D, 3 * d.D, d.N, d.dh);
         const HeadOp v = head_rows(a.qkv + 2 * d.D, 3 * d.D, d.N, d.dh);
@@ -280,12 +294,16 @@ extern "C" int te_vit_forward(const te_vit_config* cfg, const float* weights, co
                                 3 * d.D, a.ctx, d.D, nullptr, 1.f, TE_EPI_STORE, st));
         // proj + residual add1                                  (:150, :198)
         TE_TRY(te_util::linear_fwd_tc(lw.proj, a.ctx, d.D, bw.projw, bw.projb, a.attn_out, a.x_mid, a.x_in, d.M, d.D, d.D,
-                                      TE_EPI_BIAS_ADD, st));
-        TE_TRY(te_launch_layernorm(a.x_mid, bw.n2w, bw.n2b, a.xn2, a.mean2, a.rstd2, d.M, d.D, cfg->eps_block, st));
+                                      TE_EPI_BIAS_ADD, st, f16 ? &fsA_pre : nullptr));
+        if (f16)
+            TE_TRY(te_launch_layernorm_split(a.x_mid, bw.n2w, bw.n2b, a.xn2, a.mean2, a.rstd2, d.M, d.D, cfg->eps_block, ws.tD[1],
+                                             ws.tD[0], st));
+        else
+            TE_TRY(te_launch_layernorm(a.x_mid, bw.n2w, bw.n2b, a.xn2, a.mean2, a.rstd2, d.M, d.D, cfg->eps_block, st));
         TE_TRY(te_util::linear_fwd_tc(lw.fc1, a.xn2, d.D, bw.fc1w, bw.fc1b, a.h, a.g, nullptr, d.M, d.D, d.F,
-                                      TE_EPI_BIAS_GELU, st));
+                                      TE_EPI_BIAS_GELU, st, f16 ? &fsA_ready : nullptr));
         TE_TRY(te_util::linear_fwd_tc(lw.fc2, a.g, d.F, bw.fc2w, bw.fc2b, a.mlp_out, x_next, a.x_mid, d.M, d.F, d.D,
-                                      TE_EPI_BIAS_ADD, st));
+                                      TE_EPI_BIAS_ADD, st, f16 ? &fsB_pre : nullptr));
     }
     // final norm, pool token 0 (and 1), head(s)                (:318-321)
     TE_TRY(te_launch_layernorm(ws.x_last, w.normw, w.normb, ws.xf, nullptr, nullptr, d.M, d.D, cfg->eps_final, st));

@@ -61,16 +61,19 @@ def _workspace(nbytes, device):
 
 
 @_on_device
-def linear_forward(x, w, bias=None, tensor_cores=False):
-    """y = x W^T + b.  tensor_cores: fp32-grade 3xTF32 split on tcgen05 (shapes that do not qualify fall back)."""
+def linear_forward(x, w, bias=None, tensor_cores=False, f16_split=False):
+    """y = x W^T + b.  tensor_cores: fp32-grade 3xTF32 split on tcgen05 (shapes that do not qualify fall back);
+    f16_split (with tensor_cores): the row-scaled fp16 (hi, lo) split on tcgen05 kind::f16 (TE_FLAG_LINEAR_F16_SPLIT)."""
     _req(x, w, bias)
     if w.dim() != 2 or x.shape[-1] != w.shape[1] or (bias is not None and bias.numel() != w.shape[0]):
         raise ValueError("linear_forward: x [...,in], w [out,in], bias [out] expected")
     rows = x.numel() // x.shape[-1]
     y = torch.empty(*x.shape[:-1], w.shape[0], device=x.device, dtype=torch.float32)
-    scratch = torch.empty(12 * w.numel(), device=x.device, dtype=torch.float32) if tensor_cores else None
+    nscratch = 13 * w.numel() + ((x.numel() + 63) // 64 * 64 + rows * ((x.shape[-1] + 127) // 128) if f16_split else 0)
+    scratch = torch.empty(nscratch, device=x.device, dtype=torch.float32) if tensor_cores else None
+    flags = (_lib.FLAG_LINEAR_TENSOR_CORES if tensor_cores else 0) | (_lib.FLAG_LINEAR_F16_SPLIT if f16_split else 0)
     check(_lib.load().te_linear_forward_ex(ptr(x), ptr(w), ptr(bias), ptr(y), ptr(scratch), rows, x.shape[-1], w.shape[0],
-                                           _lib.FLAG_LINEAR_TENSOR_CORES if tensor_cores else 0, _stream()),
+                                           flags, _stream()),
           "te_linear_forward_ex")
     return y
 
@@ -83,7 +86,7 @@ def linear_backward(dy, w, tensor_cores=False):
         raise ValueError("linear_backward: dy [...,out], w [out,in] expected")
     rows = dy.numel() // dy.shape[-1]
     dx = torch.empty(*dy.shape[:-1], w.shape[1], device=dy.device, dtype=torch.float32)
-    scratch = torch.empty(12 * w.numel(), device=dy.device, dtype=torch.float32) if tensor_cores else None
+    scratch = torch.empty(13 * w.numel(), device=dy.device, dtype=torch.float32) if tensor_cores else None
     check(_lib.load().te_linear_backward_ex(ptr(dy), ptr(w), ptr(dx), ptr(scratch), rows, w.shape[1], w.shape[0],
                                             _lib.FLAG_LINEAR_TENSOR_CORES if tensor_cores else 0, _stream()),
           "te_linear_backward_ex")
@@ -98,7 +101,7 @@ def linear_backward_tf32(dy, w):
         raise ValueError("linear_backward_tf32: dy [...,out], w [out,in] expected")
     rows = dy.numel() // dy.shape[-1]
     dx = torch.empty(*dy.shape[:-1], w.shape[1], device=dy.device, dtype=torch.float32)
-    scratch = torch.empty(12 * w.numel(), device=dy.device, dtype=torch.float32)
+    scratch = torch.empty(13 * w.numel(), device=dy.device, dtype=torch.float32)
     check(_lib.load().te_linear_backward_ex(ptr(dy), ptr(w), ptr(dx), ptr(scratch), rows, w.shape[1], w.shape[0],
                                             _lib.FLAG_LINEAR_TENSOR_CORES | _lib.FLAG_BACKWARD_TF32, _stream()),
           "te_linear_backward_ex")
@@ -118,7 +121,7 @@ def linear_relprop(x, w, r, tensor_cores=False, y=None, bias=None, bf16=False, v
     out = torch.empty_like(x)
     nscratch = rows * w.shape[0]
     if tensor_cores:
-        nscratch = (nscratch + 63) // 64 * 64 + 12 * w.numel() + x.numel()
+        nscratch = (nscratch + 63) // 64 * 64 + 13 * w.numel() + x.numel()
     scratch = torch.empty(nscratch, device=x.device, dtype=torch.float32)
     flags = _lib.FLAG_ZPLUS_TENSOR_CORES if tensor_cores else 0
     if bf16 == "s1":
