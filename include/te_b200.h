@@ -56,6 +56,13 @@ extern "C" {
 #define TE_FLAG_LINEAR_F16_SPLIT 4096u  /* with TE_FLAG_LINEAR_TENSOR_CORES: the forward Linears on tcgen05 kind::f16 with a row-scaled
                                          * fp16 (hi, lo) split of both operands (3 MMAs per k-step, same 22-bit operand precision
                                          * as the 3xTF32 split at half the tensor cycles and a third of the staged bytes) */
+#define TE_FLAG_ZPLUS_R_F16 8192u        /* with TE_FLAG_ZPLUS_TENSOR_CORES: the second contraction of the z+ rule, x+ (S W+) + x- (S W-), on
+                                         * tcgen05 kind::f16: S as block-scaled fp16 (one power of two per row and 128 columns),
+                                         * W+^T / W-^T as row-scaled fp16 — the 11 significant bits of the TF32 form, rounded to
+                                         * nearest instead of truncated, at twice the tensor rate */
+#define TE_FLAG_BACKWARD_F16 16384u      /* with TE_FLAG_LINEAR_TENSOR_CORES: the activation-gradient backward Linears as ONE fp16 MMA per
+                                         * k-step (block-scaled fp16 gradients, row-scaled fp16 weights) instead of one TF32 MMA
+                                         * (TE_FLAG_BACKWARD_TF32): same 11 significant bits, twice the tensor rate */
 #define TE_FLAG_RULES_LRP 512u         /* the rule library of modules/layers_lrp.py (baselines/ViT/ViT_orig_LRP.py) instead of
                                          modules/layers_ours.py: Linear divides its two halves by their OWN denominators
                                          (layers_lrp.py:199-200), Add has no ratio normalisation (:98-100).  fp32 SIMT rules. */
@@ -209,13 +216,14 @@ TE_API int te_bert_tensor(const te_bert_config* cfg, int batch, int seq, void* w
  * ---------------------------------------------------------------------------------------------- */
 /* Linear.relprop, alpha=1 (layers_ours.py:207-230): x [rows,in], w [out,in], r [rows,out] -> out [rows,in].
  * flags & TE_FLAG_RULES_LRP: the layers_lrp variant (modules/layers_lrp.py:187-210, separate denominators).
- * scratch: rows*out floats; with TE_FLAG_ZPLUS_TENSOR_CORES: round_up(rows*out,64) + 13*in*out floats. */
+ * scratch: rows*out floats; with TE_FLAG_ZPLUS_TENSOR_CORES: round_up(rows*out,64) + 16*in*out floats. */
 TE_API int te_linear_relprop(const float* x, const float* w, const float* r, float* out, float* scratch, int rows,
                       int in_features, int out_features, unsigned flags, void* stream);
 /* Same rule with the Linear's saved forward output y = x W^T + bias [rows,out] supplied (what the engines do): with
  * TE_FLAG_ZPLUS_TENSOR_CORES the denominator is then formed in ONE tensor-core pass through the exact identity
  * x+ W+^T + x- W-^T == ((y - bias) + |x| |W|^T) / 2.  bias may be NULL (no bias).
- * scratch: rows*out floats; with TE_FLAG_ZPLUS_TENSOR_CORES: round_up(rows*out,64) + 13*in*out + rows*in floats
+ * scratch: rows*out floats; with TE_FLAG_ZPLUS_TENSOR_CORES: round_up(rows*out,64) + 16*in*out + round_up(rows*in,64) floats
+ * (+ round_up(rows*out/2,64) + rows*ceil(out/128) with TE_FLAG_ZPLUS_R_F16)
  * (S, the derived weight copies, the tf32(|x|) operand of the single-pass kernel). */
 TE_API int te_linear_relprop_ex(const float* x, const float* w, const float* bias, const float* y, const float* r,
                          float* out, float* scratch, int rows, int in_features, int out_features, unsigned flags,
@@ -275,8 +283,8 @@ TE_API int te_compute_rollout_attention(const float* mats, int layers, int batch
                                  float* joint, void* workspace, long long workspace_bytes, void* stream);
 
 /* Plain Linear GEMMs — exported for kernel unit tests only.  flags & TE_FLAG_LINEAR_TENSOR_CORES selects the
- * tcgen05 3xTF32 path (scratch: 13*in*out floats for the derived weight copies; may be NULL otherwise); with
- * TE_FLAG_LINEAR_F16_SPLIT as well, te_linear_forward_ex runs the fp16-split kernel (scratch: 13*in*out +
+ * tcgen05 3xTF32 path (scratch: 16*in*out floats for the derived weight copies; may be NULL otherwise); with
+ * TE_FLAG_LINEAR_F16_SPLIT as well, te_linear_forward_ex runs the fp16-split kernel (scratch: 16*in*out +
  * round_up(rows*in,64) + rows*ceil(in/128) floats). */
 TE_API int te_linear_forward(const float* x, const float* w, const float* bias, float* y, int rows, int in_features,
                       int out_features, void* stream);

@@ -43,6 +43,8 @@ def _flag_sets():
            (_lib.FLAG_ALL_FAST | _lib.FLAG_BACKWARD_TF32, 5e-3)]
     out.append((_lib.FLAG_ALL_FAST | _lib.FLAG_BACKWARD_TF32 | _lib.FLAG_RELPROP_TF32, 5e-3))        # 1331
     out.append((_lib.FLAG_ALL_FAST | _lib.FLAG_BACKWARD_TF32 | _lib.FLAG_RELPROP_TF32 | _lib.FLAG_ZPLUS_S1_BF16, 5e-3))   # 3379
+    out.append((_lib.FLAG_ALL_FAST | _lib.FLAG_BACKWARD_TF32 | _lib.FLAG_RELPROP_TF32 | _lib.FLAG_ZPLUS_S1_BF16 |
+                _lib.FLAG_LINEAR_F16_SPLIT | _lib.FLAG_ZPLUS_R_F16, 5e-3))                          # 15667: + fp16 R kernel
     if _lib.FLAG_BENCH_DEFAULT not in [f for f, _ in out]:
         out.append((_lib.FLAG_BENCH_DEFAULT, 5e-3))                     # 7475: 3379 + fp16-split forward Linears
     return out

@@ -329,3 +329,54 @@ def test_tc_f16_split_linear_is_fp32_grade(rows, inf, outf):
     assert eh < 2e-5 and eh < 2 * e3 + 1e-6          # fp32 grade, and no worse than the 3xTF32 kernel on the same data
     assert (yh[rows // 2] == 0).all() and (yh[:, 3] == 0).all()                       # zero row / zero weight row: exactly zero
     assert torch.equal(yb.cpu(), (yh.cpu() + b))                                      # the bias is added last, in fp32
+
+
+@pytest.mark.parametrize("rows,inf,outf", [(128, 256, 256), (394, 768, 3072), (1000, 3072, 768), (77, 768, 2304), (20000, 768, 768)])
+def test_tc_fp16_second_contraction(rows, inf, outf):
+    """TE_FLAG_ZPLUS_R_F16: R_in = x+ (S W+) + x- (S W-) on tcgen05 kind::f16 — S as hi-only block-scaled fp16 (one power of two
+    per row and 128 columns), W+^T / W-^T as row-scaled fp16 (te_tc_fwd16.cu, FM_R).  Same 11 significant bits as the TF32 form
+    (rounded to nearest): the rule error must not exceed the TF32 path's bound.  The relevance rows span 12 decades (S = R / Z
+    inherits them): fp16 without the block scaling would over- / underflow."""
+    from transformer_explainability_b200 import ops
+    g = torch.Generator().manual_seed(rows + 31)
+    x = torch.randn(rows, inf, generator=g)
+    w = torch.randn(outf, inf, generator=g) * 0.05
+    b = torch.randn(outf, generator=g)
+    r = torch.rand(rows, outf, generator=g) * torch.logspace(-6, 6, rows)[:, None]
+    r[rows // 3] = 0.0
+    xd, wd, rd, bd = x.cuda(), w.cuda(), r.cuda(), b.cuda()
+    y = ops.linear_forward(xd, wd, bd)
+    tf = ops.linear_relprop(xd, wd, rd, tensor_cores=True, y=y, bias=bd, bf16="s1")
+    hf = ops.linear_relprop(xd, wd, rd, tensor_cores=True, y=y, bias=bd, bf16="s1", r_f16=True)
+    torch.cuda.synchronize()
+    ref = rules.linear_relprop(x.double(), w.double(), r.double())
+    rowmax = ref.abs().amax(dim=1, keepdim=True).clamp_min(1e-300)
+    e_tf = ((tf.double().cpu() - ref).abs() / rowmax).max().item()        # per row: the rows differ by 12 decades
+    e_hf = ((hf.double().cpu() - ref).abs() / rowmax).max().item()
+    print("fp16 R rows %d in %d out %d: TF32 R %.2e  fp16 R %.2e (per row, relative to the row maximum)" % (rows, inf, outf, e_tf, e_hf))
+    assert torch.isfinite(hf).all() and (hf[rows // 3] == 0).all()
+    assert e_hf < 3e-3 and e_hf < 1.5 * e_tf + 1e-4
+    rs, hs = r.double().sum(dim=1), hf.double().cpu().sum(dim=1)          # conservation per row (Z > 0 almost surely)
+    assert ((hs - rs).abs() <= 3e-3 * rs.abs() + 1e-30).all()
+
+
+@pytest.mark.parametrize("rows,inf,outf", [(128, 256, 256), (394, 768, 3072), (1000, 3072, 768), (77, 768, 2304), (20000, 768, 768)])
+def test_tc_fp16_single_pass_backward(rows, inf, outf):
+    """TE_FLAG_BACKWARD_F16: dx = dy W as ONE fp16 MMA per k-step (te_tc_fwd16.cu, FM_LIN1): block-scaled fp16 gradient rows that
+    span 12 decades, row-scaled fp16 weights.  The operands keep TF32's 11 significant bits, rounded to nearest: the error
+    stays below the single-pass TF32 kernel's bound, per row."""
+    from transformer_explainability_b200 import ops
+    g = torch.Generator().manual_seed(rows + 41)
+    dy = torch.randn(rows, outf, generator=g) * torch.logspace(-9, 3, rows)[:, None]
+    dy[rows // 3] = 0.0
+    w = torch.randn(outf, inf, generator=g) * 0.05
+    ref = dy.double() @ w.double()
+    tf = ops.linear_backward_tf32(dy.cuda(), w.cuda())
+    hf = ops.linear_backward_f16(dy.cuda(), w.cuda())
+    torch.cuda.synchronize()
+    rowmax = ref.abs().amax(dim=1, keepdim=True).clamp_min(1e-300)
+    e_tf = ((tf.double().cpu() - ref).abs() / rowmax).max().item()
+    e_hf = ((hf.double().cpu() - ref).abs() / rowmax).max().item()
+    print("fp16 backward rows %d in %d out %d: TF32 %.2e  fp16 %.2e (per row, relative to the row maximum)" % (rows, inf, outf, e_tf, e_hf))
+    assert torch.isfinite(hf).all() and (hf[rows // 3] == 0).all()
+    assert e_hf < 2e-3 and e_hf < 1.5 * e_tf + 1e-4

@@ -40,6 +40,8 @@ FLAG_RULES_LRP = 512
 FLAG_RELPROP_TF32 = 1024
 FLAG_ZPLUS_S1_BF16 = 2048
 FLAG_LINEAR_F16_SPLIT = 4096
+FLAG_ZPLUS_R_F16 = 8192
+FLAG_BACKWARD_F16 = 16384
 FLAG_TENSOR_CORES = FLAG_ZPLUS_TENSOR_CORES | FLAG_LINEAR_TENSOR_CORES      # the ones that need derived weights
 FLAG_ALL_FAST = FLAG_TENSOR_CORES | FLAG_ATTN_TENSOR_CORES | FLAG_ROLLOUT_FUSED
 # what bench.py runs by default: updated as faster selections pass the parity tests (tests/test_gpu_parity_full.py)

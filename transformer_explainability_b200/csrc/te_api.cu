@@ -43,7 +43,7 @@ extern "C" int te_linear_forward_ex(const float* x, const float* w, const float*
     REQ(x && w && y && rows > 0 && in_features > 0 && out_features > 0, "te_linear_forward_ex: bad argument");
     if ((flags & TE_FLAG_LINEAR_TENSOR_CORES) && (flags & TE_FLAG_LINEAR_F16_SPLIT) && scratch &&
         te_tc_fwd16_supported(rows, in_features, out_features, in_features)) {
-        // scratch layout with both flags: [13*in*out derived | round_up(rows*in,64) fp16 hi,lo split of x | rows*ceil(in/128) block scales]
+        // scratch layout with both flags: [16*in*out derived | round_up(rows*in,64) fp16 hi,lo split of x | rows*ceil(in/128) block scales]
         TE_TRY(te_tc_prepare_weights(w, scratch, in_features, out_features, ST(stream)));
         float* split = scratch + te_tc_derived_floats(in_features, out_features);
         float* scale = split + (((long long)rows * in_features + 63) & ~63LL);
@@ -63,6 +63,13 @@ extern "C" int te_linear_backward_ex(const float* dy, const float* w, float* dx,
     REQ(dy && w && dx && rows > 0 && in_features > 0 && out_features > 0, "te_linear_backward_ex: bad argument");
     if ((flags & TE_FLAG_LINEAR_TENSOR_CORES) && scratch && te_tc_gemm3x_supported(rows, out_features, in_features, out_features)) {
         TE_TRY(te_tc_prepare_weights(w, scratch, in_features, out_features, ST(stream)));
+        if ((flags & TE_FLAG_BACKWARD_F16) && te_tc_f16_single_supported(rows, out_features, in_features, out_features)) {
+            // scratch layout with the flag: [16*in*out derived | round_up(rows*out/2,64) fp16 dy | rows*ceil(out/128) block scales]
+            float* split = scratch + te_tc_derived_floats(in_features, out_features);
+            float* scale = split + (((long long)rows * out_features / 2 + 63) & ~63LL);
+            return te_tc_linear_bwd16(dy, out_features, split, scale, scratch, in_features, out_features, dx, nullptr, rows,
+                                      TE_TC_EPI_STORE, ST(stream));
+        }
         if ((flags & TE_FLAG_BACKWARD_TF32) && te_tc_pair_supported(rows, out_features, in_features, out_features))
             return te_tc_pair_linear_bwd(dy, out_features, scratch, in_features, out_features, dx, nullptr, rows, TE_TC_EPI_STORE,
                                          ST(stream));
@@ -82,7 +89,7 @@ extern "C" int te_linear_relprop(const float* x, const float* w, const float* r,
                                            ST(stream));
     const float* derived = nullptr;
     if ((flags & TE_FLAG_ZPLUS_TENSOR_CORES) && te_tc_zplus_supported(rows, in_features, out_features, in_features)) {
-        // scratch layout with the flag: [rows*out S | 13*in*out derived weight copies]
+        // scratch layout with the flag: [rows*out S | 16*in*out derived weight copies]
         float* d = scratch + (((long long)rows * out_features + 63) & ~63LL);
         TE_TRY(te_tc_prepare_weights(w, d, in_features, out_features, ST(stream)));
         derived = d;
@@ -98,15 +105,20 @@ extern "C" int te_linear_relprop_ex(const float* x, const float* w, const float*
     const float* derived = nullptr;
     float* xabs = nullptr;
     if ((flags & TE_FLAG_ZPLUS_TENSOR_CORES) && te_tc_zplus_supported(rows, in_features, out_features, in_features)) {
-        // scratch layout with the flag: [rows*out S (64-float aligned) | 13*in*out derived weight copies | rows*in tf32(|x|)]
+        // scratch layout with the flag: [rows*out S (64-float aligned) | 16*in*out derived weight copies | round_up(rows*in,64) tf32(|x|) |
+        //  with TE_FLAG_ZPLUS_R_F16: round_up(rows*out/2,64) + rows*ceil(out/128) fp16 S operand]
         float* d = scratch + (((long long)rows * out_features + 63) & ~63LL);
         TE_TRY(te_tc_prepare_weights(w, d, in_features, out_features, ST(stream)));
         derived = d;
         xabs = d + te_tc_derived_floats(in_features, out_features);
     }
+    // TE_FLAG_ZPLUS_R_F16: the fp16 operand of the second contraction follows the |x| scratch (64-float aligned)
+    float* f16s = (xabs && (flags & TE_FLAG_ZPLUS_R_F16)) ? xabs + (((long long)rows * in_features + 63) & ~63LL) : nullptr;
     return te_zplus_linear_relprop_ldr(x, in_features, w, derived, r, out_features, out, scratch, rows, in_features,
                                        out_features, ST(stream), y, out_features, bias,
-                                       ((flags & TE_FLAG_ZPLUS_BF16) ? 1 : 0) | ((flags & TE_FLAG_ZPLUS_S1_BF16) ? 2 : 0), 0, xabs);
+                                       ((flags & TE_FLAG_ZPLUS_BF16) ? 1 : 0) | ((flags & TE_FLAG_ZPLUS_S1_BF16) ? 2 : 0) |
+                                           ((flags & TE_FLAG_ZPLUS_R_F16) ? 4 : 0),
+                                       0, xabs, f16s);
 }
 
 extern "C" int te_add_relprop(const float* x1, const float* x2, const float* r, float* r1, float* r2, void* scratch,

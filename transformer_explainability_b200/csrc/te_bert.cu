@@ -341,14 +341,22 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
     const float* lbase = (flags & TE_FLAG_LINEAR_TENSOR_CORES) ? derived : nullptr;
     const bool atc = (flags & TE_FLAG_ATTN_TENSOR_CORES) != 0;
     const bool btf = (flags & TE_FLAG_BACKWARD_TF32) != 0;       // single-pass TF32 backward Linears
+    // single-pass fp16 backward Linears: hi-only split of the incoming gradient in tF[1], block scales in t3D[1] (idle until the relprop)
+    const te_util::F16Split bfs_v = {ws.tF[1], ws.t3D[1], false};
+    const te_util::F16Split* bfs = (lbase && (flags & TE_FLAG_BACKWARD_F16)) ? &bfs_v : nullptr;
     const bool rtf = (flags & TE_FLAG_RELPROP_TF32) != 0;        // single-pass TF32 relevance-side attention contractions
-    const int zb = ((flags & TE_FLAG_ZPLUS_BF16) ? 1 : 0) | ((flags & TE_FLAG_ZPLUS_S1_BF16) ? 2 : 0);   // bf16 variants of the z+ rule
+    const int zb = ((flags & TE_FLAG_ZPLUS_BF16) ? 1 : 0) | ((flags & TE_FLAG_ZPLUS_S1_BF16) ? 2 : 0) |
+                   ((flags & TE_FLAG_ZPLUS_R_F16) ? 4 : 0);                                               // bf16 / fp16 variants of the z+ rule
+    // operand scratch of the fp16 R kernel: the |x| scratch of the same rule (dead once S exists) when it is large enough
+    auto f16s = [&](float* xabs, long long cap, long long rows, int outf) -> float* {
+        return te_zplus_f16_scratch_floats(rows, outf) <= cap ? xabs : nullptr;
+    };
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     Weights w;
     bind_weights(cfg, weights, w);
     const float* dbase = (flags & TE_FLAG_ZPLUS_TENSOR_CORES) ? derived : nullptr;
     const float scale = 1.0f / sqrtf((float)d.dh);
-    const long long MD = d.M * d.D, DD = (long long)d.D * d.D;
+    const long long MD = d.M * d.D, DD = (long long)d.D * d.D, MF = d.M * d.F, M3D = d.M * 3LL * d.D;
     const int low = (flags & (TE_FLAG_KEEP_ALL_CAMS | TE_FLAG_RELPROP_TO_INPUT)) ? 0 : start_layer;
 
     TE_TRY(te_launch_argmax(ws.logits, index, d.B, d.C, 1, st));
@@ -374,11 +382,11 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
         const HeadOp v = head_rows(a.qkv + 2 * d.D, 3 * d.D, d.N, d.dh);
         TE_TRY(te_launch_layernorm_bwd(dxa, a.s2, lw.ln2w, a.mean2, a.rstd2, nullptr, dsx, d.M, d.D, st));    // d s2
         const DerivedW tw = bind_derived(d, lbase, l);
-        TE_TRY(linear_bwd_tc(tw.w2, dsx, lw.w2, dF, a.hpre, d.M, d.F, d.D, TE_EPI_GELU_BWD, st, btf));
-        TE_TRY(linear_bwd_tc(tw.w1, dF, lw.w1, dxn, nullptr, d.M, d.D, d.F, TE_EPI_STORE, st, btf));
+        TE_TRY(linear_bwd_tc(tw.w2, dsx, lw.w2, dF, a.hpre, d.M, d.F, d.D, TE_EPI_GELU_BWD, st, btf, bfs));
+        TE_TRY(linear_bwd_tc(tw.w1, dF, lw.w1, dxn, nullptr, d.M, d.D, d.F, TE_EPI_STORE, st, btf, bfs));
         TE_TRY(te_launch_add2(dxn, dsx, dxn, MD, st));                                                          // d ao
         TE_TRY(te_launch_layernorm_bwd(dxn, a.s1, lw.ln1w, a.mean1, a.rstd1, nullptr, dsx, d.M, d.D, st));    // d s1
-        TE_TRY(linear_bwd_tc(tw.o, dsx, lw.ow, dctx, nullptr, d.M, d.D, d.D, TE_EPI_STORE, st, btf));
+        TE_TRY(linear_bwd_tc(tw.o, dsx, lw.ow, dctx, nullptr, d.M, d.D, d.D, TE_EPI_STORE, st, btf, bfs));
         TE_TRY(attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, dctx, d.D, a.qkv + 2 * d.D, 3 * d.D, a.G, nullptr, 1.f,
                        TE_EPI_STORE, st, btf));                                                                      // G = dctx v^T
         if (l == start_layer) break;
@@ -387,7 +395,7 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
         TE_TRY(te_launch_softmax_bwd(a.P, a.G, dS, (long long)d.B * d.H * d.N, d.N, d.NP, scale, st));
         TE_TRY(attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, dS, 0, a.qkv + d.D, 3 * d.D, dqkv, 3 * d.D, nullptr, 1.f, TE_EPI_STORE, st, btf));   // dQ
         TE_TRY(attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, dS, 1, a.qkv, 3 * d.D, dqkv + d.D, 3 * d.D, nullptr, 1.f, TE_EPI_STORE, st, btf));   // dK
-        TE_TRY(linear_bwd_tc(tw.qkv, dqkv, lw.qkvw, dxn, nullptr, d.M, d.D, 3 * d.D, TE_EPI_STORE, st, btf));
+        TE_TRY(linear_bwd_tc(tw.qkv, dqkv, lw.qkvw, dxn, nullptr, d.M, d.D, 3 * d.D, TE_EPI_STORE, st, btf, bfs));
         TE_TRY(te_launch_add2(dxn, dsx, dxa, MD, st));                                                          // d h
     }
 
@@ -416,13 +424,16 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
         const long long zr = top ? d.B : d.M;
         const long long sD = top ? (long long)d.N * d.D : d.D, sF = top ? (long long)d.N * d.F : d.F;
         TE_TRY(te_launch_add_relprop(a.d2, a.ao, R, R1, R2, ws.addpart, d.B, (long long)d.N * d.D, st));
-        TE_TRY(te_zplus_linear_relprop_ldr(a.g, sF, lw.w2, dw.w2, R1, sD, RF, S, zr, d.F, d.D, st, a.d2, sD, lw.b2, zb, sF, SF));
-        TE_TRY(te_zplus_linear_relprop_ldr(a.ao, sD, lw.w1, dw.w1, RF, sF, R1, SF, zr, d.D, d.F, st, a.hpre, sF, lw.b1, zb, sD, S));
+        TE_TRY(te_zplus_linear_relprop_ldr(a.g, sF, lw.w2, dw.w2, R1, sD, RF, S, zr, d.F, d.D, st, a.d2, sD, lw.b2, zb, sF, SF,
+                                           f16s(SF, MF, zr, d.D)));
+        TE_TRY(te_zplus_linear_relprop_ldr(a.ao, sD, lw.w1, dw.w1, RF, sF, R1, SF, zr, d.D, d.F, st, a.hpre, sF, lw.b1, zb, sD, S,
+                                           f16s(S, M3D, zr, d.F)));
         TE_TRY(te_launch_clone_relprop(a.ao, R1, R2, nullptr, R, MD, st));
         // BertSelfOutput.relprop :427-434
         TE_TRY(te_launch_add_relprop(a.d1, a.h, R, R1, R2, ws.addpart, d.B, (long long)d.N * d.D, st));
         if (top) TE_TRY(te_launch_fill(R3, 0.f, MD, st));
-        TE_TRY(te_zplus_linear_relprop_ldr(a.ctx, sD, lw.ow, dw.o, R1, sD, R3, S, zr, d.D, d.D, st, a.d1, sD, lw.ob, zb, sD, S + MD));
+        TE_TRY(te_zplus_linear_relprop_ldr(a.ctx, sD, lw.ow, dw.o, R1, sD, R3, S, zr, d.D, d.D, st, a.d1, sD, lw.ob, zb, sD, S + MD,
+                                           f16s(S + MD, M3D - MD, zr, d.D)));
         // BertSelfAttention.relprop :367-409
         TE_TRY(te_launch_sd(R3, a.ctx, S, MD, st));                                       // matmul2: Z == saved ctx
         TE_TRY(attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, S, d.D, a.qkv + 2 * d.D, 3 * d.D, a.cam, a.P, 0.5f, TE_EPI_MUL,
@@ -441,11 +452,12 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
         TE_TRY(attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, ws.tA[0], 1, a.qkv, 3 * d.D, Rqkv + d.D, 3 * d.D, a.qkv + d.D, 0.5f,
                        TE_EPI_MUL, st, rtf));
         // query / key / value z+ rules (separate Linears), Clone(3), Clone(2)
-        TE_TRY(te_zplus_linear_relprop_ldr(a.h, d.D, lw.qkvw, dw.q, Rqkv, 3 * d.D, R, S, d.M, d.D, d.D, st, a.qkv, 3 * d.D, lw.qkvb, zb, 0, S + MD));
+        TE_TRY(te_zplus_linear_relprop_ldr(a.h, d.D, lw.qkvw, dw.q, Rqkv, 3 * d.D, R, S, d.M, d.D, d.D, st, a.qkv, 3 * d.D, lw.qkvb, zb, 0, S + MD,
+                                           f16s(S + MD, M3D - MD, d.M, d.D)));
         TE_TRY(te_zplus_linear_relprop_ldr(a.h, d.D, lw.qkvw + DD, dw.k, Rqkv + d.D, 3 * d.D, R1, S, d.M, d.D, d.D, st, a.qkv + d.D, 3 * d.D,
-                                           lw.qkvb + d.D, zb, 0, S + MD));
+                                           lw.qkvb + d.D, zb, 0, S + MD, f16s(S + MD, M3D - MD, d.M, d.D)));
         TE_TRY(te_zplus_linear_relprop_ldr(a.h, d.D, lw.qkvw + 2 * DD, dw.v, Rqkv + 2 * d.D, 3 * d.D, R3, S, d.M, d.D, d.D, st,
-                                           a.qkv + 2 * d.D, 3 * d.D, lw.qkvb + 2 * d.D, zb, 0, S + MD));
+                                           a.qkv + 2 * d.D, 3 * d.D, lw.qkvb + 2 * d.D, zb, 0, S + MD, f16s(S + MD, M3D - MD, d.M, d.D)));
         TE_TRY(te_launch_clone_relprop(a.h, R, R1, R3, SF, MD, st));                      // self.clone (3-way)
         TE_TRY(te_launch_clone_relprop(a.h, SF, R2, nullptr, R, MD, st));                 // attention.clone
     }

@@ -51,8 +51,11 @@ static inline int linear_fwd_tc(const float* dw, const float* x, int lda, const 
     return linear_fwd(x, lda, w, bias, y, y2, e0, M, in, out, epi, st);
 }
 // tf32: single-pass TF32 on the persistent CTA-pair kernel (TE_FLAG_BACKWARD_TF32) instead of the 3xTF32 split
+// fs: hi-only split scratch of dy (M*out/2 floats + M*ceil(out/128)) -> single-pass fp16 kernel (TE_FLAG_BACKWARD_F16)
 static inline int linear_bwd_tc(const float* dw, const float* dy, const float* w, float* dx, const float* e0, long long M,
-                                int in, int out, int epi, cudaStream_t st, bool tf32 = false) {
+                                int in, int out, int epi, cudaStream_t st, bool tf32 = false, const F16Split* fs = nullptr) {
+    if (dw && fs && fs->split && (epi == TE_EPI_STORE || epi == TE_EPI_GELU_BWD) && te_tc_f16_single_supported(M, out, in, out))
+        return te_tc_linear_bwd16(fs->ready ? nullptr : dy, out, fs->split, fs->scale, dw, in, out, dx, e0, M, epi, st);
     if (dw && tf32 && (epi == TE_EPI_STORE || epi == TE_EPI_GELU_BWD) && te_tc_pair_supported(M, out, in, out))
         return te_tc_pair_linear_bwd(dy, out, dw, in, out, dx, e0, M, epi, st);
     if (dw && te_tc_gemm3x_supported(M, out, in, out))

@@ -14,7 +14,9 @@ bool te_tc_zplus_supported(long long rows, int in_features, int out_features, lo
 //   [ bf16(|W|) ]                    2-byte operand of the bf16 S1 kernel (TE_FLAG_ZPLUS_S1_BF16), in*out/2 floats
 //   [ fp16 hi | fp16 lo | 2^-f ]     row-scaled fp16 split of W [out,in] for the fp16-split forward GEMM (te_tc_fwd16.cu):
 //                                     in*out/2 + in*out/2 + out floats, starting at 11.5*in*out
-// = 13*in*out floats (the tail is padding)
+//   [ fp16(W^T) | 2^-f ]             row-scaled fp16 of tf32(W)^T [in,out] (single-pass backward Linear): in*out/2 + in floats at 13*in*out
+//   [ fp16(W+^T) | fp16(W-^T) | 2^-f+ | 2^-f- ]   row-scaled fp16 operands of the fp16 R kernel: at 14*in*out, scales at 15*in*out
+// = 16*in*out floats (the tails are padding)
 long long te_tc_derived_floats(int in_features, int out_features);
 int te_tc_prepare_weights(const float* w, float* derived, int in_features, int out_features, cudaStream_t st);
 // y / bias (optional): the Linear's saved forward output y = x W^T + bias [rows, out] (row stride ldy).  When given,
@@ -23,9 +25,11 @@ int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* deriv
                                float* out,
                                float* s_scratch, long long rows, int in_features, int out_features, cudaStream_t st,
                                const float* y = nullptr, long long ldy = 0, const float* bias = nullptr,
-                               int bf16 = 0 /* 1: round-1 bf16 R kernel (flag 64); 2: bf16 single-pass S kernel (flag 2048) */,
+                               int bf16 = 0 /* bit 0: round-1 bf16 R kernel (flag 64); bit 1: bf16 single-pass S kernel (flag 2048);
+                                               bit 2: fp16 R kernel (flag 8192, needs f16s) */,
                                long long ld_out = 0 /* row stride of out; 0 = in_features */,
-                               float* xabs = nullptr /* scratch [rows, in]: enables the persistent pair kernels */);
+                               float* xabs = nullptr /* scratch [rows, in]: enables the persistent pair kernels */,
+                               float* f16s = nullptr /* scratch of te_zplus_f16_scratch_floats(rows, out) floats */);
 
 // fp32-grade (3xTF32 split) Linear GEMMs on tcgen05; epilogues mirror the SIMT ones
 enum { TE_TC_EPI_STORE = 0, TE_TC_EPI_BIAS = 1, TE_TC_EPI_BIAS_GELU = 2, TE_TC_EPI_BIAS_ADD = 3, TE_TC_EPI_GELU_BWD = 4 };
@@ -41,12 +45,21 @@ int te_tc_linear_bwd(const float* dy, const float* derived, int in_features, int
 bool te_tc_fwd16_supported(long long rows, int K, int N, long long lda);
 int te_tc_rowsplit_f16(const float* x, long long ldx, long long rows, int cols, void* hi, void* lo, float* scale_inv,
                        cudaStream_t st);
-int te_tc_blocksplit_f16(const float* x, long long ldx, long long rows, int cols, float* split, float* scale_inv, cudaStream_t st);
+int te_tc_blocksplit_f16(const float* x, long long ldx, long long rows, int cols, float* split, float* scale_inv, cudaStream_t st,
+                         bool hi_only = false);
 // x != NULL: split / scale are scratch filled by the pre-pass; x == NULL: they were filled by the producer of x
 // (te_launch_layernorm_split)
 int te_tc_linear_fwd16(const float* x, long long ldx, float* split, float* scale, const float* derived, int in_features,
                        int out_features, const float* bias, float* y, float* y2, const float* e0, long long rows, int epi,
                        cudaStream_t st);
+// single-pass fp16 products on the same kernel (A = hi only: fp16 keeps TF32's 11 significant bits, rounded to nearest)
+bool te_tc_f16_single_supported(long long rows, int K, int N, long long lda);
+// dx = epi(dy W): split (rows*out/2 floats) / scale ([rows, ceil(out/128)]) hold the hi-only split of dy (dy != NULL: pre-pass here)
+int te_tc_linear_bwd16(const float* dy, long long lddy, float* split, float* scale, const float* derived, int in_features,
+                       int out_features, float* dx, const float* e0, long long rows, int epi, cudaStream_t st);
+// R_in = x+ (S W+) + x- (S W-): split / scale hold the hi-only split of S [rows, out] (s != NULL: pre-pass here)
+int te_tc_zplus_r16(const float* s, float* split, float* scale, const float* derived, const float* x, long long ldx, float* out,
+                    long long ld_out, long long rows, int in_features, int out_features, cudaStream_t st);
 
 // attention-shaped N x N contractions (Q K^T, dctx V^T, S2 V^T) on tcgen05, fp32-grade 3xTF32, head slices in place
 enum { TE_TC_ATTN_STORE = 0, TE_TC_ATTN_MUL = 1, TE_TC_ATTN_SD = 2, TE_TC_ATTN_SOFTMAX = 3 };   // SOFTMAX: N <= 256
@@ -82,7 +95,9 @@ int te_tc_abs_tf32(const float* x, long long ldx, float* out, long long rows, in
 // xabs: scratch [rows, in] for tf32(|x|), the A operand of the single-pass S kernel
 int te_tc_pair_zplus_s1(const float* x, long long ldx, float* xabs, const float* derived, const float* r, long long ldr,
                         const float* y, long long ldy, const float* bias, float* s_out, long long rows, int in_features,
-                        int out_features, cudaStream_t st, bool bf16 = false);
+                        int out_features, cudaStream_t st, bool bf16 = false, float* s16 = nullptr, float* s16_scale = nullptr);
+// s16 / s16_scale: when given, S leaves as hi-only block-scaled fp16 [rows, out] (+ [rows, out/128] scales) — the A operand of
+// te_tc_zplus_r16 — instead of fp32 in s_out
 int te_tc_pair_zplus_r(const float* s, const float* derived, const float* x, long long ldx, float* out, long long ld_out,
                        long long rows, int in_features, int out_features, cudaStream_t st);
 int te_tc_pair_linear_bwd(const float* dy, long long lddy, const float* derived, int in_features, int out_features, float* dx,

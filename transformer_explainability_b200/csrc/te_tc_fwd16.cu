@@ -35,36 +35,53 @@
 
 namespace {
 
-enum { FP_STORE = 0, FP_BIAS = 1, FP_BIAS_GELU = 2, FP_BIAS_ADD = 3 };
+enum { FP_STORE = 0, FP_BIAS = 1, FP_BIAS_GELU = 2, FP_BIAS_ADD = 3, FP_GELU_BWD = 4 };
+// FM_FWD3  fp32-grade forward Linear: A = (hi, lo), B = (hi, lo), three MMAs per k-step, 256 x 256 pair tiles
+// FM_LIN1  single-pass product (activation-gradient backward Linear): A = hi, B = hi, one MMA per k-step — fp16 keeps the 11
+//          significant bits of TF32 (rounded to nearest instead of truncated) at twice the tensor rate and half the bytes
+// FM_R     second contraction of the z+ rule, R_in = x+ (S W+) + x- (S W-): A = hi(S), B = W+^T and W-^T, two 256 x 128
+//          accumulators per pair tile (128 output columns of both products), one MMA per product and k-step
+enum { FM_FWD3 = 0, FM_LIN1 = 1, FM_R = 2 };
 
 constexpr int F16_K = 64;                                  // fp16 elements per 128-byte swizzle row = one stage of K
 constexpr int F16_TILE = 128 * 128;                        // 16 KiB: 128 rows x 64 fp16
-constexpr int F16_STAGE = 4 * F16_TILE;                    // A_hi | A_lo | B_hi half | B_lo half = 64 KiB
-constexpr int F16_NST = 3;
-constexpr int F16_CHUNK = 2;                               // stages per TMEM accumulation chunk (128 elements)
-constexpr int F16_THREADS = 320;
-constexpr int F16_DRAIN_WARPS = 8;
-constexpr int F16_NBARS = 2 * F16_NST + 4;
-constexpr int F16_SMEM = F16_NST * F16_STAGE + F16_DRAIN_WARPS * EPI16_STAGE_BYTES + 1024 + 8 * F16_NBARS + 16;
-// cta_group::2, fp16 operands (a/b format 0), fp32 accumulate, M = 256, N = 256
-constexpr uint32_t kIdesc2F16 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+constexpr int F16_CHUNK = 2;                               // stages per TMEM accumulation chunk (128 elements = one scale block)
+
+template <int MODE> struct FCfg {
+    static constexpr int NA = (MODE == FM_FWD3) ? 2 : 1;                  // A tiles per stage (hi, lo)
+    static constexpr int NB = (MODE == FM_LIN1) ? 1 : 2;                  // B tiles per stage (hi, lo | W+, W-)
+    static constexpr int TN = (MODE == FM_R) ? 128 : 256;                 // output columns of a pair tile
+    static constexpr int BT = (TN / 2) * 128;                             // one CTA's half of a B tile: TN/2 rows x 128 bytes
+    static constexpr int STAGE = NA * F16_TILE + NB * BT;                 // 64 / 32 / 32 KiB
+    static constexpr int NST = (MODE == FM_FWD3) ? 3 : 5;
+    // drain warps: a chunk of the single-pass modes is only 1024 tensor cycles (FWD3: 3072) and must be drained within one chunk
+    // time, so 16 warps share it (64 accumulator columns per thread instead of 128)
+    static constexpr int DW = (MODE == FM_FWD3) ? 8 : 16;
+    static constexpr int CW = 256 / (DW / 4);                             // accumulator columns (= register sums) per drain thread
+    static constexpr int THREADS = 64 + 32 * DW;
+    static constexpr int NBARS = 2 * NST + 4;
+    static constexpr int SMEM = NST * STAGE + DW * EPI16_STAGE_BYTES + 1024 + 8 * NBARS + 16;
+    // cta_group::2, fp16 operands (a/b format 0), fp32 accumulate, M = 256, N = TN
+    static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+};
 
 struct F16Params {
     int M, N, K;
     int tiles_m, tiles_n;
     const float* rs; int rs_ld;           // [M, rs_ld] 2^-e of the activation blocks (row, 128 k)
-    const float* cs;                      // [N] 2^-f_c of the weight rows
-    const float* bias; const float* E; long long lde;
+    const float* cs;                      // [N] 2^-f_c of the weight rows (FM_R: of W+^T)
+    const float* cs1;                     // FM_R: [N] of W-^T
+    const float* bias; const float* E; long long lde;      // E: residual (BIAS_ADD) / pre-activation (GELU_BWD) / x (FM_R)
     float* C; long long ldc; float* C2; long long ldc2;
 };
 
-// sum: one accumulator row x 128 columns per thread.  Global memory is accessed in the transposed layout of epi16_read_t (8 rows x
+// sum: one accumulator row x CW columns per thread.  Global memory is accessed in the transposed layout of epi16_read_t (8 rows x
 // 64 contiguous bytes per warp instruction).
-template <int EPI>
-__device__ __forceinline__ void fwd16_epilogue(const F16Params& p, const float (&sum)[128], float* stage, int lane, int row0, int cbase) {
+template <int EPI, int CW>
+__device__ __forceinline__ void fwd16_epilogue(const F16Params& p, const float (&sum)[CW], float* stage, int lane, int row0, int cbase) {
     const int tr = lane >> 2, tc = 4 * (lane & 3);
 #pragma unroll
-    for (int cc = 0; cc < 8; ++cc) {
+    for (int cc = 0; cc < CW / 16; ++cc) {
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = sum[cc * 16 + j];
@@ -72,7 +89,7 @@ __device__ __forceinline__ void fwd16_epilogue(const F16Params& p, const float (
         const int col = cbase + cc * 16 + tc;
         const float4 cs = __ldg(reinterpret_cast<const float4*>(p.cs + col));
         float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (EPI != FP_STORE && p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        if (EPI != FP_STORE && EPI != FP_GELU_BWD && p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col));
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int row = row0 + 8 * i + tr;
@@ -85,6 +102,9 @@ __device__ __forceinline__ void fwd16_epilogue(const F16Params& p, const float (
             } else if (EPI == FP_BIAS_ADD) {
                 const float4 e = *reinterpret_cast<const float4*>(p.E + (long long)row * p.lde + col);
                 o2 = make_float4(e.x + o.x, e.y + o.y, e.z + o.z, e.w + o.w);
+            } else if (EPI == FP_GELU_BWD) {
+                const float4 e = *reinterpret_cast<const float4*>(p.E + (long long)row * p.lde + col);
+                o = make_float4(a.x * te_gelu_grad(e.x), a.y * te_gelu_grad(e.y), a.z * te_gelu_grad(e.z), a.w * te_gelu_grad(e.w));
             }
             *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) = o;
             if (EPI == FP_BIAS_GELU || EPI == FP_BIAS_ADD) *reinterpret_cast<float4*>(p.C2 + (long long)row * p.ldc2 + col) = o2;
@@ -92,10 +112,53 @@ __device__ __forceinline__ void fwd16_epilogue(const F16Params& p, const float (
     }
 }
 
-template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F16_THREADS, 1)
+// FM_R: sum[0..31] = (S W+) and sum[32..63] = (S W-) of one row x 32 columns;  R_in = x+ * (S W+) + x- * (S W-)   (layers_ours.py:207-230)
+__device__ __forceinline__ void r16_epilogue(const F16Params& p, const float (&sum)[64], float* stage, int lane, int row0, int cbase) {
+    const int tr = lane >> 2, tc = 4 * (lane & 3);
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+        const int col = cbase + cc * 16 + tc;
+        float4 x[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = row0 + 8 * i + tr;
+            x[i] = (row < p.M) ? *reinterpret_cast<const float4*>(p.E + (long long)row * p.lde + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float4 cp = __ldg(reinterpret_cast<const float4*>(p.cs + col));
+        const float4 cn = __ldg(reinterpret_cast<const float4*>(p.cs1 + col));
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = sum[cc * 16 + j];
+        epi16_stage_rows(stage, lane, v);
+        float4 ap[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ap[i] = epi16_read_t(stage, lane, i);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = sum[32 + cc * 16 + j];
+        epi16_stage_rows(stage, lane, v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = row0 + 8 * i + tr;
+            if (row >= p.M) continue;
+            const float4 an = epi16_read_t(stage, lane, i);
+            float4 o;
+            o.x = fmaxf(x[i].x, 0.f) * (ap[i].x * cp.x) + fminf(x[i].x, 0.f) * (an.x * cn.x);
+            o.y = fmaxf(x[i].y, 0.f) * (ap[i].y * cp.y) + fminf(x[i].y, 0.f) * (an.y * cn.y);
+            o.z = fmaxf(x[i].z, 0.f) * (ap[i].z * cp.z) + fminf(x[i].z, 0.f) * (an.z * cn.z);
+            o.w = fmaxf(x[i].w, 0.f) * (ap[i].w * cp.w) + fminf(x[i].w, 0.f) * (an.w * cn.w);
+            *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) = o;
+        }
+    }
+}
+
+template <int MODE, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FCfg<MODE>::THREADS, 1)
 te_tc_fwd16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const F16Params p) {
+    using Cfg = FCfg<MODE>;
+    constexpr int F16_NST = Cfg::NST, F16_STAGE = Cfg::STAGE, F16_NBARS = Cfg::NBARS, TN = Cfg::TN, CW = Cfg::CW;
+    constexpr int F16_DRAIN_WARPS = Cfg::DW;
+    constexpr uint32_t OFF_B0 = Cfg::NA * F16_TILE, OFF_B1 = OFF_B0 + Cfg::BT;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -118,9 +181,9 @@ te_tc_fwd16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAh) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAl) : "memory");
+        if (Cfg::NA == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAl) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBl) : "memory");
+        if (Cfg::NB == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBl) : "memory");
         for (int s = 0; s < F16_NST; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -147,7 +210,7 @@ te_tc_fwd16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         if (lane == 0) {
             uint32_t it = 0;
             for (int t = cluster_id; t < ntiles; t += nclusters) {
-                const int m0 = ((t / p.tiles_n) * 2 + (int)rank) * BM, n0 = (t % p.tiles_n) * BN + (int)rank * (BN / 2);
+                const int m0 = ((t / p.tiles_n) * 2 + (int)rank) * BM, n0 = (t % p.tiles_n) * TN + (int)rank * (TN / 2);
                 for (int kk = 0; kk < kb; ++kk, ++it) {
                     const int s = (int)(it % F16_NST);
                     const uint32_t ph = (it / F16_NST) & 1u;
@@ -155,9 +218,9 @@ te_tc_fwd16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                     const uint32_t sa = smem_base + s * F16_STAGE;
                     if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * F16_STAGE);
                     tma2_load_2d(sa, &tmAh, full_bar(s), kk * F16_K, m0);
-                    tma2_load_2d(sa + 2 * F16_TILE, &tmBh, full_bar(s), kk * F16_K, n0);
-                    tma2_load_2d(sa + F16_TILE, &tmAl, full_bar(s), kk * F16_K, m0);
-                    tma2_load_2d(sa + 3 * F16_TILE, &tmBl, full_bar(s), kk * F16_K, n0);
+                    tma2_load_2d(sa + OFF_B0, &tmBh, full_bar(s), kk * F16_K, n0);
+                    if (Cfg::NA == 2) tma2_load_2d(sa + F16_TILE, &tmAl, full_bar(s), kk * F16_K, m0);
+                    if (Cfg::NB == 2) tma2_load_2d(sa + OFF_B1, &tmBl, full_bar(s), kk * F16_K, n0);
                 }
             }
         }
@@ -179,14 +242,19 @@ te_tc_fwd16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                     tcgen05_fence_after();
                     const uint32_t sa = smem_base + s * F16_STAGE;
                     const uint64_t ah = make_smem_desc(sa), al = make_smem_desc(sa + F16_TILE);
-                    const uint64_t bh = make_smem_desc(sa + 2 * F16_TILE), bl = make_smem_desc(sa + 3 * F16_TILE);
+                    const uint64_t bh = make_smem_desc(sa + OFF_B0), bl = make_smem_desc(sa + OFF_B1);
                     const uint32_t d = tmem_base + b * (uint32_t)BN;
 #pragma unroll
                     for (int k = 0; k < F16_K / 16; ++k) {
                         const uint64_t o = (uint64_t)(2 * k);
-                        umma2_bf16(d, ah + o, bh + o, kIdesc2F16, (chunk_start && k == 0) ? 0u : 1u);
-                        umma2_bf16(d, al + o, bh + o, kIdesc2F16, 1u);
-                        umma2_bf16(d, ah + o, bl + o, kIdesc2F16, 1u);
+                        const uint32_t acc = (chunk_start && k == 0) ? 0u : 1u;
+                        umma2_bf16(d, ah + o, bh + o, Cfg::IDESC, acc);
+                        if (MODE == FM_FWD3) {
+                            umma2_bf16(d, al + o, bh + o, Cfg::IDESC, 1u);
+                            umma2_bf16(d, ah + o, bl + o, Cfg::IDESC, 1u);
+                        } else if (MODE == FM_R) {
+                            umma2_bf16(d + 128u, ah + o, bl + o, Cfg::IDESC, acc);      // second product: S W-
+                        }
                     }
                     umma2_commit_both(empty_bar(s));
                     if ((kk % F16_CHUNK) == F16_CHUNK - 1 || kk == kb - 1) { umma2_commit_both(accfull_bar(b)); ++gc; }
@@ -195,15 +263,17 @@ te_tc_fwd16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         }
         __syncwarp();
     } else {
-        // ================= chunk drain + epilogue: warps 2..9 =================
+        // ================= chunk drain + epilogue: warps 2 .. 2 + DW =================
+        // lane quarter q = warp % 4 (the TMEM lanes a warp may read); column group cg: FWD3 / LIN1 own CW consecutive accumulator
+        // columns, FM_R owns 32 columns of BOTH 128-column products (sum[0..31] = S W+, sum[32..63] = S W-)
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
-        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
+        const int cg = (warp - 2) >> 2;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * (MODE == FM_R ? 32 : CW));
         float* stage = reinterpret_cast<float*>(smem_al + RING + (warp - 2) * EPI16_STAGE_BYTES);
-        float sum[128];
+        float sum[CW];
         uint32_t gc = 0;
         for (int t = cluster_id; t < ntiles; t += nclusters) {
-            const int m0 = ((t / p.tiles_n) * 2 + (int)rank) * BM, n0 = (t % p.tiles_n) * BN;
+            const int m0 = ((t / p.tiles_n) * 2 + (int)rank) * BM, n0 = (t % p.tiles_n) * TN;
             const int myrow = m0 + q * 32 + lane;                      // the accumulator row (TMEM lane) of this thread
             const float* rsr = p.rs + (long long)(myrow < p.M ? myrow : 0) * p.rs_ld;
             for (int c = 0; c < nchunks; ++c, ++gc) {
@@ -212,9 +282,10 @@ te_tc_fwd16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                 mbar_wait(accfull_bar(b), (gc >> 1) & 1u);
                 tcgen05_fence_after();
 #pragma unroll
-                for (int cc = 0; cc < 8; ++cc) {
+                for (int cc = 0; cc < CW / 16; ++cc) {
                     uint32_t v[16];
-                    tmem_ld16(tlane + b * (uint32_t)BN + (uint32_t)(cc * 16), v);
+                    // FM_R: chunks 0-1 of the first product, 2-3 of the second (128 columns further)
+                    tmem_ld16(tlane + b * (uint32_t)BN + (uint32_t)(MODE == FM_R ? (cc >> 1) * 128 + (cc & 1) * 16 : cc * 16), v);
                     tmem_ld_wait();
                     if (c == 0) {
 #pragma unroll
@@ -228,7 +299,8 @@ te_tc_fwd16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(map_to_rank0(accfree_bar(b)));
             }
-            fwd16_epilogue<EPI>(p, sum, stage, lane, m0 + q * 32, n0 + half * 128);
+            if constexpr (MODE == FM_R) r16_epilogue(p, sum, stage, lane, m0 + q * 32, n0 + cg * 32);
+            else fwd16_epilogue<EPI, CW>(p, sum, stage, lane, m0 + q * 32, n0 + cg * CW);
         }
     }
     tcgen05_fence_before();
@@ -260,7 +332,7 @@ __global__ void __launch_bounds__(256) blocksplit_f16_kernel(const float* __rest
                 uint2 h, l;
                 te_f16_split4(v, s, h, l);
                 *reinterpret_cast<uint2*>(hi + row * cols + i) = h;
-                *reinterpret_cast<uint2*>(lo + row * cols + i) = l;
+                if (lo) *reinterpret_cast<uint2*>(lo + row * cols + i) = l;
             }
             if (lane == 0) inv[row * nblk + base / 128] = si;
         }
@@ -286,7 +358,7 @@ __global__ void __launch_bounds__(256) rowsplit_f16_kernel(const float* __restri
             uint2 h, l;
             te_f16_split4(xr[c], s, h, l);
             hr[c] = h;
-            lr[c] = l;
+            if (lo) lr[c] = l;
         }
         if (lane == 0) inv[row] = si;
     }
@@ -317,27 +389,28 @@ int f16_sm_pairs() {
     return c;
 }
 
-template <int EPI>
-int launch_fwd16(const __half* ah, const __half* al, const __half* bh, const __half* bl, F16Params p, cudaStream_t st) {
-    CUtensorMap tmAh, tmAl, tmBh, tmBl;
-    if (!make_map_f16(&tmAh, ah, p.M, p.K, BM) || !make_map_f16(&tmAl, al, p.M, p.K, BM) ||
-        !make_map_f16(&tmBh, bh, p.N, p.K, BN / 2) || !make_map_f16(&tmBl, bl, p.N, p.K, BN / 2)) {
+template <int MODE, int EPI>
+int launch_f16(const __half* ah, const __half* al, const __half* b0, const __half* b1, F16Params p, cudaStream_t st) {
+    using Cfg = FCfg<MODE>;
+    CUtensorMap tmAh, tmAl, tmB0, tmB1;
+    if (!make_map_f16(&tmAh, ah, p.M, p.K, BM) || !make_map_f16(&tmAl, al ? al : ah, p.M, p.K, BM) ||
+        !make_map_f16(&tmB0, b0, p.N, p.K, Cfg::TN / 2) || !make_map_f16(&tmB1, b1 ? b1 : b0, p.N, p.K, Cfg::TN / 2)) {
         te_set_last_error("te_tc_fwd16: cuTensorMapEncodeTiled failed");
         return TE_ERR_CUDA;
     }
     static unsigned long long optin = 0;
-    if (!smem_optin(te_tc_fwd16_kernel<EPI>, F16_SMEM, optin)) {
+    if (!smem_optin(te_tc_fwd16_kernel<MODE, EPI>, Cfg::SMEM, optin)) {
         te_set_last_error("te_tc_fwd16: cannot raise dynamic shared memory");
         return TE_ERR_CUDA;
     }
     const int mt = (p.M + BM - 1) / BM;
     p.tiles_m = (mt + 1) / 2;
-    p.tiles_n = p.N / BN;
+    p.tiles_n = p.N / Cfg::TN;
     const int ntiles = p.tiles_m * p.tiles_n;
     int pairs = f16_sm_pairs();
     if (pairs <= 0) { te_set_last_error("te_tc_fwd16: cannot query the SM count"); return TE_ERR_CUDA; }
     if (pairs > ntiles) pairs = ntiles;
-    te_tc_fwd16_kernel<EPI><<<dim3(2u * (unsigned)pairs), F16_THREADS, F16_SMEM, st>>>(tmAh, tmAl, tmBh, tmBl, p);
+    te_tc_fwd16_kernel<MODE, EPI><<<dim3(2u * (unsigned)pairs), Cfg::THREADS, Cfg::SMEM, st>>>(tmAh, tmAl, tmB0, tmB1, p);
     TE_CUDA_CHECK_LAUNCH();
     return TE_OK;
 }
@@ -352,7 +425,7 @@ bool te_tc_fwd16_supported(long long rows, int K, int N, long long lda) {
 // weights: W [rows, cols] (row stride ldx) -> hi, lo fp16 [rows, cols] and ONE 2^-f per row
 int te_tc_rowsplit_f16(const float* x, long long ldx, long long rows, int cols, void* hi, void* lo, float* scale_inv,
                        cudaStream_t st) {
-    if (cols % 4 != 0 || ldx % 4 != 0 || !a16(x) || ((uintptr_t)hi & 7u) || ((uintptr_t)lo & 7u)) {
+    if (cols % 4 != 0 || ldx % 4 != 0 || !a16(x) || ((uintptr_t)hi & 7u) || (lo && ((uintptr_t)lo & 7u))) {
         te_set_last_error("te_tc_rowsplit_f16: alignment");
         return TE_ERR_ARG;
     }
@@ -367,7 +440,8 @@ int te_tc_rowsplit_f16(const float* x, long long ldx, long long rows, int cols, 
 
 // activations: x [rows, cols] (row stride ldx) -> split = [hi | lo] fp16 [rows, cols] and one 2^-e per (row, 128 columns):
 // scale_inv [rows, ceil(cols / 128)]
-int te_tc_blocksplit_f16(const float* x, long long ldx, long long rows, int cols, float* split, float* scale_inv, cudaStream_t st) {
+int te_tc_blocksplit_f16(const float* x, long long ldx, long long rows, int cols, float* split, float* scale_inv, cudaStream_t st,
+                         bool hi_only) {
     if (cols % 4 != 0 || ldx % 4 != 0 || !a16(x) || !a16(split) || !scale_inv) {
         te_set_last_error("te_tc_blocksplit_f16: alignment");
         return TE_ERR_ARG;
@@ -376,7 +450,7 @@ int te_tc_blocksplit_f16(const float* x, long long ldx, long long rows, int cols
     if (blocks > 148LL * 8) blocks = 148LL * 8;
     if (blocks < 1) blocks = 1;
     __half* hi = reinterpret_cast<__half*>(split);
-    blocksplit_f16_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, ldx, rows, cols, hi, hi + rows * cols, scale_inv);
+    blocksplit_f16_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, ldx, rows, cols, hi, hi_only ? nullptr : hi + rows * cols, scale_inv);
     TE_CUDA_CHECK_LAUNCH();
     return TE_OK;
 }
@@ -404,11 +478,59 @@ int te_tc_linear_fwd16(const float* x, long long ldx, float* split, float* scale
     p.rs = scale; p.rs_ld = (in_features + 127) / 128; p.cs = derived + 12 * n + n / 2;
     p.bias = bias; p.E = e0; p.lde = out_features; p.C = y; p.ldc = out_features; p.C2 = y2; p.ldc2 = out_features;
     switch (epi) {
-        case TE_TC_EPI_STORE: return launch_fwd16<FP_STORE>(ah, al, bh, bl, p, st);
-        case TE_TC_EPI_BIAS: return launch_fwd16<FP_BIAS>(ah, al, bh, bl, p, st);
-        case TE_TC_EPI_BIAS_GELU: return launch_fwd16<FP_BIAS_GELU>(ah, al, bh, bl, p, st);
-        case TE_TC_EPI_BIAS_ADD: return launch_fwd16<FP_BIAS_ADD>(ah, al, bh, bl, p, st);
+        case TE_TC_EPI_STORE: return launch_f16<FM_FWD3, FP_STORE>(ah, al, bh, bl, p, st);
+        case TE_TC_EPI_BIAS: return launch_f16<FM_FWD3, FP_BIAS>(ah, al, bh, bl, p, st);
+        case TE_TC_EPI_BIAS_GELU: return launch_f16<FM_FWD3, FP_BIAS_GELU>(ah, al, bh, bl, p, st);
+        case TE_TC_EPI_BIAS_ADD: return launch_f16<FM_FWD3, FP_BIAS_ADD>(ah, al, bh, bl, p, st);
     }
     te_set_last_error("te_tc_linear_fwd16: unsupported epilogue");
     return TE_ERR_UNSUPPORTED;
+}
+
+// ---- single-pass products -------------------------------------------------------------------------------------------
+// dx[rows, in] = epi(dy[rows, out] W)  (activation-gradient backward Linear; TE_FLAG_F16_SINGLE_PASS).  split / scale: hi-only
+// block-scaled split of dy ([rows, out] fp16 = rows*out/2 floats; [rows, ceil(out/128)]); dy != NULL: filled here by the pre-pass,
+// dy == NULL: already filled by the producer.  fp16(W^T) [in, out] + its row scales live in the derived buffer at 13 n.
+int te_tc_linear_bwd16(const float* dy, long long lddy, float* split, float* scale, const float* derived, int in_features,
+                       int out_features, float* dx, const float* e0, long long rows, int epi, cudaStream_t st) {
+    const long long n = (long long)in_features * out_features;
+    if (!a16(split) || !scale || !a16(derived) || !a16(dx) || (e0 && !a16(e0))) {
+        te_set_last_error("te_tc_linear_bwd16: bad operands");
+        return TE_ERR_ARG;
+    }
+    if (dy) TE_TRY(te_tc_blocksplit_f16(dy, lddy, rows, out_features, split, scale, st, true));
+    F16Params p;
+    memset(&p, 0, sizeof(p));
+    p.M = (int)rows; p.N = in_features; p.K = out_features;
+    p.rs = scale; p.rs_ld = (out_features + 127) / 128; p.cs = derived + 13 * n + n / 2;
+    p.E = e0; p.lde = in_features; p.C = dx; p.ldc = in_features;
+    const __half* ah = reinterpret_cast<const __half*>(split);
+    const __half* bt = reinterpret_cast<const __half*>(derived + 13 * n);
+    if (epi == TE_TC_EPI_GELU_BWD) return launch_f16<FM_LIN1, FP_GELU_BWD>(ah, nullptr, bt, nullptr, p, st);
+    if (epi == TE_TC_EPI_STORE) return launch_f16<FM_LIN1, FP_STORE>(ah, nullptr, bt, nullptr, p, st);
+    te_set_last_error("te_tc_linear_bwd16: unsupported epilogue");
+    return TE_ERR_UNSUPPORTED;
+}
+
+// R_in[rows, in] = x+ * (S W+) + x- * (S W-)  (second contraction of the z+ rule).  split / scale: hi-only block-scaled split of
+// S [rows, out]; s != NULL: filled here by the pre-pass.  fp16(W+^T), fp16(W-^T) [in, out] + row scales: derived buffer at 14 n.
+int te_tc_zplus_r16(const float* s, float* split, float* scale, const float* derived, const float* x, long long ldx, float* out,
+                    long long ld_out, long long rows, int in_features, int out_features, cudaStream_t st) {
+    const long long n = (long long)in_features * out_features;
+    if (!a16(split) || !scale || !a16(derived) || !a16(x) || !a16(out) || ldx % 4 != 0 || ld_out % 4 != 0) {
+        te_set_last_error("te_tc_zplus_r16: bad operands");
+        return TE_ERR_ARG;
+    }
+    if (s) TE_TRY(te_tc_blocksplit_f16(s, out_features, rows, out_features, split, scale, st, true));
+    F16Params p;
+    memset(&p, 0, sizeof(p));
+    p.M = (int)rows; p.N = in_features; p.K = out_features;
+    p.rs = scale; p.rs_ld = (out_features + 127) / 128; p.cs = derived + 15 * n; p.cs1 = derived + 15 * n + in_features;
+    p.E = x; p.lde = ldx; p.C = out; p.ldc = ld_out;
+    const __half* ah = reinterpret_cast<const __half*>(split);
+    const __half* bp = reinterpret_cast<const __half*>(derived + 14 * n);
+    return launch_f16<FM_R, FP_STORE>(ah, nullptr, bp, bp + n, p, st);
+}
+bool te_tc_f16_single_supported(long long rows, int K, int N, long long lda) {
+    return rows > 0 && rows < (1LL << 31) && K % F16_K == 0 && N % BN == 0 && lda % 4 == 0 && get_encode() != nullptr;
 }

@@ -34,12 +34,14 @@
 //   empty[s]    local, tcgen05.commit.cta_group::2 multicast from the leader when the MMAs of the stage retire
 //   accfull[b]  local, multicast commit after the last k-block of a tile into accumulator buffer b
 //   accfree[b]  leader, one remote arrive per epilogue warp of both CTAs (16) once buffer b has been read out
+#include <cuda_fp16.h>
+
 #include "te_tc_common.cuh"
 
 namespace {
 
 enum { PM_R = 0, PM_S1 = 1, PM_LIN = 2 };
-enum { PE_STORE = 0, PE_GELU_BWD = 4 };
+enum { PE_STORE = 0, PE_F16 = 1 /* PM_S1: S as block-scaled fp16 for the fp16 R kernel */, PE_GELU_BWD = 4 };
 
 struct PairParams {
     int M, N, K;
@@ -48,6 +50,7 @@ struct PairParams {
     float* C; long long ldc;
     const float* Y; long long ldy; const float* bias;                   // PM_S1: saved forward output y = x W^T + b
     const float* X; long long ldx; const float* Wp; const float* Wn;    // PM_S1: exact fallback of a cancelled denominator
+    __half* H; float* HS;                 // PM_S1 / PE_F16: S as hi-only block-scaled fp16 [M, N] + 2^-e per (row, 128 columns) [M, N/128]
 };
 
 template <int MODE> struct PairCfg {
@@ -211,6 +214,7 @@ te_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(accfull_bar(b), (ti / ACC_BUFS) & 1u);
             tcgen05_fence_after();
             const uint32_t tcol = tlane + b * (uint32_t)(NB * BN) + (uint32_t)(half * (BN / 2));
+            float rmax[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};          // PE_F16: max |S| of rows 4i + tr over this warp's 128 columns
 #pragma unroll 1
             for (int c = 0; c < BN / 2 / 32; ++c) {
                 const int col = n0 + c * 32 + tc;
@@ -272,9 +276,37 @@ te_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         for (int u = 0; u < 4; ++u) {
                             const float z = 0.5f * (yy[u] + aa[u]);
                             if (z < aa[u] * 0.0078125f && aa[u] > 0.f) redo |= 1u << (4 * i + u);
-                            o[u] = to_tf32(te_sd(rr[u], fmaxf(z, 0.f)));
+                            const float sv = te_sd(rr[u], fmaxf(z, 0.f));
+                            o[u] = (EPI == PE_F16) ? sv : to_tf32(sv);
                         }
                         r[i] = make_float4(o[0], o[1], o[2], o[3]);          // r[] now holds S
+                    }
+                    if (EPI == PE_F16) {
+                        // S leaves as block-scaled fp16: one power of two per (row, this warp's 128 columns).  The chunk's S values are
+                        // parked in the TMEM columns the accumulator chunk just vacated (a thread reads back exactly the registers it
+                        // stored, so the transposed layout needs no second transposition) until the row maxima of all 4 chunks exist.
+                        if (__any_sync(0xffffffffu, redo != 0u)) {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) {
+                                if (!((redo >> e) & 1u)) continue;
+                                const int i = e >> 2, u = e & 3;
+                                const int row = m0 + 4 * i + tr;
+                                if (row >= p.M) continue;
+                                const float z = zplus_exact(p.X + (long long)row * p.ldx, p.Wp + (long long)(col + u) * p.K,
+                                                            p.Wn + (long long)(col + u) * p.K, p.K);
+                                const float sv = te_sd(p.E[(long long)row * p.lde + col + u], fmaxf(z, 0.f));
+                                if (u == 0) r[i].x = sv; else if (u == 1) r[i].y = sv; else if (u == 2) r[i].z = sv; else r[i].w = sv;
+                            }
+                        }
+                        uint32_t sv32[32];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            rmax[i] = fmaxf(rmax[i], te_absmax4(r[i]));
+                            sv32[4 * i] = __float_as_uint(r[i].x); sv32[4 * i + 1] = __float_as_uint(r[i].y);
+                            sv32[4 * i + 2] = __float_as_uint(r[i].z); sv32[4 * i + 3] = __float_as_uint(r[i].w);
+                        }
+                        tmem_st32(tcol + (uint32_t)(c * 32), sv32);
+                        continue;
                     }
                     if (__any_sync(0xffffffffu, redo != 0u)) {
                         // r[] was overwritten: reload the relevance of the few cancelled elements
@@ -327,6 +359,39 @@ te_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             o.z *= te_gelu_grad(e[i].z); o.w *= te_gelu_grad(e[i].w);
                         }
                         if (row < p.M) *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) = o;
+                    }
+                }
+            }
+            if (MODE == PM_S1 && EPI == PE_F16) {
+                tmem_st_wait();
+                float sc[8];
+                const int nblk = p.N / 128;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float m = rmax[i];
+                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                    float si;
+                    te_f16_block_scale(m, sc[i], si);
+                    const int row = m0 + 4 * i + tr;
+                    if ((lane & 7) == 0 && row < p.M) p.HS[(long long)row * nblk + n0 / 128] = si;
+                }
+#pragma unroll 1
+                for (int c = 0; c < BN / 2 / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(tcol + (uint32_t)(c * 32), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = m0 + 4 * i + tr;
+                        if (row >= p.M) continue;
+                        const __half2 h01 = __floats2half2_rn(__uint_as_float(v[4 * i]) * sc[i], __uint_as_float(v[4 * i + 1]) * sc[i]);
+                        const __half2 h23 = __floats2half2_rn(__uint_as_float(v[4 * i + 2]) * sc[i], __uint_as_float(v[4 * i + 3]) * sc[i]);
+                        uint2 h;
+                        h.x = *reinterpret_cast<const uint32_t*>(&h01);
+                        h.y = *reinterpret_cast<const uint32_t*>(&h23);
+                        *reinterpret_cast<uint2*>(p.H + (long long)row * p.N + n0 + c * 32 + tc) = h;
                     }
                 }
             }
@@ -430,7 +495,7 @@ int te_tc_abs_tf32(const float* x, long long ldx, float* out, long long rows, in
 // xabs: scratch [rows, in] that receives tf32(|x|)
 int te_tc_pair_zplus_s1(const float* x, long long ldx, float* xabs, const float* derived, const float* r, long long ldr,
                         const float* y, long long ldy, const float* bias, float* s_out, long long rows, int in_features,
-                        int out_features, cudaStream_t st, bool bf16) {
+                        int out_features, cudaStream_t st, bool bf16, float* s16, float* s16_scale) {
     const long long n = (long long)in_features * out_features;
     if (bf16 && in_features % 64 == 0) {
         PairParams p;
@@ -445,6 +510,10 @@ int te_tc_pair_zplus_s1(const float* x, long long ldx, float* xabs, const float*
         abs_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, ldx, reinterpret_cast<__nv_bfloat16*>(xabs), rows, in_features / 4);
         TE_CUDA_CHECK_LAUNCH();
         // bf16(|W|) [out, in] lives at derived + 11 n (te_tc_prepare_weights)
+        if (s16) {                     // S straight to the fp16 R kernel's operand format: no fp32 S, no pre-pass
+            p.H = reinterpret_cast<__half*>(s16); p.HS = s16_scale;
+            return launch_pair<PM_S1, PE_F16, true>(xabs, in_features, derived + 11 * n, nullptr, p, st);
+        }
         return launch_pair<PM_S1, PE_STORE, true>(xabs, in_features, derived + 11 * n, nullptr, p, st);
     }
     TE_TRY(te_tc_abs_tf32(x, ldx, xabs, rows, in_features, st));
@@ -453,6 +522,10 @@ int te_tc_pair_zplus_s1(const float* x, long long ldx, float* xabs, const float*
     p.M = (int)rows; p.N = out_features; p.K = in_features;
     p.E = r; p.lde = ldr; p.C = s_out; p.ldc = out_features; p.Y = y; p.ldy = ldy; p.bias = bias;
     p.X = x; p.ldx = ldx; p.Wp = derived; p.Wn = derived + n;
+    if (s16) {
+        p.H = reinterpret_cast<__half*>(s16); p.HS = s16_scale;
+        return launch_pair<PM_S1, PE_F16>(xabs, in_features, derived + 8 * n, nullptr, p, st);
+    }
     return launch_pair<PM_S1, PE_STORE>(xabs, in_features, derived + 8 * n, nullptr, p, st);
 }
 

@@ -578,7 +578,7 @@ static bool use_persistent() {
 }
 void te_tc_set_zplus_persistent(int on) { g_zplus_persistent = on ? 1 : 0; }
 
-long long te_tc_derived_floats(int in_features, int out_features) { return 13LL * in_features * out_features; }
+long long te_tc_derived_floats(int in_features, int out_features) { return 16LL * in_features * out_features; }
 
 int te_tc_prepare_weights(const float* w, float* derived, int in_features, int out_features, cudaStream_t st) {
     dim3 grid((in_features + 31) / 32, (out_features + 31) / 32), block(32, 8);
@@ -588,12 +588,21 @@ int te_tc_prepare_weights(const float* w, float* derived, int in_features, int o
     if (in_features % 8 == 0 && in_features >= 8 && a16(w))        // row-scaled fp16 split: [hi | lo | 2^-f] from 11.5 n
         TE_TRY(te_tc_rowsplit_f16(w, in_features, out_features, in_features, derived + 11 * n + n / 2, derived + 12 * n,
                                   derived + 12 * n + n / 2, st));
+    if (out_features % 8 == 0 && in_features >= 2) {               // single-pass fp16 operands from the TF32-rounded transposes [in, out]
+        TE_TRY(te_tc_rowsplit_f16(derived + 6 * n, out_features, in_features, out_features, derived + 13 * n, nullptr,
+                                  derived + 13 * n + n / 2, st));
+        TE_TRY(te_tc_rowsplit_f16(derived + 2 * n, out_features, in_features, out_features, derived + 14 * n, nullptr,
+                                  derived + 15 * n, st));
+        TE_TRY(te_tc_rowsplit_f16(derived + 3 * n, out_features, in_features, out_features, derived + 14 * n + n / 2, nullptr,
+                                  derived + 15 * n + in_features, st));
+    }
     return TE_OK;
 }
 
 int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* derived, const float* r, long long ldr,
                                float* out, float* s_scratch, long long rows, int in_features, int out_features, cudaStream_t st,
-                               const float* y, long long ldy, const float* bias, int bf16, long long ld_out, float* xabs) {
+                               const float* y, long long ldy, const float* bias, int bf16, long long ld_out, float* xabs,
+                               float* f16s) {
     if (ld_out == 0) ld_out = in_features;
     if (!a16(x) || !a16(derived) || !a16(r) || !a16(out) || !a16(s_scratch)) {
         te_set_last_error("te_gemm_tc: operands must be 16-byte aligned");
@@ -606,6 +615,15 @@ int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* deriv
     if (!rb && use_persistent() && xabs && a16(xabs) && y && a16(y) && ldy % 4 == 0 && (!bias || a16(bias)) &&
         te_tc_pair_supported(rows, in_features, out_features, ldx) && te_tc_pair_supported(rows, out_features, in_features, out_features)) {
         // persistent CTA-pair kernels (te_tc_pair.cu): single-pass S, then R with the A operand shared by both products
+        if ((bf16 & 4) && te_tc_f16_single_supported(rows, out_features, in_features, out_features)) {
+            // second contraction on kind::f16 (te_tc_fwd16.cu, FM_R).  Its A operand — S as hi-only block-scaled fp16 — is written
+            // by the S kernel's epilogue straight into s_scratch ([rows, out] fp16, then the [rows, out/128] scales): rows*out
+            // floats hold both (out/2 + out/128 <= out).  f16s is not needed on this path.
+            float* s16_scale = s_scratch + ((rows * out_features / 2 + 63) & ~63LL);
+            TE_TRY(te_tc_pair_zplus_s1(x, ldx, xabs, derived, r, ldr, y, ldy, bias, nullptr, rows, in_features, out_features, st,
+                                       (bf16 & 2) != 0, s_scratch, s16_scale));
+            return te_tc_zplus_r16(nullptr, s_scratch, s16_scale, derived, x, ldx, out, ld_out, rows, in_features, out_features, st);
+        }
         TE_TRY(te_tc_pair_zplus_s1(x, ldx, xabs, derived, r, ldr, y, ldy, bias, s_scratch, rows, in_features, out_features, st,
                                    (bf16 & 2) != 0));
         return te_tc_pair_zplus_r(s_scratch, derived, x, ldx, out, ld_out, rows, in_features, out_features, st);

@@ -69,7 +69,7 @@ def linear_forward(x, w, bias=None, tensor_cores=False, f16_split=False):
         raise ValueError("linear_forward: x [...,in], w [out,in], bias [out] expected")
     rows = x.numel() // x.shape[-1]
     y = torch.empty(*x.shape[:-1], w.shape[0], device=x.device, dtype=torch.float32)
-    nscratch = 13 * w.numel() + ((x.numel() + 63) // 64 * 64 + rows * ((x.shape[-1] + 127) // 128) if f16_split else 0)
+    nscratch = 16 * w.numel() + ((x.numel() + 63) // 64 * 64 + rows * ((x.shape[-1] + 127) // 128) if f16_split else 0)
     scratch = torch.empty(nscratch, device=x.device, dtype=torch.float32) if tensor_cores else None
     flags = (_lib.FLAG_LINEAR_TENSOR_CORES if tensor_cores else 0) | (_lib.FLAG_LINEAR_F16_SPLIT if f16_split else 0)
     check(_lib.load().te_linear_forward_ex(ptr(x), ptr(w), ptr(bias), ptr(y), ptr(scratch), rows, x.shape[-1], w.shape[0],
@@ -86,9 +86,25 @@ def linear_backward(dy, w, tensor_cores=False):
         raise ValueError("linear_backward: dy [...,out], w [out,in] expected")
     rows = dy.numel() // dy.shape[-1]
     dx = torch.empty(*dy.shape[:-1], w.shape[1], device=dy.device, dtype=torch.float32)
-    scratch = torch.empty(13 * w.numel(), device=dy.device, dtype=torch.float32) if tensor_cores else None
+    scratch = torch.empty(16 * w.numel(), device=dy.device, dtype=torch.float32) if tensor_cores else None
     check(_lib.load().te_linear_backward_ex(ptr(dy), ptr(w), ptr(dx), ptr(scratch), rows, w.shape[1], w.shape[0],
                                             _lib.FLAG_LINEAR_TENSOR_CORES if tensor_cores else 0, _stream()),
+          "te_linear_backward_ex")
+    return dx
+
+
+@_on_device
+def linear_backward_f16(dy, w):
+    """dx = dy W as a single-pass fp16 GEMM (block-scaled fp16 gradient, row-scaled fp16 weights; TE_FLAG_BACKWARD_F16)."""
+    _req(dy, w)
+    if w.dim() != 2 or dy.shape[-1] != w.shape[0]:
+        raise ValueError("linear_backward_f16: dy [...,out], w [out,in] expected")
+    rows = dy.numel() // dy.shape[-1]
+    dx = torch.empty(*dy.shape[:-1], w.shape[1], device=dy.device, dtype=torch.float32)
+    n = 16 * w.numel() + (dy.numel() // 2 + 63) // 64 * 64 + rows * ((w.shape[0] + 127) // 128)
+    scratch = torch.empty(n, device=dy.device, dtype=torch.float32)
+    check(_lib.load().te_linear_backward_ex(ptr(dy), ptr(w), ptr(dx), ptr(scratch), rows, w.shape[1], w.shape[0],
+                                            _lib.FLAG_LINEAR_TENSOR_CORES | _lib.FLAG_BACKWARD_F16, _stream()),
           "te_linear_backward_ex")
     return dx
 
@@ -101,7 +117,7 @@ def linear_backward_tf32(dy, w):
         raise ValueError("linear_backward_tf32: dy [...,out], w [out,in] expected")
     rows = dy.numel() // dy.shape[-1]
     dx = torch.empty(*dy.shape[:-1], w.shape[1], device=dy.device, dtype=torch.float32)
-    scratch = torch.empty(13 * w.numel(), device=dy.device, dtype=torch.float32)
+    scratch = torch.empty(16 * w.numel(), device=dy.device, dtype=torch.float32)
     check(_lib.load().te_linear_backward_ex(ptr(dy), ptr(w), ptr(dx), ptr(scratch), rows, w.shape[1], w.shape[0],
                                             _lib.FLAG_LINEAR_TENSOR_CORES | _lib.FLAG_BACKWARD_TF32, _stream()),
           "te_linear_backward_ex")
@@ -109,7 +125,7 @@ def linear_backward_tf32(dy, w):
 
 
 @_on_device
-def linear_relprop(x, w, r, tensor_cores=False, y=None, bias=None, bf16=False, variant="ours"):
+def linear_relprop(x, w, r, tensor_cores=False, y=None, bias=None, bf16=False, variant="ours", r_f16=False):
     """``Linear.relprop`` (layers_ours.py:207-230): x [...,in], w [out,in], r [...,out] -> [...,in].
     y / bias: the layer's saved forward output (and bias) — lets the tensor-core path form the denominator in one pass.
     variant="lrp": the rule of ``modules/layers_lrp.py:187-210`` (separate denominators; fp32 SIMT)."""
@@ -121,9 +137,13 @@ def linear_relprop(x, w, r, tensor_cores=False, y=None, bias=None, bf16=False, v
     out = torch.empty_like(x)
     nscratch = rows * w.shape[0]
     if tensor_cores:
-        nscratch = (nscratch + 63) // 64 * 64 + 13 * w.numel() + x.numel()
+        nscratch = (nscratch + 63) // 64 * 64 + 16 * w.numel() + (x.numel() + 63) // 64 * 64
+        if r_f16:           # fp16 operand of the second contraction (TE_FLAG_ZPLUS_R_F16): hi-only split of S + block scales
+            nscratch += (rows * w.shape[0] // 2 + 63) // 64 * 64 + rows * ((w.shape[0] + 127) // 128)
     scratch = torch.empty(nscratch, device=x.device, dtype=torch.float32)
     flags = _lib.FLAG_ZPLUS_TENSOR_CORES if tensor_cores else 0
+    if r_f16:
+        flags |= _lib.FLAG_ZPLUS_R_F16
     if bf16 == "s1":
         flags |= _lib.FLAG_ZPLUS_S1_BF16              # bf16 operands for the |x||W|^T term of the single-pass denominator
     elif bf16:
