@@ -222,8 +222,7 @@ TE_API int te_linear_relprop(const float* x, const float* w, const float* r, flo
 /* Same rule with the Linear's saved forward output y = x W^T + bias [rows,out] supplied (what the engines do): with
  * TE_FLAG_ZPLUS_TENSOR_CORES the denominator is then formed in ONE tensor-core pass through the exact identity
  * x+ W+^T + x- W-^T == ((y - bias) + |x| |W|^T) / 2.  bias may be NULL (no bias).
- * scratch: rows*out floats; with TE_FLAG_ZPLUS_TENSOR_CORES: round_up(rows*out,64) + 16*in*out + round_up(rows*in,64) floats
- * (+ round_up(rows*out/2,64) + rows*ceil(out/128) with TE_FLAG_ZPLUS_R_F16)
+ * scratch: rows*out floats; with TE_FLAG_ZPLUS_TENSOR_CORES: round_up(rows*out,64) + 16*in*out + rows*in floats
  * (S, the derived weight copies, the tf32(|x|) operand of the single-pass kernel). */
 TE_API int te_linear_relprop_ex(const float* x, const float* w, const float* bias, const float* y, const float* r,
                          float* out, float* scratch, int rows, int in_features, int out_features, unsigned flags,

@@ -105,20 +105,17 @@ extern "C" int te_linear_relprop_ex(const float* x, const float* w, const float*
     const float* derived = nullptr;
     float* xabs = nullptr;
     if ((flags & TE_FLAG_ZPLUS_TENSOR_CORES) && te_tc_zplus_supported(rows, in_features, out_features, in_features)) {
-        // scratch layout with the flag: [rows*out S (64-float aligned) | 16*in*out derived weight copies | round_up(rows*in,64) tf32(|x|) |
-        //  with TE_FLAG_ZPLUS_R_F16: round_up(rows*out/2,64) + rows*ceil(out/128) fp16 S operand]
+        // scratch layout with the flag: [rows*out S (64-float aligned) | 16*in*out derived weight copies | rows*in tf32(|x|)]
         float* d = scratch + (((long long)rows * out_features + 63) & ~63LL);
         TE_TRY(te_tc_prepare_weights(w, d, in_features, out_features, ST(stream)));
         derived = d;
         xabs = d + te_tc_derived_floats(in_features, out_features);
     }
-    // TE_FLAG_ZPLUS_R_F16: the fp16 operand of the second contraction follows the |x| scratch (64-float aligned)
-    float* f16s = (xabs && (flags & TE_FLAG_ZPLUS_R_F16)) ? xabs + (((long long)rows * in_features + 63) & ~63LL) : nullptr;
     return te_zplus_linear_relprop_ldr(x, in_features, w, derived, r, out_features, out, scratch, rows, in_features,
                                        out_features, ST(stream), y, out_features, bias,
                                        ((flags & TE_FLAG_ZPLUS_BF16) ? 1 : 0) | ((flags & TE_FLAG_ZPLUS_S1_BF16) ? 2 : 0) |
                                            ((flags & TE_FLAG_ZPLUS_R_F16) ? 4 : 0),
-                                       0, xabs, f16s);
+                                       0, xabs);
 }
 
 extern "C" int te_add_relprop(const float* x1, const float* x2, const float* r, float* r1, float* r2, void* scratch,

@@ -347,16 +347,12 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
     const bool rtf = (flags & TE_FLAG_RELPROP_TF32) != 0;        // single-pass TF32 relevance-side attention contractions
     const int zb = ((flags & TE_FLAG_ZPLUS_BF16) ? 1 : 0) | ((flags & TE_FLAG_ZPLUS_S1_BF16) ? 2 : 0) |
                    ((flags & TE_FLAG_ZPLUS_R_F16) ? 4 : 0);                                               // bf16 / fp16 variants of the z+ rule
-    // operand scratch of the fp16 R kernel: the |x| scratch of the same rule (dead once S exists) when it is large enough
-    auto f16s = [&](float* xabs, long long cap, long long rows, int outf) -> float* {
-        return te_zplus_f16_scratch_floats(rows, outf) <= cap ? xabs : nullptr;
-    };
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     Weights w;
     bind_weights(cfg, weights, w);
     const float* dbase = (flags & TE_FLAG_ZPLUS_TENSOR_CORES) ? derived : nullptr;
     const float scale = 1.0f / sqrtf((float)d.dh);
-    const long long MD = d.M * d.D, DD = (long long)d.D * d.D, MF = d.M * d.F, M3D = d.M * 3LL * d.D;
+    const long long MD = d.M * d.D, DD = (long long)d.D * d.D;
     const int low = (flags & (TE_FLAG_KEEP_ALL_CAMS | TE_FLAG_RELPROP_TO_INPUT)) ? 0 : start_layer;
 
     TE_TRY(te_launch_argmax(ws.logits, index, d.B, d.C, 1, st));
@@ -424,16 +420,13 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
         const long long zr = top ? d.B : d.M;
         const long long sD = top ? (long long)d.N * d.D : d.D, sF = top ? (long long)d.N * d.F : d.F;
         TE_TRY(te_launch_add_relprop(a.d2, a.ao, R, R1, R2, ws.addpart, d.B, (long long)d.N * d.D, st));
-        TE_TRY(te_zplus_linear_relprop_ldr(a.g, sF, lw.w2, dw.w2, R1, sD, RF, S, zr, d.F, d.D, st, a.d2, sD, lw.b2, zb, sF, SF,
-                                           f16s(SF, MF, zr, d.D)));
-        TE_TRY(te_zplus_linear_relprop_ldr(a.ao, sD, lw.w1, dw.w1, RF, sF, R1, SF, zr, d.D, d.F, st, a.hpre, sF, lw.b1, zb, sD, S,
-                                           f16s(S, M3D, zr, d.F)));
+        TE_TRY(te_zplus_linear_relprop_ldr(a.g, sF, lw.w2, dw.w2, R1, sD, RF, S, zr, d.F, d.D, st, a.d2, sD, lw.b2, zb, sF, SF));
+        TE_TRY(te_zplus_linear_relprop_ldr(a.ao, sD, lw.w1, dw.w1, RF, sF, R1, SF, zr, d.D, d.F, st, a.hpre, sF, lw.b1, zb, sD, S));
         TE_TRY(te_launch_clone_relprop(a.ao, R1, R2, nullptr, R, MD, st));
         // BertSelfOutput.relprop :427-434
         TE_TRY(te_launch_add_relprop(a.d1, a.h, R, R1, R2, ws.addpart, d.B, (long long)d.N * d.D, st));
         if (top) TE_TRY(te_launch_fill(R3, 0.f, MD, st));
-        TE_TRY(te_zplus_linear_relprop_ldr(a.ctx, sD, lw.ow, dw.o, R1, sD, R3, S, zr, d.D, d.D, st, a.d1, sD, lw.ob, zb, sD, S + MD,
-                                           f16s(S + MD, M3D - MD, zr, d.D)));
+        TE_TRY(te_zplus_linear_relprop_ldr(a.ctx, sD, lw.ow, dw.o, R1, sD, R3, S, zr, d.D, d.D, st, a.d1, sD, lw.ob, zb, sD, S + MD));
         // BertSelfAttention.relprop :367-409
         TE_TRY(te_launch_sd(R3, a.ctx, S, MD, st));                                       // matmul2: Z == saved ctx
         TE_TRY(attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, S, d.D, a.qkv + 2 * d.D, 3 * d.D, a.cam, a.P, 0.5f, TE_EPI_MUL,
@@ -452,12 +445,11 @@ extern "C" int te_bert_attribute(const te_bert_config* cfg, const float* weights
         TE_TRY(attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, ws.tA[0], 1, a.qkv, 3 * d.D, Rqkv + d.D, 3 * d.D, a.qkv + d.D, 0.5f,
                        TE_EPI_MUL, st, rtf));
         // query / key / value z+ rules (separate Linears), Clone(3), Clone(2)
-        TE_TRY(te_zplus_linear_relprop_ldr(a.h, d.D, lw.qkvw, dw.q, Rqkv, 3 * d.D, R, S, d.M, d.D, d.D, st, a.qkv, 3 * d.D, lw.qkvb, zb, 0, S + MD,
-                                           f16s(S + MD, M3D - MD, d.M, d.D)));
+        TE_TRY(te_zplus_linear_relprop_ldr(a.h, d.D, lw.qkvw, dw.q, Rqkv, 3 * d.D, R, S, d.M, d.D, d.D, st, a.qkv, 3 * d.D, lw.qkvb, zb, 0, S + MD));
         TE_TRY(te_zplus_linear_relprop_ldr(a.h, d.D, lw.qkvw + DD, dw.k, Rqkv + d.D, 3 * d.D, R1, S, d.M, d.D, d.D, st, a.qkv + d.D, 3 * d.D,
-                                           lw.qkvb + d.D, zb, 0, S + MD, f16s(S + MD, M3D - MD, d.M, d.D)));
+                                           lw.qkvb + d.D, zb, 0, S + MD));
         TE_TRY(te_zplus_linear_relprop_ldr(a.h, d.D, lw.qkvw + 2 * DD, dw.v, Rqkv + 2 * d.D, 3 * d.D, R3, S, d.M, d.D, d.D, st,
-                                           a.qkv + 2 * d.D, 3 * d.D, lw.qkvb + 2 * d.D, zb, 0, S + MD, f16s(S + MD, M3D - MD, d.M, d.D)));
+                                           a.qkv + 2 * d.D, 3 * d.D, lw.qkvb + 2 * d.D, zb, 0, S + MD));
         TE_TRY(te_launch_clone_relprop(a.h, R, R1, R3, SF, MD, st));                      // self.clone (3-way)
         TE_TRY(te_launch_clone_relprop(a.h, SF, R2, nullptr, R, MD, st));                 // attention.clone
     }

@@ -26,10 +26,9 @@ int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* deriv
                                float* s_scratch, long long rows, int in_features, int out_features, cudaStream_t st,
                                const float* y = nullptr, long long ldy = 0, const float* bias = nullptr,
                                int bf16 = 0 /* bit 0: round-1 bf16 R kernel (flag 64); bit 1: bf16 single-pass S kernel (flag 2048);
-                                               bit 2: fp16 R kernel (flag 8192, needs f16s) */,
+                                               bit 2: fp16 R kernel fed by the S kernel's fp16 epilogue (flag 8192) */,
                                long long ld_out = 0 /* row stride of out; 0 = in_features */,
-                               float* xabs = nullptr /* scratch [rows, in]: enables the persistent pair kernels */,
-                               float* f16s = nullptr /* scratch of te_zplus_f16_scratch_floats(rows, out) floats */);
+                               float* xabs = nullptr /* scratch [rows, in]: enables the persistent pair kernels */);
 
 // fp32-grade (3xTF32 split) Linear GEMMs on tcgen05; epilogues mirror the SIMT ones
 enum { TE_TC_EPI_STORE = 0, TE_TC_EPI_BIAS = 1, TE_TC_EPI_BIAS_GELU = 2, TE_TC_EPI_BIAS_ADD = 3, TE_TC_EPI_GELU_BWD = 4 };

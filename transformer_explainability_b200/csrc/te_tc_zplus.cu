@@ -601,8 +601,7 @@ int te_tc_prepare_weights(const float* w, float* derived, int in_features, int o
 
 int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* derived, const float* r, long long ldr,
                                float* out, float* s_scratch, long long rows, int in_features, int out_features, cudaStream_t st,
-                               const float* y, long long ldy, const float* bias, int bf16, long long ld_out, float* xabs,
-                               float* f16s) {
+                               const float* y, long long ldy, const float* bias, int bf16, long long ld_out, float* xabs) {
     if (ld_out == 0) ld_out = in_features;
     if (!a16(x) || !a16(derived) || !a16(r) || !a16(out) || !a16(s_scratch)) {
         te_set_last_error("te_gemm_tc: operands must be 16-byte aligned");
@@ -618,7 +617,7 @@ int te_tc_zplus_linear_relprop(const float* x, long long ldx, const float* deriv
         if ((bf16 & 4) && te_tc_f16_single_supported(rows, out_features, in_features, out_features)) {
             // second contraction on kind::f16 (te_tc_fwd16.cu, FM_R).  Its A operand — S as hi-only block-scaled fp16 — is written
             // by the S kernel's epilogue straight into s_scratch ([rows, out] fp16, then the [rows, out/128] scales): rows*out
-            // floats hold both (out/2 + out/128 <= out).  f16s is not needed on this path.
+            // floats hold both (out/2 + out/128 <= out).
             float* s16_scale = s_scratch + ((rows * out_features / 2 + 63) & ~63LL);
             TE_TRY(te_tc_pair_zplus_s1(x, ldx, xabs, derived, r, ldr, y, ldy, bias, nullptr, rows, in_features, out_features, st,
                                        (bf16 & 2) != 0, s_scratch, s16_scale));

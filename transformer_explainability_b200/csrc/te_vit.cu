@@ -359,7 +359,7 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
     Weights w;
     bind_weights(cfg, weights, w);
     const float scale = 1.0f / sqrtf((float)d.dh);
-    const long long MD = d.M * d.D, MF = d.M * d.F, M3D = d.M * 3LL * d.D;
+    const long long MD = d.M * d.D;
     const int low = (flags & (TE_FLAG_KEEP_ALL_CAMS | TE_FLAG_RELPROP_TO_INPUT)) ? 0 : start_layer;   // lowest block the relprop must reach
     const float* dbase = (flags & TE_FLAG_ZPLUS_TENSOR_CORES) ? derived : nullptr;
     if ((flags & (TE_FLAG_ZPLUS_TENSOR_CORES | TE_FLAG_LINEAR_TENSOR_CORES)) && !derived) {
@@ -433,12 +433,9 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
     // z+ rule / Add rule of the selected rule library (layers_ours, or layers_lrp with TE_FLAG_RULES_LRP)
     auto zrule = [&](const float* x, long long ldx, const float* wt, const float* dwt, const float* r, long long ldr, float* out,
                      float* sbuf, long long rows, int in, int outf, const float* y, long long ldy, const float* bias,
-                     long long ld_out, float* xabs, long long xcap = 0) -> int {
+                     long long ld_out, float* xabs) -> int {
         if (lrpv) return te_zplus_linear_relprop_lrp(x, ldx, wt, r, ldr, out, sbuf, rows, in, outf, st);
-        // the fp16 R kernel's operand scratch reuses the |x| scratch (xcap floats available there): |x| is dead once S exists
-        float* f16s = (xabs && te_zplus_f16_scratch_floats(rows, outf) <= xcap) ? xabs : nullptr;
-        return te_zplus_linear_relprop_ldr(x, ldx, wt, dwt, r, ldr, out, sbuf, rows, in, outf, st, y, ldy, bias, zb, ld_out, xabs,
-                                           f16s);
+        return te_zplus_linear_relprop_ldr(x, ldx, wt, dwt, r, ldr, out, sbuf, rows, in, outf, st, y, ldy, bias, zb, ld_out, xabs);
     };
     auto addrule = [&](const float* x1, const float* x2, const float* r, float* r1, float* r2) -> int {
         return te_launch_add_relprop(x1, x2, r, r1, r2, lrpv ? nullptr : ws.addpart, d.B, (long long)d.N * d.D, st);
@@ -466,14 +463,13 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
         const long long zr = top ? d.B : d.M;                          // rows the z+ rules of this block touch
         const long long sD = top ? (long long)d.N * d.D : d.D, sF = top ? (long long)d.N * d.F : d.F;
         TE_TRY(addrule(a.x_mid, a.mlp_out, R, R1, R2));                                                            // add2
-        TE_TRY(zrule(a.g, sF, bw.fc2w, dw.fc2, R2, sD, RF, S, zr, d.F, d.D, a.mlp_out, sD, bw.fc2b, sF, SF, MF));  // fc2 ; GELU id
-        TE_TRY(zrule(a.xn2, sD, bw.fc1w, dw.fc1, RF, sF, R2, SF, zr, d.D, d.F, a.h, sF, bw.fc1b, sD, S, M3D));     // fc1 ; norm2 id
+        TE_TRY(zrule(a.g, sF, bw.fc2w, dw.fc2, R2, sD, RF, S, zr, d.F, d.D, a.mlp_out, sD, bw.fc2b, sF, SF));      // fc2 ; GELU id
+        TE_TRY(zrule(a.xn2, sD, bw.fc1w, dw.fc1, RF, sF, R2, SF, zr, d.D, d.F, a.h, sF, bw.fc1b, sD, S));          // fc1 ; norm2 id
         TE_TRY(te_launch_clone_relprop(a.x_mid, R1, R2, nullptr, R, MD, st));                                      // clone2
         TE_TRY(addrule(a.x_in, a.attn_out, R, R1, R2));                                                            // add1
         // Attention.relprop :154-177
         if (top) TE_TRY(te_launch_fill(R3, 0.f, MD, st));                                   // rows the strided rule does not write
-        TE_TRY(zrule(a.ctx, sD, bw.projw, dw.proj, R2, sD, R3, S, zr, d.D, d.D, a.attn_out, sD, bw.projb, sD, S + MD,
-                     M3D - MD));   // proj
+        TE_TRY(zrule(a.ctx, sD, bw.projw, dw.proj, R2, sD, R3, S, zr, d.D, d.D, a.attn_out, sD, bw.projb, sD, S + MD));   // proj
         // matmul2 rule: Z = attn v is the saved ctx itself (bit-identical recomputation in the reference)
         TE_TRY(te_launch_sd(R3, a.ctx, S, MD, st));
         TE_TRY(te_util::attn_nn(atc, d.B, d.H, d.N, d.NP, d.dh, S, d.D, a.qkv + 2 * d.D, 3 * d.D, a.cam, a.P, 0.5f,
@@ -488,7 +484,7 @@ extern "C" int te_vit_attribute(const te_vit_config* cfg, const float* weights, 
                                 TE_EPI_MUL, st, rtf));                                   // cam_q
         TE_TRY(te_util::attn_nk(atc, d.B, d.H, d.N, d.NP, d.dh, S1, 1, a.qkv, 3 * d.D, Rqkv + d.D, 3 * d.D, a.qkv + d.D, 0.5f,
                                 TE_EPI_MUL, st, rtf));                                   // cam_k
-        TE_TRY(zrule(a.xn1, d.D, bw.qkvw, dw.qkv, Rqkv, 3 * d.D, R2, S, d.M, d.D, 3 * d.D, a.qkv, 3 * d.D, bw.qkvb, 0, RF, MF));   // qkv ; norm1 id
+        TE_TRY(zrule(a.xn1, d.D, bw.qkvw, dw.qkv, Rqkv, 3 * d.D, R2, S, d.M, d.D, 3 * d.D, a.qkv, 3 * d.D, bw.qkvb, 0, RF));   // qkv ; norm1 id
         TE_TRY(te_launch_clone_relprop(a.x_in, R1, R2, nullptr, R, MD, st));                                       // clone1
     }
 

@@ -16,10 +16,9 @@ int te_zplus_linear_relprop_ldr(const float* x, long long ldx, const float* w, c
                                 long long ldr, float* out, float* s_scratch, long long rows, int in_features,
                                 int out_features, cudaStream_t st, const float* y = nullptr, long long ldy = 0,
                                 const float* bias = nullptr, int bf16 = 0, long long ld_out = 0,
-                                float* xabs = nullptr, float* f16s = nullptr);
+                                float* xabs = nullptr);
 // bf16: bit 0 round-1 bf16 R kernel (TE_FLAG_ZPLUS_BF16), bit 1 bf16 |x||W|^T term (TE_FLAG_ZPLUS_S1_BF16), bit 2 second
-// contraction on tcgen05 kind::f16 with a block-scaled fp16 S (TE_FLAG_ZPLUS_R_F16; needs f16s)
-// f16s: scratch of te_zplus_f16_scratch_floats(rows, out) floats (may alias xabs: it is written after the S kernel has finished)
+// contraction on tcgen05 kind::f16 with a block-scaled fp16 S written by the S kernel's epilogue (TE_FLAG_ZPLUS_R_F16)
 // xabs: scratch [rows, in] (the tf32(|x|) operand of the persistent single-pass S kernel); without it the tensor-core path
 // uses the round-1 kernels.
 // ld_out: row stride of out (0 = in_features).  With row strides on x, r, y and out the rule runs on a strided subset of
@@ -29,7 +28,3 @@ int te_zplus_linear_relprop_ldr(const float* x, long long ldx, const float* w, c
 // S2 = sd(R, x- W-^T) (separate denominators), R_in = x+ * (S1 W+) + x- * (S2 W-).  fp32 SIMT; s_scratch [rows, out].
 int te_zplus_linear_relprop_lrp(const float* x, long long ldx, const float* w, const float* r, long long ldr, float* out,
                                 float* s_scratch, long long rows, int in_features, int out_features, cudaStream_t st);
-// floats of the f16s scratch: hi-only block-scaled fp16 split of S [rows, out] (64-float aligned) + [rows, ceil(out/128)] scales
-static inline long long te_zplus_f16_scratch_floats(long long rows, int out_features) {
-    return ((rows * out_features / 2 + 63) & ~63LL) + rows * ((out_features + 127) / 128);
-}

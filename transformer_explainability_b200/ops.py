@@ -137,9 +137,7 @@ def linear_relprop(x, w, r, tensor_cores=False, y=None, bias=None, bf16=False, v
     out = torch.empty_like(x)
     nscratch = rows * w.shape[0]
     if tensor_cores:
-        nscratch = (nscratch + 63) // 64 * 64 + 16 * w.numel() + (x.numel() + 63) // 64 * 64
-        if r_f16:           # fp16 operand of the second contraction (TE_FLAG_ZPLUS_R_F16): hi-only split of S + block scales
-            nscratch += (rows * w.shape[0] // 2 + 63) // 64 * 64 + rows * ((w.shape[0] + 127) // 128)
+        nscratch = (nscratch + 63) // 64 * 64 + 16 * w.numel() + x.numel()
     scratch = torch.empty(nscratch, device=x.device, dtype=torch.float32)
     flags = _lib.FLAG_ZPLUS_TENSOR_CORES if tensor_cores else 0
     if r_f16:
