@@ -1,4 +1,5 @@
 // C-ABI wrappers for the stand-alone rules and rollout entry points declared in include/te_b200.h.
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 #include <string>
@@ -187,6 +188,15 @@ extern "C" int te_matmul_qk_relprop(const float* q, const float* k, const float*
 static int g_cls_rows = 1;
 bool te_engine_cls_rows() { return g_cls_rows != 0; }
 void te_engine_set_cls_rows(int on) { g_cls_rows = on ? 1 : 0; }
+static int g_gelu_split = -1;
+bool te_engine_gelu_split() {
+    if (g_gelu_split < 0) {
+        const char* e = getenv("TE_B200_GELU_SPLIT");
+        g_gelu_split = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_gelu_split != 0;
+}
+void te_engine_set_gelu_split(int on) { g_gelu_split = on ? 1 : 0; }
 
 extern "C" int te_set_option(const char* name, int value) {
     REQ(name != nullptr, "te_set_option: null name");
@@ -196,6 +206,7 @@ extern "C" int te_set_option(const char* name, int value) {
     if (strcmp(name, "linear_mixed") == 0) { te_tc_set_mixed_linear(value); return TE_OK; }
     if (strcmp(name, "zplus_persistent") == 0) { te_tc_set_zplus_persistent(value); return TE_OK; }
     if (strcmp(name, "cls_row_top_block") == 0) { te_engine_set_cls_rows(value); return TE_OK; }
+    if (strcmp(name, "gelu_split_fused") == 0) { te_engine_set_gelu_split(value); return TE_OK; }
     te_set_last_error("te_set_option: unknown option");
     return TE_ERR_ARG;
 }

@@ -273,7 +273,9 @@ extern "C" int te_bert_forward(const te_bert_config* cfg, const float* weights, 
                      te_tc_fwd16_supported(d.M, d.F, d.D, d.F);
     const te_util::F16Split fsA_ready = {ws.tD[1], ws.tD[2], true};
     const te_util::F16Split fsA_pre = {ws.tD[1], ws.tD[2], false};
-    const te_util::F16Split fsB_pre = {ws.tF[1], ws.tD[3], false};
+    const bool gsf = te_engine_gelu_split();
+    const te_util::F16Split fsA_w1 = {ws.tD[1], ws.tD[2], true, gsf ? ws.tF[1] : nullptr, gsf ? ws.tD[3] : nullptr};
+    const te_util::F16Split fsB = {ws.tF[1], ws.tD[3], gsf};
     auto layernorm = [&](const float* x, const float* g, const float* b, float* y, float* mean, float* rstd) {
         return f16 ? te_launch_layernorm_split(x, g, b, y, mean, rstd, d.M, d.D, d.eps, ws.tD[1], ws.tD[2], st)
                    : te_launch_layernorm(x, g, b, y, mean, rstd, d.M, d.D, d.eps, st);
@@ -308,9 +310,9 @@ extern "C" int te_bert_forward(const te_bert_config* cfg, const float* weights, 
         TE_TRY(layernorm(a.s1, lw.ln1w, lw.ln1b, a.ao, a.mean1, a.rstd1));
         // BertIntermediate (dense + GELU), BertOutput (dense -> add -> LayerNorm)
         TE_TRY(linear_fwd_tc(tw.w1, a.ao, d.D, lw.w1, lw.b1, a.hpre, a.g, nullptr, d.M, d.D, d.F, TE_EPI_BIAS_GELU, st,
-                             f16 ? &fsA_ready : nullptr));
+                             f16 ? &fsA_w1 : nullptr));
         TE_TRY(linear_fwd_tc(tw.w2, a.g, d.F, lw.w2, lw.b2, a.d2, a.s2, a.ao, d.M, d.F, d.D, TE_EPI_BIAS_ADD, st,
-                             f16 ? &fsB_pre : nullptr));
+                             f16 ? &fsB : nullptr));
         TE_TRY(layernorm(a.s2, lw.ln2w, lw.ln2b, h_next, a.mean2, a.rstd2));
     }
     // pooler (first token -> dense -> tanh), classifier

@@ -34,6 +34,15 @@ __device__ __forceinline__ T te_sd(T a, T b) {
     return (a / den) * ((b != (T)0) ? (T)1 : (T)0);
 }
 
+// same rule with the quotient as a * rcp.approx(den) (2 ulp; |den| < 2^126): epilogues of the tensor-core attention kernels, whose
+// operands are already products of rounded factors
+__device__ __forceinline__ float te_sd_fast(float a, float b) {
+    const float eps = 1e-9f;
+    float den = b + eps;
+    den = (den == 0.f) ? eps : den;
+    return __fdividef(a, den) * ((b != 0.f) ? 1.f : 0.f);          // non-finite a keeps the reference's NaN (x * 0)
+}
+
 __device__ __forceinline__ float te_gelu(float x) {           // exact (erf) GELU, nn.GELU default
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
@@ -41,6 +50,22 @@ __device__ __forceinline__ float te_gelu_grad(float x) {
     const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
     const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
     return cdf + x * pdf;
+}
+
+// GELU'(x) = Phi(x) + x phi(x) for the single-pass (TF32-grade) backward epilogues: erf by Abramowitz-Stegun 7.1.26 (absolute
+// error 1.5e-7), one ex2.approx shared by erf's exp(-x^2/2) and the density — ~15 instructions against ~45 for erff + expf.
+__device__ __forceinline__ float te_gelu_grad_fast(float x) {
+    const float ax = fabsf(x);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-0.72134752044448170368f * x * x));        // exp(-x^2 / 2)
+    const float t = __frcp_rn(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float erfa = fmaf(-p * t, e, 1.0f);                     // erf(|x| / sqrt 2)
+    const float cdf = 0.5f * (1.0f + copysignf(erfa, x));
+    return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 
 __device__ __forceinline__ float te_warp_sum(float v) {

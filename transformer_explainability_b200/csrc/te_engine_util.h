@@ -10,6 +10,10 @@
 // restores the all-rows form for A/B comparison
 bool te_engine_cls_rows();
 void te_engine_set_cls_rows(int on);
+// 1 (default): with TE_FLAG_LINEAR_F16_SPLIT the fc1 GEMM's GELU epilogue emits the fp16 split of gelu(y) for the fc2 GEMM;
+// te_set_option("gelu_split_fused", 0) / TE_B200_GELU_SPLIT=0 restores the stand-alone pre-pass
+bool te_engine_gelu_split();
+void te_engine_set_gelu_split(int on);
 
 namespace te_util {
 
@@ -39,13 +43,15 @@ static inline int linear_bwd(const float* dy, const float* w, float* dx, const f
 
 // tensor-core (3xTF32) variants when the derived weight copies are supplied and the shape qualifies
 // fp16-split forward Linear (TE_FLAG_LINEAR_F16_SPLIT, te_tc_fwd16.cu): where the block-scaled split of the input lives
-// (M*in floats + M*ceil(in/128) floats) and whether its producer already filled it (ready: te_launch_layernorm_split)
-struct F16Split { float* split; float* scale; bool ready; };
+// (M*in floats + M*ceil(in/128) floats), whether its producer already filled it (ready: te_launch_layernorm_split or the previous
+// GEMM's GELU epilogue), and where the GELU epilogue puts the split of y2 for the next Linear (may be NULL)
+struct F16Split { float* split; float* scale; bool ready; float* split_out; float* scale_out; };
 static inline int linear_fwd_tc(const float* dw, const float* x, int lda, const float* w, const float* bias, float* y,
                                 float* y2, const float* e0, long long M, int in, int out, int epi, cudaStream_t st,
                                 const F16Split* fs = nullptr) {
     if (dw && fs && fs->split && epi != TE_EPI_GELU_BWD && te_tc_fwd16_supported(M, in, out, lda))
-        return te_tc_linear_fwd16(fs->ready ? nullptr : x, lda, fs->split, fs->scale, dw, in, out, bias, y, y2, e0, M, epi, st);
+        return te_tc_linear_fwd16(fs->ready ? nullptr : x, lda, fs->split, fs->scale, dw, in, out, bias, y, y2, e0, M, epi, st,
+                                  epi == TE_EPI_BIAS_GELU ? fs->split_out : nullptr, epi == TE_EPI_BIAS_GELU ? fs->scale_out : nullptr);
     if (dw && te_tc_gemm3x_supported(M, in, out, lda))
         return te_tc_linear_fwd(x, lda, dw, in, out, bias, y, y2, e0, M, epi, st);      // epilogue ids coincide
     return linear_fwd(x, lda, w, bias, y, y2, e0, M, in, out, epi, st);

@@ -47,10 +47,10 @@ int te_tc_rowsplit_f16(const float* x, long long ldx, long long rows, int cols, 
 int te_tc_blocksplit_f16(const float* x, long long ldx, long long rows, int cols, float* split, float* scale_inv, cudaStream_t st,
                          bool hi_only = false);
 // x != NULL: split / scale are scratch filled by the pre-pass; x == NULL: they were filled by the producer of x
-// (te_launch_layernorm_split)
+// (te_launch_layernorm_split or the split_out / scale_out of the previous call, TE_TC_EPI_BIAS_GELU only: the split of y2)
 int te_tc_linear_fwd16(const float* x, long long ldx, float* split, float* scale, const float* derived, int in_features,
                        int out_features, const float* bias, float* y, float* y2, const float* e0, long long rows, int epi,
-                       cudaStream_t st);
+                       cudaStream_t st, float* split_out = nullptr, float* scale_out = nullptr);
 // single-pass fp16 products on the same kernel (A = hi only: fp16 keeps TF32's 11 significant bits, rounded to nearest)
 bool te_tc_f16_single_supported(long long rows, int K, int N, long long lda);
 // dx = epi(dy W): split (rows*out/2 floats) / scale ([rows, ceil(out/128)]) hold the hi-only split of dy (dy != NULL: pre-pass here)

@@ -20,6 +20,13 @@ namespace {
 constexpr int AT_SMEM = 2 * (A_BYTES + B_BYTES) + 1024 + 256;
 enum { AT_STORE = 0, AT_MUL = 1, AT_SD = 2, AT_RESID = 3, AT_SOFTMAX = 4 };
 
+// 2^x for x <= 0 in one MUFU instruction (ex2.approx.ftz: 2^-22 relative; results below the normal range flush to 0)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 struct AtParams {
     int N, H, dh, ld_out;            // tokens, heads, head_dim, row stride of out / E
     const float* E; float* out; float alpha;
@@ -42,26 +49,43 @@ __device__ __forceinline__ void attn_nn_epilogue(const AtParams& p, uint32_t tla
                 uint32_t acc[32];
                 tmem_ld32(tlane + (uint32_t)(cc * 32), acc);
                 tmem_ld_wait();
+                if (cc * 32 + 32 <= ncols) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (cc * 32 + j < ncols) mx = fmaxf(mx, p.alpha * __uint_as_float(acc[j]));
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, p.alpha * __uint_as_float(acc[j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (cc * 32 + j < ncols) mx = fmaxf(mx, p.alpha * __uint_as_float(acc[j]));
+                }
             }
-            // pass 2: e = exp(score - max), summed, and written back over the scores in TMEM (one expf per element)
+            // pass 2: e = exp(score - max) = 2^(alpha log2e * acc - max log2e): one fma (single rounding of the argument) + ex2.approx
+            // (2^-22 relative) per element, summed, and written back over the scores in TMEM
             float sum = 0.f;
+            const float a2 = p.alpha * 1.4426950408889634f, m2 = -mx * 1.4426950408889634f;
 #pragma unroll 1
             for (int cc = 0; cc < nchunks; ++cc) {
                 uint32_t acc[32];
                 tmem_ld32(tlane + (uint32_t)(cc * 32), acc);
                 tmem_ld_wait();
+                if (cc * 32 + 32 <= ncols) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float e = (cc * 32 + j < ncols) ? expf(p.alpha * __uint_as_float(acc[j]) - mx) : 0.f;
-                    sum += e;
-                    acc[j] = __float_as_uint(e);
+                    for (int j = 0; j < 32; ++j) {
+                        const float e = ex2_approx(fmaf(a2, __uint_as_float(acc[j]), m2));
+                        sum += e;
+                        acc[j] = __float_as_uint(e);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float e = (cc * 32 + j < ncols) ? ex2_approx(fmaf(a2, __uint_as_float(acc[j]), m2)) : 0.f;
+                        sum += e;
+                        acc[j] = __float_as_uint(e);
+                    }
                 }
                 tmem_st32(tlane + (uint32_t)(cc * 32), acc);
             }
             tmem_st_wait();
+            const float inv = 1.0f / sum;
             // pass 3: normalise in the row layout, store in the transposed (coalesced) layout of epi_read_t
 #pragma unroll 1
             for (int cc = 0; cc < nchunks; ++cc) {
@@ -69,7 +93,7 @@ __device__ __forceinline__ void attn_nn_epilogue(const AtParams& p, uint32_t tla
                 tmem_ld32(tlane + (uint32_t)(cc * 32), acc);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) / sum);   // padding holds e = 0
+                for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) * inv);   // padding holds e = 0
                 epi_stage_rows(stage, lane, acc);
                 const int col = cc * 32 + tc;
 #pragma unroll
@@ -113,7 +137,7 @@ __device__ __forceinline__ void attn_nn_epilogue(const AtParams& p, uint32_t tla
                     float v;
                     if (EPI == AT_STORE) v = av;
                     else if (EPI == AT_MUL) v = av * e[u];
-                    else v = te_sd(e[u], av);
+                    else v = te_sd_fast(e[u], av);
                     o[u] = (col + u < ncols) ? v : 0.f;                                  // zero the row padding
                 }
                 *reinterpret_cast<float4*>(p.out + ((long long)bh * p.N + r) * p.ld_out + n0 + col) = make_float4(o[0], o[1], o[2], o[3]);
@@ -225,7 +249,7 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         // split A (16 KiB) and B (32 KiB) of every k-block: hi in place, lo to the *_lo regions (same swizzled offsets)
         for (int kk = 0; kk < (SP ? 0 : kb); ++kk) {
-            mbar_wait(full_bar, (uint32_t)(kk & 1));
+            mbar_wait_sleep(full_bar, (uint32_t)(kk & 1));
             float4* a4 = reinterpret_cast<float4*>(smem_al + OFF_AH);
             float4* l4 = reinterpret_cast<float4*>(smem_al + OFF_AL);
 #pragma unroll
@@ -256,7 +280,7 @@ te_tc_attn_nn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int ncols = min(p.N - n0, BN);              // valid key columns of this tile
         // per-warp staging buffer of the coalesced epilogue: the operand buffer is idle once the accumulator is complete
         float* stage = reinterpret_cast<float*>(smem_al + (warp - 2) * EPI_STAGE_BYTES);
-        mbar_wait(accum_bar, 0);
+        mbar_wait_sleep(accum_bar, 0);
         tcgen05_fence_after();
         attn_nn_epilogue<EPI, SP>(p, tlane, stage, lane, q, bh, m0, n0, ncols);
     }
@@ -595,7 +619,7 @@ te_tc_attn_nk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int it = 0; it < (SP ? 0 : kb); ++it) {
             const int s = it % NK_STAGES;
             const uint32_t ph = (it / NK_STAGES) & 1u;
-            mbar_wait(full_bar(s), ph);
+            mbar_wait_sleep(full_bar(s), ph);
             // split A_hi (16 KiB) and B_hi (8 KiB) slots -> hi in place, lo into the matching *_lo slot
             float4* base4 = reinterpret_cast<float4*>(smem_al + s * NK_STAGE);
             for (int i = et; i < NK_XF4; i += XF_THREADS) {
@@ -621,7 +645,7 @@ te_tc_attn_nk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
             for (int j = 0; j < NB * 8; ++j) ebuf[j] = *reinterpret_cast<const float4*>(p.E + off + j * 4);
         }
-        mbar_wait(accum_bar, 0);
+        mbar_wait_sleep(accum_bar, 0);
         tcgen05_fence_after();
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
         const float rscale = (EPI == AT_RESID && live && p.rowscale) ? p.rowscale[(long long)b * p.N + m] : 1.f;

@@ -43,6 +43,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}\n" ::"r"(bar), "r"(parity)
         : "memory");
 }
+// Same wait for warps that expect to wait LONG (epilogue warps waiting for a whole tile's MMAs, split warps waiting for a TMA round
+// trip) while a co-resident CTA's warps do useful work on the same schedulers: back off between polls instead of spinning
+// (ncu of the N x N attention kernels: SYNCS + BRA + YIELD of waiting warps were 17 % of all issued instructions).
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(32);
+    }
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),

@@ -58,7 +58,11 @@ template <int MODE> struct FCfg {
     // time, so 16 warps share it (64 accumulator columns per thread instead of 128)
     static constexpr int DW = (MODE == FM_FWD3) ? 8 : 16;
     static constexpr int CW = 256 / (DW / 4);                             // accumulator columns (= register sums) per drain thread
-    static constexpr int THREADS = 64 + 32 * DW;
+    // FWD3: 12 warps = 3 warpgroups — {TMA, MMA, 2 idle} gives registers back (setmaxnreg 40) and the two drain warpgroups take
+    // them (232 each: 128 sums + the epilogue's staging without spilling; ncu of the 168-register build showed the GELU epilogue
+    // waiting on local-memory loads that missed the 8 KiB L1 left beside 218 KiB of shared memory).  Single-pass modes: 2 + 16 warps.
+    static constexpr int W0 = (MODE == FM_FWD3) ? 4 : 2;                  // first drain warp
+    static constexpr int THREADS = 32 * (W0 + DW);
     static constexpr int NBARS = 2 * NST + 4;
     static constexpr int SMEM = NST * STAGE + DW * EPI16_STAGE_BYTES + 1024 + 8 * NBARS + 16;
     // cta_group::2, fp16 operands (a/b format 0), fp32 accumulate, M = 256, N = TN
@@ -73,13 +77,19 @@ struct F16Params {
     const float* cs1;                     // FM_R: [N] of W-^T
     const float* bias; const float* E; long long lde;      // E: residual (BIAS_ADD) / pre-activation (GELU_BWD) / x (FM_R)
     float* C; long long ldc; float* C2; long long ldc2;
+    __half* hi2; __half* lo2; float* rs2;  // SPLIT epilogue: block-scaled split of C2 [M, N] and its scales [M, N/128]
 };
 
 // sum: one accumulator row x CW columns per thread.  Global memory is accessed in the transposed layout of epi16_read_t (8 rows x
 // 64 contiguous bytes per warp instruction).
-template <int EPI, int CW>
+// SPLIT (GELU epilogue of the 232-register FWD3 build, CW = 128): the warp's 32 rows x 128 columns of C2 = gelu(...) are one scale
+// block per row of the NEXT Linear's A operand: the values stay in registers, the row maxima are reduced over the 4 lanes that share
+// a row, and hi / lo / scale are written next to the fp32 tensors — the next GEMM needs no pre-pass.
+template <int EPI, int CW, bool SPLIT = false>
 __device__ __forceinline__ void fwd16_epilogue(const F16Params& p, const float (&sum)[CW], float* stage, int lane, int row0, int cbase) {
     const int tr = lane >> 2, tc = 4 * (lane & 3);
+    float4 g[SPLIT ? CW / 4 : 1];
+    float rmax[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int cc = 0; cc < CW / 16; ++cc) {
         float v[16];
@@ -93,12 +103,17 @@ __device__ __forceinline__ void fwd16_epilogue(const F16Params& p, const float (
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int row = row0 + 8 * i + tr;
-            if (row >= p.M) continue;
+            if (!SPLIT && row >= p.M) continue;
             float4 a = epi16_read_t(stage, lane, i);
             a.x *= cs.x; a.y *= cs.y; a.z *= cs.z; a.w *= cs.w;                         // exact (powers of two)
             float4 o = make_float4(a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w), o2 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (EPI == FP_BIAS_GELU) {
                 o2 = make_float4(te_gelu(o.x), te_gelu(o.y), te_gelu(o.z), te_gelu(o.w));
+                if (SPLIT) {
+                    g[cc * 4 + i] = o2;
+                    rmax[i] = fmaxf(rmax[i], te_absmax4(o2));
+                    if (row >= p.M) continue;
+                }
             } else if (EPI == FP_BIAS_ADD) {
                 const float4 e = *reinterpret_cast<const float4*>(p.E + (long long)row * p.lde + col);
                 o2 = make_float4(e.x + o.x, e.y + o.y, e.z + o.z, e.w + o.w);
@@ -108,6 +123,28 @@ __device__ __forceinline__ void fwd16_epilogue(const F16Params& p, const float (
             }
             *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) = o;
             if (EPI == FP_BIAS_GELU || EPI == FP_BIAS_ADD) *reinterpret_cast<float4*>(p.C2 + (long long)row * p.ldc2 + col) = o2;
+        }
+    }
+    if (SPLIT) {
+        const int nblk = p.N / 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float m = rmax[i];
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            float sc, si;
+            te_f16_block_scale(m, sc, si);
+            const int row = row0 + 8 * i + tr;
+            if (row >= p.M) continue;
+            if ((lane & 3) == 0) p.rs2[(long long)row * nblk + cbase / 128] = si;
+#pragma unroll
+            for (int cc = 0; cc < CW / 16; ++cc) {
+                uint2 h, l;
+                te_f16_split4(g[cc * 4 + i], sc, h, l);
+                const long long off = (long long)row * p.N + cbase + cc * 16 + tc;
+                *reinterpret_cast<uint2*>(p.hi2 + off) = h;
+                *reinterpret_cast<uint2*>(p.lo2 + off) = l;
+            }
         }
     }
 }
@@ -151,7 +188,7 @@ __device__ __forceinline__ void r16_epilogue(const F16Params& p, const float (&s
     }
 }
 
-template <int MODE, int EPI>
+template <int MODE, int EPI, bool SPLIT = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FCfg<MODE>::THREADS, 1)
 te_tc_fwd16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const F16Params p) {
@@ -205,6 +242,10 @@ te_tc_fwd16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    if (warp < Cfg::W0) {
+    // register reallocation between the warpgroups (see FCfg): issued inside the role branches so that the allocator sees which
+    // budget governs which code
+    if (MODE == FM_FWD3) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0) {
         // ================= TMA producer (both CTAs: own activation rows + own half of the weight tile) =================
         if (lane == 0) {
@@ -262,14 +303,16 @@ te_tc_fwd16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
             }
         }
         __syncwarp();
+    }
     } else {
-        // ================= chunk drain + epilogue: warps 2 .. 2 + DW =================
+        if (MODE == FM_FWD3) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        // ================= chunk drain + epilogue: warps W0 .. W0 + DW =================
         // lane quarter q = warp % 4 (the TMEM lanes a warp may read); column group cg: FWD3 / LIN1 own CW consecutive accumulator
         // columns, FM_R owns 32 columns of BOTH 128-column products (sum[0..31] = S W+, sum[32..63] = S W-)
         const int q = warp & 3;
-        const int cg = (warp - 2) >> 2;
+        const int cg = (warp - Cfg::W0) >> 2;
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * (MODE == FM_R ? 32 : CW));
-        float* stage = reinterpret_cast<float*>(smem_al + RING + (warp - 2) * EPI16_STAGE_BYTES);
+        float* stage = reinterpret_cast<float*>(smem_al + RING + (warp - Cfg::W0) * EPI16_STAGE_BYTES);
         float sum[CW];
         uint32_t gc = 0;
         for (int t = cluster_id; t < ntiles; t += nclusters) {
@@ -300,7 +343,7 @@ te_tc_fwd16_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                 if (lane == 0) mbar_arrive_cluster(map_to_rank0(accfree_bar(b)));
             }
             if constexpr (MODE == FM_R) r16_epilogue(p, sum, stage, lane, m0 + q * 32, n0 + cg * 32);
-            else fwd16_epilogue<EPI, CW>(p, sum, stage, lane, m0 + q * 32, n0 + cg * CW);
+            else fwd16_epilogue<EPI, CW, SPLIT>(p, sum, stage, lane, m0 + q * 32, n0 + cg * CW);
         }
     }
     tcgen05_fence_before();
@@ -389,7 +432,7 @@ int f16_sm_pairs() {
     return c;
 }
 
-template <int MODE, int EPI>
+template <int MODE, int EPI, bool SPLIT = false>
 int launch_f16(const __half* ah, const __half* al, const __half* b0, const __half* b1, F16Params p, cudaStream_t st) {
     using Cfg = FCfg<MODE>;
     CUtensorMap tmAh, tmAl, tmB0, tmB1;
@@ -399,7 +442,7 @@ int launch_f16(const __half* ah, const __half* al, const __half* b0, const __hal
         return TE_ERR_CUDA;
     }
     static unsigned long long optin = 0;
-    if (!smem_optin(te_tc_fwd16_kernel<MODE, EPI>, Cfg::SMEM, optin)) {
+    if (!smem_optin(te_tc_fwd16_kernel<MODE, EPI, SPLIT>, Cfg::SMEM, optin)) {
         te_set_last_error("te_tc_fwd16: cannot raise dynamic shared memory");
         return TE_ERR_CUDA;
     }
@@ -410,7 +453,7 @@ int launch_f16(const __half* ah, const __half* al, const __half* b0, const __hal
     int pairs = f16_sm_pairs();
     if (pairs <= 0) { te_set_last_error("te_tc_fwd16: cannot query the SM count"); return TE_ERR_CUDA; }
     if (pairs > ntiles) pairs = ntiles;
-    te_tc_fwd16_kernel<MODE, EPI><<<dim3(2u * (unsigned)pairs), Cfg::THREADS, Cfg::SMEM, st>>>(tmAh, tmAl, tmB0, tmB1, p);
+    te_tc_fwd16_kernel<MODE, EPI, SPLIT><<<dim3(2u * (unsigned)pairs), Cfg::THREADS, Cfg::SMEM, st>>>(tmAh, tmAl, tmB0, tmB1, p);
     TE_CUDA_CHECK_LAUNCH();
     return TE_OK;
 }
@@ -457,13 +500,16 @@ int te_tc_blocksplit_f16(const float* x, long long ldx, long long rows, int cols
 
 // y[rows,out] = x[rows,in] W^T (+ epilogue), fp32-grade.
 //   split / scale: the block-scaled split of x ([hi | lo] fp16 [rows, in] = rows*in floats; [rows, ceil(in/128)] floats).  x != NULL:
-//   scratch, filled here by the pre-pass.  x == NULL: already filled by the producer of x (te_launch_layernorm_split).
+//   scratch, filled here by the pre-pass.  x == NULL: already filled by the producer of x (te_launch_layernorm_split, or the
+//   split_out / scale_out of the previous call).
+//   split_out / scale_out (TE_TC_EPI_BIAS_GELU only, may be NULL): receive the split of y2 = gelu(y) for the next Linear.
 // The weight split lives in the derived buffer (te_gemm_tc.h).
 int te_tc_linear_fwd16(const float* x, long long ldx, float* split, float* scale, const float* derived, int in_features,
                        int out_features, const float* bias, float* y, float* y2, const float* e0, long long rows, int epi,
-                       cudaStream_t st) {
+                       cudaStream_t st, float* split_out, float* scale_out) {
     const long long n = (long long)in_features * out_features;
-    if (!a16(split) || !scale || !a16(derived) || !a16(y) || (y2 && !a16(y2)) || (e0 && !a16(e0)) || (bias && !a16(bias))) {
+    if (!a16(split) || !scale || !a16(derived) || !a16(y) || (y2 && !a16(y2)) || (e0 && !a16(e0)) || (bias && !a16(bias)) ||
+        (split_out && (!a16(split_out) || !scale_out || epi != TE_TC_EPI_BIAS_GELU))) {
         te_set_last_error("te_tc_linear_fwd16: bad operands");
         return TE_ERR_ARG;
     }
@@ -477,6 +523,12 @@ int te_tc_linear_fwd16(const float* x, long long ldx, float* split, float* scale
     p.M = (int)rows; p.N = out_features; p.K = in_features;
     p.rs = scale; p.rs_ld = (in_features + 127) / 128; p.cs = derived + 12 * n + n / 2;
     p.bias = bias; p.E = e0; p.lde = out_features; p.C = y; p.ldc = out_features; p.C2 = y2; p.ldc2 = out_features;
+    if (split_out) {
+        p.hi2 = reinterpret_cast<__half*>(split_out);
+        p.lo2 = p.hi2 + rows * out_features;
+        p.rs2 = scale_out;
+        return launch_f16<FM_FWD3, FP_BIAS_GELU, true>(ah, al, bh, bl, p, st);
+    }
     switch (epi) {
         case TE_TC_EPI_STORE: return launch_f16<FM_FWD3, FP_STORE>(ah, al, bh, bl, p, st);
         case TE_TC_EPI_BIAS: return launch_f16<FM_FWD3, FP_BIAS>(ah, al, bh, bl, p, st);

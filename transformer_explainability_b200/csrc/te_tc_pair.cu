@@ -276,7 +276,7 @@ te_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         for (int u = 0; u < 4; ++u) {
                             const float z = 0.5f * (yy[u] + aa[u]);
                             if (z < aa[u] * 0.0078125f && aa[u] > 0.f) redo |= 1u << (4 * i + u);
-                            const float sv = te_sd(rr[u], fmaxf(z, 0.f));
+                            const float sv = te_sd_fast(rr[u], fmaxf(z, 0.f));      // 2 ulp; S is rounded to 11 bits right below
                             o[u] = (EPI == PE_F16) ? sv : to_tf32(sv);
                         }
                         r[i] = make_float4(o[0], o[1], o[2], o[3]);          // r[] now holds S
@@ -355,8 +355,8 @@ te_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         // systematic part; what is left is a zero-mean error of the same size as round-to-nearest would give.
                         o.x *= kTruncComp; o.y *= kTruncComp; o.z *= kTruncComp; o.w *= kTruncComp;
                         if (EPI == PE_GELU_BWD) {
-                            o.x *= te_gelu_grad(e[i].x); o.y *= te_gelu_grad(e[i].y);
-                            o.z *= te_gelu_grad(e[i].z); o.w *= te_gelu_grad(e[i].w);
+                            o.x *= te_gelu_grad_fast(e[i].x); o.y *= te_gelu_grad_fast(e[i].y);
+                            o.z *= te_gelu_grad_fast(e[i].z); o.w *= te_gelu_grad_fast(e[i].w);
                         }
                         if (row < p.M) *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) = o;
                     }

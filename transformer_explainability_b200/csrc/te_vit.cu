@@ -257,7 +257,9 @@ extern "C" int te_vit_forward(const te_vit_config* cfg, const float* weights, co
                      te_tc_fwd16_supported(d.M, d.F, d.D, d.F);
     const te_util::F16Split fsA_ready = {ws.tD[1], ws.tD[0], true};
     const te_util::F16Split fsA_pre = {ws.tD[1], ws.tD[0], false};
-    const te_util::F16Split fsB_pre = {ws.tF[1], ws.tD[2], false};
+    const bool gsf = te_engine_gelu_split();
+    const te_util::F16Split fsA_fc1 = {ws.tD[1], ws.tD[0], true, gsf ? ws.tF[1] : nullptr, gsf ? ws.tD[2] : nullptr};
+    const te_util::F16Split fsB = {ws.tF[1], ws.tD[2], gsf};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     Weights w;
     bind_weights(cfg, weights, w);
@@ -301,9 +303,9 @@ extern "C" int te_vit_forward(const te_vit_config* cfg, const float* weights, co
         else
             TE_TRY(te_launch_layernorm(a.x_mid, bw.n2w, bw.n2b, a.xn2, a.mean2, a.rstd2, d.M, d.D, cfg->eps_block, st));
         TE_TRY(te_util::linear_fwd_tc(lw.fc1, a.xn2, d.D, bw.fc1w, bw.fc1b, a.h, a.g, nullptr, d.M, d.D, d.F,
-                                      TE_EPI_BIAS_GELU, st, f16 ? &fsA_ready : nullptr));
+                                      TE_EPI_BIAS_GELU, st, f16 ? &fsA_fc1 : nullptr));
         TE_TRY(te_util::linear_fwd_tc(lw.fc2, a.g, d.F, bw.fc2w, bw.fc2b, a.mlp_out, x_next, a.x_mid, d.M, d.F, d.D,
-                                      TE_EPI_BIAS_ADD, st, f16 ? &fsB_pre : nullptr));
+                                      TE_EPI_BIAS_ADD, st, f16 ? &fsB : nullptr));
     }
     // final norm, pool token 0 (and 1), head(s)                (:318-321)
     TE_TRY(te_launch_layernorm(ws.x_last, w.normw, w.normb, ws.xf, nullptr, nullptr, d.M, d.D, cfg->eps_final, st));
