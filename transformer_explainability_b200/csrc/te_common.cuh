@@ -43,6 +43,12 @@ __device__ __forceinline__ float te_sd_fast(float a, float b) {
     return __fdividef(a, den) * ((b != 0.f) ? 1.f : 0.f);          // non-finite a keeps the reference's NaN (x * 0)
 }
 
+// safe_divide for a denominator that is known to be >= 0 (the z+ rule: a clamped sum of non-negative products): b + eps > 0, so only
+// the (b != 0) mask of the rule remains
+__device__ __forceinline__ float te_sd_fast_nonneg(float a, float b) {
+    return (b > 0.f) ? __fdividef(a, b + 1e-9f) : a * 0.f;            // a * 0 keeps the reference's NaN for a non-finite a
+}
+
 __device__ __forceinline__ float te_gelu(float x) {           // exact (erf) GELU, nn.GELU default
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
@@ -58,7 +64,8 @@ __device__ __forceinline__ float te_gelu_grad_fast(float x) {
     const float ax = fabsf(x);
     float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-0.72134752044448170368f * x * x));        // exp(-x^2 / 2)
-    const float t = __frcp_rn(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f));
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f)));    // argument in [1, inf)
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);

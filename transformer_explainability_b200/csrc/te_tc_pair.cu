@@ -211,6 +211,17 @@ te_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int j = 0; j < BN / 2; j += 32) prefetch_l2(y + j);
                 }
             }
+            // PM_R: its accumulators fill TMEM, so this epilogue is NOT overlapped by the next tile's MMAs — keep it short.  The x operand
+            // does not depend on the accumulators: chunk 0's loads are issued before the wait for the last MMA, and every chunk reloads
+            // its x registers for the NEXT chunk as soon as it has consumed them (software pipeline without extra registers).
+            float4 xr[MODE == PM_R ? 8 : 1];
+            if (MODE == PM_R) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = m0 + 4 * i + tr;
+                    xr[i] = (row < p.M) ? *reinterpret_cast<const float4*>(p.E + (long long)row * p.lde + n0 + tc) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
             mbar_wait(accfull_bar(b), (ti / ACC_BUFS) & 1u);
             tcgen05_fence_after();
             const uint32_t tcol = tlane + b * (uint32_t)(NB * BN) + (uint32_t)(half * (BN / 2));
@@ -223,12 +234,6 @@ te_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (MODE == PM_R) {
                     uint32_t accn[32];
                     tmem_ld32(tcol + (uint32_t)(BN + c * 32), accn);
-                    float4 x[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int row = m0 + 4 * i + tr;
-                        x[i] = (row < p.M) ? *reinterpret_cast<const float4*>(p.E + (long long)row * p.lde + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
                     tmem_ld_wait();
                     epi_stage_rows(stage, lane, acc);
                     float4 ap[8];
@@ -239,11 +244,14 @@ te_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int i = 0; i < 8; ++i) {
                         const float4 an = epi_read_t(stage, lane, i);
                         const int row = m0 + 4 * i + tr;
+                        const float4 x = xr[MODE == PM_R ? i : 0];
                         float4 o;
-                        o.x = fmaxf(x[i].x, 0.f) * ap[i].x + fminf(x[i].x, 0.f) * an.x;
-                        o.y = fmaxf(x[i].y, 0.f) * ap[i].y + fminf(x[i].y, 0.f) * an.y;
-                        o.z = fmaxf(x[i].z, 0.f) * ap[i].z + fminf(x[i].z, 0.f) * an.z;
-                        o.w = fmaxf(x[i].w, 0.f) * ap[i].w + fminf(x[i].w, 0.f) * an.w;
+                        o.x = fmaxf(x.x, 0.f) * ap[i].x + fminf(x.x, 0.f) * an.x;
+                        o.y = fmaxf(x.y, 0.f) * ap[i].y + fminf(x.y, 0.f) * an.y;
+                        o.z = fmaxf(x.z, 0.f) * ap[i].z + fminf(x.z, 0.f) * an.z;
+                        o.w = fmaxf(x.w, 0.f) * ap[i].w + fminf(x.w, 0.f) * an.w;
+                        if (c + 1 < BN / 2 / 32 && row < p.M)                 // next chunk's x into the register just consumed
+                            xr[MODE == PM_R ? i : 0] = *reinterpret_cast<const float4*>(p.E + (long long)row * p.lde + col + 32);
                         if (row < p.M) *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) = o;
                     }
                 } else if (MODE == PM_S1) {
@@ -276,7 +284,7 @@ te_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         for (int u = 0; u < 4; ++u) {
                             const float z = 0.5f * (yy[u] + aa[u]);
                             if (z < aa[u] * 0.0078125f && aa[u] > 0.f) redo |= 1u << (4 * i + u);
-                            const float sv = te_sd_fast(rr[u], fmaxf(z, 0.f));      // 2 ulp; S is rounded to 11 bits right below
+                            const float sv = te_sd_fast_nonneg(rr[u], fmaxf(z, 0.f));      // 2 ulp; S is rounded to 11 bits right below
                             o[u] = (EPI == PE_F16) ? sv : to_tf32(sv);
                         }
                         r[i] = make_float4(o[0], o[1], o[2], o[3]);          // r[] now holds S
