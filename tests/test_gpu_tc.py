@@ -380,3 +380,25 @@ def test_tc_fp16_single_pass_backward(rows, inf, outf):
     print("fp16 backward rows %d in %d out %d: TF32 %.2e  fp16 %.2e (per row, relative to the row maximum)" % (rows, inf, outf, e_tf, e_hf))
     assert torch.isfinite(hf).all() and (hf[rows // 3] == 0).all()
     assert e_hf < 2e-3 and e_hf < 1.5 * e_tf + 1e-4
+
+
+def test_f16_block_split_format_bit_exact():
+    """The operand format of the fp16-split forward Linear, GPU pre-pass against its CPU restatement (oracle/f16_split.py): hi, lo and
+    the block scales are BIT-EXACT (integer / byte work: exact power-of-two scaling, round-to-nearest-even fp16 conversions)."""
+    import numpy as np
+    from oracle import f16_split as F
+    from transformer_explainability_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(300, 768, generator=g) * torch.logspace(-3, 1, 768)
+    x = x * torch.logspace(-30, 30, 300)[:, None]                # rows spanning 60 decades
+    x[7] = 0.0
+    x[9, 5] = float("inf")                                       # a non-finite block keeps scale 1 and propagates
+    hi, lo, si = ops.f16_block_split(x.cuda())
+    torch.cuda.synchronize()
+    with np.errstate(invalid="ignore", over="ignore"):
+        rh, rl, rs = F.split_rows(x.numpy())
+    assert np.array_equal(si.cpu().numpy(), rs)
+    assert np.array_equal(hi.cpu().numpy().view(np.uint16), rh.view(np.uint16))
+    ok = np.ones_like(rh, dtype=bool)
+    ok[9, :128] = False                                          # lo of the non-finite block is inf - inf = NaN (payload unspecified)
+    assert np.array_equal(lo.cpu().numpy().view(np.uint16)[ok], rl.view(np.uint16)[ok])

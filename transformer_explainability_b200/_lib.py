@@ -104,6 +104,7 @@ PROTOTYPES = {
     "te_linear_forward": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "te_linear_forward_ex": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_uint, _P]),
     "te_linear_backward_ex": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_uint, _P]),
+    "te_f16_block_split": (c_int, [_P, c_int, c_int, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -59,6 +59,13 @@ extern "C" int te_linear_forward_ex(const float* x, const float* w, const float*
     return te_linear_forward(x, w, bias, y, rows, in_features, out_features, stream);
 }
 
+extern "C" int te_f16_block_split(const float* x, int rows, int cols, void* hi, void* lo, float* scale_inv, void* stream) {
+    REQ(x && hi && lo && scale_inv && rows > 0 && cols > 0 && cols % 4 == 0, "te_f16_block_split: bad argument");
+    REQ(reinterpret_cast<char*>(lo) == reinterpret_cast<char*>(hi) + (long long)rows * cols * 2,
+        "te_f16_block_split: lo must follow hi ([hi | lo] in one buffer, as the kernels lay the split out)");
+    return te_tc_blocksplit_f16(x, cols, rows, cols, reinterpret_cast<float*>(hi), scale_inv, ST(stream));
+}
+
 extern "C" int te_linear_backward_ex(const float* dy, const float* w, float* dx, float* scratch, int rows, int in_features,
                                      int out_features, unsigned flags, void* stream) {
     REQ(dy && w && dx && rows > 0 && in_features > 0 && out_features > 0, "te_linear_backward_ex: bad argument");

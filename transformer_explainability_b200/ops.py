@@ -79,6 +79,20 @@ def linear_forward(x, w, bias=None, tensor_cores=False, f16_split=False):
 
 
 @_on_device
+def f16_block_split(x):
+    """The block-scaled fp16 (hi, lo) operand format of the fp16-split forward Linear: x [rows, cols] fp32 ->
+    (hi, lo) fp16 [rows, cols], scale_inv fp32 [rows, ceil(cols / 128)]  (see include/te_b200.h: te_f16_block_split)."""
+    _req(x)
+    if x.dim() != 2 or x.shape[1] % 4 != 0:
+        raise ValueError("f16_block_split: x [rows, cols] with cols % 4 == 0 expected")
+    rows, cols = x.shape
+    buf = torch.empty(2, rows, cols, device=x.device, dtype=torch.float16)
+    scale = torch.empty(rows, (cols + 127) // 128, device=x.device, dtype=torch.float32)
+    check(_lib.load().te_f16_block_split(ptr(x), rows, cols, ptr(buf[0]), ptr(buf[1]), ptr(scale), _stream()), "te_f16_block_split")
+    return buf[0], buf[1], scale
+
+
+@_on_device
 def linear_backward(dy, w, tensor_cores=False):
     """dx = dy W  (activation gradient of a Linear; no dW on this path)."""
     _req(dy, w)
