@@ -1,4 +1,4 @@
-// fp32-grade forward Linear GEMM on tcgen05 kind::f16: row-scaled fp16 (hi, lo) split of BOTH operands, three MMAs per k-step
+// fp32-grade forward Linear GEMM on tcgen05 kind::f16: block-scaled fp16 (hi, lo) split of BOTH operands, three MMAs per k-step
 // (hi*hi + lo*hi + hi*lo), persistent CTA pairs, chunked accumulation.
 //
 // Why: the 3xTF32 forward Linears are the largest family of the step (29 %, profiles/r02_results.md) and sit on two limits at
@@ -26,7 +26,10 @@
 // round-to-nearest) while the MMAs of the next chunk run — ACROSS tile boundaries, so the epilogue of tile i overlaps the first
 // chunks of tile i+1.
 //
-// Warp roles (both CTAs): warp 0 TMA producer · warp 1 TMEM allocator + (leader) MMA issuer · warps 2-9 drain + epilogue.
+// Warp roles (both CTAs), FM_FWD3: warpgroup 0 = warp 0 TMA producer · warp 1 TMEM allocator + (leader) MMA issuer · warps 2-3
+// idle; warpgroups 1-2 = warps 4-11 drain + epilogue.  The producer warpgroup gives registers back (setmaxnreg 40) and the drain
+// warpgroups take 232 each, so the 128 register sums plus the epilogue's staging do not spill (FCfg).  The single-pass modes
+// (FM_LIN1, FM_R; opt-in, see the enum) run 2 + 16 warps without the reallocation.
 // Barriers: full[s] LEADER's (both CTAs' TMA bytes) · empty[s] local, multicast tcgen05.commit · accfull[b] local, multicast
 // commit at the end of a chunk · accfree[b] leader, one remote arrive per drain warp of both CTAs (16).
 #include <cuda_fp16.h>
