@@ -537,7 +537,7 @@ def main():
             line["roofline_linear"] = roofline_linear(w, batch, flags, pk)
             rb = min(batch, 256 if w["tokens"] <= 256 else 32)
             line["roofline_rollout"] = roofline_rollout(w, flags, pk, B=rb)
-            line["roofline_rollout_dense"] = roofline_rollout(w, flags, pk, B=min(rb, 64), dense=True)
+            line["roofline_rollout_dense"] = roofline_rollout(w, flags, pk, B=rb, dense=True)       # same batch as the row-only line
         if world == 1 and not args.no_cpu_baseline:
             del eng._ws
             eng._ws = None
