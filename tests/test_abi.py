@@ -144,3 +144,20 @@ def test_baseline_and_generator_surfaces_resolve():
                  "generate_rollout", "generate_attn_gradcam"):
         params = list(inspect.signature(getattr(Generator, name)).parameters)
         assert params[:3] == ["self", "input_ids", "attention_mask"], name
+
+
+def test_flag_constants_match_the_header():
+    """Every TE_FLAG_* of include/te_b200.h has the same value in the Python binding, and the bench default is a union of them."""
+    from transformer_explainability_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "te_b200.h")).read()
+    flags = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+TE_FLAG_(\w+)\s+(\d+)u", src)}
+    assert len(flags) >= 12
+    for name, value in flags.items():
+        assert getattr(_lib, "FLAG_" + name) == value, "FLAG_%s differs from the header" % name
+        assert value & (value - 1) == 0, "TE_FLAG_%s is not a single bit" % name
+    assert len(set(flags.values())) == len(flags), "two flags share a bit"
+    known = 0
+    for v in flags.values():
+        known |= v
+    assert _lib.FLAG_BENCH_DEFAULT & ~known == 0
+    assert _lib.FLAG_BENCH_DEFAULT == 7475           # what DESIGN.md / profiles/ document as the benched selection
