@@ -8,8 +8,9 @@ full-size parity evidence:
 1. **Conditioned full-size models** (``oracle.conditioned``: every ``safe_divide`` denominator bounded away from zero;
    the fp32 CPU oracle agrees with the fp64 oracle to ~1e-5 of the map maximum) at every BASELINE config — ViT-B/16,
    ViT-L/16, DeiT-B distilled (198 tokens), BERT-base S=512 ``start_layer=0`` with one padded row — single draws at
-   flags 0 (fp32 SIMT), 51 (round-1 tensor-core selection), 307 (+ TF32 backward), 1331 (+ TF32 relevance-side attention
-   contractions) and the bench default (3379: + bf16 z+ denominator term), against the fp64 oracle: class index
+   flags 0 (fp32 SIMT), 51 (round-1 tensor-core selection), 4147 (51 with the fp16-split forward Linears), 307 (+ TF32
+   backward), 1331 (+ TF32 relevance-side attention contractions), 3379 (+ bf16 z+ denominator term), 15667 (+ the opt-in
+   fp16 second z+ contraction) and the bench default 7475 (3379 + fp16-split forward), against the fp64 oracle: class index
    bit-exact, logits, attention gradients and attn_cam of bottom / middle / top layers, final map.
 2. **Teacher-forced rules at ViT-B size on the REAL (ill-conditioned) random-init data**: every rule kernel is fed the
    oracle's inputs for that step, so kernel error is separated from the chain's chaotic amplification.
